@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- NeFeS render-path throughput on B200 (rays/s, forward + backward, 64 + 64 samples).
+
+Workload = BASELINE.json configs[1]: the stage-1 colour-only training step of
+run_nefes.py on a 7-Scenes-stairs-shaped synthetic camera (640x480 intrinsics -> 60x80 ray grid,
+focal 65.688, near 0, far 4), 4 images x 1536 random rays = 6144 rays per GPU per step:
+get_rays_batch -> gather -> render() [stratified sampling, coarse field, compositing, sample_pdf,
+fine field with transient heads, compositing] -> NeRF-W colour loss -> backward to all weights ->
+(N>1: one all-reduce of the flat gradients) -> Adam.  Weights are the reference constructor's
+random init; data is synthetic.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--precision fp32|bf16]
+
+One JSON line on stdout (rank 0).  `value` times K steps with inputs resident in HBM; `e2e` times the
+same steps through the public API with the step's host inputs copied from pinned memory and the loss
+read back every step.  `--impl reference` times the CPU oracle port of the reference path on the
+host cores (the reference itself is Python and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, FOCAL, NEAR, FAR = 60, 80, 525.505 / 2 / 4, 0., 4.
+N_IMAGES, N_RAND = 4, 1536
+RAYS = N_IMAGES * N_RAND
+# algorithmic MLP work per ray, SURVEY.md 8d: fwd 68.32 MFLOP, fwd+bwd 204.96 MFLOP (train mode)
+MLP_FLOP_PER_RAY_FWD_BWD = 204.96e6
+METRIC = "NeFeS rays/sec (fwd+bwd, 64+64 samples)"
+
+
+def nerfw_loss(ret, target, lambda_u=0.01):
+    """Caller-side loss of the stage-1 step: script/models/losses.py:112-132 (coef 1)."""
+    c_l = 0.5 * ((ret["rgb0"] - target) ** 2).mean()
+    f_l = ((ret["rgb_map"] - target) ** 2 / (2 * ret["beta"].unsqueeze(1) ** 2)).mean()
+    return c_l + f_l + 3 + torch.log(ret["beta"]).mean() + lambda_u * ret["transient_sigmas"].mean()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1387.4), d.get("hbm_gbs", 6553.3), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def host_batches(n_steps, seed, pinned=True):
+    """Per-step host inputs, as the reference's DataLoader + np.random.choice produce them
+    (run_nefes.py:47-71): poses [4,3,4], pixel indices [4,1536], target rgb [6144,3], hist [4,10]."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
+    poses = torch.tensor(g["train_gt"][:N_IMAGES].reshape(N_IMAGES, 3, 4), dtype=torch.float32)
+    rng = np.random.RandomState(seed)
+    pin = (lambda t: t.pin_memory()) if (pinned and torch.cuda.is_available()) else (lambda t: t)
+    out = []
+    for _ in range(n_steps):
+        idx = np.stack([rng.choice(H * W, N_RAND, replace=False) for _ in range(N_IMAGES)])
+        out.append(dict(pose=pin(poses.clone()), idx=pin(torch.from_numpy(idx).long()),
+                        target=pin(torch.from_numpy(rng.rand(RAYS, 3).astype(np.float32))),
+                        hist=pin(torch.zeros(N_IMAGES, 10))))
+    return out
+
+
+def run_engine(a):
+    import torch.distributed as dist
+    import nefes_b200 as nb
+    from nefes_b200 import _lib, ops, parallel
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+    _lib.lib()
+
+    coarse = nb.NeRFH_NFF("coarse", W=128, precision=a.precision).to(dev)
+    fine = nb.NeRFH_NFF("fine", W=128, encode_appearance=True, encode_transient=True, precision=a.precision).to(dev)
+    params = [coarse.flat, fine.flat]          # stage 1 trains the two fields (FusionNet joins at stage 3)
+    opt = nb.FlatAdam(params, lr=5e-4)
+
+    class Args:
+        nerfh_nff, use_fine_only, NeRFW, transient_at_test, netchunk = True, False, True, True, 1 << 21
+    q = lambda i, v, ts, fn, typ, ot, test_time, store_rgb: nb.run_network_NeRFH_NFF(
+        i, v, ts, fn, typ=typ, output_transient=ot, netchunk=Args.netchunk, test_time=test_time, store_rgb=store_rgb)
+    kw = dict(network_query_fn=q, N_importance=64, N_samples=64, network_fn=coarse, network_fine=fine,
+              use_viewdirs=True, white_bkgd=False, args=Args(), ndc=False, lindisp=False, near=NEAR, far=FAR,
+              perturb=1., raw_noise_std=0., test_time=False, retraw=True)
+
+    def step(b):
+        """b: dict of DEVICE tensors.  One optimiser step, returns the loss tensor."""
+        ro, rd = nb.get_rays_batch(H, W, FOCAL, b["pose"])                      # [4,60,80,3]
+        ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, b["idx"][..., None].expand(-1, -1, 3)).reshape(-1, 3)
+        rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, b["idx"][..., None].expand(-1, -1, 3)).reshape(-1, 3)
+        hist = b["hist"][:, None, :].expand(-1, N_RAND, -1).reshape(-1, 10)
+        rgb, disp, acc, ex = nb.render(H, W, FOCAL, chunk=32768, rays=(ro, rd), img_idx=hist, **kw)
+        loss = nerfw_loss(dict(rgb_map=rgb, **ex), b["target"])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_grads(params)
+        opt.step(grad_scale=1.0 / world)
+        return loss
+
+    n_total = a.warmup + a.steps
+    host = host_batches(n_total, seed=1000 + rank)
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for b in resident[:a.warmup]:
+        step(b)
+    barrier()
+    ops.PROFILE = []
+    l0 = _lib.lib().nefes_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for b in resident[a.warmup:]:
+            step(b)
+        ev1.record()
+        barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(_lib.lib().nefes_launch_count() - l0)
+    prof, ops.PROFILE = ops.PROFILE, None
+    mlp_ms = sum(s.elapsed_time(e) for _, s, e in prof) / a.steps
+    value = world * RAYS * a.steps / (ms / 1e3)
+
+    # ---- end to end: host inputs from pinned memory, loss read back, every step ----------------
+    losses = []
+    barrier()
+    ev0.record()
+    for b in host[a.warmup:]:
+        d = {k: v.to(dev, non_blocking=True) for k, v in b.items()}
+        losses.append(float(step(d).item()))
+    ev1.record()
+    barrier()
+    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
+    e2e_value = world * RAYS * a.steps / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    tf_peak, hbm_peak, which = measured_peaks()
+    achieved = MLP_FLOP_PER_RAY_FWD_BWD * RAYS / (mlp_ms / 1e3) / 1e12
+    out = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": "C2 stage-1 colour-only NeRF-W training step, 7-Scenes-stairs camera 640x480 -> 60x80, "
+                               "4 images x 1536 rays = 6144 rays/GPU/step, 64 coarse + 64 fine samples, Adam",
+                   "rays_per_gpu_per_step": RAYS, "global_rays_per_step": RAYS * world, "parallelism": f"dp{world} (rays sharded, 1 gradient all-reduce)",
+                   "mlp_precision": a.precision,
+                   "l2": "no explicit flush: each step streams ~7 GB of saved activations (>> 126 MB L2)"},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "field MLP (K5) forward+backward, all launches of one step",
+                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                     "traffic": None, "peak_source": which, "ms_per_step_in_kernel": mlp_ms,
+                     "share_of_step": mlp_ms / (ms / a.steps)},
+        "clocks": clk.summary(),
+        "final_loss": losses[-1] if losses else None,
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(sample_rays=a.cpu_rays, reps=a.cpu_reps)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_baseline(sample_rays=1024, reps=3):
+    """The reference path's CPU arithmetic (oracle port, torch CPU fp32, all host threads) on a bounded
+    sample of the same step: sample_rays of the 6144 rays, forward + NeRF-W loss + backward + Adam."""
+    from oracle import nefes_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    Pc, Pf = O.clone_params(O.init_field("coarse"), requires_grad=True), O.clone_params(O.init_field("fine"), requires_grad=True)
+    opt = torch.optim.Adam(list(Pc.values()) + list(Pf.values()), lr=5e-4)
+    b = host_batches(1, seed=7, pinned=False)[0]
+    ro, rd = O.camera_rays_batch(H, W, FOCAL, b["pose"])
+    idx = b["idx"][..., None].expand(-1, -1, 3)
+    ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:sample_rays]
+    rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:sample_rays]
+    times = []
+    for i in range(reps + 1):
+        t_rand, u = torch.rand(sample_rays, 64), torch.rand(sample_rays, 64)
+        t0 = time.perf_counter()
+        ret = O.render(H, W, FOCAL, Pc, Pf, rays=(ro, rd), near=NEAR, far=FAR, test_time=False, t_rand=t_rand, u=u)
+        loss = nerfw_loss(ret, b["target"][:sample_rays])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    med = float(np.median(times[1:]))
+    return {"value": sample_rays / med, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": f"{sample_rays} of the step's 6144 rays, 64+64 samples, fwd+loss+bwd+Adam, median of {reps} after 1 warm-up, "
+                      f"torch {torch.__version__} CPU fp32, autograd anomaly mode off (the stock scripts turn it on)",
+            "seconds_per_sample": med}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps, warm = max(1, a.steps), max(1, a.warmup)
+    from oracle import nefes_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n = a.cpu_rays
+    Pc, Pf = O.clone_params(O.init_field("coarse"), requires_grad=True), O.clone_params(O.init_field("fine"), requires_grad=True)
+    opt = torch.optim.Adam(list(Pc.values()) + list(Pf.values()), lr=5e-4)
+    hb = host_batches(1, seed=7, pinned=False)[0]
+    ro, rd = O.camera_rays_batch(H, W, FOCAL, hb["pose"])
+    idx = hb["idx"][..., None].expand(-1, -1, 3)
+    ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n]
+    rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n]
+    # keep the whole run within a few minutes: cap the number of timed steps
+    budget_s, t_first = 150.0, None
+    times = []
+    for i in range(warm + steps):
+        t_rand, u = torch.rand(n, 64), torch.rand(n, 64)
+        t0 = time.perf_counter()
+        ret = O.render(H, W, FOCAL, Pc, Pf, rays=(ro, rd), near=NEAR, far=FAR, test_time=False, t_rand=t_rand, u=u)
+        loss = nerfw_loss(ret, hb["target"][:n])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+        if sum(times) > budget_s:
+            break
+    k = len(times)
+    tot = sum(times)
+    v = n * k / tot
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": a.gpus, "steps": k,
+           "warmup": warm, "ms_per_step": 1e3 * tot / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "C2 stage-1 colour-only NeRF-W training step (same as the engine arm); each step is a bounded "
+                                  f"sample of {n} of the 6144 rays", "rays_per_step_sample": n},
+           "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                            "sample": f"{n} rays/step x {k} steps, oracle port of the reference path (the reference is Python "
+                                      "and absent on the GPU box), torch CPU fp32, all host threads"},
+           "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    p.add_argument("--precision", default=os.environ.get("NEFES_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    p.add_argument("--cpu-rays", type=int, default=1024)
+    p.add_argument("--cpu-reps", type=int, default=3)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    a = p.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "engine" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_engine(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,186 @@
+/*
+ * nefes_b200 -- C ABI of the B200-native NeFeS render engine (libnefes_b200.so).
+ *
+ * The reference (ActiveVisionLab/NeFeS) has no FFI: its render path is Python callables
+ * wired through a `render_kwargs` dict.  Each entry point below names the
+ * reference callable (file:line under /root/reference/) whose arithmetic it replaces.  The Python
+ * host side (nefes_b200/*.py) keeps the reference's call surface and reaches these symbols
+ * through ctypes; no torch types cross this boundary -- plain device pointers, sizes and a
+ * cudaStream_t (passed as void*).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - all tensors are dense row-major fp32 unless stated; `ld*` arguments are row strides in
+ *     elements;
+ *   - all functions are asynchronous on `stream` and return 0 on success, a NEFES_E* code
+ *     otherwise (nefes_last_error() gives the text).  There is no CPU fallback.
+ */
+#ifndef NEFES_B200_H_
+#define NEFES_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEFES_VERSION 100          /* 0.1.0 */
+
+enum {
+  NEFES_OK = 0,
+  NEFES_EINVAL = 1,                /* bad shape / mode / null pointer                       */
+  NEFES_EALIGN = 2,                /* pointer not aligned as required                       */
+  NEFES_ECUDA = 3,                 /* a CUDA runtime call or launch failed                  */
+  NEFES_EUNSUPPORTED = 4           /* valid request this build does not implement           */
+};
+
+int nefes_version(void);
+const char* nefes_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t nefes_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Field (MLP) description.  Architecture is the one every reference config uses:
+ * D=8, W=128, skip at layer 4, xyz PE 63, dir PE 27, head 3+128 (script/models/nerfh_nff.py:
+ * 421-505, options.py:30-31,99-100).  `net` selects which layers exist.
+ * ------------------------------------------------------------------------------------------ */
+enum { NEFES_NET_COARSE = 0, NEFES_NET_FINE = 1 };
+/* forward modes == the three cases of run_network_NeRFH_NFF (nerfh_nff.py:192-231) */
+enum {
+  NEFES_MODE_SIGMA = 0,            /* NeRFH_NFF.forward(sigma_only=True)       -> raw [M,1]   */
+  NEFES_MODE_STATIC = 1,           /* forward(output_transient=False)          -> raw [M,132] */
+  NEFES_MODE_FULL = 2              /* forward(output_transient=True), fine net -> raw [M,137] */
+};
+/* arithmetic of the MLP */
+enum {
+  NEFES_PREC_FP32 = 0,             /* SIMT fp32 FMA -- the 1e-3 parity path                 */
+  NEFES_PREC_BF16 = 1              /* tcgen05 bf16 operands, fp32 TMEM accumulators         */
+};
+
+#define NEFES_MAX_LAYERS 18
+typedef struct {
+  int n_layers;                    /* 12 (coarse) or 18 (fine)                              */
+  int64_t n_params;                /* total floats in the flat buffer                       */
+  int out_dim[NEFES_MAX_LAYERS];
+  int in_dim[NEFES_MAX_LAYERS];
+  int64_t w_off[NEFES_MAX_LAYERS]; /* offset of weight [out,in] (torch Linear layout)       */
+  int64_t b_off[NEFES_MAX_LAYERS]; /* offset of bias [out]                                  */
+  const char* name[NEFES_MAX_LAYERS]; /* state_dict prefix, e.g. "xyz_encoding_1.0"         */
+} nefes_layout_t;
+/* Flat fp32 parameter buffer layout (host struct filled in). Replaces the per-module
+ * nn.Linear storage of nerfh_nff.py:469-505; names are the reference's state_dict keys. */
+int nefes_param_layout(int net, nefes_layout_t* out_host);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  get_rays / get_rays_batch            script/models/ray_utils.py:5-16, 46-59
+ * c2w [B,3,4] -> rays_o, rays_d [B,H,W,3].  bwd: d_c2w [B,3,4] (zero-filled then accumulated).
+ * ------------------------------------------------------------------------------------------ */
+int nefes_get_rays_fwd(const float* c2w, int B, int H, int W, float focal,
+                       float* rays_o, float* rays_d, void* stream);
+int nefes_get_rays_bwd(const float* d_rays_o, const float* d_rays_d, int B, int H, int W,
+                       float focal, float* d_c2w, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  stratified coarse depths              script/models/rendering.py:96-112
+ * near/far: one value per ray read at near[i*ld_nf], far[i*ld_nf] (ray_batch columns 6,7).
+ * t_vals [S] = torch.linspace(0,1,S) supplied by the host (never recomputed: SURVEY 7.3).
+ * t_rand [N,S] or NULL (perturb == 0).
+ * ------------------------------------------------------------------------------------------ */
+int nefes_sample_coarse(const float* near, const float* far, int ld_nf, const float* t_vals,
+                        const float* t_rand, int N, int S, float* z_vals, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  sample_pdf                            script/models/rendering.py:23-66
+ * bins [N,nb], weights [N,nb-1]; u [N,ns] (per-ray) or [ns] when u_per_ray == 0 (det=True).
+ * Outputs: samples [N,ns]; inds int32 [N,ns] = searchsorted(cdf,u,right=True) (may be NULL);
+ * cdf_out [N,nb] (may be NULL).  nb <= 256, ns <= 256.
+ * nefes_sample_pdf_from_cdf skips the pdf->cdf step (stage-level index parity).
+ * ------------------------------------------------------------------------------------------ */
+int nefes_sample_pdf(const float* bins, const float* weights, const float* u, int u_per_ray,
+                     int N, int nb, int ns, float* samples, int32_t* inds, float* cdf_out,
+                     void* stream);
+int nefes_sample_pdf_from_cdf(const float* bins, const float* cdf, const float* u, int u_per_ray,
+                              int N, int nb, int ns, float* samples, int32_t* inds, void* stream);
+/* Fused hierarchical step of render_rays (rendering.py:132-141): mids of z_coarse [N,S],
+ * weights_coarse[:,1:-1], sample_pdf, detach, sort(cat(z_coarse, z_samples)) -> z_fine [N,S+ns].
+ * z_samples [N,ns] and inds [N,ns] may be NULL. */
+int nefes_sample_fine(const float* z_coarse, const float* weights_coarse, const float* u,
+                      int u_per_ray, int N, int S, int ns, float* z_fine, float* z_samples,
+                      int32_t* inds, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4a frequency positional encoding         script/models/nerfh_nff.py:241-270
+ * x [M,3] -> out [M, 3+6*n_freqs] written with row stride ld_out.
+ * bwd: d_x [M,3] = d_out chained through sin/cos (overwrites d_x).
+ * ------------------------------------------------------------------------------------------ */
+int nefes_encode_pe_fwd(const float* x, int64_t M, int n_freqs, float* out, int ld_out, void* stream);
+int nefes_encode_pe_bwd(const float* x, const float* d_out, int ld_out, int64_t M, int n_freqs,
+                        float* d_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  the NeFeS field: PE + MLP             script/models/nerfh_nff.py:168-231 (query) and
+ *                                           :525-576 (NeRFH_NFF.forward)
+ * pts [M,3] with M = N*S, dirs [N,3] (unit view directions, one per ray, broadcast over the S
+ * samples of the ray exactly as nerfh_nff.py:206-207 expands them; ignored in MODE_SIGMA).
+ * raw [M,C], C = 1 / 132 / 137.
+ * `saved` keeps the activations backward needs (NULL => inference only); `scratch` is
+ * temporary.  Sizes from nefes_mlp_workspace.
+ * ------------------------------------------------------------------------------------------ */
+int nefes_mlp_workspace(int net, int mode, int prec, int64_t M, int64_t N,
+                        int64_t* saved_bytes_host, int64_t* scratch_fwd_bytes_host,
+                        int64_t* scratch_bwd_bytes_host);
+int nefes_mlp_fwd(const float* params, int net, int mode, int prec, const float* pts,
+                  const float* dirs, int64_t N, int S, float* raw, void* saved, void* scratch,
+                  void* stream);
+/* d_params (flat, same layout as params) is ACCUMULATED into (caller zero-fills) or NULL
+ * (frozen weights: refinement); d_pts [M,3] / d_dirs [N,3] are overwritten, or NULL. */
+int nefes_mlp_bwd(const float* params, int net, int mode, int prec, const float* pts,
+                  const float* dirs, int64_t N, int S, const float* raw, const float* d_raw,
+                  const void* saved, void* scratch, float* d_params, float* d_pts, float* d_dirs,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  raw2outputs_NeRFH_NFF                 script/models/nerfh_nff.py:25-166
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  NEFES_COMP_SIGMA = 0,            /* coarse & test_time: raw [N,S,1] -> acc, weights only (:83-89) */
+  NEFES_COMP_STATIC = 1,           /* output_transient=False: raw [N,S,132]          (:153-165) */
+  NEFES_COMP_TRANSIENT = 2,        /* raw [N,S,137], static+transient composite      (:119-150) */
+  NEFES_COMP_TRANSIENT_STATIC_ONLY = 3 /* test_time && !transient_at_test             (:92-117) */
+};
+typedef struct {
+  float* rgb;                      /* [N,3]   */
+  float* feat;                     /* [N,128] */
+  float* disp;                     /* [N]     */
+  float* acc;                      /* [N]     */
+  float* weights;                  /* [N,S]   */
+  float* depth;                    /* [N]     */
+  float* beta;                     /* [N]     */
+} nefes_comp_out_t;
+/* noise [N,S] = randn * raw_noise_std or NULL.  transient_sigmas is a view of raw (column
+ * 135) and is taken by the host, not copied here. */
+int nefes_composite_fwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
+                        int mode, float beta_min, const nefes_comp_out_t* out_host, void* stream);
+/* Cotangents (any may be NULL = zero): same shapes as the outputs, plus d_tsig [N,S] for the
+ * transient_sigmas view.  d_raw [N,S,C] is overwritten.  No gradient flows to z_vals (they are
+ * detached constants on this path: rendering.py:136). */
+typedef struct {
+  const float* rgb; const float* feat; const float* disp; const float* acc;
+  const float* weights; const float* depth; const float* beta; const float* tsig;
+} nefes_comp_grad_t;
+int nefes_composite_bwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
+                        int mode, const nefes_comp_grad_t* g_host, float* d_raw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Caller-side helpers on the "next" rows of SURVEY 8f that the training step needs resident.
+ * Fused Adam on the flat buffers (torch.optim.Adam, betas (0.9, 0.999), eps 1e-8, no weight
+ * decay: nerfh_nff.py:682); grad is scaled by grad_scale first (1/world_size after all-reduce).
+ * ------------------------------------------------------------------------------------------ */
+int nefes_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                    int64_t n, float lr, float beta1, float beta2, float eps, int step,
+                    float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* NEFES_B200_H_ */

@@ -1,0 +1,95 @@
+// extern "C" dispatch for the field MLP (K5) and the fused Adam step.
+#include "common.cuh"
+
+namespace nefes {
+int mlp_fwd_fp32(const float*, int, int, const float*, const float*, int64_t, int, float*, void*, void*, cudaStream_t);
+int mlp_bwd_fp32(const float*, int, int, const float*, const float*, int64_t, int, const float*, const float*,
+                 const void*, void*, float*, float*, float*, cudaStream_t);
+int mlp_workspace_fp32(int, int64_t, int64_t, int64_t*, int64_t*, int64_t*);
+int mlp_fwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, float*, void*, void*, cudaStream_t);
+int mlp_bwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, const float*, const float*,
+                 const void*, void*, float*, float*, float*, cudaStream_t);
+int mlp_workspace_bf16(int, int, int64_t, int64_t, int64_t*, int64_t*, int64_t*);
+
+// torch.optim.Adam semantics (amsgrad=False, weight_decay=0, maximize=False)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt, float gscale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+static int check_mlp(const char* who, int net, int mode, int prec, int64_t N, int S) {
+  NEFES_REQUIRE(net == NEFES_NET_COARSE || net == NEFES_NET_FINE, NEFES_EINVAL, "%s: bad net %d", who, net);
+  NEFES_REQUIRE(mode >= NEFES_MODE_SIGMA && mode <= NEFES_MODE_FULL, NEFES_EINVAL, "%s: bad mode %d", who, mode);
+  NEFES_REQUIRE(mode != NEFES_MODE_FULL || net == NEFES_NET_FINE, NEFES_EINVAL,
+                "%s: MODE_FULL needs the fine net (the coarse net has no transient heads)", who);
+  NEFES_REQUIRE(prec == NEFES_PREC_FP32 || prec == NEFES_PREC_BF16, NEFES_EINVAL, "%s: bad precision %d", who, prec);
+  NEFES_REQUIRE(N >= 0 && S >= 1 && N * (int64_t)S < (int64_t)1 << 31, NEFES_EINVAL,
+                "%s: bad shape N=%lld S=%d", who, (long long)N, S);
+  return NEFES_OK;
+}
+}  // namespace nefes
+
+extern "C" {
+
+int nefes_mlp_workspace(int net, int mode, int prec, int64_t M, int64_t N, int64_t* saved_bytes_host,
+                        int64_t* scratch_fwd_bytes_host, int64_t* scratch_bwd_bytes_host) {
+  NEFES_REQUIRE(saved_bytes_host && scratch_fwd_bytes_host && scratch_bwd_bytes_host, NEFES_EINVAL,
+                "nefes_mlp_workspace: null output");
+  if (int e = nefes::check_mlp("nefes_mlp_workspace", net, mode, prec, N > 0 ? N : 1, 1)) return e;
+  if (prec == NEFES_PREC_BF16)
+    return nefes::mlp_workspace_bf16(net, mode, M, N, saved_bytes_host, scratch_fwd_bytes_host, scratch_bwd_bytes_host);
+  return nefes::mlp_workspace_fp32(mode, M, N, saved_bytes_host, scratch_fwd_bytes_host, scratch_bwd_bytes_host);
+}
+
+int nefes_mlp_fwd(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
+                  int64_t N, int S, float* raw, void* saved, void* scratch, void* stream) {
+  if (int e = nefes::check_mlp("nefes_mlp_fwd", net, mode, prec, N, S)) return e;
+  NEFES_REQUIRE(params && pts && raw && saved, NEFES_EINVAL, "nefes_mlp_fwd: null pointer");
+  NEFES_REQUIRE(mode == NEFES_MODE_SIGMA || (dirs && scratch), NEFES_EINVAL, "nefes_mlp_fwd: dirs/scratch required");
+  NEFES_REQUIRE(((uintptr_t)saved & 15) == 0 && ((uintptr_t)scratch & 15) == 0, NEFES_EALIGN,
+                "nefes_mlp_fwd: workspaces must be 16-byte aligned");
+  if (N == 0) return NEFES_OK;
+  if (prec == NEFES_PREC_BF16)
+    return nefes::mlp_fwd_bf16(params, net, mode, pts, dirs, N, S, raw, saved, scratch, (cudaStream_t)stream);
+  return nefes::mlp_fwd_fp32(params, net, mode, pts, dirs, N, S, raw, saved, scratch, (cudaStream_t)stream);
+}
+
+int nefes_mlp_bwd(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
+                  int64_t N, int S, const float* raw, const float* d_raw, const void* saved, void* scratch,
+                  float* d_params, float* d_pts, float* d_dirs, void* stream) {
+  if (int e = nefes::check_mlp("nefes_mlp_bwd", net, mode, prec, N, S)) return e;
+  NEFES_REQUIRE(params && pts && raw && d_raw && saved && scratch, NEFES_EINVAL, "nefes_mlp_bwd: null pointer");
+  NEFES_REQUIRE(mode == NEFES_MODE_SIGMA || dirs, NEFES_EINVAL, "nefes_mlp_bwd: dirs required");
+  NEFES_REQUIRE(((uintptr_t)saved & 15) == 0 && ((uintptr_t)scratch & 15) == 0, NEFES_EALIGN,
+                "nefes_mlp_bwd: workspaces must be 16-byte aligned");
+  if (N == 0) return NEFES_OK;
+  if (prec == NEFES_PREC_BF16)
+    return nefes::mlp_bwd_bf16(params, net, mode, pts, dirs, N, S, raw, d_raw, saved, scratch, d_params, d_pts,
+                               d_dirs, (cudaStream_t)stream);
+  return nefes::mlp_bwd_fp32(params, net, mode, pts, dirs, N, S, raw, d_raw, saved, scratch, d_params, d_pts,
+                             d_dirs, (cudaStream_t)stream);
+}
+
+int nefes_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  NEFES_REQUIRE(params && grads && exp_avg && exp_avg_sq, NEFES_EINVAL, "nefes_adam_step: null pointer");
+  NEFES_REQUIRE(n >= 0 && step >= 1, NEFES_EINVAL, "nefes_adam_step: bad n/step");
+  if (n == 0) return NEFES_OK;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  nefes::adam_kernel<<<(unsigned)nefes::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  NEFES_CHECK_LAUNCH("adam");
+  return NEFES_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,350 @@
+"""Host-side mirror of the reference's script/models/nerfh_nff.py for the render hot path:
+same names, argument meaning and return conventions, arithmetic on the B200 kernels.
+
+    raw2outputs_NeRFH_NFF   nerfh_nff.py:25-166
+    run_network_NeRFH_NFF   nerfh_nff.py:168-231
+    get_embedder / Embedder nerfh_nff.py:234-354
+    NeRFH_NFF               nerfh_nff.py:421-626
+    create_nerf             nerfh_nff.py:628-737
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+FEATURE_DIM = 128
+img2mse = lambda x, y: torch.mean((x - y) ** 2)
+mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))
+to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
+
+# default arithmetic of the MLP: "fp32" (parity path) or "bf16" (tcgen05); see NeRFH_NFF.precision
+DEFAULT_PRECISION = os.environ.get("NEFES_PRECISION", "fp32")
+_PREC = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}
+
+
+# ------------------------------------------------------------------------------------------------
+def raw2outputs_NeRFH_NFF(raw, z_vals, raw_noise_std=0, output_transient=False, beta_min=0.1, white_bkgd=False,
+                          test_time=False, typ="coarse", store_rgb=False, transient_at_test=False, noise=None):
+    """Drop-in for nerfh_nff.py:25.  Returns (rgb_map, features_map, disp_map, acc_map, weights,
+    depth_map, transient_sigmas, beta).  `noise` (extra, optional) supplies randn*raw_noise_std
+    explicitly for RNG parity; otherwise it is drawn on the device when raw_noise_std > 0."""
+    if white_bkgd:
+        raise RuntimeError("nefes_b200: white_bkgd=True is not supported (no reference config uses it)")
+    if typ == "coarse" and test_time and not store_rgb:                      # :33-35, :83-89
+        acc, weights = ops.composite(raw[..., :1], z_vals, None, L.COMP_SIGMA, beta_min)
+        return None, None, None, acc, weights, None, None, None
+    if output_transient:
+        if raw.shape[-1] != 137:
+            raise RuntimeError(f"nefes_b200: transient compositing expects 137 channels, got {raw.shape[-1]}")
+        mode = L.COMP_TRANSIENT_STATIC_ONLY if (test_time and not transient_at_test) else L.COMP_TRANSIENT
+        rgb, feat, disp, acc, weights, depth, beta = ops.composite(raw, z_vals, None, mode, beta_min)
+        return rgb, feat, disp, acc, weights, depth, raw[..., 135], beta
+    if raw.shape[-1] != 132:
+        raise RuntimeError(f"nefes_b200: static compositing expects 132 channels, got {raw.shape[-1]}")
+    if noise is None and raw_noise_std > 0.:
+        noise = torch.randn(raw.shape[:2], device=raw.device) * raw_noise_std
+    rgb, feat, disp, acc, weights, depth, beta = ops.composite(raw, z_vals, noise, L.COMP_STATIC, beta_min)
+    return rgb, feat, disp, acc, weights, depth, None, beta
+
+
+def run_network_NeRFH_NFF(inputs, viewdirs, ts, fn, embed_fn=None, embeddirs_fn=None, typ="coarse",
+                          output_transient=False, netchunk=1024 * 64, test_time=False, store_rgb=False):
+    """Drop-in for nerfh_nff.py:168.  `ts` is accepted and ignored, as in the reference.  The
+    positional encodings are fused into the field kernel, so embed_fn / embeddirs_fn are unused;
+    netchunk bounds the rays handed to one launch (activation workspace), not the arithmetic."""
+    n_rays, n_samples = inputs.shape[0], inputs.shape[1]
+    if typ == "coarse" and test_time:
+        mode = L.MODE_SIGMA
+    elif typ == "fine" and output_transient:
+        mode = L.MODE_FULL
+    else:
+        mode = L.MODE_STATIC
+    rays_per_chunk = max(1, int(netchunk) // n_samples)
+    if n_rays <= rays_per_chunk:
+        return fn.query(inputs, viewdirs, mode)
+    outs = [fn.query(inputs[i:i + rays_per_chunk], None if viewdirs is None else viewdirs[i:i + rays_per_chunk], mode)
+            for i in range(0, n_rays, rays_per_chunk)]
+    return torch.cat(outs, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+class Embedder:
+    """nerfh_nff.py:234-270: [x, sin(2^k x), cos(2^k x)]_k with log-sampled bands."""
+
+    def __init__(self, **kwargs):
+        self.kwargs = kwargs
+        self.N_freqs = kwargs["num_freqs"]
+        d = kwargs["input_dims"]
+        if d != 3 or not kwargs.get("include_input", True) or not kwargs.get("log_sampling", True):
+            raise RuntimeError("nefes_b200: only the 3-D, include_input, log-sampled embedder is built")
+        self.out_dim = d + 2 * d * self.N_freqs
+
+    def embed(self, inputs):
+        if self.kwargs["max_freq_log2"] == 0:
+            return inputs
+        return ops.encode_pe(inputs, self.N_freqs)
+
+
+def get_embedder(multires, i=0, reduce_mode=-1, epochToMaxFreq=-1):
+    """nerfh_nff.py:303-354 (reduce_mode -1: the paper default, the only one the configs use)."""
+    if i == -1:
+        return nn.Identity(), 3
+    if reduce_mode not in (-1,):
+        raise RuntimeError("nefes_b200: reduce_embedding modes 0/1/2 are not built")
+    obj = Embedder(include_input=True, input_dims=3, max_freq_log2=multires - 1, num_freqs=multires,
+                   log_sampling=True, periodic_fns=[torch.sin, torch.cos])
+    return (lambda x, eo=obj: eo.embed(x)), obj.out_dim, obj
+
+
+# ------------------------------------------------------------------------------------------------
+class FusionNet(nn.Module):
+    """nerfh_nff.py:356-418 -- caller-side CNN after the render path ("next");
+    kept as plain torch so checkpoints load and run_fusion_net works."""
+    mean = [0.485, 0.456, 0.406]
+    std = [0.229, 0.224, 0.225]
+
+    def __init__(self, f_dim, fusion_residule=False, no_BN=False):
+        super().__init__()
+        self.fusion_residule, self.no_BN = fusion_residule, no_BN
+        layers = [nn.Conv2d(3 + f_dim, 64, 3, 1, 1), nn.ReLU(), nn.Conv2d(64, 64, 3, 1, 1), nn.ReLU(),
+                  nn.Conv2d(64, 64, 3, 1, 1), nn.ReLU(), nn.Conv2d(64, f_dim, 5, 1, 2)]
+        if not no_BN:
+            layers.append(nn.BatchNorm2d(f_dim))
+        self.net = nn.Sequential(*layers)
+
+    def forward(self, x):
+        mean, std = x.new_tensor(self.mean), x.new_tensor(self.std)
+        x[:, :3] = (x[:, :3] - mean[:, None, None]) / std[:, None, None]
+        y = self.net(x)
+        return x[:, 3:] + y if self.fusion_residule else y
+
+
+class NeRFH_NFF(nn.Module):
+    """The NeFeS field (nerfh_nff.py:421-626): xyz PE(63) -> 8x128 ReLU trunk with a skip at layer
+    4 -> softplus sigma, 128 'final' -> [final | dir PE(27)] -> 64 -> 131 (rgb 3 + feature 128),
+    plus NeRF-W transient heads on the fine net.
+
+    Storage: ONE flat fp32 nn.Parameter (`flat`) laid out by nefes_param_layout; state_dict() /
+    load_state_dict() speak the reference's per-layer keys (xyz_encoding_1.0.weight, ...), so
+    reference checkpoints load unchanged.  Only the architecture every reference config uses is
+    built (D=8, W=128, skips=[4], 63/27 input channels, f_dim=128).
+    """
+
+    def __init__(self, typ, D=8, W=256, skips=[4], in_channels_xyz=63, in_channels_dir=27,
+                 encode_appearance=False, in_channels_a=48, encode_transient=False, in_channels_t=16,
+                 beta_min=0.1, out_ch_size=3, f_dim=FEATURE_DIM, fusion_residule=False, no_BN=False,
+                 precision=None):
+        super().__init__()
+        if (D, W, list(skips), in_channels_xyz, in_channels_dir, out_ch_size, f_dim) != (8, 128, [4], 63, 27, 3, 128):
+            raise RuntimeError("nefes_b200: only D=8, W=128, skips=[4], xyz 63, dir 27, rgb 3 + 128 features is built "
+                               f"(got D={D} W={W} skips={skips} xyz={in_channels_xyz} dir={in_channels_dir})")
+        torch.manual_seed(0)                                     # nerfh_nff.py:446
+        self.typ = typ
+        self.D, self.W, self.skips = D, W, skips
+        self.in_channels_xyz, self.in_channels_dir = in_channels_xyz, in_channels_dir
+        self.encode_appearance = False if typ == "coarse" else encode_appearance
+        self.encode_transient = False if typ == "coarse" else encode_transient
+        self.beta_min = beta_min
+        self.W_features = f_dim
+        self.out_ch_size = out_ch_size + f_dim
+        self.fusion_residule, self.no_BN = fusion_residule, no_BN
+        self.net_id = L.NET_FINE if self.encode_transient else L.NET_COARSE
+        self.precision = precision or DEFAULT_PRECISION
+
+        # Same construction order as the reference so the default init is bit-identical.
+        init = OrderedDict()
+
+        def lin(name, fan_in, fan_out):
+            layer = nn.Linear(fan_in, fan_out)
+            init[name] = (layer.weight.detach(), layer.bias.detach())
+        for i in range(D):
+            lin(f"xyz_encoding_{i + 1}.0", in_channels_xyz if i == 0 else (W + in_channels_xyz if i in skips else W), W)
+        lin("xyz_encoding_final", W, W)
+        lin("dir_encoding.0", W + in_channels_dir, W // 2)
+        lin("static_sigma.0", W, 1)
+        lin("static_rgb.0", W // 2, self.out_ch_size)
+        if self.encode_transient:
+            lin("transient_encoding.0", W + in_channels_dir, W // 2)
+            lin("transient_encoding.2", W // 2, W // 2)
+            lin("transient_encoding.4", W // 2, W // 2)
+            lin("transient_sigma.0", W // 2, 1)
+            lin("transient_rgb.0", W // 2, 3)
+            lin("transient_beta.0", W // 2, 1)
+        rows, n_params = L.layout(self.net_id)
+        assert set(r[0] for r in rows) == set(init), "layout / constructor mismatch"
+        flat = torch.empty(n_params)
+        for name, out_d, in_d, w_off, b_off in rows:
+            w, b = init[name]
+            assert tuple(w.shape) == (out_d, in_d)
+            flat[w_off:w_off + out_d * in_d] = w.reshape(-1)
+            flat[b_off:b_off + out_d] = b
+        self.flat = nn.Parameter(flat)
+        self._rows = rows
+        if typ == "coarse":
+            self.fusion_net = FusionNet(self.W_features, fusion_residule, no_BN)
+        self.sigmoid = nn.Sigmoid()
+
+    # ---- reference-keyed views -------------------------------------------------------------
+    def layer_views(self, tensor=None):
+        """OrderedDict name.weight / name.bias -> view into `tensor` (default: self.flat.data),
+        in the reference's state_dict order."""
+        t = self.flat.data if tensor is None else tensor
+        by = {r[0]: r for r in self._rows}
+        order = [f"xyz_encoding_{i + 1}.0" for i in range(8)] + ["xyz_encoding_final", "dir_encoding.0",
+                                                                 "static_sigma.0", "static_rgb.0"]
+        if self.net_id == L.NET_FINE:
+            order += ["transient_encoding.0", "transient_encoding.2", "transient_encoding.4", "transient_sigma.0",
+                      "transient_rgb.0", "transient_beta.0"]
+        out = OrderedDict()
+        for name in order:
+            _, o, i, w_off, b_off = by[name]
+            out[name + ".weight"] = t[w_off:w_off + o * i].view(o, i)
+            out[name + ".bias"] = t[b_off:b_off + o]
+        return out
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for k, v in self.layer_views().items():
+            destination[prefix + k] = v if keep_vars else v.detach().clone()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        mine = self.layer_views()
+        with torch.no_grad():
+            for k, view in mine.items():
+                src = state_dict.get(prefix + k)
+                if src is None:
+                    missing_keys.append(prefix + k)
+                elif tuple(src.shape) != tuple(view.shape):
+                    error_msgs.append(f"size mismatch for {prefix + k}: {tuple(src.shape)} vs {tuple(view.shape)}")
+                else:
+                    view.copy_(src)
+        own = {prefix + k for k in mine} | {prefix + "flat"}
+        child = tuple(prefix + c + "." for c, _ in self.named_children())
+        for k in state_dict:
+            if k.startswith(prefix) and k not in own and not k.startswith(child):
+                # reference-only tensors with no counterpart on this path (tcnn exposure MLP)
+                if k == prefix + "exposure_embedding.params":
+                    continue
+                unexpected_keys.append(k)
+
+    # ---- kernels ---------------------------------------------------------------------------
+    def query(self, pts, viewdirs, mode):
+        """pts [N,S,3], viewdirs [N,3] -> raw [N,S,C] (PE fused)."""
+        prec = _PREC[self.precision]
+        if mode == L.MODE_FULL and self.net_id != L.NET_FINE:
+            raise RuntimeError("nefes_b200: transient output requested from the coarse net")
+        return ops.field_query(pts, None if mode == L.MODE_SIGMA else viewdirs, self.flat, self.net_id, mode, prec)
+
+    def forward(self, x, sigma_only=False, output_transient=True):
+        """Drop-in for nerfh_nff.py:525-576.  `x` is the embedded input [B, 63] / [B, 90]; the raw
+        xyz / direction are its leading 3 channels of each block (include_input=True), and the
+        encoding is recomputed inside the kernel."""
+        xyz = x[:, None, 0:3]
+        if sigma_only:
+            return self.query(xyz, None, L.MODE_SIGMA)[:, 0]
+        dirs = x[:, self.in_channels_xyz:self.in_channels_xyz + 3]
+        mode = L.MODE_FULL if (output_transient and self.net_id == L.NET_FINE) else L.MODE_STATIC
+        return self.query(xyz, dirs, mode)[:, 0]
+
+    def run_fusion_net(self, rgb, feature, H, W, B):
+        """nerfh_nff.py:578-603."""
+        render_rgb = rgb.reshape(B, H, W, 3).permute(0, 3, 1, 2)
+        render_feature = feature.reshape(B, H, W, self.W_features).permute(0, 3, 1, 2)
+        fusion_input = torch.cat([render_rgb, render_feature], dim=1)
+        return render_rgb, render_feature, self.fusion_net(fusion_input)
+
+    def affine_color_transform(self, args, rgb, hist, batch_size):
+        raise RuntimeError("nefes_b200: affine_color_transform needs the tiny-cuda-nn exposure MLP, which is outside "
+                           "the render hot path (SURVEY.md 8f-2) and not built in this round")
+
+
+# ------------------------------------------------------------------------------------------------
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr, betas=(0.9,0.999)) semantics (nerfh_nff.py:682) as one fused kernel per
+    flat parameter buffer.  param_groups[...]['lr'] can be rewritten by the caller's schedule
+    (run_nefes.py:266-270).  grad_scale multiplies gradients first (1/world_size after all-reduce)."""
+
+    def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=1.0):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                st["step"] += 1
+                if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous():
+                    ops.adam_step(p, p.grad, st["exp_avg"], st["exp_avg_sq"], group["lr"], group["betas"][0],
+                                  group["betas"][1], group["eps"], st["step"], grad_scale)
+                else:
+                    raise RuntimeError("nefes_b200.FlatAdam: parameters must be contiguous fp32 CUDA tensors")
+
+
+def create_nerf(args, device=None):
+    """Drop-in for nerfh_nff.py:628-737: (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer)."""
+    device = torch.device(device or "cuda")
+    embed_fn, input_ch, _ = get_embedder(args.multires, args.i_embed, getattr(args, "reduce_embedding", -1))
+    embeddirs_fn, input_ch_views = None, 0
+    if args.use_viewdirs:
+        embeddirs_fn, input_ch_views, _ = get_embedder(args.multires_views, args.i_embed,
+                                                       getattr(args, "reduce_embedding", -1))
+    skips = [4]
+    model = NeRFH_NFF("coarse", D=args.netdepth, W=args.netwidth, skips=skips, in_channels_xyz=input_ch,
+                      in_channels_dir=input_ch_views, fusion_residule=getattr(args, "use_fusion_res", False),
+                      no_BN=getattr(args, "no_fusion_BN", False)).to(device)
+    grad_vars = list(model.parameters())
+    model_fine = None
+    if args.N_importance > 0:
+        model_fine = NeRFH_NFF("fine", D=args.netdepth, W=args.netwidth, skips=skips, in_channels_xyz=input_ch,
+                               in_channels_dir=input_ch_views, encode_appearance=True, encode_transient=True,
+                               in_channels_a=getattr(args, "in_channels_a", 48),
+                               in_channels_t=getattr(args, "in_channels_t", 16)).to(device)
+        grad_vars += list(model_fine.parameters())
+
+    network_query_fn = lambda inputs, viewdirs, ts, network_fn, typ, output_transient, test_time, store_rgb: \
+        run_network_NeRFH_NFF(inputs, viewdirs, ts, network_fn, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn,
+                              typ=typ, output_transient=output_transient, netchunk=args.netchunk,
+                              test_time=test_time, store_rgb=store_rgb)
+    if getattr(args, "no_grad_update", False):
+        grad_vars, optimizer = None, None
+    else:
+        optimizer = FlatAdam(grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+
+    start = 0
+    ckpts = []
+    if getattr(args, "ft_path", None) not in (None, "None"):
+        ckpts = [args.ft_path]
+    elif getattr(args, "basedir", None) and os.path.isdir(os.path.join(args.basedir, args.expname)):
+        d = os.path.join(args.basedir, args.expname)
+        ckpts = [os.path.join(d, f) for f in sorted(os.listdir(d)) if "tar" in f]
+    if ckpts and not getattr(args, "no_reload", False):
+        ckpt = torch.load(ckpts[-1], map_location=device)
+        start = ckpt["global_step"]
+        model.load_state_dict(ckpt["network_fn_state_dict"], strict=False)
+        if model_fine is not None:
+            model_fine.load_state_dict(ckpt["network_fine_state_dict"])
+
+    render_kwargs_train = dict(network_query_fn=network_query_fn, perturb=args.perturb, N_importance=args.N_importance,
+                               N_samples=args.N_samples, network_fn=model, use_viewdirs=args.use_viewdirs,
+                               white_bkgd=args.white_bkgd, raw_noise_std=args.raw_noise_std, test_time=False, args=args)
+    if model_fine is not None:
+        render_kwargs_train["network_fine"] = model_fine
+    if args.dataset_type != "llff" or args.no_ndc:
+        render_kwargs_train["ndc"] = False
+        render_kwargs_train["lindisp"] = args.lindisp
+    render_kwargs_test = dict(render_kwargs_train)
+    render_kwargs_test.update(perturb=False, raw_noise_std=0., test_time=True)
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer

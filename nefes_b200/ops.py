@@ -1,0 +1,291 @@
+"""torch.autograd wrappers around the C-ABI kernels.  One Function per stage of the path so each
+can stand in for the matching reference callable on its own."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+
+_lin_cache = {}
+
+# bench.py sets this to a list to collect (tag, start_event, end_event) around every field-MLP launch
+# group on the launching stream (roofline: achieved = algorithmic FLOPs / measured duration).
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s, self.e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e.record()
+            PROFILE.append((self.tag, self.s, self.e))
+
+
+def linspace01(n: int, device):
+    """torch.linspace(0,1,n) as the reference builds it (rendering.py:94, :33) -- produced by
+    torch on the host so the fp32 knots are bit-identical, then kept on the device."""
+    key = (n, str(device))
+    if key not in _lin_cache:
+        _lin_cache[key] = torch.linspace(0., 1., steps=n).to(device)
+    return _lin_cache[key]
+
+
+def _buf(nbytes: int, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 get_rays
+# ------------------------------------------------------------------------------------------------
+class _GetRays(Function):
+    @staticmethod
+    def forward(ctx, c2w, H, W, focal):
+        L.need_cuda(c2w)
+        m = L.f32c(c2w[..., :3, :4])
+        B = m.shape[0]
+        o = torch.empty(B, H, W, 3, device=m.device)
+        d = torch.empty_like(o)
+        L.check(L.lib().nefes_get_rays_fwd(L.ptr(m), B, H, W, float(focal), L.ptr(o), L.ptr(d), L.stream_of(m)),
+                "nefes_get_rays_fwd")
+        ctx.meta = (B, H, W, float(focal), tuple(c2w.shape))
+        return o, d
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        B, H, W, focal, shape = ctx.meta
+        g_o, g_d = L.f32c(g_o), L.f32c(g_d)
+        ref = g_o if g_o is not None else g_d
+        out = torch.empty(B, 3, 4, device=ref.device)
+        L.check(L.lib().nefes_get_rays_bwd(L.ptr(g_o), L.ptr(g_d), B, H, W, focal, L.ptr(out), L.stream_of(ref)),
+                "nefes_get_rays_bwd")
+        if shape[-2] == 3 and shape[-1] == 4:
+            return out.reshape(shape), None, None, None
+        full = torch.zeros(shape, device=ref.device)
+        full[..., :3, :4] = out.reshape(shape[:-2] + (3, 4))
+        return full, None, None, None
+
+
+def get_rays(H, W, focal, c2w_batched):
+    """c2w [B,3|4,4] -> rays_o, rays_d [B,H,W,3]"""
+    return _GetRays.apply(c2w_batched, int(H), int(W), float(focal))
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 / K3 sampling (no gradients flow through sample positions: rendering.py:51,136)
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def sample_coarse(near, far, ld, n_rays, n_samples, t_rand=None):
+    """near/far: fp32 CUDA tensors addressed as near[i*ld]."""
+    L.need_cuda(near, far, t_rand)
+    t_vals = linspace01(n_samples, near.device)
+    z = torch.empty(n_rays, n_samples, device=near.device)
+    t_rand = L.f32c(t_rand)
+    L.check(L.lib().nefes_sample_coarse(L.ptr(near), L.ptr(far), ld, L.ptr(t_vals), L.ptr(t_rand), n_rays,
+                                        n_samples, L.ptr(z), L.stream_of(near)), "nefes_sample_coarse")
+    return z
+
+
+@torch.no_grad()
+def sample_pdf(bins, weights, n_samples, u=None, cdf=None, return_inds=False):
+    """u None -> det=True (linspace).  cdf given -> skip the pdf->cdf step."""
+    L.need_cuda(bins, weights, u, cdf)
+    bins = L.f32c(bins)
+    N, nb = bins.shape
+    per_ray = 1
+    if u is None:
+        u, per_ray = linspace01(n_samples, bins.device), 0
+    u = L.f32c(u)
+    out = torch.empty(N, n_samples, device=bins.device)
+    inds = torch.empty(N, n_samples, dtype=torch.int32, device=bins.device) if return_inds else None
+    st = L.stream_of(bins)
+    if cdf is not None:
+        cdf = L.f32c(cdf)
+        L.check(L.lib().nefes_sample_pdf_from_cdf(L.ptr(bins), L.ptr(cdf), L.ptr(u), per_ray, N, nb, n_samples,
+                                                  L.ptr(out), L.ptr(inds), st), "nefes_sample_pdf_from_cdf")
+    else:
+        weights = L.f32c(weights)
+        L.check(L.lib().nefes_sample_pdf(L.ptr(bins), L.ptr(weights), L.ptr(u), per_ray, N, nb, n_samples,
+                                         L.ptr(out), L.ptr(inds), None, st), "nefes_sample_pdf")
+    return (out, inds) if return_inds else out
+
+
+@torch.no_grad()
+def sample_fine(z_coarse, weights_coarse, n_fine, u=None, want_aux=True):
+    """mids -> sample_pdf(weights[:,1:-1]) -> sort(cat) in one kernel.  Returns z_fine, z_samples, inds."""
+    L.need_cuda(z_coarse, weights_coarse, u)
+    z_coarse, weights_coarse = L.f32c(z_coarse), L.f32c(weights_coarse)
+    N, S = z_coarse.shape
+    per_ray = 1
+    if u is None:
+        u, per_ray = linspace01(n_fine, z_coarse.device), 0
+    u = L.f32c(u)
+    z_fine = torch.empty(N, S + n_fine, device=z_coarse.device)
+    z_s = torch.empty(N, n_fine, device=z_coarse.device) if want_aux else None
+    inds = torch.empty(N, n_fine, dtype=torch.int32, device=z_coarse.device) if want_aux else None
+    L.check(L.lib().nefes_sample_fine(L.ptr(z_coarse), L.ptr(weights_coarse), L.ptr(u), per_ray, N, S, n_fine,
+                                      L.ptr(z_fine), L.ptr(z_s), L.ptr(inds), L.stream_of(z_coarse)),
+            "nefes_sample_fine")
+    return z_fine, z_s, inds
+
+
+# ------------------------------------------------------------------------------------------------
+# K4a positional encoding
+# ------------------------------------------------------------------------------------------------
+class _EncodePE(Function):
+    @staticmethod
+    def forward(ctx, x, n_freqs):
+        L.need_cuda(x)
+        xc = L.f32c(x.reshape(-1, 3))
+        M = xc.shape[0]
+        ch = 3 + 6 * n_freqs
+        out = torch.empty(M, ch, device=xc.device)
+        L.check(L.lib().nefes_encode_pe_fwd(L.ptr(xc), M, n_freqs, L.ptr(out), ch, L.stream_of(xc)),
+                "nefes_encode_pe_fwd")
+        ctx.save_for_backward(xc)
+        ctx.meta = (n_freqs, tuple(x.shape))
+        return out.reshape(tuple(x.shape[:-1]) + (ch,))
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        n_freqs, shape = ctx.meta
+        ch = 3 + 6 * n_freqs
+        g = L.f32c(g.reshape(-1, ch))
+        dx = torch.empty_like(xc)
+        L.check(L.lib().nefes_encode_pe_bwd(L.ptr(xc), L.ptr(g), ch, xc.shape[0], n_freqs, L.ptr(dx),
+                                            L.stream_of(xc)), "nefes_encode_pe_bwd")
+        return dx.reshape(shape), None
+
+
+def encode_pe(x, n_freqs):
+    return _EncodePE.apply(x, int(n_freqs))
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 field query (PE + MLP)
+# ------------------------------------------------------------------------------------------------
+class _FieldQuery(Function):
+    """pts [N,S,3], dirs [N,3] (or None for MODE_SIGMA), flat params -> raw [N,S,C]."""
+
+    @staticmethod
+    def forward(ctx, pts, dirs, flat, net, mode, prec):
+        L.need_cuda(pts, dirs, flat)
+        pts_c = L.f32c(pts)
+        N, S = pts_c.shape[0], pts_c.shape[1]
+        dirs_c = L.f32c(dirs) if dirs is not None else None
+        flat_c = flat.detach()
+        if not flat_c.is_contiguous() or flat_c.dtype != torch.float32:
+            raise RuntimeError("nefes_b200: flat parameter buffer must be contiguous fp32")
+        Cc = L.RAW_CH[mode]
+        dev = pts_c.device
+        need_bwd = any(ctx.needs_input_grad[:3])
+        sv, sf, _ = L.mlp_workspace(net, mode, prec, N * S, N)
+        saved = _buf(sv, dev)
+        scratch = _buf(sf, dev)
+        raw = torch.empty(N, S, Cc, device=dev)
+        with torch.cuda.device(dev), _Timed("mlp_fwd"):
+            L.check(L.lib().nefes_mlp_fwd(L.ptr(flat_c), net, mode, prec, L.ptr(pts_c), L.ptr(dirs_c), N, S,
+                                          L.ptr(raw), L.ptr(saved), L.ptr(scratch), L.stream_of(pts_c)),
+                    "nefes_mlp_fwd")
+        if need_bwd:
+            ctx.save_for_backward(pts_c, dirs_c, flat_c, raw, saved)
+            ctx.meta = (net, mode, prec, N, S, tuple(pts.shape), None if dirs is None else tuple(dirs.shape))
+        return raw
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        pts_c, dirs_c, flat_c, raw, saved = ctx.saved_tensors
+        net, mode, prec, N, S, pshape, dshape = ctx.meta
+        dev = pts_c.device
+        d_raw = L.f32c(d_raw)
+        need_p, need_d, need_w = ctx.needs_input_grad[:3]
+        d_pts = torch.empty_like(pts_c) if need_p else None
+        d_dirs = torch.empty_like(dirs_c) if (need_d and dirs_c is not None) else None
+        d_flat = torch.zeros_like(flat_c) if need_w else None
+        _, _, sb = L.mlp_workspace(net, mode, prec, N * S, N)
+        scratch = _buf(sb, dev)
+        with torch.cuda.device(dev), _Timed("mlp_bwd"):
+            L.check(L.lib().nefes_mlp_bwd(L.ptr(flat_c), net, mode, prec, L.ptr(pts_c), L.ptr(dirs_c), N, S,
+                                          L.ptr(raw), L.ptr(d_raw), L.ptr(saved), L.ptr(scratch), L.ptr(d_flat),
+                                          L.ptr(d_pts), L.ptr(d_dirs), L.stream_of(pts_c)), "nefes_mlp_bwd")
+        return (d_pts.reshape(pshape) if d_pts is not None else None,
+                d_dirs.reshape(dshape) if d_dirs is not None else None, d_flat, None, None, None)
+
+
+def field_query(pts, dirs, flat, net, mode, prec=L.PREC_FP32):
+    return _FieldQuery.apply(pts, dirs, flat, int(net), int(mode), int(prec))
+
+
+# ------------------------------------------------------------------------------------------------
+# K6 compositing
+# ------------------------------------------------------------------------------------------------
+class _Composite(Function):
+    """raw [N,S,C], z [N,S] -> rgb, feat, disp, acc, weights, depth, beta.
+    (transient_sigmas is a view of raw taken by the caller.)"""
+
+    @staticmethod
+    def forward(ctx, raw, z, noise, mode, beta_min):
+        L.need_cuda(raw, z, noise)
+        raw_c, z_c, noise_c = L.f32c(raw), L.f32c(z), L.f32c(noise)
+        N, S = z_c.shape
+        dev = raw_c.device
+        acc = torch.empty(N, device=dev)
+        weights = torch.empty(N, S, device=dev)
+        if mode == L.COMP_SIGMA:
+            rgb = feat = disp = depth = beta = None
+        else:
+            rgb = torch.empty(N, 3, device=dev)
+            feat = torch.empty(N, 128, device=dev)
+            disp, depth, beta = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
+        out = L.CompOut(L.ptr(rgb), L.ptr(feat), L.ptr(disp), L.ptr(acc), L.ptr(weights), L.ptr(depth), L.ptr(beta))
+        with torch.cuda.device(dev):
+            L.check(L.lib().nefes_composite_fwd(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode,
+                                                float(beta_min), C.byref(out), L.stream_of(raw_c)),
+                    "nefes_composite_fwd")
+        ctx.save_for_backward(raw_c, z_c, noise_c)
+        ctx.meta = (mode, N, S, tuple(raw.shape))
+        if mode == L.COMP_SIGMA:
+            ctx.mark_non_differentiable()
+            return acc, weights
+        return rgb, feat, disp, acc, weights, depth, beta
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raw_c, z_c, noise_c = ctx.saved_tensors
+        mode, N, S, rshape = ctx.meta
+        if mode == L.COMP_SIGMA:
+            g_acc, g_w = grads
+            g = dict(acc=g_acc, weights=g_w)
+        else:
+            g = dict(zip(("rgb", "feat", "disp", "acc", "weights", "depth", "beta"), grads))
+        g = {k: L.f32c(v) for k, v in g.items() if v is not None}
+        gs = L.CompGrad(*[L.ptr(g.get(k)) for k in ("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig")])
+        d_raw = torch.empty_like(raw_c)
+        with torch.cuda.device(raw_c.device):
+            L.check(L.lib().nefes_composite_bwd(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode, C.byref(gs),
+                                                L.ptr(d_raw), L.stream_of(raw_c)), "nefes_composite_bwd")
+        return d_raw.reshape(rshape), None, None, None, None
+
+
+def composite(raw, z, noise, mode, beta_min=0.1):
+    return _Composite.apply(raw, z, noise, int(mode), float(beta_min))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused Adam on flat buffers
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    L.need_cuda(p, g, m, v)
+    L.check(L.lib().nefes_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, beta1, beta2, eps,
+                                    int(step), grad_scale, L.stream_of(p)), "nefes_adam_step")

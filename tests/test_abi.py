@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads and exports every symbol include/nefes_b200.h declares; the flat
+parameter layout matches the reference's state_dict; host-side argument checks fire without a GPU."""
+import ctypes
+import os
+import re
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "nefes_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nefes_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nefes_b200 import _lib
+    lib = _lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert sorted(_lib.exported_symbols()) == syms, "ctypes table and header disagree"
+    assert lib.nefes_version() == 100
+
+
+def test_layout_matches_reference_state_dict(weights):
+    from nefes_b200 import _lib
+    wc, wf = weights
+    for net, ref in ((0, wc), (1, wf)):
+        rows, n = _lib.layout(net)
+        assert n == sum(v.numel() for v in ref.values())
+        spans = []
+        for name, o, i, w_off, b_off in rows:
+            assert tuple(ref[name + ".weight"].shape) == (o, i)
+            assert tuple(ref[name + ".bias"].shape) == (o,)
+            spans += [(w_off, w_off + o * i), (b_off, b_off + o)]
+        spans.sort()
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])), "layout has gaps or overlaps"
+
+
+def test_host_argument_checks_without_gpu():
+    from nefes_b200 import _lib
+    lib = _lib.lib()
+    assert lib.nefes_get_rays_fwd(None, 1, 60, 80, 65.0, None, None, None) == 1          # NEFES_EINVAL
+    assert b"null" in lib.nefes_last_error()
+    a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    assert lib.nefes_mlp_workspace(0, 2, 0, 64, 1, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)) == 1
+    assert b"fine net" in lib.nefes_last_error()
+    assert lib.nefes_mlp_workspace(1, 2, 0, 128 * 64, 64, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)) == 0
+    assert a.value > 0 and c.value > 0
+
+
+def test_model_state_dict_round_trip(weights):
+    import nefes_b200 as nb
+    wc, wf = weights
+    f = nb.NeRFH_NFF("fine", W=128, encode_appearance=True, encode_transient=True)
+    sd = f.state_dict()
+    assert list(sd) == list(wf)                      # same keys, same order as the reference
+    assert all(torch.equal(sd[k], wf[k]) for k in wf)   # default init == reference constructor init
+    c = nb.NeRFH_NFF("coarse", W=128)
+    sdc = c.state_dict()
+    assert all(torch.equal(sdc[k], wc[k]) for k in wc)
+    assert any(k.startswith("fusion_net.net.") for k in sdc)
+    missing = c.load_state_dict({**wc, "exposure_embedding.params": torch.zeros(3)}, strict=False)
+    assert all(k.startswith("fusion_net") for k in missing.missing_keys) and not missing.unexpected_keys
+
+
+def test_cpu_tensors_are_rejected():
+    import pytest
+    import nefes_b200 as nb
+    with pytest.raises(RuntimeError, match="CUDA"):
+        nb.get_rays(4, 4, 10.0, torch.eye(4))

@@ -1,0 +1,359 @@
+"""GPU parity: every CUDA stage, through the C ABI (nefes_b200 -> ctypes -> libnefes_b200.so),
+against (a) the committed golden vectors produced by the unmodified reference and (b) the CPU
+oracle on larger seeded inputs.  Bars: bit-exact for rays / coarse depths / sample indices given
+the same cdf; fp32 tolerances stated per test (north star: 1e-3 relative)."""
+import math
+
+import pytest
+import torch
+
+from oracle import nefes_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+H, W, FOCAL, NEAR, FAR = 60, 80, 525.505 / 2 / 4, 0., 4.
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nefes_b200
+    from nefes_b200 import _lib
+    _lib.lib()
+    return nefes_b200
+
+
+@pytest.fixture(scope="module")
+def models(nb, weights):
+    wc, wf = weights
+    c = nb.NeRFH_NFF("coarse", W=128)
+    f = nb.NeRFH_NFF("fine", W=128, encode_appearance=True, encode_transient=True)
+    c.load_state_dict(wc, strict=False)
+    f.load_state_dict(wf)
+    return c.to(DEV), f.to(DEV)
+
+
+class Args:
+    nerfh_nff = True
+    use_fine_only = False
+    NeRFW = True
+    transient_at_test = True
+    netchunk = 1 << 21
+
+
+def render_kwargs(nb, models, test_time):
+    c, f = models
+    q = lambda inputs, viewdirs, ts, fn, typ, output_transient, test_time, store_rgb: \
+        nb.run_network_NeRFH_NFF(inputs, viewdirs, ts, fn, typ=typ, output_transient=output_transient,
+                                 netchunk=Args.netchunk, test_time=test_time, store_rgb=store_rgb)
+    return dict(network_query_fn=q, N_importance=64, N_samples=64, network_fn=c, network_fine=f,
+                use_viewdirs=True, white_bkgd=False, args=Args(), ndc=False, lindisp=False, near=NEAR, far=FAR,
+                perturb=0. if test_time else 1., raw_noise_std=0., test_time=test_time)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_get_rays_bit_exact_and_pose_gradient(nb, golden):
+    g = golden("g1_rays.npz")
+    c2w = g["c2w"].to(DEV).requires_grad_(True)
+    o, d = nb.get_rays(H, W, FOCAL, c2w)
+    assert torch.equal(o.cpu(), g["rays_o"]) and torch.equal(d.detach().cpu(), g["rays_d"])
+    ob, db = nb.get_rays_batch(H, W, FOCAL, g["c2w_b"].to(DEV))
+    assert torch.equal(ob.cpu(), g["rays_o_b"]) and torch.equal(db.cpu(), g["rays_d_b"])
+    gen = torch.Generator().manual_seed(1)
+    ko, kd = torch.randn(H, W, 3, generator=gen), torch.randn(H, W, 3, generator=gen)
+    ((o * ko.to(DEV)).sum() + (d * kd.to(DEV)).sum()).backward()
+    c_ref = g["c2w"].clone().requires_grad_(True)
+    o2, d2 = O.camera_rays(H, W, FOCAL, c_ref)
+    ((o2 * ko).sum() + (d2 * kd).sum()).backward()
+    assert rel_err(c2w.grad, c_ref.grad) < 1e-5
+
+
+def test_sample_coarse_bit_exact(nb):
+    from nefes_b200 import ops
+    gen = torch.Generator().manual_seed(2)
+    n = 777
+    near = torch.rand(n, 1, generator=gen)
+    far = near + 1 + 5 * torch.rand(n, 1, generator=gen)
+    t_rand = torch.rand(n, 64, generator=gen)
+    rb = torch.cat([torch.zeros(n, 6), near, far, torch.zeros(n, 13)], 1).to(DEV)
+    for tr in (None, t_rand):
+        z = ops.sample_coarse(rb[:, 6], rb[:, 7], 21, n, 64, None if tr is None else tr.to(DEV))
+        assert torch.equal(z.cpu(), O.coarse_depths(near, far, 64, tr))
+
+
+def test_sample_pdf_indices_exact_given_cdf(nb, golden):
+    """Stage-level known-answer test: same (bins, cdf, u) -> identical inds and samples."""
+    from nefes_b200 import ops
+    g = golden("g2_sample_pdf.npz")
+    bins, cdf = g["bins"].to(DEV), g["cdf"].to(DEV)
+    for tag, u in (("rand", g["u_rand"]), ("pytest", g["u_pytest"]), ("det", None)):
+        s, inds = ops.sample_pdf(bins, None, 64, u=None if u is None else u.to(DEV), cdf=cdf, return_inds=True)
+        assert torch.equal(inds.cpu(), g["inds_" + tag]), tag
+        assert torch.equal(s.cpu(), g["samples_" + tag]), tag
+
+
+def test_sample_pdf_from_weights(nb, golden):
+    """Full sample_pdf: the pdf normaliser is a SIMD-order-dependent torch.sum on the CPU, so the cdf
+    may differ in the last ulp; indices may flip only where u sits within 2 ulp of a cdf knot."""
+    from nefes_b200 import ops
+    g = golden("g2_sample_pdf.npz")
+    bins, wts, cdf_ref = g["bins"].to(DEV), g["weights"].to(DEV), g["cdf"]
+    for tag, u in (("rand", g["u_rand"]), ("det", None)):
+        s, inds = ops.sample_pdf(bins, wts, 64, u=None if u is None else u.to(DEV), return_inds=True)
+        bad = inds.cpu() != g["inds_" + tag]
+        if bad.any():
+            uu = (g["u_det"].expand(96, 64) if u is None else u)[bad]
+            rows = bad.nonzero()[:, 0]
+            near_knot = (cdf_ref[rows] - uu[:, None]).abs().min(-1)[0]
+            assert float(near_knot.max()) <= 3e-7
+        assert float(bad.float().mean()) < 0.02
+        assert float((s.cpu() - g["samples_" + tag]).abs().max()) < 2e-5
+    out = nb.sample_pdf(bins, wts, 64, det=False, pytest=True)          # the reference's own determinism hook
+    assert float((out.cpu() - g["samples_pytest"]).abs().max()) < 2e-5
+
+
+def test_sample_fine_sorted_union(nb):
+    from nefes_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    n = 513
+    zc = O.coarse_depths(torch.zeros(n, 1), 4 * torch.ones(n, 1), 64, torch.rand(n, 64, generator=gen))
+    w = torch.rand(n, 64, generator=gen) ** 3
+    u = torch.rand(n, 64, generator=gen)
+    for uu in (u, None):
+        zf, zs, inds = ops.sample_fine(zc.to(DEV), w.to(DEV), 64, None if uu is None else uu.to(DEV))
+        mids = .5 * (zc[:, 1:] + zc[:, :-1])
+        s_ref, i_ref, cdf = O.importance_depths(mids, w[:, 1:-1], 64, uu)
+        zf_ref = torch.sort(torch.cat([zc, s_ref], -1), -1)[0]
+        assert float((inds.cpu() != i_ref.int()).float().mean()) < 0.01
+        assert float((zs.cpu() - s_ref).abs().max()) < 2e-5
+        assert float((zf.cpu() - zf_ref).abs().max()) < 2e-5
+        assert bool((zf[:, 1:] >= zf[:, :-1]).all())
+        # exact multiset property: z_fine is a permutation of cat(z_coarse, z_samples)
+        assert torch.equal(torch.sort(torch.cat([zc.to(DEV), zs], -1), -1)[0], zf)
+
+
+def test_positional_encoding(nb):
+    from nefes_b200 import ops
+    gen = torch.Generator().manual_seed(6)
+    x = (torch.rand(1000, 3, generator=gen) * 8 - 4)
+    for L_ in (10, 4):
+        xg = x.to(DEV).requires_grad_(True)
+        e = ops.encode_pe(xg, L_)
+        xr = x.clone().requires_grad_(True)
+        er = O.freq_encode(xr, L_)
+        # |arg| reaches 2^9*4 rad: fp32 argument spacing is 2.4e-4 there, both sides evaluate sin of the
+        # same rounded argument; libm differences are a few ulp.
+        assert float((e.detach().cpu() - er.detach()).abs().max()) < 2e-6
+        k = torch.randn(er.shape, generator=gen)
+        (e * k.to(DEV)).sum().backward()
+        (er * k).sum().backward()
+        assert rel_err(xg.grad, xr.grad) < 1e-5
+
+
+CASES = {
+    "coarse_train": dict(typ="coarse", test_time=False),
+    "fine_train": dict(typ="fine", test_time=False, output_transient=True, transient_at_test=True),
+    "fine_test_tat": dict(typ="fine", test_time=True, output_transient=True, transient_at_test=True),
+    "fine_test_static": dict(typ="fine", test_time=True, output_transient=True, transient_at_test=False),
+    "fine_notransient": dict(typ="fine", test_time=False),
+}
+NAMES = ("rgb", "feat", "disp", "acc", "weights", "depth", "transient_sigmas", "beta")
+
+
+def test_composite_golden_all_modes(nb, golden):
+    g = golden("g3_composite.npz")
+    for case, kw in CASES.items():
+        raw = g[case + "/raw"].to(DEV).requires_grad_(True)
+        z = (g["z64"] if raw.shape[1] == 64 else g["z128"]).to(DEV)
+        out = nb.raw2outputs_NeRFH_NFF(raw, z, raw_noise_std=0, **kw)
+        gg = torch.Generator().manual_seed(17)
+        loss = 0
+        for name, t in zip(NAMES, out):
+            key = f"{case}/{name}"
+            if key in g:
+                assert rel_err(t, g[key]) < 2e-6, key
+            ref_present = key in g
+            if t is not None and t.requires_grad:
+                assert ref_present or name == "beta"
+                loss = loss + (t * torch.randn(t.shape, generator=gg).to(DEV)).sum()
+        loss.backward()
+        assert rel_err(raw.grad, g[case + "/d_raw"]) < 2e-5, case
+    acc, w = nb.raw2outputs_NeRFH_NFF(g["coarse_test/raw"].to(DEV), g["z64"].to(DEV), typ="coarse", test_time=True)[3:5]
+    assert rel_err(w, g["coarse_test/weights"]) < 2e-6 and rel_err(acc, g["coarse_test/acc"]) < 2e-6
+
+
+def test_composite_vs_oracle_large(nb):
+    gen = torch.Generator().manual_seed(8)
+    n = 300
+    z = torch.sort(torch.rand(n, 128, generator=gen) * 4, -1)[0]
+    raw = torch.randn(n, 128, 137, generator=gen)
+    raw[..., 131] = torch.nn.functional.softplus(raw[..., 131] * 4)
+    raw[..., 132:135] = torch.sigmoid(raw[..., 132:135])
+    raw[..., 135:137] = torch.nn.functional.softplus(raw[..., 135:137])
+    raw[:10, :, 131] = 0                                       # empty rays: acc = 0
+    raw[10:20, 5, 131] = 1e4                                   # opaque wall: transmittance hits 0
+    rg = raw.to(DEV).requires_grad_(True)
+    out = nb.raw2outputs_NeRFH_NFF(rg, z.to(DEV), output_transient=True, typ="fine", transient_at_test=True)
+    rr = raw.clone().requires_grad_(True)
+    ref = O.composite(rr, z, output_transient=True, typ="fine", transient_at_test=True).astuple()
+    k = [torch.randn(t.shape, generator=gen) for t in ref]
+    sum((a * b.to(DEV)).sum() for a, b in zip(out, k)).backward()
+    sum((a * b).sum() for a, b in zip(ref, k)).backward()
+    for name, a, b in zip(NAMES, out, ref):
+        if name == "disp":      # 1/max(1e-10, depth/acc): 0/0 on empty rays is NaN on both sides
+            m = torch.isfinite(b)
+            assert rel_err(a.cpu()[m], b[m]) < 1e-4
+            continue
+        assert rel_err(a, b) < 5e-6, name
+    gm = torch.isfinite(rr.grad).all(-1).all(-1)
+    assert rel_err(rg.grad.cpu()[gm], rr.grad[gm]) < 5e-5
+
+
+def test_mlp_forward_golden(nb, golden, models):
+    g = golden("g4_mlp.npz")
+    c, f = models
+    emb = g["emb"].to(DEV)
+    with torch.no_grad():
+        assert rel_err(c(emb[:, :63], sigma_only=True), g["sigma"]) < 2e-5
+        assert rel_err(c(emb, output_transient=False), g["static"]) < 2e-5
+        assert rel_err(f(emb, output_transient=True), g["full"]) < 2e-5
+
+
+def test_mlp_backward_vs_oracle(nb, weights, models):
+    """Gradients to every parameter, to the sample positions and to the view directions."""
+    wc, wf = weights
+    c, f = models
+    gen = torch.Generator().manual_seed(10)
+    n, s = 40, 16
+    pts = torch.rand(n, s, 3, generator=gen) * 4 - 2
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    for model, P, mode, typ, tr in ((f, wf, 2, "fine", True), (c, wc, 1, "coarse", False), (c, wc, 0, "coarse", False)):
+        model.zero_grad()
+        pg, dg = pts.to(DEV).requires_grad_(True), dirs.to(DEV).requires_grad_(True)
+        raw = model.query(pg, dg, mode)
+        Pg = O.clone_params(P, requires_grad=True)
+        pr, dr = pts.clone().requires_grad_(True), dirs.clone().requires_grad_(True)
+        ref = O.query_field(Pg, pr, dr, typ, tr, test_time=(mode == 0))
+        assert rel_err(raw, ref) < 2e-5
+        k = torch.randn(ref.shape, generator=gen)
+        (raw * k.to(DEV)).sum().backward()
+        (ref * k).sum().backward()
+        assert rel_err(pg.grad, pr.grad) < 2e-4
+        if mode != 0:
+            assert rel_err(dg.grad, dr.grad) < 2e-4
+        views = model.layer_views(model.flat.grad)
+        for key, ref_g in Pg.items():
+            if mode == 0 and ref_g.grad is None:
+                continue
+            assert rel_err(views[key], ref_g.grad) < 2e-4, key
+
+
+def test_render_train_golden(nb, golden, models):
+    """End-to-end render() in train mode on the reference's RNG draws: outputs, sample indices, loss and
+    weight gradients against the unmodified reference (fixture g5)."""
+    g = golden("g5_render.npz")
+    c, f = models
+    c.zero_grad(), f.zero_grad()
+    rays = (g["rays_o"].to(DEV), g["rays_d"].to(DEV))
+    rgb, disp, acc, ex = nb.render(H, W, FOCAL, chunk=32768, rays=rays, img_idx=torch.zeros(1, 10),
+                                   t_rand=g["train/t_rand"].to(DEV), u=g["train/u"].to(DEV), return_aux=True,
+                                   retraw=True, **render_kwargs(nb, models, False))
+    out = dict(rgb_map=rgb, disp_map=disp, acc_map=acc, **ex)
+    assert torch.equal(out["aux_z_coarse"].cpu(), g["train/z_coarse"])
+    mism = (out["aux_inds"].cpu() != g["train/inds"]).float().mean()
+    assert float(mism) < 0.005                                  # flips only at cdf knots
+    assert float((out["aux_z_fine"].cpu() - g["train/z_fine"]).abs().max()) < 1e-4
+    for k in ("rgb_map", "acc_map", "feat_map", "rgb0", "acc0", "feat0", "beta", "transient_sigmas", "disp_map", "disp0"):
+        assert rel_err(out[k], g["train/" + k]) < 1e-3, k       # north-star bar; observed ~1e-5
+    assert rel_err(out["z_std"], g["train/z_std"]) < 1e-3
+    outn = {k: v for k, v in out.items()}
+    loss = O.nerfw_loss(outn, g["train/target"].to(DEV)) + 0.04 * (out["feat_map"].abs().mean() + out["feat0"].abs().mean())
+    assert abs(float(loss) - float(g["train/loss"])) < 1e-4 * abs(float(g["train/loss"]))
+    loss.backward()
+    vf, vc = f.layer_views(f.flat.grad), c.layer_views(c.flat.grad)
+    for key, ref in g.items():
+        if key.startswith("train/grad_fine/"):
+            assert rel_err(vf[key[len("train/grad_fine/"):]], ref) < 2e-3, key
+        if key.startswith("train/grad_coarse/"):
+            assert rel_err(vc[key[len("train/grad_coarse/"):]], ref) < 2e-3, key
+
+
+def test_render_refinement_pose_gradient_golden(nb, golden, models):
+    """test_time=True full-image render from c2w, cosine feature loss, gradient to the 3x4 pose."""
+    g = golden("g5_render.npz")
+    c, f = models
+    for p in list(c.parameters()) + list(f.parameters()):
+        p.requires_grad_(False)
+    try:
+        c2w = g["test/c2w"].to(DEV).requires_grad_(True)
+        rgb, disp, acc, ex = nb.render(H, W, FOCAL, chunk=32768, c2w=c2w, img_idx=torch.zeros(1, 10), return_aux=True,
+                                       **render_kwargs(nb, models, True))
+        sub = g["test/sub"].to(DEV)
+        assert set(k for k in ex if not k.startswith("aux_")) == {"feat_map"}
+        assert rel_err(ex["feat_map"][sub], g["test/feat_map"]) < 1e-3
+        assert rel_err(rgb[sub], g["test/rgb_map"]) < 1e-3
+        assert float((ex["aux_inds"][sub].cpu() != g["test/inds"]).float().mean()) < 0.01
+        loss = O.cosine_feature_loss(ex["feat_map"][sub].t(), g["test/feat_target"].to(DEV)) + rgb[sub].mean()
+        assert abs(float(loss) - float(g["test/loss"])) < 1e-4
+        loss.backward()
+        assert rel_err(c2w.grad, g["test/d_c2w"]) < 5e-3
+    finally:
+        for p in list(c.parameters()) + list(f.parameters()):
+            p.requires_grad_(True)
+
+
+def test_render_vs_oracle_1024_rays_and_properties(nb, weights, models):
+    """Seeded batch larger than the fixtures, checked against the oracle run on the host, plus
+    size-independent properties."""
+    wc, wf = weights
+    gen = torch.Generator().manual_seed(12)
+    n = 1024
+    pose = torch.eye(4)[:3]
+    o, d = O.camera_rays(H, W, FOCAL, pose)
+    pix = torch.randperm(H * W, generator=gen)[:n]
+    rays = (o.reshape(-1, 3)[pix] + torch.rand(n, 3, generator=gen) * 0.1, d.reshape(-1, 3)[pix])
+    t_rand, u = torch.rand(n, 64, generator=gen), torch.rand(n, 64, generator=gen)
+    with torch.no_grad():
+        ref = O.render(H, W, FOCAL, wc, wf, rays=rays, near=NEAR, far=FAR, test_time=False, t_rand=t_rand, u=u)
+        rgb, disp, acc, ex = nb.render(H, W, FOCAL, rays=(rays[0].to(DEV), rays[1].to(DEV)),
+                                       img_idx=torch.zeros(1, 10), t_rand=t_rand.to(DEV), u=u.to(DEV),
+                                       return_aux=True, **render_kwargs(nb, models, False))
+    for k, v in dict(rgb_map=rgb, acc_map=acc, feat_map=ex["feat_map"], rgb0=ex["rgb0"], feat0=ex["feat0"],
+                     beta=ex["beta"]).items():
+        assert rel_err(v, ref[k]) < 1e-3, k
+    assert bool((ex["aux_z_fine"][:, 1:] >= ex["aux_z_fine"][:, :-1]).all())
+    assert bool((acc <= 1 + 1e-5).all()) and bool((acc >= 0).all())
+    assert bool((ex["aux_inds"] >= 1).all()) and bool((ex["aux_inds"] <= 63).all())
+    assert bool((ex["beta"] >= 0.1).all())
+
+
+def test_flat_adam_matches_torch(nb):
+    from nefes_b200 import FlatAdam
+    gen = torch.Generator().manual_seed(3)
+    p0 = torch.randn(10007, generator=gen)
+    a = torch.nn.Parameter(p0.clone().to(DEV))
+    b = torch.nn.Parameter(p0.clone().to(DEV))
+    oa, ob = FlatAdam([a], lr=5e-4), torch.optim.Adam([b], lr=5e-4, betas=(0.9, 0.999))
+    for i in range(5):
+        gr = torch.randn(10007, generator=gen).to(DEV)
+        a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step(), ob.step()
+    assert rel_err(a, b) < 1e-6
+
+
+def test_error_paths(nb, models):
+    """Bad arguments raise (no silent fallback): CPU tensors, wrong channel count, coarse net asked for
+    transient output."""
+    c, f = models
+    with pytest.raises(RuntimeError):
+        nb.get_rays(H, W, FOCAL, torch.eye(4))
+    with pytest.raises(RuntimeError):
+        nb.raw2outputs_NeRFH_NFF(torch.zeros(2, 8, 100, device=DEV), torch.zeros(2, 8, device=DEV))
+    with pytest.raises(RuntimeError):
+        c.query(torch.zeros(2, 4, 3, device=DEV), torch.zeros(2, 3, device=DEV), 2)
+    z = nb.raw2outputs_NeRFH_NFF(torch.zeros(0, 64, 132, device=DEV), torch.zeros(0, 64, device=DEV))
+    assert z[0].shape == (0, 3)                                 # empty batch is a no-op, not an error
