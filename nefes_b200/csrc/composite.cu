@@ -268,7 +268,7 @@ __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float*
 extern "C" {
 
 static int comp_check(const char* who, const float* raw, const float* z, int N, int S, int mode) {
-  NEFES_REQUIRE(raw && z, NEFES_EINVAL, "%s: null pointer", who);
+  NEFES_REQUIRE(N == 0 || (raw && z), NEFES_EINVAL, "%s: null pointer", who);
   NEFES_REQUIRE(N >= 0 && S >= 1 && S <= nefes::kMaxS, NEFES_EINVAL, "%s: need 1 <= S <= 256 (S=%d)", who, S);
   NEFES_REQUIRE(mode >= 0 && mode <= 3, NEFES_EINVAL, "%s: bad mode %d", who, mode);
   return NEFES_OK;
@@ -277,6 +277,7 @@ static int comp_check(const char* who, const float* raw, const float* z, int N, 
 int nefes_composite_fwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
                         int mode, float beta_min, const nefes_comp_out_t* out_host, void* stream) {
   if (int e = comp_check("nefes_composite_fwd", raw, z_vals, N, S, mode)) return e;
+  if (N == 0) return NEFES_OK;
   NEFES_REQUIRE(out_host && out_host->acc && out_host->weights, NEFES_EINVAL,
                 "nefes_composite_fwd: acc and weights outputs are required");
   if (mode != NEFES_COMP_SIGMA)
@@ -299,8 +300,8 @@ int nefes_composite_fwd(const float* raw, const float* z_vals, const float* nois
 int nefes_composite_bwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
                         int mode, const nefes_comp_grad_t* g_host, float* d_raw, void* stream) {
   if (int e = comp_check("nefes_composite_bwd", raw, z_vals, N, S, mode)) return e;
-  NEFES_REQUIRE(g_host && d_raw, NEFES_EINVAL, "nefes_composite_bwd: null pointer");
   if (N == 0) return NEFES_OK;
+  NEFES_REQUIRE(g_host && d_raw, NEFES_EINVAL, "nefes_composite_bwd: null pointer");
   const int threads = (int)nefes::round_up(S > 160 ? S : (mode == NEFES_COMP_SIGMA ? S : 160), 32);
   cudaStream_t st = (cudaStream_t)stream;
   nefes_comp_grad_t g = *g_host;
