@@ -39,8 +39,13 @@ void count_launch(int n = 1);
     }                                                                             \
   } while (0)
 
-static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
-static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+#ifdef __CUDACC__
+#define NEFES_HD __host__ __device__
+#else
+#define NEFES_HD
+#endif
+NEFES_HD static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+NEFES_HD static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 // ---- architecture constants (script/models/nerfh_nff.py:421-505, options.py) ------------
 constexpr int kW = 128;         // hidden width

@@ -1,19 +1,854 @@
-// K5, NEFES_PREC_BF16 path (tcgen05 / TMEM).  Placeholder until the tensor-core kernels land:
-// the entry points fail loudly rather than fall back.
-#include "common.cuh"
+// K5, NEFES_PREC_BF16 path: the NeFeS field MLP on the 5th-generation tensor cores.
+//
+//   tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by one thread, accumulators in TMEM,
+//   operands in shared memory as UMMA "interleaved" images, tiles moved by 1-D bulk async copies
+//   (TMA engine, UBLKCP) completing on mbarriers; warp-specialised persistent CTAs:
+//   warp 0 = copy producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM -> registers ->
+//   bias / activation / ReLU bit-mask -> bf16 image in shared memory -> bulk store).
+//
+// Three kernels:
+//   tile_gemm_kernel   D[128 pts, N] = A_tile[128, K] * W^T        forward layers and dgrad
+//                      (weights stay resident in shared memory for the whole launch)
+//   wgrad_kernel       dW[N, K] += G_tile^T[N, 128 pts] * A_tile[128 pts, K] over all tiles, both
+//                      operands read MN-major from the SAME images forward/dgrad wrote; bias
+//                      gradients fall out of an extra MMA against a tile of ones
+//   plus small SIMT kernels: weight repack, PE -> images, head gradients -> images.
+// script/models/nerfh_nff.py:168-231, :525-576.
+#include "tc05.cuh"
+#include "tc_layers.cuh"
 
 namespace nefes {
-int mlp_workspace_bf16(int, int, int64_t, int64_t, int64_t*, int64_t*, int64_t*) {
-  set_error("NEFES_PREC_BF16 is not built yet");
-  return NEFES_EUNSUPPORTED;
+using namespace tc05;
+
+constexpr int kTile = 128;
+constexpr uint32_t kChunkBytes = kTile * 16;          // one 8-channel chunk of a tile image = 2 KB
+constexpr int kEpiWarp0 = 2;                          // warps 2..5 are the epilogue
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
-int mlp_fwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, float*, void*, void*, cudaStream_t) {
-  set_error("NEFES_PREC_BF16 is not built yet");
-  return NEFES_EUNSUPPORTED;
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct ASrc { const uint8_t* base; int64_t tile_stride; uint32_t bytes; };
+
+// =================================================================================================
+// tile_gemm_kernel
+// =================================================================================================
+enum { RAW_ACT_NONE = 0, RAW_ACT_SOFTPLUS = 2, RAW_ACT_THEADS = 4 };
+
+struct TileGemmArgs {
+  ASrc a[2]; int n_src;
+  int K, N;                        // MMA K (multiple of 16) and N (multiple of 16, <= 256)
+  const uint8_t* w_img;            // B image [K/8][w_rows][8] bf16
+  int w_rows, w_row0;              // image row count, first row used
+  const float* bias;               // [N] or null
+  int n_tiles; int64_t M;
+  // bf16 image output: D columns [0, out_ch)
+  uint8_t* out_img; int64_t out_tile_stride; int out_ch; int relu;
+  uint4* mask_out; const uint4* mask_in; int mask_shift;
+  // fp32 output: D columns [d_col0, d_col0 + raw_ncol) -> raw[row*raw_ld + raw_col0 + i]
+  float* raw; int raw_ld, raw_col0, d_col0, raw_ncol, raw_act;
+  // shared-memory carve-up (bytes from the dynamic base), computed on the host
+  uint32_t off_a, a_stage_stride, off_out, out_bytes, off_raw, raw_pitch, off_bias;
+};
+
+__device__ __forceinline__ float raw_activation(float x, int act, int col) {
+  if (act == RAW_ACT_SOFTPLUS) return softplus_f(x);
+  if (act == RAW_ACT_THEADS) return col < 3 ? sigmoid_f(x) : softplus_f(x);
+  return x;
 }
-int mlp_bwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, const float*, const float*,
-                 const void*, void*, float*, float*, float*, cudaStream_t) {
-  set_error("NEFES_PREC_BF16 is not built yet");
-  return NEFES_EUNSUPPORTED;
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) tile_gemm_kernel(const TileGemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_w, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sW = smem;
+  float* sBias = reinterpret_cast<float*>(smem + g.off_bias);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_w, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_slot);
+  for (int i = threadIdx.x; i < g.N; i += kThreads) sBias[i] = g.bias ? g.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t a_bytes = (uint32_t)g.K * 256u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- producer: weights once, then the activation tiles ----------------------
+      const uint32_t w_bytes = (uint32_t)g.K * g.w_rows * 2u;
+      mbar_arrive_expect_tx(&bar_w, w_bytes);
+      for (uint32_t off = 0; off < w_bytes; off += 16384u)
+        bulk_g2s(sW + off, g.w_img + off, min(16384u, w_bytes - off), &bar_w);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&bar_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bar_full[s], a_bytes);
+        uint8_t* dst = smem + g.off_a + s * g.a_stage_stride;
+        for (int q = 0; q < g.n_src; ++q) {
+          bulk_g2s(dst, g.a[q].base + (int64_t)tile * g.a[q].tile_stride, g.a[q].bytes, &bar_full[s]);
+          dst += g.a[q].bytes;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer -------------------------------------------------------------
+      const uint32_t idesc = idesc_bf16(128, g.N, 0, 0);
+      const uint32_t w_base = smem_u32(sW) + (uint32_t)g.w_row0 * 16u;
+      const uint32_t w_lbo = (uint32_t)g.w_rows * 16u;
+      mbar_wait(&bar_w, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&bar_tempty[acc], aph ^ 1);
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + g.off_a + s * g.a_stage_stride);
+        const uint32_t d = tmem + acc * 256;
+        for (int k = 0; k < g.K / 16; ++k) {
+          const uint64_t da = smem_desc(a_base + k * 2 * kChunkBytes, kChunkBytes, 128);
+          const uint64_t db = smem_desc(w_base + k * 2 * w_lbo, w_lbo, 128);
+          mma_ss(d, da, db, idesc, k > 0);
+        }
+        mma_commit(&bar_empty[s]);      // the A stage may be refilled once these MMAs retire
+        mma_commit(&bar_tfull[acc]);    // ... and the accumulator may be drained
+      }
+    }
+  } else {
+    // ---------------- epilogue: 4 warps, thread = one point (TMEM lane) -----------------------
+    const int q = warp & 3;                           // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;
+    const int et = (warp - kEpiWarp0) * 32 + lane;    // 0..127
+    float* sRaw = reinterpret_cast<float*>(smem + g.off_raw);
+    const bool raw_staged = g.raw != nullptr && g.raw_ncol > 8;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int64_t grow = (int64_t)tile * kTile + row;
+      uint8_t* sOut = smem + g.off_out + (it & 1) * g.out_bytes;
+      if (g.out_img != nullptr) {
+        if (et == 0) bulk_wait_read<1>();             // the store that used this staging buffer two tiles ago
+        epi_barrier();
+      }
+      uint4 min4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      if (g.mask_in != nullptr) min4 = g.mask_in[grow];
+      uint4 mout4 = make_uint4(0u, 0u, 0u, 0u);
+      mbar_wait(&bar_tfull[acc], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem + acc * 256 + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < g.N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                 // two 8-channel chunks
+          const int c = c0 + h * 8;
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[h * 8 + e]) + sBias[c + e];
+          if (c < g.out_ch) {
+            // the 8 channels of a chunk share one byte of the 128-bit ReLU mask (mask_shift % 8 == 0)
+            const int bit0 = g.mask_shift + c;
+            const int word = bit0 >> 5, sh = bit0 & 31;
+            const uint32_t inw = word == 0 ? min4.x : word == 1 ? min4.y : word == 2 ? min4.z : min4.w;
+            const uint32_t inb = (inw >> sh) & 0xffu;
+            uint32_t outb = 0u;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (g.relu) {
+                const bool on = x[e] > 0.f;
+                x[e] = on ? x[e] : 0.f;
+                outb |= on ? (1u << e) : 0u;
+              }
+              x[e] = ((inb >> e) & 1u) ? x[e] : 0.f;
+            }
+            outb <<= sh;
+            if (word == 0) mout4.x |= outb; else if (word == 1) mout4.y |= outb; else if (word == 2) mout4.z |= outb; else mout4.w |= outb;
+            uint4 pk;
+            pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]);
+            pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
+            *reinterpret_cast<uint4*>(sOut + (c >> 3) * kChunkBytes + row * 16) = pk;
+          }
+          if (g.raw != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int rc = c + e - g.d_col0;
+              if (rc >= 0 && rc < g.raw_ncol) {
+                const float y = raw_activation(x[e], g.raw_act, rc);
+                if (raw_staged) sRaw[row * g.raw_pitch + rc] = y;
+                else if (grow < g.M) g.raw[grow * g.raw_ld + g.raw_col0 + rc] = y;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_tempty[acc]);                  // accumulator drained
+      if (g.mask_out != nullptr) g.mask_out[grow] = mout4;
+      if (g.out_img != nullptr) {
+        fence_async_smem();                           // generic smem writes -> async proxy
+        epi_barrier();
+        if (et == 0) {
+          bulk_s2g(g.out_img + (int64_t)tile * g.out_tile_stride, sOut, g.out_bytes);
+          bulk_commit();
+        }
+      }
+      if (raw_staged) {
+        epi_barrier();
+        for (int rr = warp - kEpiWarp0; rr < kTile; rr += 4) {
+          const int64_t gr = (int64_t)tile * kTile + rr;
+          if (gr < g.M)
+            for (int c = lane; c < g.raw_ncol; c += 32) g.raw[gr * g.raw_ld + g.raw_col0 + c] = sRaw[rr * g.raw_pitch + c];
+        }
+        epi_barrier();
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
+
+// =================================================================================================
+// wgrad_kernel: persistent CTAs over a cost-balanced list of (layer job, tile range) pieces
+// =================================================================================================
+constexpr int kMaxJobs = 18;
+struct WgradJob {
+  ASrc g; int g_ch;                // gradient image (MN = output channel)
+  ASrc a[2]; int n_src; int a_ch;  // activation image(s) (MN = input channel)
+  int pl;                          // packed layer (scatter map)
+  int64_t cost_begin;              // prefix sum of tiles*bytes_per_tile over jobs
+  uint32_t tile_bytes;
+};
+struct WgradArgs {
+  WgradJob job[kMaxJobs]; int n_jobs;
+  int64_t total_cost;
+  int n_tiles;
+  PackSrc ps; float* d_flat;
+  uint32_t off_ones, off_stage, stage_stride;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_slot);
+  {  // two 8-channel groups of ones: B operand of the bias-gradient MMA
+    uint4 ones;
+    ones.x = ones.y = ones.z = ones.w = 0x3F803F80u;
+    for (int i = threadIdx.x; i < 2 * (int)kChunkBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem + w.off_ones)[i] = ones;
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  // this CTA's share of the cost line
+  const int64_t c_lo = w.total_cost * blockIdx.x / gridDim.x;
+  const int64_t c_hi = w.total_cost * (blockIdx.x + 1) / gridDim.x;
+
+  int it = 0;          // pipeline iteration counter (same sequence in every role)
+  int piece = 0;       // flush counter
+  for (int j = 0; j < w.n_jobs; ++j) {
+    const WgradJob& J = w.job[j];
+    const int64_t jb = J.cost_begin, je = jb + (int64_t)w.n_tiles * J.tile_bytes;
+    const int64_t lo = max(c_lo, jb), hi = min(c_hi, je);
+    if (lo >= hi) continue;
+    // tiles whose START lies in [lo, hi)
+    const int t0 = (int)((lo - jb + J.tile_bytes - 1) / J.tile_bytes);
+    const int t1 = (int)((hi - jb + J.tile_bytes - 1) / J.tile_bytes);
+    if (t0 >= t1) continue;
+    const int n_mblk = (J.g_ch > 128) ? 2 : 1;
+    const uint32_t g_bytes = (uint32_t)J.g_ch * 256u;
+    if (warp == 0) {
+      if (lane == 0)
+        for (int t = t0; t < t1; ++t) {
+          const int s = (it + t - t0) % STAGES;
+          const uint32_t ph = ((it + t - t0) / STAGES) & 1;
+          mbar_wait(&bar_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&bar_full[s], J.tile_bytes);
+          uint8_t* dst = smem + w.off_stage + s * w.stage_stride;
+          bulk_g2s(dst, J.g.base + (int64_t)t * J.g.tile_stride, J.g.bytes, &bar_full[s]);
+          dst += g_bytes;
+          for (int q = 0; q < J.n_src; ++q) {
+            bulk_g2s(dst, J.a[q].base + (int64_t)t * J.a[q].tile_stride, J.a[q].bytes, &bar_full[s]);
+            dst += J.a[q].bytes;
+          }
+        }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc_w = idesc_bf16(128, J.a_ch, 1, 1);
+        const uint32_t idesc_b = idesc_bf16(128, 16, 1, 1);
+        const uint32_t ones = smem_u32(smem + w.off_ones);
+        for (int t = t0; t < t1; ++t) {
+          const int s = (it + t - t0) % STAGES;
+          const uint32_t ph = ((it + t - t0) / STAGES) & 1;
+          mbar_wait(&bar_full[s], ph);
+          tc_fence_after();
+          const uint32_t gs = smem_u32(smem + w.off_stage + s * w.stage_stride);
+          const uint32_t as = gs + g_bytes;
+          for (int k = 0; k < kTile / 16; ++k) {        // 16 points per MMA
+            for (int mb = 0; mb < n_mblk; ++mb) {
+              const uint64_t da = smem_desc(gs + mb * 16 * kChunkBytes + k * 256, 128, kChunkBytes);
+              const uint64_t db = smem_desc(as + k * 256, 128, kChunkBytes);
+              const uint64_t d1 = smem_desc(ones + k * 256, 128, kChunkBytes);
+              const uint32_t accum = (t > t0 || k > 0) ? 1u : 0u;
+              mma_ss(tmem + mb * 256, da, db, idesc_w, accum);
+              mma_ss(tmem + mb * 256 + J.a_ch, da, d1, idesc_b, accum);
+            }
+          }
+          mma_commit(&bar_empty[s]);
+        }
+        mma_commit(&bar_done);
+      }
+    }
+    it += t1 - t0;
+    // ---- flush this piece: TMEM -> atomicAdd into the flat fp32 gradient ------------------------
+    if (warp >= kEpiWarp0) {
+      mbar_wait(&bar_done, piece & 1);
+      tc_fence_after();
+      const int q = warp & 3;
+      const PackedDims dims = packed_dims(J.pl);
+      for (int mb = 0; mb < n_mblk; ++mb) {
+        const int n = mb * 128 + q * 32 + lane;          // output channel of this thread
+        const uint32_t taddr = tmem + mb * 256 + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < J.a_ch + 16; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (n < dims.N) {
+            if (c0 < J.a_ch) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int64_t idx = packed_weight_index(w.ps, J.pl, n, c0 + e);
+                if (idx >= 0) atomicAdd(w.d_flat + idx, __uint_as_float(v[e]));
+              }
+            } else {
+              const int64_t idx = packed_bias_index(w.ps, J.pl, n);
+              if (idx >= 0) atomicAdd(w.d_flat + idx, __uint_as_float(v[0]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    ++piece;
+    __syncthreads();      // accumulators are reused by the next piece
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// =================================================================================================
+// SIMT helpers
+// =================================================================================================
+// flat fp32 parameters -> bf16 W / WT images + padded fp32 biases
+__global__ void prepack_kernel(const float* __restrict__ P, PackSrc ps, PackedArena ar, uint8_t* __restrict__ arena, int fine) {
+  __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(arena);
+  float* bb = reinterpret_cast<float*>(arena + round_up(ar.n_bf16 * 2, 256));
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int pl = 0; pl < PL_COUNT; ++pl) {
+    const bool fine_only = (pl == PL_DT || pl == PL_TE1 || pl == PL_TE2 || pl == PL_TH);
+    if (fine_only && !fine) continue;
+    const PackedDims d = packed_dims(pl);
+    const int64_t n_el = (int64_t)d.N * d.K;
+    for (int64_t i = tid; i < n_el; i += stride) {
+      const int n = (int)(i / d.K), k = (int)(i % d.K);
+      const int64_t idx = packed_weight_index(ps, pl, n, k);
+      const __nv_bfloat16 v = __float2bfloat16(idx >= 0 ? P[idx] : 0.f);
+      wb[ar.w_off[pl] + ((int64_t)(k >> 3) * d.N + n) * 8 + (k & 7)] = v;       // W  image [K/8][N][8]
+      wb[ar.wt_off[pl] + ((int64_t)(n >> 3) * d.K + k) * 8 + (n & 7)] = v;      // WT image [N/8][K][8]
+    }
+    for (int64_t i = tid; i < d.N; i += stride) {
+      const int64_t idx = packed_bias_index(ps, pl, (int)i);
+      bb[ar.bias_off[pl] + i] = idx >= 0 ? P[idx] : 0.f;
+    }
+  }
+}
+
+// pts [M,3] -> X image (64 ch: PE 63 + 0); dirs [N,3] -> DIRPE image (32 ch: PE 27 + 0 x5), one thread per point
+__global__ void encode_images_kernel(const float* __restrict__ pts, const float* __restrict__ dirs, int S, int64_t M,
+                                     int64_t Mp, uint8_t* __restrict__ ximg, uint8_t* __restrict__ dimg) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mp) return;
+  const int64_t tile = m / kTile;
+  const int row = (int)(m % kTile);
+  const bool ok = m < M;
+  {
+    float e[64];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = ok ? pts[m * 3 + c] : 0.f;
+      e[c] = v;
+      float f = 1.f;
+#pragma unroll
+      for (int l = 0; l < kXyzFreqs; ++l, f *= 2.f) {
+        float s, co;
+        sincosf(v * f, &s, &co);
+        e[3 + 6 * l + c] = ok ? s : 0.f;
+        e[6 + 6 * l + c] = ok ? co : 0.f;
+      }
+    }
+    e[63] = 0.f;
+    uint8_t* base = ximg + tile * (64 * 256) + row * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 pk;
+      pk.x = pack_bf16(e[8 * j], e[8 * j + 1]); pk.y = pack_bf16(e[8 * j + 2], e[8 * j + 3]);
+      pk.z = pack_bf16(e[8 * j + 4], e[8 * j + 5]); pk.w = pack_bf16(e[8 * j + 6], e[8 * j + 7]);
+      *reinterpret_cast<uint4*>(base + j * kChunkBytes) = pk;
+    }
+  }
+  if (dimg != nullptr) {
+    float e[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) e[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = ok ? dirs[(m / S) * 3 + c] : 0.f;
+      e[c] = v;
+      float f = 1.f;
+#pragma unroll
+      for (int l = 0; l < kDirFreqs; ++l, f *= 2.f) {
+        float s, co;
+        sincosf(v * f, &s, &co);
+        e[3 + 6 * l + c] = ok ? s : 0.f;
+        e[6 + 6 * l + c] = ok ? co : 0.f;
+      }
+    }
+    uint8_t* base = dimg + tile * (32 * 256) + row * 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 pk;
+      pk.x = pack_bf16(e[8 * j], e[8 * j + 1]); pk.y = pack_bf16(e[8 * j + 2], e[8 * j + 3]);
+      pk.z = pack_bf16(e[8 * j + 4], e[8 * j + 5]); pk.w = pack_bf16(e[8 * j + 6], e[8 * j + 7]);
+      *reinterpret_cast<uint4*>(base + j * kChunkBytes) = pk;
+    }
+  }
+}
+
+// d_raw (fp32, row-major) -> gradient images of the head pre-activations.
+//   C == 137: GRGB (144 ch), GTH (16 ch), sigma grad into channel 128 of GFS (chunks 16,17)
+//   C == 132: GRGB, GFS chunks 16,17            C == 1: GSIG (16 ch)
+__global__ void head_grad_images_kernel(const float* __restrict__ raw, const float* __restrict__ d_raw, int C, int64_t M,
+                                        int64_t Mp, uint8_t* __restrict__ grgb, uint8_t* __restrict__ gth,
+                                        uint8_t* __restrict__ gfs, int64_t gfs_tile_stride, int gfs_chunk0) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mp) return;
+  const int64_t tile = m / kTile;
+  const int row = (int)(m % kTile);
+  const bool ok = m < M;
+  const float* y = raw + m * C;
+  const float* gd = d_raw + m * C;
+  const int sig_col = (C == 1) ? 0 : 131;
+  const float dsig = ok ? gd[sig_col] * (1.f - expf(-y[sig_col])) : 0.f;
+  {  // sigma pre-activation gradient: channel 0 of a 16-channel group, rest zero
+    uint8_t* base = gfs + tile * gfs_tile_stride + (int64_t)gfs_chunk0 * kChunkBytes + row * 16;
+    uint4 pk = make_uint4(pack_bf16(dsig, 0.f), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(base) = pk;
+    *reinterpret_cast<uint4*>(base + kChunkBytes) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (C == 1) return;
+  uint8_t* rb = grgb + tile * (144 * 256) + row * 16;
+  for (int j = 0; j < 18; ++j) {
+    float e[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = 8 * j + q;
+      e[q] = (ok && c < kHeadCh) ? gd[c] : 0.f;
+    }
+    uint4 pk;
+    pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
+    *reinterpret_cast<uint4*>(rb + j * kChunkBytes) = pk;
+  }
+  if (C == 137) {
+    float e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) e[c] = gd[132 + c] * y[132 + c] * (1.f - y[132 + c]);
+      e[3] = gd[135] * (1.f - expf(-y[135]));
+      e[4] = gd[136] * (1.f - expf(-y[136]));
+    }
+    uint8_t* tb = gth + tile * (16 * 256) + row * 16;
+    uint4 pk;
+    pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
+    *reinterpret_cast<uint4*>(tb) = pk;
+    *reinterpret_cast<uint4*>(tb + kChunkBytes) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// =================================================================================================
+// host orchestration
+// =================================================================================================
+namespace {
+
+constexpr uint32_t kSmemBudget = 216 * 1024;
+constexpr int kSmemAttr = 224 * 1024;         // opt-in dynamic shared memory per CTA (227 KB max incl. static)
+constexpr uint32_t kMinSmem = 120 * 1024;     // keep one CTA per SM (each CTA allocates all 512 TMEM columns)
+
+inline uint32_t r1k(uint32_t x) { return (x + 1023u) & ~1023u; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// image bookkeeping: all images of a workspace are carved from one allocation
+struct Img { uint8_t* p; int ch; int64_t tile_stride() const { return (int64_t)ch * 256; } };
+
+struct Ws {             // saved-for-backward (forward writes, backward reads)
+  uint8_t* arena;
+  Img X, DIRPE, H[8], FIN, DT, T2, T3;
+  uint4* mask[11];      // 0..7: h1..h8, 8: DT, 9: t2, 10: t3
+  int64_t bytes;
+};
+struct WsB {            // backward scratch
+  Img GTH, GT3, GT2, GDT, GRGB, GFS, G[8], GSIG;
+  int64_t bytes;
+};
+
+Ws carve_ws(void* base, int64_t T, int mode) {
+  Ws w = {};
+  uint8_t* p = (uint8_t*)base;
+  auto take = [&](int64_t n) { uint8_t* q = p; p += round_up(n, 1024); return q; };
+  auto img = [&](int ch) { Img i; i.ch = ch; i.p = take(T * ch * 256); return i; };
+  w.arena = take(packed_arena().bytes);
+  w.X = img(64);
+  for (int l = 0; l < 8; ++l) w.H[l] = img(128);
+  for (int l = 0; l < 8; ++l) w.mask[l] = (uint4*)take(T * kTile * 16);
+  if (mode != NEFES_MODE_SIGMA) {
+    w.DIRPE = img(32);
+    w.FIN = img(128);
+    w.DT = img(mode == NEFES_MODE_FULL ? 128 : 64);
+    w.mask[8] = (uint4*)take(T * kTile * 16);
+    if (mode == NEFES_MODE_FULL) {
+      w.T2 = img(64); w.T3 = img(64);
+      w.mask[9] = (uint4*)take(T * kTile * 16);
+      w.mask[10] = (uint4*)take(T * kTile * 16);
+    }
+  }
+  w.bytes = (int64_t)(p - (uint8_t*)base);
+  return w;
+}
+WsB carve_wsb(void* base, int64_t T, int mode) {
+  WsB w = {};
+  uint8_t* p = (uint8_t*)base;
+  auto img = [&](int ch) { Img i; i.ch = ch; i.p = p; p += round_up(T * ch * 256, 1024); return i; };
+  for (int l = 0; l < 8; ++l) w.G[l] = img(128);
+  if (mode == NEFES_MODE_SIGMA) {
+    w.GSIG = img(16);
+  } else {
+    w.GFS = img(144); w.GRGB = img(144);
+    w.GDT = img(mode == NEFES_MODE_FULL ? 128 : 64);
+    if (mode == NEFES_MODE_FULL) { w.GTH = img(16); w.GT3 = img(64); w.GT2 = img(64); }
+  }
+  w.bytes = (int64_t)(p - (uint8_t*)base);
+  return w;
+}
+
+ASrc src_of(const Img& i, int ch0 = 0, int nch = -1) {
+  ASrc s;
+  s.base = i.p + (int64_t)ch0 * 256;
+  s.tile_stride = i.tile_stride();
+  s.bytes = (uint32_t)((nch < 0 ? i.ch - ch0 : nch) * 256);
+  return s;
+}
+
+struct GemmDesc {
+  ASrc a[2]; int n_src = 1;
+  int K = 0, N = 0;
+  const uint8_t* w_img = nullptr; int w_rows = 0, w_row0 = 0;
+  const float* bias = nullptr;
+  uint8_t* out_img = nullptr; int64_t out_tile_stride = 0; int out_ch = 0; int relu = 0;
+  uint4* mask_out = nullptr; const uint4* mask_in = nullptr; int mask_shift = 0;
+  float* raw = nullptr; int raw_ld = 0, raw_col0 = 0, d_col0 = 0, raw_ncol = 0, raw_act = 0;
+};
+
+int launch_tile_gemm(const GemmDesc& d, int n_tiles, int64_t M, cudaStream_t st, const char* what) {
+  TileGemmArgs g = {};
+  g.a[0] = d.a[0]; g.a[1] = d.a[1]; g.n_src = d.n_src;
+  g.K = d.K; g.N = d.N; g.w_img = d.w_img; g.w_rows = d.w_rows; g.w_row0 = d.w_row0; g.bias = d.bias;
+  g.n_tiles = n_tiles; g.M = M;
+  g.out_img = d.out_img; g.out_tile_stride = d.out_tile_stride; g.out_ch = d.out_img ? d.out_ch : 0; g.relu = d.relu;
+  g.mask_out = d.mask_out; g.mask_in = d.mask_in; g.mask_shift = d.mask_shift;
+  g.raw = d.raw; g.raw_ld = d.raw_ld; g.raw_col0 = d.raw_col0; g.d_col0 = d.d_col0; g.raw_ncol = d.raw_ncol; g.raw_act = d.raw_act;
+  uint32_t src_bytes = 0;
+  for (int q = 0; q < d.n_src; ++q) src_bytes += d.a[q].bytes;
+  NEFES_REQUIRE(src_bytes == (uint32_t)d.K * 256u, NEFES_EINVAL, "%s: A sources (%u B) do not add up to K=%d", what, src_bytes, d.K);
+  NEFES_REQUIRE(d.K % 16 == 0 && d.N % 16 == 0 && d.N <= 256 && d.N >= 16, NEFES_EINVAL, "%s: bad K/N %d/%d", what, d.K, d.N);
+  const uint32_t w_bytes = (uint32_t)d.K * d.w_rows * 2u;
+  const uint32_t a_stage = r1k((uint32_t)d.K * 256u);
+  g.out_bytes = (uint32_t)g.out_ch * 256u;
+  const uint32_t out_total = 2 * r1k(g.out_bytes);
+  g.raw_pitch = (uint32_t)(d.raw_ncol | 1);
+  const uint32_t raw_total = (d.raw && d.raw_ncol > 8) ? r1k(kTile * g.raw_pitch * 4u) : 0u;
+  const uint32_t bias_total = 1024;
+  const uint32_t fixed = r1k(w_bytes) + out_total + raw_total + bias_total;
+  NEFES_REQUIRE(fixed + 2 * a_stage <= kSmemBudget, NEFES_EINVAL, "%s: shared memory budget exceeded", what);
+  int stages = (int)((kSmemBudget - fixed) / a_stage);
+  if (stages > 4) stages = 4;
+  g.off_a = r1k(w_bytes);
+  g.a_stage_stride = a_stage;
+  g.off_out = g.off_a + stages * a_stage;
+  g.off_raw = g.off_out + out_total;
+  g.off_bias = g.off_raw + raw_total;
+  uint32_t smem = g.off_bias + bias_total;
+  if (smem < kMinSmem) smem = kMinSmem;
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr); };
+  static bool attr_done = false;
+  if (!attr_done) {
+    NEFES_CUDA(set_attr(tile_gemm_kernel<2>));
+    NEFES_CUDA(set_attr(tile_gemm_kernel<3>));
+    NEFES_CUDA(set_attr(tile_gemm_kernel<4>));
+    attr_done = true;
+  }
+  switch (stages) {
+    case 2: tile_gemm_kernel<2><<<grid, kThreads, smem, st>>>(g); break;
+    case 3: tile_gemm_kernel<3><<<grid, kThreads, smem, st>>>(g); break;
+    default: tile_gemm_kernel<4><<<grid, kThreads, smem, st>>>(g); break;
+  }
+  NEFES_CHECK_LAUNCH(what);
+  return NEFES_OK;
+}
+
+PackSrc pack_src(int net) {
+  const Layout& L = layout_for(net);
+  PackSrc s;
+  for (int i = 0; i < NEFES_MAX_LAYERS; ++i) { s.w[i] = L.w[i]; s.b[i] = L.b[i]; }
+  s.fine = net == NEFES_NET_FINE;
+  return s;
+}
+
+struct Arena {
+  const uint8_t* base; PackedArena ar;
+  const uint8_t* W(int pl) const { return base + ar.w_off[pl] * 2; }
+  const uint8_t* WT(int pl) const { return base + ar.wt_off[pl] * 2; }
+  const float* bias(int pl) const { return reinterpret_cast<const float*>(base + round_up(ar.n_bf16 * 2, 256)) + ar.bias_off[pl]; }
+};
+
+#define TRY(x) do { if (int e__ = (x)) return e__; } while (0)
+
+}  // namespace
+
+int mlp_workspace_bf16(int net, int mode, int64_t M, int64_t N, int64_t* saved, int64_t* sf, int64_t* sb) {
+  (void)net; (void)N;
+  const int64_t T = ceil_div(M, kTile);
+  *saved = carve_ws(nullptr, T, mode).bytes + 1024;
+  *sf = 1024;
+  *sb = carve_wsb(nullptr, T, mode).bytes + 1024;
+  return NEFES_OK;
+}
+
+int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const float* dirs, int64_t N, int S, float* raw,
+                 void* saved, void* scratch, cudaStream_t st) {
+  (void)scratch;
+  const int64_t M = N * S;
+  const int T = (int)ceil_div(M, kTile);
+  const int64_t Mp = (int64_t)T * kTile;
+  Ws w = carve_ws(saved, T, mode);
+  const int C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
+  const bool fine = net == NEFES_NET_FINE;
+  Arena A = {w.arena, packed_arena()};
+
+  prepack_kernel<<<256, 256, 0, st>>>(P, pack_src(net), A.ar, w.arena, fine ? 1 : 0);
+  NEFES_CHECK_LAUNCH("prepack");
+  encode_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(pts, dirs, S, M, Mp, w.X.p,
+                                                                    mode == NEFES_MODE_SIGMA ? nullptr : w.DIRPE.p);
+  NEFES_CHECK_LAUNCH("encode_images");
+
+  auto hidden = [&](int pl, ASrc a0, const ASrc* a1, Img out, uint4* mask) {
+    GemmDesc d;
+    const PackedDims pd = packed_dims(pl);
+    d.a[0] = a0; if (a1) { d.a[1] = *a1; d.n_src = 2; }
+    d.K = pd.K; d.N = pd.N; d.w_img = A.W(pl); d.w_rows = pd.N; d.bias = A.bias(pl);
+    d.out_img = out.p; d.out_tile_stride = out.tile_stride(); d.out_ch = out.ch; d.relu = 1; d.mask_out = mask;
+    return launch_tile_gemm(d, T, M, st, "fwd hidden layer");
+  };
+  TRY(hidden(PL_T0, src_of(w.X), nullptr, w.H[0], w.mask[0]));
+  for (int l = 1; l < 8; ++l) {
+    if (l == 4) { ASrc h4 = src_of(w.H[3]); TRY(hidden(PL_T4, src_of(w.X), &h4, w.H[4], w.mask[4])); }
+    else TRY(hidden(PL_T0 + l, src_of(w.H[l - 1]), nullptr, w.H[l], w.mask[l]));
+  }
+  if (mode == NEFES_MODE_SIGMA) {
+    GemmDesc d;
+    d.a[0] = src_of(w.H[7]); d.K = 128; d.N = 16; d.w_img = A.W(PL_SIG); d.w_rows = 16; d.bias = A.bias(PL_SIG);
+    d.raw = raw; d.raw_ld = 1; d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = 1; d.raw_act = RAW_ACT_SOFTPLUS;
+    return launch_tile_gemm(d, T, M, st, "fwd sigma head");
+  }
+  {  // final (128, no activation) + sigma (softplus -> raw[:,131])
+    GemmDesc d;
+    d.a[0] = src_of(w.H[7]); d.K = 128; d.N = 144; d.w_img = A.W(PL_FS); d.w_rows = 144; d.bias = A.bias(PL_FS);
+    d.out_img = w.FIN.p; d.out_tile_stride = w.FIN.tile_stride(); d.out_ch = 128; d.relu = 0;
+    d.raw = raw; d.raw_ld = C; d.raw_col0 = 131; d.d_col0 = 128; d.raw_ncol = 1; d.raw_act = RAW_ACT_SOFTPLUS;
+    TRY(launch_tile_gemm(d, T, M, st, "fwd final+sigma"));
+  }
+  {  // [final | dirPE] -> dir hidden (+ transient hidden 0)
+    const int pl = (mode == NEFES_MODE_FULL) ? PL_DT : PL_DIR;
+    ASrc dp = src_of(w.DIRPE);
+    TRY(hidden(pl, src_of(w.FIN), &dp, w.DT, w.mask[8]));
+  }
+  {  // rgb + feature head (131, no activation) -> raw[:, 0:131]
+    GemmDesc d;
+    d.a[0] = src_of(w.DT, 0, 64); d.K = 64; d.N = 144; d.w_img = A.W(PL_RGB); d.w_rows = 144; d.bias = A.bias(PL_RGB);
+    d.raw = raw; d.raw_ld = C; d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = kHeadCh; d.raw_act = RAW_ACT_NONE;
+    TRY(launch_tile_gemm(d, T, M, st, "fwd rgb head"));
+  }
+  if (mode == NEFES_MODE_FULL) {
+    TRY(hidden(PL_TE1, src_of(w.DT, 64, 64), nullptr, w.T2, w.mask[9]));
+    TRY(hidden(PL_TE2, src_of(w.T2), nullptr, w.T3, w.mask[10]));
+    GemmDesc d;
+    d.a[0] = src_of(w.T3); d.K = 64; d.N = 16; d.w_img = A.W(PL_TH); d.w_rows = 16; d.bias = A.bias(PL_TH);
+    d.raw = raw; d.raw_ld = C; d.raw_col0 = 132; d.d_col0 = 0; d.raw_ncol = 5; d.raw_act = RAW_ACT_THEADS;
+    TRY(launch_tile_gemm(d, T, M, st, "fwd transient heads"));
+  }
+  return NEFES_OK;
+}
+
+int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const float* dirs, int64_t N, int S,
+                 const float* raw, const float* d_raw, const void* saved, void* scratch, float* dP, float* d_pts,
+                 float* d_dirs, cudaStream_t st) {
+  (void)P; (void)pts; (void)dirs;
+  if (d_pts != nullptr || d_dirs != nullptr) {
+    set_error("NEFES_PREC_BF16: gradients to sample positions / view directions are not built yet; use NEFES_PREC_FP32 "
+              "for pose refinement");
+    return NEFES_EUNSUPPORTED;
+  }
+  const int64_t M = N * S;
+  const int T = (int)ceil_div(M, kTile);
+  const int64_t Mp = (int64_t)T * kTile;
+  const Ws w = carve_ws(const_cast<void*>(saved), T, mode);
+  WsB b = carve_wsb(scratch, T, mode);
+  const int C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
+  Arena A = {w.arena, packed_arena()};
+
+  const Img& gsig_img = (mode == NEFES_MODE_SIGMA) ? b.GSIG : b.GFS;
+  head_grad_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(
+      raw, d_raw, C, M, Mp, b.GRGB.p, b.GTH.p, gsig_img.p, gsig_img.tile_stride(), mode == NEFES_MODE_SIGMA ? 0 : 16);
+  NEFES_CHECK_LAUNCH("head_grad_images");
+
+  // dA[pts, Kin] = G[pts, Nout] * W  (B operand = WT image rows [row0, row0 + n_out_cols))
+  auto dgrad = [&](int pl, ASrc gsrc, int g_ch, int row0, int n_cols, uint8_t* out, int64_t out_stride, int out_ch,
+                   const uint4* mask, int mask_shift) {
+    GemmDesc d;
+    const PackedDims pd = packed_dims(pl);
+    d.a[0] = gsrc; d.K = g_ch; d.N = n_cols; d.w_img = A.WT(pl); d.w_rows = pd.K; d.w_row0 = row0;
+    d.out_img = out; d.out_tile_stride = out_stride; d.out_ch = out_ch; d.relu = 0; d.mask_in = mask; d.mask_shift = mask_shift;
+    return launch_tile_gemm(d, T, M, st, "dgrad");
+  };
+
+  if (mode != NEFES_MODE_SIGMA) {
+    const int dt_ch = w.DT.ch;
+    if (mode == NEFES_MODE_FULL) {
+      TRY(dgrad(PL_TH, src_of(b.GTH), 16, 0, 64, b.GT3.p, b.GT3.tile_stride(), 64, w.mask[10], 0));
+      TRY(dgrad(PL_TE2, src_of(b.GT3), 64, 0, 64, b.GT2.p, b.GT2.tile_stride(), 64, w.mask[9], 0));
+      TRY(dgrad(PL_TE1, src_of(b.GT2), 64, 0, 64, b.GDT.p + 64 * 256, b.GDT.tile_stride(), 64, w.mask[8], 64));
+    }
+    TRY(dgrad(PL_RGB, src_of(b.GRGB), 144, 0, 64, b.GDT.p, b.GDT.tile_stride(), 64, w.mask[8], 0));
+    TRY(dgrad(mode == NEFES_MODE_FULL ? PL_DT : PL_DIR, src_of(b.GDT), dt_ch, 0, 128, b.GFS.p, b.GFS.tile_stride(), 128,
+              nullptr, 0));
+    TRY(dgrad(PL_FS, src_of(b.GFS), 144, 0, 128, b.G[7].p, b.G[7].tile_stride(), 128, w.mask[7], 0));
+  } else {
+    TRY(dgrad(PL_SIG, src_of(b.GSIG), 16, 0, 128, b.G[7].p, b.G[7].tile_stride(), 128, w.mask[7], 0));
+  }
+  for (int l = 7; l >= 1; --l)   // G[l] = grad wrt pre-activation of trunk layer l  ->  G[l-1]
+    TRY(dgrad(PL_T0 + l, src_of(b.G[l]), 128, l == 4 ? 64 : 0, 128, b.G[l - 1].p, b.G[l - 1].tile_stride(), 128,
+              w.mask[l - 1], 0));
+
+  if (dP == nullptr) return NEFES_OK;
+
+  // ---- weight + bias gradients: one persistent launch over all layers ---------------------------
+  WgradArgs wa = {};
+  int nj = 0;
+  uint32_t max_tile_bytes = 0;
+  auto job = [&](int pl, const Img& gimg, int g_ch0, int g_ch, ASrc a0, const ASrc* a1) {
+    WgradJob& J = wa.job[nj++];
+    J.g = src_of(gimg, g_ch0, g_ch); J.g_ch = g_ch;
+    J.a[0] = a0; J.n_src = 1; J.a_ch = (int)(a0.bytes / 256);
+    if (a1) { J.a[1] = *a1; J.n_src = 2; J.a_ch += (int)(a1->bytes / 256); }
+    J.pl = pl;
+    J.tile_bytes = (uint32_t)(J.g_ch + J.a_ch) * 256u;
+    if (J.tile_bytes > max_tile_bytes) max_tile_bytes = J.tile_bytes;
+  };
+  if (mode == NEFES_MODE_FULL) {
+    job(PL_TH, b.GTH, 0, 16, src_of(w.T3), nullptr);
+    job(PL_TE2, b.GT3, 0, 64, src_of(w.T2), nullptr);
+    job(PL_TE1, b.GT2, 0, 64, src_of(w.DT, 64, 64), nullptr);
+  }
+  if (mode != NEFES_MODE_SIGMA) {
+    ASrc dp = src_of(w.DIRPE);
+    job(PL_RGB, b.GRGB, 0, 144, src_of(w.DT, 0, 64), nullptr);
+    job(mode == NEFES_MODE_FULL ? PL_DT : PL_DIR, b.GDT, 0, w.DT.ch, src_of(w.FIN), &dp);
+    job(PL_FS, b.GFS, 0, 144, src_of(w.H[7]), nullptr);
+  } else {
+    job(PL_SIG, b.GSIG, 0, 16, src_of(w.H[7]), nullptr);
+  }
+  for (int l = 7; l >= 1; --l) {
+    if (l == 4) { ASrc h = src_of(w.H[3]); job(PL_T4, b.G[4], 0, 128, src_of(w.X), &h); }
+    else job(PL_T0 + l, b.G[l], 0, 128, src_of(w.H[l - 1]), nullptr);
+  }
+  job(PL_T0, b.G[0], 0, 128, src_of(w.X), nullptr);
+  wa.n_jobs = nj;
+  int64_t cost = 0;
+  for (int j = 0; j < nj; ++j) { wa.job[j].cost_begin = cost; cost += (int64_t)T * wa.job[j].tile_bytes; }
+  wa.total_cost = cost;
+  wa.n_tiles = T;
+  wa.ps = pack_src(net);
+  wa.d_flat = dP;
+  wa.off_ones = 0;
+  wa.off_stage = 4096;
+  wa.stage_stride = r1k(max_tile_bytes);
+  const int stages = 2;
+  // the M=128 gradient operand may read up to 32 KB past a short gradient image: keep that in bounds
+  const uint32_t smem = wa.off_stage + stages * wa.stage_stride + 36 * 1024;
+  NEFES_REQUIRE(smem <= (uint32_t)kSmemAttr, NEFES_EINVAL, "wgrad: shared memory budget exceeded (%u)", smem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    NEFES_CUDA(cudaFuncSetAttribute(wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr));
+    attr_done = true;
+  }
+  int grid = num_sms();
+  if (grid > T * nj) grid = T * nj;
+  wgrad_kernel<2><<<grid, kThreads, smem < kMinSmem ? kMinSmem : smem, st>>>(wa);
+  NEFES_CHECK_LAUNCH("wgrad");
+  return NEFES_OK;
+}
+
 }  // namespace nefes

@@ -377,3 +377,65 @@ def test_error_paths(nb, models):
         c.query(torch.zeros(2, 4, 3, device=DEV), torch.zeros(2, 3, device=DEV), 2)
     z = nb.raw2outputs_NeRFH_NFF(torch.zeros(0, 64, 132, device=DEV), torch.zeros(0, 64, device=DEV))
     assert z[0].shape == (0, 3)                                 # empty batch is a no-op, not an error
+
+
+# ---------------------------------------------------------------------------------------------
+# bf16 tensor-core path (tcgen05).  Stated tolerance: operands are rounded to bf16 (2^-9 relative) at every
+# layer, accumulation is fp32; against the fp32 oracle the raw outputs agree to ~1e-2 of their scale.
+# ---------------------------------------------------------------------------------------------
+BF16_TOL = 3e-2
+
+
+def nrm_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_bf16_mlp_forward_and_backward_vs_oracle(nb, weights, models):
+    from nefes_b200 import _lib as L, ops
+    wc, wf = weights
+    c, f = models
+    gen = torch.Generator().manual_seed(20)
+    n, s = 37, 64                                     # 2368 points: 18.5 tiles -> exercises the ragged last tile
+    pts = torch.rand(n, s, 3, generator=gen) * 4 - 2
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    for model, P, mode, typ, tr in ((f, wf, 2, "fine", True), (c, wc, 1, "coarse", False), (c, wc, 0, "coarse", False)):
+        model.zero_grad()
+        raw = ops.field_query(pts.to(DEV), None if mode == 0 else dirs.to(DEV), model.flat, model.net_id, mode, L.PREC_BF16)
+        Pg = O.clone_params(P, requires_grad=True)
+        ref = O.query_field(Pg, pts, dirs, typ, tr, test_time=(mode == 0))
+        assert raw.shape == ref.shape
+        assert rel_err(raw, ref) < BF16_TOL, (mode, rel_err(raw, ref))
+        k = torch.randn(ref.shape, generator=gen)
+        (raw * k.to(DEV)).sum().backward()
+        (ref * k).sum().backward()
+        views = model.layer_views(model.flat.grad)
+        for key, ref_g in Pg.items():
+            if ref_g.grad is None:
+                continue
+            assert nrm_err(views[key], ref_g.grad) < 6e-2, (mode, key, nrm_err(views[key], ref_g.grad))
+
+
+def test_bf16_render_train_step(nb, weights, models):
+    wc, wf = weights
+    c, f = models
+    gen = torch.Generator().manual_seed(21)
+    n = 512
+    o, d = O.camera_rays(H, W, FOCAL, torch.eye(4)[:3])
+    pix = torch.randperm(H * W, generator=gen)[:n]
+    rays = (o.reshape(-1, 3)[pix].contiguous(), d.reshape(-1, 3)[pix].contiguous())
+    t_rand, u = torch.rand(n, 64, generator=gen), torch.rand(n, 64, generator=gen)
+    with torch.no_grad():
+        ref = O.render(H, W, FOCAL, wc, wf, rays=rays, near=NEAR, far=FAR, test_time=False, t_rand=t_rand, u=u)
+    c.precision = f.precision = "bf16"
+    try:
+        c.zero_grad(), f.zero_grad()
+        rgb, disp, acc, ex = nb.render(H, W, FOCAL, rays=(rays[0].to(DEV), rays[1].to(DEV)), img_idx=torch.zeros(1, 10),
+                                       t_rand=t_rand.to(DEV), u=u.to(DEV), **render_kwargs(nb, models, False))
+        for k, v in dict(rgb_map=rgb, feat_map=ex["feat_map"], rgb0=ex["rgb0"], acc_map=acc, beta=ex["beta"]).items():
+            assert rel_err(v, ref[k]) < BF16_TOL, (k, rel_err(v, ref[k]))
+        (rgb.mean() + ex["feat_map"].mean() + ex["rgb0"].mean()).backward()
+        assert torch.isfinite(f.flat.grad).all() and torch.isfinite(c.flat.grad).all()
+        assert float(f.flat.grad.abs().max()) > 0
+    finally:
+        c.precision = f.precision = "fp32"
