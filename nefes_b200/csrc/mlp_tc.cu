@@ -31,14 +31,20 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
 struct ASrc { const uint8_t* base; int64_t tile_stride; uint32_t bytes; };
 
 // =================================================================================================
 // tile_gemm_kernel
 // =================================================================================================
 enum { RAW_ACT_NONE = 0, RAW_ACT_SOFTPLUS = 2, RAW_ACT_THEADS = 4 };
+enum { EPI_HIDDEN = 0,    // bias + ReLU + ReLU bit-mask out -> bf16 image            (forward hidden layers)
+       EPI_DGRAD = 1,     // ReLU bit-mask in (optional)     -> bf16 image            (backward data gradients)
+       EPI_GENERIC = 2 }; // bias, optional image columns, optional fp32 columns with head activations
+
+constexpr int kEpiWarps = 8;                          // two warps per TMEM lane quarter, interleaved 16-column blocks
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGemmThreads = 64 + kEpiThreads;
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct TileGemmArgs {
   ASrc a[2]; int n_src;
@@ -49,7 +55,7 @@ struct TileGemmArgs {
   int n_tiles; int64_t M;
   // bf16 image output: D columns [0, out_ch)
   uint8_t* out_img; int64_t out_tile_stride; int out_ch; int relu;
-  uint4* mask_out; const uint4* mask_in; int mask_shift;
+  uint4* mask_out; const uint4* mask_in; int mask_shift;      // mask_shift: first mask bit of D column 0 (multiple of 16)
   // fp32 output: D columns [d_col0, d_col0 + raw_ncol) -> raw[row*raw_ld + raw_col0 + i]
   float* raw; int raw_ld, raw_col0, d_col0, raw_ncol, raw_act;
   // shared-memory carve-up (bytes from the dynamic base), computed on the host
@@ -62,8 +68,56 @@ __device__ __forceinline__ float raw_activation(float x, int act, int col) {
   return x;
 }
 
-template <int STAGES>
-__global__ void __launch_bounds__(kThreads, 1) tile_gemm_kernel(const TileGemmArgs g) {
+// one 16-column block of one row: v = accumulators, c0 = first D column
+template <int EPI>
+__device__ __forceinline__ void epi_block(const TileGemmArgs& g, const uint32_t (&v)[16], int c0, int row, int64_t grow,
+                                          const float* __restrict__ sBias, uint8_t* __restrict__ sOut,
+                                          float* __restrict__ sRaw, bool raw_staged, uint32_t in16, uint32_t& out16) {
+  out16 = 0u;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = c0 + h * 8;
+    float x[8];
+    if (EPI == EPI_DGRAD) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = ((in16 >> (h * 8 + e)) & 1u) ? __uint_as_float(v[h * 8 + e]) : 0.f;
+    } else {
+      const float4 b0 = *reinterpret_cast<const float4*>(sBias + c);
+      const float4 b1 = *reinterpret_cast<const float4*>(sBias + c + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[h * 8 + e]) + bb[e];
+    }
+    if (EPI == EPI_HIDDEN || (EPI == EPI_GENERIC && g.relu)) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool on = x[e] > 0.f;
+        x[e] = on ? x[e] : 0.f;
+        out16 |= on ? (1u << (h * 8 + e)) : 0u;
+      }
+    }
+    if (EPI != EPI_GENERIC || c < g.out_ch) {
+      uint4 pk;
+      pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]);
+      pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
+      *reinterpret_cast<uint4*>(sOut + (c >> 3) * kChunkBytes + row * 16) = pk;
+    }
+    if (EPI == EPI_GENERIC && g.raw != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int rc = c + e - g.d_col0;
+        if (rc >= 0 && rc < g.raw_ncol) {
+          const float y = raw_activation(x[e], g.raw_act, rc);
+          if (raw_staged) sRaw[row * g.raw_pitch + rc] = y;
+          else if (grow < g.M) g.raw[grow * g.raw_ld + g.raw_col0 + rc] = y;
+        }
+      }
+    }
+  }
+}
+
+template <int STAGES, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1) tile_gemm_kernel(const TileGemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_w, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
@@ -74,11 +128,11 @@ __global__ void __launch_bounds__(kThreads, 1) tile_gemm_kernel(const TileGemmAr
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], kEpiThreads); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_slot);
-  for (int i = threadIdx.x; i < g.N; i += kThreads) sBias[i] = g.bias ? g.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < g.N; i += kGemmThreads) sBias[i] = g.bias ? g.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -133,78 +187,63 @@ __global__ void __launch_bounds__(kThreads, 1) tile_gemm_kernel(const TileGemmAr
       }
     }
   } else {
-    // ---------------- epilogue: 4 warps, thread = one point (TMEM lane) -----------------------
+    // ---------------- epilogue: 8 warps; thread = one point (TMEM lane) x every other 16-column block ----
     const int q = warp & 3;                           // TMEM lane quarter this warp may touch
+    const int half = (warp - kEpiWarp0) >> 2;         // which 16-column blocks: b & 1 == half
     const int row = q * 32 + lane;
-    const int et = (warp - kEpiWarp0) * 32 + lane;    // 0..127
+    const int et = (warp - kEpiWarp0) * 32 + lane;    // 0..255
     float* sRaw = reinterpret_cast<float*>(smem + g.off_raw);
-    const bool raw_staged = g.raw != nullptr && g.raw_ncol > 8;
+    const bool raw_staged = (EPI == EPI_GENERIC) && g.raw != nullptr && g.raw_ncol > 8;
+    const bool has_img = (EPI != EPI_GENERIC) || g.out_img != nullptr;
+    const int n_blk = g.N >> 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int64_t grow = (int64_t)tile * kTile + row;
       uint8_t* sOut = smem + g.off_out + (it & 1) * g.out_bytes;
-      if (g.out_img != nullptr) {
+      if (has_img) {
         if (et == 0) bulk_wait_read<1>();             // the store that used this staging buffer two tiles ago
         epi_barrier();
       }
-      uint4 min4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      if (g.mask_in != nullptr) min4 = g.mask_in[grow];
-      uint4 mout4 = make_uint4(0u, 0u, 0u, 0u);
+      const uint16_t* min_row = (EPI == EPI_DGRAD && g.mask_in != nullptr) ? reinterpret_cast<const uint16_t*>(g.mask_in + grow) : nullptr;
+      uint16_t* mout_row = (g.mask_out != nullptr) ? reinterpret_cast<uint16_t*>(g.mask_out + grow) : nullptr;
       mbar_wait(&bar_tfull[acc], aph);
       tc_fence_after();
       const uint32_t taddr = tmem + acc * 256 + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < g.N; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
+      // my blocks: half, half+2, ...; loaded four at a time so the TMEM reads overlap
+      for (int b0 = half; b0 < n_blk; b0 += 8) {
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        const bool h1 = b0 + 2 < n_blk, h2 = b0 + 4 < n_blk, h3 = b0 + 6 < n_blk;
+        tmem_ld16(taddr + b0 * 16, v0);
+        if (h1) tmem_ld16(taddr + (b0 + 2) * 16, v1);
+        if (h2) tmem_ld16(taddr + (b0 + 4) * 16, v2);
+        if (h3) tmem_ld16(taddr + (b0 + 6) * 16, v3);
+        uint32_t in0 = 0xffffu, in1 = 0xffffu, in2 = 0xffffu, in3 = 0xffffu;
+        if (min_row != nullptr) {
+          const int mb = (g.mask_shift >> 4) + b0;
+          in0 = min_row[mb];
+          if (h1) in1 = min_row[mb + 2];
+          if (h2) in2 = min_row[mb + 4];
+          if (h3) in3 = min_row[mb + 6];
+        }
         tmem_ld_wait();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {                 // two 8-channel chunks
-          const int c = c0 + h * 8;
-          float x[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[h * 8 + e]) + sBias[c + e];
-          if (c < g.out_ch) {
-            // the 8 channels of a chunk share one byte of the 128-bit ReLU mask (mask_shift % 8 == 0)
-            const int bit0 = g.mask_shift + c;
-            const int word = bit0 >> 5, sh = bit0 & 31;
-            const uint32_t inw = word == 0 ? min4.x : word == 1 ? min4.y : word == 2 ? min4.z : min4.w;
-            const uint32_t inb = (inw >> sh) & 0xffu;
-            uint32_t outb = 0u;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (g.relu) {
-                const bool on = x[e] > 0.f;
-                x[e] = on ? x[e] : 0.f;
-                outb |= on ? (1u << e) : 0u;
-              }
-              x[e] = ((inb >> e) & 1u) ? x[e] : 0.f;
-            }
-            outb <<= sh;
-            if (word == 0) mout4.x |= outb; else if (word == 1) mout4.y |= outb; else if (word == 2) mout4.z |= outb; else mout4.w |= outb;
-            uint4 pk;
-            pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]);
-            pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
-            *reinterpret_cast<uint4*>(sOut + (c >> 3) * kChunkBytes + row * 16) = pk;
-          }
-          if (g.raw != nullptr) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int rc = c + e - g.d_col0;
-              if (rc >= 0 && rc < g.raw_ncol) {
-                const float y = raw_activation(x[e], g.raw_act, rc);
-                if (raw_staged) sRaw[row * g.raw_pitch + rc] = y;
-                else if (grow < g.M) g.raw[grow * g.raw_ld + g.raw_col0 + rc] = y;
-              }
-            }
-          }
+        uint32_t o0, o1 = 0, o2 = 0, o3 = 0;
+        epi_block<EPI>(g, v0, b0 * 16, row, grow, sBias, sOut, sRaw, raw_staged, in0, o0);
+        if (h1) epi_block<EPI>(g, v1, (b0 + 2) * 16, row, grow, sBias, sOut, sRaw, raw_staged, in1, o1);
+        if (h2) epi_block<EPI>(g, v2, (b0 + 4) * 16, row, grow, sBias, sOut, sRaw, raw_staged, in2, o2);
+        if (h3) epi_block<EPI>(g, v3, (b0 + 6) * 16, row, grow, sBias, sOut, sRaw, raw_staged, in3, o3);
+        if (mout_row != nullptr) {
+          const int mb = (g.mask_shift >> 4) + b0;
+          mout_row[mb] = (uint16_t)o0;
+          if (h1) mout_row[mb + 2] = (uint16_t)o1;
+          if (h2) mout_row[mb + 4] = (uint16_t)o2;
+          if (h3) mout_row[mb + 6] = (uint16_t)o3;
         }
       }
       tc_fence_before();
       mbar_arrive(&bar_tempty[acc]);                  // accumulator drained
-      if (g.mask_out != nullptr) g.mask_out[grow] = mout4;
-      if (g.out_img != nullptr) {
+      if (has_img) {
         fence_async_smem();                           // generic smem writes -> async proxy
         epi_barrier();
         if (et == 0) {
@@ -214,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) tile_gemm_kernel(const TileGemmAr
       }
       if (raw_staged) {
         epi_barrier();
-        for (int rr = warp - kEpiWarp0; rr < kTile; rr += 4) {
+        for (int rr = warp - kEpiWarp0; rr < kTile; rr += kEpiWarps) {
           const int64_t gr = (int64_t)tile * kTile + rr;
           if (gr < g.M)
             for (int c = lane; c < g.raw_ncol; c += 32) g.raw[gr * g.raw_ld + g.raw_col0 + c] = sRaw[rr * g.raw_pitch + c];
@@ -245,17 +284,17 @@ struct WgradArgs {
   int64_t total_cost;
   int n_tiles;
   PackSrc ps; float* d_flat;
-  uint32_t off_ones, off_stage, stage_stride;
+  uint32_t off_ones, off_stage, ring_bytes;
 };
 
-template <int STAGES>
+constexpr int kWgradMaxStages = 4;
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_done;
+  __shared__ uint64_t bar_full[kWgradMaxStages], bar_empty[kWgradMaxStages], bar_done;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < kWgradMaxStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_done, 1);
     fence_mbar_init();
   }
@@ -275,8 +314,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
   const int64_t c_lo = w.total_cost * blockIdx.x / gridDim.x;
   const int64_t c_hi = w.total_cost * (blockIdx.x + 1) / gridDim.x;
 
-  int it = 0;          // pipeline iteration counter (same sequence in every role)
-  int piece = 0;       // flush counter
+  uint32_t ph_bits = 0;   // per-role phase bit of every ring slot (producer: empty barriers, MMA: full barriers)
+  int piece = 0;          // flush counter
   for (int j = 0; j < w.n_jobs; ++j) {
     const WgradJob& J = w.job[j];
     const int64_t jb = J.cost_begin, je = jb + (int64_t)w.n_tiles * J.tile_bytes;
@@ -288,32 +327,40 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
     if (t0 >= t1) continue;
     const int n_mblk = (J.g_ch > 128) ? 2 : 1;
     const uint32_t g_bytes = (uint32_t)J.g_ch * 256u;
+    // ring geometry of this job: as many slots as fit (the M=128 gradient operand may read past a short image)
+    const uint32_t stride = (J.tile_bytes + 1023u) & ~1023u;
+    const uint32_t reach = (uint32_t)n_mblk * 32768u;
+    const uint32_t over = reach > stride ? reach - stride : 0u;
+    int ns = (int)((w.ring_bytes - over) / stride);
+    ns = ns > kWgradMaxStages ? kWgradMaxStages : ns;
     if (warp == 0) {
-      if (lane == 0)
+      if (lane == 0) {
+        int s = 0;
         for (int t = t0; t < t1; ++t) {
-          const int s = (it + t - t0) % STAGES;
-          const uint32_t ph = ((it + t - t0) / STAGES) & 1;
-          mbar_wait(&bar_empty[s], ph ^ 1);
+          mbar_wait(&bar_empty[s], ((ph_bits >> s) & 1u) ^ 1u);
+          ph_bits ^= 1u << s;
           mbar_arrive_expect_tx(&bar_full[s], J.tile_bytes);
-          uint8_t* dst = smem + w.off_stage + s * w.stage_stride;
+          uint8_t* dst = smem + w.off_stage + s * stride;
           bulk_g2s(dst, J.g.base + (int64_t)t * J.g.tile_stride, J.g.bytes, &bar_full[s]);
           dst += g_bytes;
           for (int q = 0; q < J.n_src; ++q) {
             bulk_g2s(dst, J.a[q].base + (int64_t)t * J.a[q].tile_stride, J.a[q].bytes, &bar_full[s]);
             dst += J.a[q].bytes;
           }
+          s = (s + 1 == ns) ? 0 : s + 1;
         }
+      }
     } else if (warp == 1) {
       if (lane == 0) {
         const uint32_t idesc_w = idesc_bf16(128, J.a_ch, 1, 1);
         const uint32_t idesc_b = idesc_bf16(128, 16, 1, 1);
         const uint32_t ones = smem_u32(smem + w.off_ones);
+        int s = 0;
         for (int t = t0; t < t1; ++t) {
-          const int s = (it + t - t0) % STAGES;
-          const uint32_t ph = ((it + t - t0) / STAGES) & 1;
-          mbar_wait(&bar_full[s], ph);
+          mbar_wait(&bar_full[s], (ph_bits >> s) & 1u);
+          ph_bits ^= 1u << s;
           tc_fence_after();
-          const uint32_t gs = smem_u32(smem + w.off_stage + s * w.stage_stride);
+          const uint32_t gs = smem_u32(smem + w.off_stage + s * stride);
           const uint32_t as = gs + g_bytes;
           for (int k = 0; k < kTile / 16; ++k) {        // 16 points per MMA
             for (int mb = 0; mb < n_mblk; ++mb) {
@@ -326,11 +373,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
             }
           }
           mma_commit(&bar_empty[s]);
+          s = (s + 1 == ns) ? 0 : s + 1;
         }
         mma_commit(&bar_done);
       }
     }
-    it += t1 - t0;
     // ---- flush this piece: TMEM -> atomicAdd into the flat fp32 gradient ------------------------
     if (warp >= kEpiWarp0) {
       mbar_wait(&bar_done, piece & 1);
@@ -632,19 +679,29 @@ int launch_tile_gemm(const GemmDesc& d, int n_tiles, int64_t M, cudaStream_t st,
   uint32_t smem = g.off_bias + bias_total;
   if (smem < kMinSmem) smem = kMinSmem;
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
-  auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr); };
+  int epi = EPI_GENERIC;
+  if (d.out_img && !d.raw && d.out_ch == d.N && d.N <= 128) {
+    if (d.relu && d.bias && d.mask_out && !d.mask_in) epi = EPI_HIDDEN;
+    else if (!d.relu && !d.bias && !d.mask_out) epi = EPI_DGRAD;
+  }
   static bool attr_done = false;
   if (!attr_done) {
-    NEFES_CUDA(set_attr(tile_gemm_kernel<2>));
-    NEFES_CUDA(set_attr(tile_gemm_kernel<3>));
-    NEFES_CUDA(set_attr(tile_gemm_kernel<4>));
+#define NEFES_SET(ST, EP) NEFES_CUDA(cudaFuncSetAttribute(tile_gemm_kernel<ST, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr))
+    NEFES_SET(2, EPI_HIDDEN); NEFES_SET(3, EPI_HIDDEN); NEFES_SET(4, EPI_HIDDEN);
+    NEFES_SET(2, EPI_DGRAD); NEFES_SET(3, EPI_DGRAD); NEFES_SET(4, EPI_DGRAD);
+    NEFES_SET(2, EPI_GENERIC); NEFES_SET(3, EPI_GENERIC); NEFES_SET(4, EPI_GENERIC);
+#undef NEFES_SET
     attr_done = true;
   }
+#define NEFES_GO(ST, EP) tile_gemm_kernel<ST, EP><<<grid, kGemmThreads, smem, st>>>(g)
+#define NEFES_GO_EPI(ST) do { if (epi == EPI_HIDDEN) NEFES_GO(ST, EPI_HIDDEN); else if (epi == EPI_DGRAD) NEFES_GO(ST, EPI_DGRAD); else NEFES_GO(ST, EPI_GENERIC); } while (0)
   switch (stages) {
-    case 2: tile_gemm_kernel<2><<<grid, kThreads, smem, st>>>(g); break;
-    case 3: tile_gemm_kernel<3><<<grid, kThreads, smem, st>>>(g); break;
-    default: tile_gemm_kernel<4><<<grid, kThreads, smem, st>>>(g); break;
+    case 2: NEFES_GO_EPI(2); break;
+    case 3: NEFES_GO_EPI(3); break;
+    default: NEFES_GO_EPI(4); break;
   }
+#undef NEFES_GO_EPI
+#undef NEFES_GO
   NEFES_CHECK_LAUNCH(what);
   return NEFES_OK;
 }
@@ -834,19 +891,17 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   wa.d_flat = dP;
   wa.off_ones = 0;
   wa.off_stage = 4096;
-  wa.stage_stride = r1k(max_tile_bytes);
-  const int stages = 2;
-  // the M=128 gradient operand may read up to 32 KB past a short gradient image: keep that in bounds
-  const uint32_t smem = wa.off_stage + stages * wa.stage_stride + 36 * 1024;
-  NEFES_REQUIRE(smem <= (uint32_t)kSmemAttr, NEFES_EINVAL, "wgrad: shared memory budget exceeded (%u)", smem);
+  wa.ring_bytes = 192 * 1024;
+  const uint32_t smem = wa.off_stage + wa.ring_bytes;
+  NEFES_REQUIRE(2 * r1k(max_tile_bytes) <= wa.ring_bytes, NEFES_EINVAL, "wgrad: tile too large for the ring");
   static bool attr_done = false;
   if (!attr_done) {
-    NEFES_CUDA(cudaFuncSetAttribute(wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr));
+    NEFES_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr));
     attr_done = true;
   }
   int grid = num_sms();
   if (grid > T * nj) grid = T * nj;
-  wgrad_kernel<2><<<grid, kThreads, smem < kMinSmem ? kMinSmem : smem, st>>>(wa);
+  wgrad_kernel<<<grid, kThreads, smem, st>>>(wa);
   NEFES_CHECK_LAUNCH("wgrad");
   return NEFES_OK;
 }

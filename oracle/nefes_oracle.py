@@ -171,47 +171,64 @@ def freq_encode(x, n_freqs: int):
     return torch.cat(parts, -1)
 
 
-def field_forward(P: Dict[str, torch.Tensor], enc_xyz, enc_dir=None, mode: str = "full"):
+def field_forward(P: Dict[str, torch.Tensor], enc_xyz, enc_dir=None, mode: str = "full", q=None):
     """script/models/nerfh_nff.py:525-576.
 
     mode 'sigma'  -> [M,1]   (sigma_only=True)
     mode 'static' -> [M,132] (output_transient=False)
     mode 'full'   -> [M,137] (fine net with transient heads)
+
+    q (optional, not in the reference): rounding applied to every tensor that is a matmul operand
+    (inputs and hidden activations).  q = bf16 round-trip emulates the engine's bf16 tensor-core path
+    (bf16 operands, fp32 accumulate) so that path can be checked against like-for-like arithmetic.
     """
+    q = q or (lambda t: t)
+    enc_xyz = q(enc_xyz)
     h = enc_xyz
     for i in range(DEPTH):
         if i == SKIP_AT:
             h = torch.cat([enc_xyz, h], 1)
-        h = F.relu(F.linear(h, P[f"xyz_encoding_{i + 1}.0.weight"], P[f"xyz_encoding_{i + 1}.0.bias"]))
+        h = q(F.relu(F.linear(h, P[f"xyz_encoding_{i + 1}.0.weight"], P[f"xyz_encoding_{i + 1}.0.bias"])))
     sigma = F.softplus(F.linear(h, P["static_sigma.0.weight"], P["static_sigma.0.bias"]))
     if mode == "sigma":
         return sigma
-    fin = F.linear(h, P["xyz_encoding_final.weight"], P["xyz_encoding_final.bias"])
-    both = torch.cat([fin, enc_dir], 1)
-    dh = F.relu(F.linear(both, P["dir_encoding.0.weight"], P["dir_encoding.0.bias"]))
+    fin = q(F.linear(h, P["xyz_encoding_final.weight"], P["xyz_encoding_final.bias"]))
+    both = torch.cat([fin, q(enc_dir)], 1)
+    dh = q(F.relu(F.linear(both, P["dir_encoding.0.weight"], P["dir_encoding.0.bias"])))
     rgbf = F.linear(dh, P["static_rgb.0.weight"], P["static_rgb.0.bias"])      # 131 ch, no activation
     static = torch.cat([rgbf, sigma], 1)
     if mode == "static":
         return static
     t = both
     for j in (0, 2, 4):
-        t = F.relu(F.linear(t, P[f"transient_encoding.{j}.weight"], P[f"transient_encoding.{j}.bias"]))
+        t = q(F.relu(F.linear(t, P[f"transient_encoding.{j}.weight"], P[f"transient_encoding.{j}.bias"])))
     t_sigma = F.softplus(F.linear(t, P["transient_sigma.0.weight"], P["transient_sigma.0.bias"]))
     t_rgb = torch.sigmoid(F.linear(t, P["transient_rgb.0.weight"], P["transient_rgb.0.bias"]))
     t_beta = F.softplus(F.linear(t, P["transient_beta.0.weight"], P["transient_beta.0.bias"]))
     return torch.cat([static, t_rgb, t_sigma, t_beta], 1)
 
 
-def query_field(P, pts, viewdirs, typ: str, output_transient: bool, test_time: bool):
+def query_field(P, pts, viewdirs, typ: str, output_transient: bool, test_time: bool, q=None):
     """script/models/nerfh_nff.py:168-231 (netchunk loop dropped: one chunk)."""
     n, s = pts.shape[:2]
     flat = pts.reshape(-1, 3)
     ex = freq_encode(flat, XYZ_FREQS)
     if typ == "coarse" and test_time:
-        return field_forward(P, ex, mode="sigma").reshape(n, s, -1)
+        return field_forward(P, ex, mode="sigma", q=q).reshape(n, s, -1)
     ed = freq_encode(viewdirs[:, None].expand(pts.shape).reshape(-1, 3), DIR_FREQS)
     mode = "full" if (typ == "fine" and output_transient) else "static"
-    return field_forward(P, ex, ed, mode).reshape(n, s, -1)
+    return field_forward(P, ex, ed, mode, q=q).reshape(n, s, -1)
+
+
+def bf16_round(t):
+    """Round-to-nearest-even to bf16 and back (differentiable as identity)."""
+    return t + (t.detach().bfloat16().float() - t.detach())
+
+
+def bf16_weights(P):
+    """Weights rounded to bf16 (what the tensor-core path multiplies with); biases stay fp32.  The
+    returned leaves are the ORIGINAL fp32 tensors' rounded copies with straight-through gradients."""
+    return {k: (bf16_round(v) if k.endswith(".weight") else v) for k, v in P.items()}
 
 
 # --------------------------------------------------------------------------------------

@@ -392,6 +392,10 @@ def nrm_err(a, b):
 
 
 def test_bf16_mlp_forward_and_backward_vs_oracle(nb, weights, models):
+    """Two references: (a) the fp32 oracle -- outputs within BF16_TOL; weight gradients within a loose bound,
+    because a forward computed in bf16 flips the ReLU sign of pre-activations that are ~0 (a fraction p of
+    flipped units moves a gradient by ~sqrt(p) in norm: inherent to any reduced-precision forward); (b) the
+    oracle run with the SAME rounding points (bf16 operands, fp32 accumulate) -- gradients within 3e-2."""
     from nefes_b200 import _lib as L, ops
     wc, wf = weights
     c, f = models
@@ -402,18 +406,20 @@ def test_bf16_mlp_forward_and_backward_vs_oracle(nb, weights, models):
     for model, P, mode, typ, tr in ((f, wf, 2, "fine", True), (c, wc, 1, "coarse", False), (c, wc, 0, "coarse", False)):
         model.zero_grad()
         raw = ops.field_query(pts.to(DEV), None if mode == 0 else dirs.to(DEV), model.flat, model.net_id, mode, L.PREC_BF16)
-        Pg = O.clone_params(P, requires_grad=True)
-        ref = O.query_field(Pg, pts, dirs, typ, tr, test_time=(mode == 0))
-        assert raw.shape == ref.shape
-        assert rel_err(raw, ref) < BF16_TOL, (mode, rel_err(raw, ref))
-        k = torch.randn(ref.shape, generator=gen)
+        k = torch.randn(raw.shape, generator=gen)
         (raw * k.to(DEV)).sum().backward()
-        (ref * k).sum().backward()
         views = model.layer_views(model.flat.grad)
-        for key, ref_g in Pg.items():
-            if ref_g.grad is None:
-                continue
-            assert nrm_err(views[key], ref_g.grad) < 6e-2, (mode, key, nrm_err(views[key], ref_g.grad))
+        for emulate, tol_raw, tol_g in ((False, BF16_TOL, 0.2), (True, 4e-3, 3e-2)):
+            Pg = O.clone_params(P, requires_grad=True)
+            ref = O.query_field(O.bf16_weights(Pg) if emulate else Pg, pts, dirs, typ, tr, test_time=(mode == 0),
+                                q=O.bf16_round if emulate else None)
+            assert raw.shape == ref.shape
+            assert rel_err(raw, ref) < tol_raw, (mode, emulate, rel_err(raw, ref))
+            (ref * k).sum().backward()
+            for key, ref_g in Pg.items():
+                if ref_g.grad is None:
+                    continue
+                assert nrm_err(views[key], ref_g.grad) < tol_g, (mode, emulate, key, nrm_err(views[key], ref_g.grad))
 
 
 def test_bf16_render_train_step(nb, weights, models):
