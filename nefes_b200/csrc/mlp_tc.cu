@@ -39,7 +39,9 @@ struct ASrc { const uint8_t* base; int64_t tile_stride; uint32_t bytes; };
 enum { RAW_ACT_NONE = 0, RAW_ACT_SOFTPLUS = 2, RAW_ACT_THEADS = 4 };
 enum { EPI_HIDDEN = 0,    // bias + ReLU + ReLU bit-mask out -> bf16 image            (forward hidden layers)
        EPI_DGRAD = 1,     // ReLU bit-mask in (optional)     -> bf16 image            (backward data gradients)
-       EPI_GENERIC = 2 }; // bias, optional image columns, optional fp32 columns with head activations
+       EPI_IMG = 2,       // bias -> bf16 image for columns < out_ch (may be none); plus up to 5 activated fp32
+                          // columns starting at d_col0 (a multiple of 16), stored directly     (final+sigma, heads)
+       EPI_RAWBULK = 3 }; // bias -> many fp32 columns, staged in shared memory, coalesced rows   (rgb+feature head)
 
 constexpr int kEpiWarps = 8;                          // two warps per TMEM lane quarter, interleaved 16-column blocks
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -70,9 +72,9 @@ __device__ __forceinline__ float raw_activation(float x, int act, int col) {
 
 // one 16-column block of one row: v = accumulators, c0 = first D column
 template <int EPI>
-__device__ __forceinline__ void epi_block(const TileGemmArgs& g, const uint32_t (&v)[16], int c0, int row, int64_t grow,
+__device__ __forceinline__ void epi_block(const TileGemmArgs& g, const uint32_t (&v)[16], int c0, int row,
                                           const float* __restrict__ sBias, uint8_t* __restrict__ sOut,
-                                          float* __restrict__ sRaw, bool raw_staged, uint32_t in16, uint32_t& out16) {
+                                          float* __restrict__ sRaw, uint32_t in16, uint32_t& out16) {
   out16 = 0u;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -88,7 +90,7 @@ __device__ __forceinline__ void epi_block(const TileGemmArgs& g, const uint32_t 
 #pragma unroll
       for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[h * 8 + e]) + bb[e];
     }
-    if (EPI == EPI_HIDDEN || (EPI == EPI_GENERIC && g.relu)) {
+    if (EPI == EPI_HIDDEN) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const bool on = x[e] > 0.f;
@@ -96,22 +98,16 @@ __device__ __forceinline__ void epi_block(const TileGemmArgs& g, const uint32_t 
         out16 |= on ? (1u << (h * 8 + e)) : 0u;
       }
     }
-    if (EPI != EPI_GENERIC || c < g.out_ch) {
+    if (EPI == EPI_HIDDEN || EPI == EPI_DGRAD || (EPI == EPI_IMG && c < g.out_ch)) {
       uint4 pk;
       pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]);
       pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
       *reinterpret_cast<uint4*>(sOut + (c >> 3) * kChunkBytes + row * 16) = pk;
     }
-    if (EPI == EPI_GENERIC && g.raw != nullptr) {
+    if (EPI == EPI_RAWBULK) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int rc = c + e - g.d_col0;
-        if (rc >= 0 && rc < g.raw_ncol) {
-          const float y = raw_activation(x[e], g.raw_act, rc);
-          if (raw_staged) sRaw[row * g.raw_pitch + rc] = y;
-          else if (grow < g.M) g.raw[grow * g.raw_ld + g.raw_col0 + rc] = y;
-        }
-      }
+      for (int e = 0; e < 8; ++e)
+        if (c + e < g.raw_ncol) sRaw[row * g.raw_pitch + c + e] = x[e];
     }
   }
 }
@@ -177,11 +173,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tile_gemm_kernel(const TileGe
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + g.off_a + s * g.a_stage_stride);
         const uint32_t d = tmem + acc * 256;
-        for (int k = 0; k < g.K / 16; ++k) {
-          const uint64_t da = smem_desc(a_base + k * 2 * kChunkBytes, kChunkBytes, 128);
-          const uint64_t db = smem_desc(w_base + k * 2 * w_lbo, w_lbo, 128);
-          mma_ss(d, da, db, idesc, k > 0);
-        }
+        const uint64_t da0 = smem_desc(a_base, kChunkBytes, 128);
+        const uint64_t db0 = smem_desc(w_base, w_lbo, 128);
+        for (int k = 0; k < g.K / 16; ++k)              // one K step = two 8-channel chunks of both images
+          mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k * (2 * w_lbo >> 4)), idesc, k > 0);
         mma_commit(&bar_empty[s]);      // the A stage may be refilled once these MMAs retire
         mma_commit(&bar_tfull[acc]);    // ... and the accumulator may be drained
       }
@@ -193,8 +188,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tile_gemm_kernel(const TileGe
     const int row = q * 32 + lane;
     const int et = (warp - kEpiWarp0) * 32 + lane;    // 0..255
     float* sRaw = reinterpret_cast<float*>(smem + g.off_raw);
-    const bool raw_staged = (EPI == EPI_GENERIC) && g.raw != nullptr && g.raw_ncol > 8;
-    const bool has_img = (EPI != EPI_GENERIC) || g.out_img != nullptr;
+    const bool raw_staged = (EPI == EPI_RAWBULK);
+    const bool has_img = (EPI == EPI_HIDDEN) || (EPI == EPI_DGRAD) || (EPI == EPI_IMG && g.out_img != nullptr);
     const int n_blk = g.N >> 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
@@ -229,16 +224,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tile_gemm_kernel(const TileGe
         }
         tmem_ld_wait();
         uint32_t o0, o1 = 0, o2 = 0, o3 = 0;
-        epi_block<EPI>(g, v0, b0 * 16, row, grow, sBias, sOut, sRaw, raw_staged, in0, o0);
-        if (h1) epi_block<EPI>(g, v1, (b0 + 2) * 16, row, grow, sBias, sOut, sRaw, raw_staged, in1, o1);
-        if (h2) epi_block<EPI>(g, v2, (b0 + 4) * 16, row, grow, sBias, sOut, sRaw, raw_staged, in2, o2);
-        if (h3) epi_block<EPI>(g, v3, (b0 + 6) * 16, row, grow, sBias, sOut, sRaw, raw_staged, in3, o3);
+        epi_block<EPI>(g, v0, b0 * 16, row, sBias, sOut, sRaw, in0, o0);
+        if (h1) epi_block<EPI>(g, v1, (b0 + 2) * 16, row, sBias, sOut, sRaw, in1, o1);
+        if (h2) epi_block<EPI>(g, v2, (b0 + 4) * 16, row, sBias, sOut, sRaw, in2, o2);
+        if (h3) epi_block<EPI>(g, v3, (b0 + 6) * 16, row, sBias, sOut, sRaw, in3, o3);
         if (mout_row != nullptr) {
           const int mb = (g.mask_shift >> 4) + b0;
           mout_row[mb] = (uint16_t)o0;
           if (h1) mout_row[mb + 2] = (uint16_t)o1;
           if (h2) mout_row[mb + 4] = (uint16_t)o2;
           if (h3) mout_row[mb + 6] = (uint16_t)o3;
+        }
+      }
+      if (EPI == EPI_IMG && g.raw != nullptr) {
+        // a handful of activated fp32 head outputs (sigma; transient rgb/sigma/beta): one copy of the
+        // activation code, outside the unrolled block loop
+        const int bF = g.d_col0 >> 4;
+        if ((bF & 1) == half) {
+          uint32_t v[16];
+          tmem_ld16(taddr + bF * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 5; ++e)
+            if (e < g.raw_ncol && grow < g.M)
+              g.raw[grow * g.raw_ld + g.raw_col0 + e] = raw_activation(__uint_as_float(v[e]) + sBias[g.d_col0 + e], g.raw_act, e);
         }
       }
       tc_fence_before();
@@ -299,12 +308,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_slot);
-  {  // two 8-channel groups of ones: B operand of the bias-gradient MMA
-    uint4 ones;
-    ones.x = ones.y = ones.z = ones.w = 0x3F803F80u;
-    for (int i = threadIdx.x; i < 2 * (int)kChunkBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem + w.off_ones)[i] = ones;
-    fence_async_smem();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -328,11 +331,23 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
     const int n_mblk = (J.g_ch > 128) ? 2 : 1;
     const uint32_t g_bytes = (uint32_t)J.g_ch * 256u;
     // ring geometry of this job: as many slots as fit (the M=128 gradient operand may read past a short image)
-    const uint32_t stride = (J.tile_bytes + 1023u) & ~1023u;
+    // slot = [gradient image | activation image(s) | 16 channels of ones]: the ones make the bias gradient
+    // (column sums of G) fall out of the same MMA as 16 extra output columns.
+    const uint32_t stride = (J.tile_bytes + 2 * kChunkBytes + 1023u) & ~1023u;
     const uint32_t reach = (uint32_t)n_mblk * 32768u;
     const uint32_t over = reach > stride ? reach - stride : 0u;
     int ns = (int)((w.ring_bytes - over) / stride);
     ns = ns > kWgradMaxStages ? kWgradMaxStages : ns;
+    {
+      uint4 ones;
+      ones.x = ones.y = ones.z = ones.w = 0x3F803F80u;
+      for (int sl = 0; sl < ns; ++sl) {
+        uint4* dst = reinterpret_cast<uint4*>(smem + w.off_stage + sl * stride + J.tile_bytes);
+        for (int i = threadIdx.x; i < 2 * (int)kChunkBytes / 16; i += kThreads) dst[i] = ones;
+      }
+      fence_async_smem();
+      __syncthreads();
+    }
     if (warp == 0) {
       if (lane == 0) {
         int s = 0;
@@ -352,9 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        const uint32_t idesc_w = idesc_bf16(128, J.a_ch, 1, 1);
-        const uint32_t idesc_b = idesc_bf16(128, 16, 1, 1);
-        const uint32_t ones = smem_u32(smem + w.off_ones);
+        const uint32_t idesc_w = idesc_bf16(128, J.a_ch + 16, 1, 1);
         int s = 0;
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&bar_full[s], (ph_bits >> s) & 1u);
@@ -362,15 +375,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
           tc_fence_after();
           const uint32_t gs = smem_u32(smem + w.off_stage + s * stride);
           const uint32_t as = gs + g_bytes;
-          for (int k = 0; k < kTile / 16; ++k) {        // 16 points per MMA
-            for (int mb = 0; mb < n_mblk; ++mb) {
-              const uint64_t da = smem_desc(gs + mb * 16 * kChunkBytes + k * 256, 128, kChunkBytes);
-              const uint64_t db = smem_desc(as + k * 256, 128, kChunkBytes);
-              const uint64_t d1 = smem_desc(ones + k * 256, 128, kChunkBytes);
-              const uint32_t accum = (t > t0 || k > 0) ? 1u : 0u;
-              mma_ss(tmem + mb * 256, da, db, idesc_w, accum);
-              mma_ss(tmem + mb * 256 + J.a_ch, da, d1, idesc_b, accum);
-            }
+          const uint64_t db0 = smem_desc(as, 128, kChunkBytes);
+          const uint64_t da0 = smem_desc(gs, 128, kChunkBytes);
+          const uint64_t da1 = smem_desc(gs + 16 * kChunkBytes, 128, kChunkBytes);
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k) {        // 16 points per MMA: +256 B in both images
+            const uint32_t accum = (t > t0 || k > 0) ? 1u : 0u;
+            mma_ss(tmem, da0 + (uint64_t)(k * 16), db0 + (uint64_t)(k * 16), idesc_w, accum);
+            if (n_mblk == 2) mma_ss(tmem + 256, da1 + (uint64_t)(k * 16), db0 + (uint64_t)(k * 16), idesc_w, accum);
           }
           mma_commit(&bar_empty[s]);
           s = (s + 1 == ns) ? 0 : s + 1;
@@ -665,7 +677,7 @@ int launch_tile_gemm(const GemmDesc& d, int n_tiles, int64_t M, cudaStream_t st,
   g.out_bytes = (uint32_t)g.out_ch * 256u;
   const uint32_t out_total = 2 * r1k(g.out_bytes);
   g.raw_pitch = (uint32_t)(d.raw_ncol | 1);
-  const uint32_t raw_total = (d.raw && d.raw_ncol > 8) ? r1k(kTile * g.raw_pitch * 4u) : 0u;
+  const uint32_t raw_total = (d.raw && d.raw_ncol > 8) ? r1k(kTile * g.raw_pitch * 4u) : 0u;   // EPI_RAWBULK staging
   const uint32_t bias_total = 1024;
   const uint32_t fixed = r1k(w_bytes) + out_total + raw_total + bias_total;
   NEFES_REQUIRE(fixed + 2 * a_stage <= kSmemBudget, NEFES_EINVAL, "%s: shared memory budget exceeded", what);
@@ -679,22 +691,30 @@ int launch_tile_gemm(const GemmDesc& d, int n_tiles, int64_t M, cudaStream_t st,
   uint32_t smem = g.off_bias + bias_total;
   if (smem < kMinSmem) smem = kMinSmem;
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
-  int epi = EPI_GENERIC;
-  if (d.out_img && !d.raw && d.out_ch == d.N && d.N <= 128) {
-    if (d.relu && d.bias && d.mask_out && !d.mask_in) epi = EPI_HIDDEN;
-    else if (!d.relu && !d.bias && !d.mask_out) epi = EPI_DGRAD;
+  int epi = EPI_IMG;
+  if (d.raw && d.raw_ncol > 8) {
+    NEFES_REQUIRE(!d.out_img && d.d_col0 == 0 && d.raw_act == RAW_ACT_NONE, NEFES_EINVAL, "%s: unsupported bulk fp32 epilogue", what);
+    epi = EPI_RAWBULK;
+  } else if (d.out_img && !d.raw && d.out_ch == d.N && d.N <= 128 && d.relu && d.bias && d.mask_out && !d.mask_in) {
+    epi = EPI_HIDDEN;
+  } else if (d.out_img && !d.raw && d.out_ch == d.N && d.N <= 128 && !d.relu && !d.bias && !d.mask_out) {
+    epi = EPI_DGRAD;
+  } else {
+    NEFES_REQUIRE(!d.relu && !d.mask_out && !d.mask_in && (!d.raw || (d.raw_ncol <= 5 && d.d_col0 % 16 == 0)), NEFES_EINVAL,
+                  "%s: unsupported epilogue combination", what);
   }
   static bool attr_done = false;
   if (!attr_done) {
 #define NEFES_SET(ST, EP) NEFES_CUDA(cudaFuncSetAttribute(tile_gemm_kernel<ST, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr))
-    NEFES_SET(2, EPI_HIDDEN); NEFES_SET(3, EPI_HIDDEN); NEFES_SET(4, EPI_HIDDEN);
-    NEFES_SET(2, EPI_DGRAD); NEFES_SET(3, EPI_DGRAD); NEFES_SET(4, EPI_DGRAD);
-    NEFES_SET(2, EPI_GENERIC); NEFES_SET(3, EPI_GENERIC); NEFES_SET(4, EPI_GENERIC);
+#define NEFES_SET3(EP) NEFES_SET(2, EP); NEFES_SET(3, EP); NEFES_SET(4, EP)
+    NEFES_SET3(EPI_HIDDEN); NEFES_SET3(EPI_DGRAD); NEFES_SET3(EPI_IMG); NEFES_SET3(EPI_RAWBULK);
+#undef NEFES_SET3
 #undef NEFES_SET
     attr_done = true;
   }
 #define NEFES_GO(ST, EP) tile_gemm_kernel<ST, EP><<<grid, kGemmThreads, smem, st>>>(g)
-#define NEFES_GO_EPI(ST) do { if (epi == EPI_HIDDEN) NEFES_GO(ST, EPI_HIDDEN); else if (epi == EPI_DGRAD) NEFES_GO(ST, EPI_DGRAD); else NEFES_GO(ST, EPI_GENERIC); } while (0)
+#define NEFES_GO_EPI(ST) do { if (epi == EPI_HIDDEN) NEFES_GO(ST, EPI_HIDDEN); else if (epi == EPI_DGRAD) NEFES_GO(ST, EPI_DGRAD); \
+                              else if (epi == EPI_RAWBULK) NEFES_GO(ST, EPI_RAWBULK); else NEFES_GO(ST, EPI_IMG); } while (0)
   switch (stages) {
     case 2: NEFES_GO_EPI(2); break;
     case 3: NEFES_GO_EPI(3); break;
@@ -893,7 +913,7 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   wa.off_stage = 4096;
   wa.ring_bytes = 192 * 1024;
   const uint32_t smem = wa.off_stage + wa.ring_bytes;
-  NEFES_REQUIRE(2 * r1k(max_tile_bytes) <= wa.ring_bytes, NEFES_EINVAL, "wgrad: tile too large for the ring");
+  NEFES_REQUIRE(2 * r1k(max_tile_bytes + 4096) <= wa.ring_bytes, NEFES_EINVAL, "wgrad: tile too large for the ring");
   static bool attr_done = false;
   if (!attr_done) {
     NEFES_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr));
