@@ -156,9 +156,9 @@ typedef struct {
   float* weights;                  /* [N,S]   */
   float* depth;                    /* [N]     */
   float* beta;                     /* [N]     */
+  float* tsig;                     /* [N,S] transient_sigmas = raw[...,135] (transient modes) or NULL */
 } nefes_comp_out_t;
-/* noise [N,S] = randn * raw_noise_std or NULL.  transient_sigmas is a view of raw (column
- * 135) and is taken by the host, not copied here. */
+/* noise [N,S] = randn * raw_noise_std or NULL. */
 int nefes_composite_fwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
                         int mode, float beta_min, const nefes_comp_out_t* out_host, void* stream);
 /* Cotangents (any may be NULL = zero): same shapes as the outputs, plus d_tsig [N,S] for the

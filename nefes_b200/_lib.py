@@ -30,7 +30,7 @@ class Layout(C.Structure):
 
 
 class CompOut(C.Structure):
-    _fields_ = [(n, vp) for n in ("rgb", "feat", "disp", "acc", "weights", "depth", "beta")]
+    _fields_ = [(n, vp) for n in ("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig")]
 
 
 class CompGrad(C.Structure):

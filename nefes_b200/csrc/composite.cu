@@ -125,6 +125,7 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw, const float*
     s_ws[t] = w_static;
     s_wt[t] = w_t;
     o.weights[(int64_t)r * S + t] = w_out;
+    if (TR && o.tsig != nullptr) o.tsig[(int64_t)r * S + t] = rr[(int64_t)t * C + 135];
   }
   const float acc = block_total(ok ? w : 0.f, sc);           // acc_map = sum of combined weights
   if (t == 0) o.acc[r] = acc;
@@ -159,7 +160,6 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw, const float*
     if (c < 3) o.rgb[(int64_t)r * 3 + c] = v;
     else o.feat[(int64_t)r * kFeat + (c - 3)] = v;
   }
-  (void)TR;
 }
 
 template <int MODE>

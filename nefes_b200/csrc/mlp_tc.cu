@@ -567,6 +567,21 @@ __global__ void head_grad_images_kernel(const float* __restrict__ raw, const flo
   }
 }
 
+// out[n, c] = sum_s src[(n*S + s)*ld + c], c < ncol (per-ray sum of a per-point fp32 gradient)
+__global__ void ray_reduce_kernel(const float* __restrict__ src, int ld, int ncol, int S, int64_t N, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * ncol) return;
+  const int64_t n = idx / ncol;
+  const int c = (int)(idx % ncol);
+  float a = 0.f;
+  for (int s = 0; s < S; ++s) a += src[(n * S + s) * ld + c];
+  out[idx] = a;
+}
+
+}  // namespace nefes
+extern "C" int nefes_encode_pe_bwd(const float*, const float*, int, int64_t, int, float*, void*);
+namespace nefes {
+
 // =================================================================================================
 // host orchestration
 // =================================================================================================
@@ -600,6 +615,9 @@ struct Ws {             // saved-for-backward (forward writes, backward reads)
 };
 struct WsB {            // backward scratch
   Img GTH, GT3, GT2, GDT, GRGB, GFS, G[8], GSIG;
+  float* dX;            // [Mp,64] fp32 gradient w.r.t. the xyz PE      (pose refinement only)
+  float* dDIR;          // [Mp,32] fp32 gradient w.r.t. the dir PE, per point
+  float* dDIRray;       // [N,32]  ... summed over the samples of a ray
   int64_t bytes;
 };
 
@@ -626,7 +644,7 @@ Ws carve_ws(void* base, int64_t T, int mode) {
   w.bytes = (int64_t)(p - (uint8_t*)base);
   return w;
 }
-WsB carve_wsb(void* base, int64_t T, int mode) {
+WsB carve_wsb(void* base, int64_t T, int mode, int64_t N) {
   WsB w = {};
   uint8_t* p = (uint8_t*)base;
   auto img = [&](int ch) { Img i; i.ch = ch; i.p = p; p += round_up(T * ch * 256, 1024); return i; };
@@ -638,6 +656,9 @@ WsB carve_wsb(void* base, int64_t T, int mode) {
     w.GDT = img(mode == NEFES_MODE_FULL ? 128 : 64);
     if (mode == NEFES_MODE_FULL) { w.GTH = img(16); w.GT3 = img(64); w.GT2 = img(64); }
   }
+  w.dX = (float*)p; p += round_up(T * kTile * 64 * 4, 1024);
+  w.dDIR = (float*)p; p += round_up(T * kTile * 32 * 4, 1024);
+  w.dDIRray = (float*)p; p += round_up(N * 32 * 4, 1024);
   w.bytes = (int64_t)(p - (uint8_t*)base);
   return w;
 }
@@ -746,11 +767,11 @@ struct Arena {
 }  // namespace
 
 int mlp_workspace_bf16(int net, int mode, int64_t M, int64_t N, int64_t* saved, int64_t* sf, int64_t* sb) {
-  (void)net; (void)N;
+  (void)net;
   const int64_t T = ceil_div(M, kTile);
   *saved = carve_ws(nullptr, T, mode).bytes + 1024;
   *sf = 1024;
-  *sb = carve_wsb(nullptr, T, mode).bytes + 1024;
+  *sb = carve_wsb(nullptr, T, mode, N).bytes + 1024;
   return NEFES_OK;
 }
 
@@ -822,17 +843,12 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
 int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const float* dirs, int64_t N, int S,
                  const float* raw, const float* d_raw, const void* saved, void* scratch, float* dP, float* d_pts,
                  float* d_dirs, cudaStream_t st) {
-  (void)P; (void)pts; (void)dirs;
-  if (d_pts != nullptr || d_dirs != nullptr) {
-    set_error("NEFES_PREC_BF16: gradients to sample positions / view directions are not built yet; use NEFES_PREC_FP32 "
-              "for pose refinement");
-    return NEFES_EUNSUPPORTED;
-  }
+  (void)P;
   const int64_t M = N * S;
   const int T = (int)ceil_div(M, kTile);
   const int64_t Mp = (int64_t)T * kTile;
   const Ws w = carve_ws(const_cast<void*>(saved), T, mode);
-  WsB b = carve_wsb(scratch, T, mode);
+  WsB b = carve_wsb(scratch, T, mode, N);
   const int C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
   Arena A = {w.arena, packed_arena()};
 
@@ -868,6 +884,27 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   for (int l = 7; l >= 1; --l)   // G[l] = grad wrt pre-activation of trunk layer l  ->  G[l-1]
     TRY(dgrad(PL_T0 + l, src_of(b.G[l]), 128, l == 4 ? 64 : 0, 128, b.G[l - 1].p, b.G[l - 1].tile_stride(), 128,
               w.mask[l - 1], 0));
+
+  // ---- gradients to the inputs (pose refinement): fp32 out of the GEMM, then the SIMT PE backward ------
+  if (d_pts != nullptr) {        // d xyzPE = G5 W_T4[:, :63] + G1 W_T0 as ONE GEMM over the concatenated K = [G5 | G1]
+    GemmDesc d;
+    ASrc g1 = src_of(b.G[0]);
+    d.a[0] = src_of(b.G[4]); d.a[1] = g1; d.n_src = 2;
+    d.K = 256; d.N = 64; d.w_img = A.W(PL_DX); d.w_rows = 64;
+    d.raw = b.dX; d.raw_ld = 64; d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = 64; d.raw_act = RAW_ACT_NONE;
+    TRY(launch_tile_gemm(d, T, Mp, st, "dgrad xyz PE"));
+    TRY(nefes_encode_pe_bwd(pts, b.dX, 64, M, kXyzFreqs, d_pts, st));
+  }
+  if (d_dirs != nullptr && mode != NEFES_MODE_SIGMA) {   // d dirPE = GDT W_DT[:, 128:155], summed over each ray's samples
+    GemmDesc d;
+    const int pl = (mode == NEFES_MODE_FULL) ? PL_DT : PL_DIR;
+    d.a[0] = src_of(b.GDT); d.K = w.DT.ch; d.N = 32; d.w_img = A.WT(pl); d.w_rows = packed_dims(pl).K; d.w_row0 = 128;
+    d.raw = b.dDIR; d.raw_ld = 32; d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = 32; d.raw_act = RAW_ACT_NONE;
+    TRY(launch_tile_gemm(d, T, Mp, st, "dgrad dir PE"));
+    ray_reduce_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(b.dDIR, 32, 32, S, N, b.dDIRray);
+    NEFES_CHECK_LAUNCH("ray_reduce");
+    TRY(nefes_encode_pe_bwd(dirs, b.dDIRray, 32, N, kDirFreqs, d_dirs, st));
+  }
 
   if (dP == nullptr) return NEFES_OK;
 

@@ -23,6 +23,7 @@ enum PackedLayer {
   PL_TE1,     // transient_encoding.2                              N=64  K=64
   PL_TE2,     // transient_encoding.4                              N=64  K=64
   PL_TH,      // [t_rgb(3) ; t_sigma ; t_beta ; 0 x11] <- t3       N=16  K=64
+  PL_DX,      // backward only: d xyzPE(64) <- [G5 | G1] through W_T4[:, :63] and W_T0   N=64 K=256
   PL_COUNT
 };
 
@@ -31,7 +32,8 @@ __host__ __device__ constexpr PackedDims packed_dims(int pl) {
   return pl <= PL_T7 ? (pl == PL_T0 ? PackedDims{128, 64} : pl == PL_T4 ? PackedDims{128, 192} : PackedDims{128, 128})
        : pl == PL_FS ? PackedDims{144, 128} : pl == PL_SIG ? PackedDims{16, 128}
        : pl == PL_DT ? PackedDims{128, 160} : pl == PL_DIR ? PackedDims{64, 160}
-       : pl == PL_RGB ? PackedDims{144, 64} : pl == PL_TH ? PackedDims{16, 64} : PackedDims{64, 64};
+       : pl == PL_RGB ? PackedDims{144, 64} : pl == PL_TH ? PackedDims{16, 64}
+       : pl == PL_DX ? PackedDims{64, 256} : PackedDims{64, 64};
 }
 
 // flat-parameter offsets needed to (un)pack: filled on the host from Layout
@@ -62,6 +64,9 @@ __host__ __device__ inline int64_t packed_weight_index(const PackSrc& S, int pl,
     case PL_TE1: return S.w[L_TENC1] + (int64_t)n * 64 + k;
     case PL_TE2: return S.w[L_TENC2] + (int64_t)n * 64 + k;
     case PL_TH: return (n < 5) ? S.w[L_TRGB] + (int64_t)n * 64 + k : -1;   // t_rgb, t_sigma, t_beta adjacent
+    case PL_DX:                            // n = xyz-PE channel, k = output unit of layer 5 (k<128) / layer 1
+      if (n >= kXyzCh) return -1;
+      return k < 128 ? S.w[L_T4] + (int64_t)k * 191 + n : S.w[L_T0] + (int64_t)(k - 128) * kXyzCh + n;
   }
   return -1;
 }
@@ -74,6 +79,7 @@ __host__ __device__ inline int64_t packed_bias_index(const PackSrc& S, int pl, i
     case PL_TE1: return S.b[L_TENC1] + n;
     case PL_TE2: return S.b[L_TENC2] + n;
     case PL_TH: return n < 5 ? S.b[L_TRGB] + n : -1;
+    case PL_DX: return -1;
     default: return S.b[L_T0 + (pl - PL_T0)] + n;
   }
 }

@@ -44,8 +44,8 @@ def raw2outputs_NeRFH_NFF(raw, z_vals, raw_noise_std=0, output_transient=False, 
         if raw.shape[-1] != 137:
             raise RuntimeError(f"nefes_b200: transient compositing expects 137 channels, got {raw.shape[-1]}")
         mode = L.COMP_TRANSIENT_STATIC_ONLY if (test_time and not transient_at_test) else L.COMP_TRANSIENT
-        rgb, feat, disp, acc, weights, depth, beta = ops.composite(raw, z_vals, None, mode, beta_min)
-        return rgb, feat, disp, acc, weights, depth, raw[..., 135], beta
+        rgb, feat, disp, acc, weights, depth, beta, tsig = ops.composite(raw, z_vals, None, mode, beta_min)
+        return rgb, feat, disp, acc, weights, depth, tsig, beta
     if raw.shape[-1] != 132:
         raise RuntimeError(f"nefes_b200: static compositing expects 132 channels, got {raw.shape[-1]}")
     if noise is None and raw_noise_std > 0.:

@@ -230,8 +230,9 @@ def field_query(pts, dirs, flat, net, mode, prec=L.PREC_FP32):
 # K6 compositing
 # ------------------------------------------------------------------------------------------------
 class _Composite(Function):
-    """raw [N,S,C], z [N,S] -> rgb, feat, disp, acc, weights, depth, beta.
-    (transient_sigmas is a view of raw taken by the caller.)"""
+    """raw [N,S,C], z [N,S] -> rgb, feat, disp, acc, weights, depth, beta[, transient_sigmas].
+    transient_sigmas (= raw[...,135]) is an output of the op so its cotangent reaches d_raw inside the
+    backward kernel instead of through a dense zero-filled slice gradient."""
 
     @staticmethod
     def forward(ctx, raw, z, noise, mode, beta_min):
@@ -241,13 +242,17 @@ class _Composite(Function):
         dev = raw_c.device
         acc = torch.empty(N, device=dev)
         weights = torch.empty(N, S, device=dev)
+        tsig = None
         if mode == L.COMP_SIGMA:
             rgb = feat = disp = depth = beta = None
         else:
             rgb = torch.empty(N, 3, device=dev)
             feat = torch.empty(N, 128, device=dev)
             disp, depth, beta = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
-        out = L.CompOut(L.ptr(rgb), L.ptr(feat), L.ptr(disp), L.ptr(acc), L.ptr(weights), L.ptr(depth), L.ptr(beta))
+            if mode in (L.COMP_TRANSIENT, L.COMP_TRANSIENT_STATIC_ONLY):
+                tsig = torch.empty(N, S, device=dev)
+        out = L.CompOut(L.ptr(rgb), L.ptr(feat), L.ptr(disp), L.ptr(acc), L.ptr(weights), L.ptr(depth), L.ptr(beta),
+                        L.ptr(tsig))
         with torch.cuda.device(dev):
             L.check(L.lib().nefes_composite_fwd(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode,
                                                 float(beta_min), C.byref(out), L.stream_of(raw_c)),
@@ -255,9 +260,10 @@ class _Composite(Function):
         ctx.save_for_backward(raw_c, z_c, noise_c)
         ctx.meta = (mode, N, S, tuple(raw.shape))
         if mode == L.COMP_SIGMA:
-            ctx.mark_non_differentiable()
             return acc, weights
-        return rgb, feat, disp, acc, weights, depth, beta
+        if tsig is None:
+            return rgb, feat, disp, acc, weights, depth, beta
+        return rgb, feat, disp, acc, weights, depth, beta, tsig
 
     @staticmethod
     def backward(ctx, *grads):
@@ -267,7 +273,7 @@ class _Composite(Function):
             g_acc, g_w = grads
             g = dict(acc=g_acc, weights=g_w)
         else:
-            g = dict(zip(("rgb", "feat", "disp", "acc", "weights", "depth", "beta"), grads))
+            g = dict(zip(("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig"), grads))
         g = {k: L.f32c(v) for k, v in g.items() if v is not None}
         gs = L.CompGrad(*[L.ptr(g.get(k)) for k in ("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig")])
         d_raw = torch.empty_like(raw_c)
