@@ -218,7 +218,8 @@ def run_engine(a):
                                "4 images x 1536 rays = 6144 rays/GPU/step, 64 coarse + 64 fine samples, Adam",
                    "rays_per_gpu_per_step": RAYS, "global_rays_per_step": RAYS * world, "parallelism": f"dp{world} (rays sharded, 1 gradient all-reduce)",
                    "mlp_precision": a.precision,
-                   "l2": "no explicit flush: each step streams ~7 GB of saved activations (>> 126 MB L2)"},
+                   "l2": "no explicit flush: each step streams >20 GB of activation / gradient tiles through HBM (>> 126 MB L2); "
+                         "only the 1.4 MB of weights is legitimately L2-resident"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches,
@@ -229,12 +230,60 @@ def run_engine(a):
         "clocks": clk.summary(),
         "final_loss": losses[-1] if losses else None,
     }
+    if world == 1 and not a.no_extras:
+        out["extras"] = side_measurements(a, nb, step, coarse, fine, resident, kw, dev)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_rays=a.cpu_rays, reps=a.cpu_reps)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def side_measurements(a, nb, step, coarse, fine, resident, kw, dev):
+    """Reported next to the headline, not part of it: the same training step with the fp32 (parity) field path, and
+    BASELINE's second metric -- refinement iterations/s (C4: full 60x80 render from a pose, test_time, cosine
+    feature loss, backward to the 6 pose parameters, Adam), in both arithmetics."""
+    from nefes_b200 import refine
+    ex = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if a.precision != "fp32":
+        coarse.precision = fine.precision = "fp32"
+        for b in resident[:2]:
+            step(b)
+        torch.cuda.synchronize()
+        ev0.record()
+        for b in resident[:5]:
+            step(b)
+        ev1.record()
+        torch.cuda.synchronize()
+        ex["train_step_fp32_field"] = {"rays_per_s": RAYS * 5 / (ev0.elapsed_time(ev1) / 1e3), "ms_per_step": ev0.elapsed_time(ev1) / 5}
+        coarse.precision = fine.precision = a.precision
+    g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
+    init = torch.tensor(g["dfnet_init"][0].reshape(3, 4), dtype=torch.float32, device=dev)
+    target = torch.randn(128, H * W, device=dev)
+    kwt = dict(kw)
+    kwt.update(perturb=0., test_time=True)
+    kwt.pop("retraw", None)
+    for p in (coarse.flat, fine.flat):
+        p.requires_grad_(False)
+    try:
+        for prec in ("fp32", "bf16"):
+            coarse.precision = fine.precision = prec
+            refine.refine_pose(init, target, H, W, FOCAL, kwt, n_iters=3)
+            torch.cuda.synchronize()
+            ev0.record()
+            refine.refine_pose(init, target, H, W, FOCAL, kwt, n_iters=20)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / 20
+            ex[f"refine_{prec}"] = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "rays_per_iter": H * W,
+                                    "queries_per_s_at_50_iters": 1e3 / ms / 50}
+    finally:
+        coarse.precision = fine.precision = a.precision
+        for p in (coarse.flat, fine.flat):
+            p.requires_grad_(True)
+    return ex
 
 
 # --------------------------------------------------------------------------------------------------
@@ -322,7 +371,8 @@ def main():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    p.add_argument("--precision", default=os.environ.get("NEFES_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    p.add_argument("--precision", default=os.environ.get("NEFES_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    p.add_argument("--no-extras", action="store_true", help="skip the fp32-path and refinement side measurements")
     p.add_argument("--cpu-rays", type=int, default=1024)
     p.add_argument("--cpu-reps", type=int, default=3)
     p.add_argument("--no-cpu-baseline", action="store_true")
