@@ -259,6 +259,28 @@ def side_measurements(a, nb, step, coarse, fine, resident, kw, dev):
         torch.cuda.synchronize()
         ex["train_step_fp32_field"] = {"rays_per_s": RAYS * 5 / (ev0.elapsed_time(ev1) / 1e3), "ms_per_step": ev0.elapsed_time(ev1) / 5}
         coarse.precision = fine.precision = a.precision
+    # encoder front-end B (K4b): HashGrid gather, forward and backward, at the bench step's point count
+    from nefes_b200.hashgrid import HashGridEncoding
+    enc = HashGridEncoding().to(dev)
+    npts = RAYS * 192
+    xs = torch.rand(npts, 3, device=dev)
+    for tag, need_grad in (("fwd", False), ("fwd_bwd", True)):
+        for rep in range(2):                          # first pass = warm-up
+            torch.cuda.synchronize()
+            ev0.record()
+            y = enc(xs)
+            if need_grad:
+                y.backward(torch.ones_like(y))
+                enc.params.grad = None
+            ev1.record()
+            torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        # algorithmic bytes per point: 16 levels x 8 corners x 2 features x 4 B gathered (+ the same again scattered
+        # in backward) + 128 B of output row (+ 128 B of cotangent)
+        bytes_pt = 16 * 8 * 8 + 128 if not need_grad else 2 * (16 * 8 * 8 + 128) + 16 * 8 * 8
+        ex[f"hashgrid_{tag}"] = {"points": npts, "ms": ms, "gather_GB_per_s": npts * bytes_pt / ms / 1e6,
+                                 "table_MB": float(enc.params.numel() * 4 / 1e6), "note": "fp32 table, T=2^19, L2-resident"}
+    del enc, xs
     g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
     init = torch.tensor(g["dfnet_init"][0].reshape(3, 4), dtype=torch.float32, device=dev)
     target = torch.randn(128, H * W, device=dev)

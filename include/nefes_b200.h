@@ -118,6 +118,38 @@ int nefes_encode_pe_bwd(const float* x, const float* d_out, int ld_out, int64_t 
                         float* d_x, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K4b encoder front-end B: multiresolution HashGrid + spherical harmonics (tiny-cuda-nn's
+ * algorithm, reached by the reference through tcnn.Encoding: script/models/nerfh_tcnn.py:65-75,
+ * 97-103, 156, 209-210).  x [M,3] in [0,1]; table [n_entries, 2] fp32 (levels concatenated);
+ * out [M, 2*n_levels], feature index = level*2 + f.  bwd: d_table is ACCUMULATED (fp32 atomics;
+ * may be NULL), d_x [M,3] overwritten (may be NULL).  SH: d [M,3] in [0,1] (unit vector = 2d-1),
+ * out [M,16] (degree 4).  Parity for this row is unpinned (oracle/hashgrid_oracle.py header).
+ * ------------------------------------------------------------------------------------------ */
+#define NEFES_HASH_MAX_LEVELS 32
+typedef struct { float scale; uint32_t res; uint32_t size; uint32_t offset; uint32_t dense; } nefes_hash_level_t;
+typedef struct { int n_levels; int64_t n_entries; nefes_hash_level_t level[NEFES_HASH_MAX_LEVELS]; } nefes_hash_layout_t;
+int nefes_hash_layout(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale,
+                      nefes_hash_layout_t* out_host);
+int nefes_encode_hash_fwd(const float* x, const float* table, int64_t M, const nefes_hash_layout_t* layout_host,
+                          float* out, void* stream);
+int nefes_encode_hash_bwd(const float* x, const float* d_out, const float* table, int64_t M,
+                          const nefes_hash_layout_t* layout_host, float* d_table, float* d_x, void* stream);
+int nefes_encode_sh_fwd(const float* d, int64_t M, float* out, void* stream);
+int nefes_encode_sh_bwd(const float* d, const float* d_out, int64_t M, float* d_d, void* stream);
+
+/* Generic fp32 linear layer on the SIMT GEMM (torch Linear layout W [N,K]); used by front-end B's
+ * small bias-free MLPs (tcnn FullyFusedMLP call sites nerfh_tcnn.py:79-89, 111-121).
+ *   fwd:   C[M,N] = act(A[M,K] W^T + bias)      act: 0 none, 1 relu, 3 sigmoid; bias may be NULL
+ *   dgrad: dA[M,K] = dC[M,N] W, multiplied by (mask[M,K] > 0) when mask != NULL (ReLU backward)
+ *   wgrad: dW[N,K] += dC^T A                     (accumulated, fp32 atomics)                          */
+int nefes_linear_fwd(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc,
+                     int64_t M, int N, int K, int act, void* stream);
+int nefes_linear_dgrad(const float* dC, int64_t ldc, const float* W, float* dA, int64_t lda, int64_t M, int N, int K,
+                       const float* mask, int64_t ldm, void* stream);
+int nefes_linear_wgrad(const float* dC, int64_t ldc, const float* A, int64_t lda, float* dW, int64_t M, int N, int K,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K5  the NeFeS field: PE + MLP             script/models/nerfh_nff.py:168-231 (query) and
  *                                           :525-576 (NeRFH_NFF.forward)
  * pts [M,3] with M = N*S, dirs [N,3] (unit view directions, one per ray, broadcast over the S

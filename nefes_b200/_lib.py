@@ -37,6 +37,14 @@ class CompGrad(C.Structure):
     _fields_ = [(n, vp) for n in ("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig")]
 
 
+class HashLevel(C.Structure):
+    _fields_ = [("scale", f32), ("res", C.c_uint32), ("size", C.c_uint32), ("offset", C.c_uint32), ("dense", C.c_uint32)]
+
+
+class HashLayout(C.Structure):
+    _fields_ = [("n_levels", i32), ("n_entries", i64), ("level", HashLevel * 32)]
+
+
 _SIGS = {
     "nefes_version": (i32, []),
     "nefes_last_error": (C.c_char_p, []),
@@ -50,6 +58,14 @@ _SIGS = {
     "nefes_sample_fine": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "nefes_encode_pe_fwd": (i32, [vp, i64, i32, vp, i32, vp]),
     "nefes_encode_pe_bwd": (i32, [vp, vp, i32, i64, i32, vp, vp]),
+    "nefes_hash_layout": (i32, [i32, i32, i32, f32, C.POINTER(HashLayout)]),
+    "nefes_encode_hash_fwd": (i32, [vp, vp, i64, C.POINTER(HashLayout), vp, vp]),
+    "nefes_encode_hash_bwd": (i32, [vp, vp, vp, i64, C.POINTER(HashLayout), vp, vp, vp]),
+    "nefes_encode_sh_fwd": (i32, [vp, i64, vp, vp]),
+    "nefes_encode_sh_bwd": (i32, [vp, vp, i64, vp, vp]),
+    "nefes_linear_fwd": (i32, [vp, i64, vp, vp, vp, i64, i64, i32, i32, i32, vp]),
+    "nefes_linear_dgrad": (i32, [vp, i64, vp, vp, i64, i64, i32, i32, vp, i64, vp]),
+    "nefes_linear_wgrad": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, vp]),
     "nefes_mlp_workspace": (i32, [i32, i32, i32, i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "nefes_mlp_fwd": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp]),
     "nefes_mlp_bwd": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -276,3 +276,26 @@ int mlp_workspace_fp32(int mode, int64_t M, int64_t N, int64_t* saved, int64_t* 
 }
 
 }  // namespace nefes
+
+extern "C" {
+int nefes_linear_fwd(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc, int64_t M,
+                     int N, int K, int act, void* stream) {
+  if (M == 0) return NEFES_OK;
+  NEFES_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, NEFES_EINVAL, "nefes_linear_fwd: bad argument");
+  NEFES_REQUIRE(act == nefes::ACT_NONE || act == nefes::ACT_RELU || act == nefes::ACT_SIGMOID || act == nefes::ACT_SOFTPLUS,
+                NEFES_EINVAL, "nefes_linear_fwd: bad activation %d", act);
+  return nefes::linear_fwd((cudaStream_t)stream, A, lda, W, K, bias, C, ldc, M, N, K, act, 0);
+}
+int nefes_linear_dgrad(const float* dC, int64_t ldc, const float* W, float* dA, int64_t lda, int64_t M, int N, int K,
+                       const float* mask, int64_t ldm, void* stream) {
+  if (M == 0) return NEFES_OK;
+  NEFES_REQUIRE(dC && W && dA && M > 0 && N > 0 && K > 0, NEFES_EINVAL, "nefes_linear_dgrad: bad argument");
+  return nefes::linear_dgrad((cudaStream_t)stream, dC, ldc, W, K, dA, lda, M, N, K, mask, ldm, 0);
+}
+int nefes_linear_wgrad(const float* dC, int64_t ldc, const float* A, int64_t lda, float* dW, int64_t M, int N, int K,
+                       void* stream) {
+  if (M == 0) return NEFES_OK;
+  NEFES_REQUIRE(dC && A && dW && M > 0 && N > 0 && K > 0, NEFES_EINVAL, "nefes_linear_wgrad: bad argument");
+  return nefes::linear_wgrad((cudaStream_t)stream, dC, ldc, A, lda, dW, K, M, N, K);
+}
+}  // extern "C"
