@@ -14,6 +14,8 @@
 //                      gradients fall out of an extra MMA against a tile of ones
 //   plus small SIMT kernels: weight repack, PE -> images, head gradients -> images.
 // script/models/nerfh_nff.py:168-231, :525-576.
+#include <cstdlib>
+
 #include "tc05.cuh"
 #include "tc_layers.cuh"
 
@@ -579,6 +581,7 @@ __global__ void ray_reduce_kernel(const float* __restrict__ src, int ld, int nco
 }
 
 }  // namespace nefes
+#include "mlp_chain.cuh"
 extern "C" int nefes_encode_pe_bwd(const float*, const float*, int, int64_t, int, float*, void*);
 namespace nefes {
 
@@ -766,6 +769,60 @@ struct Arena {
 
 }  // namespace
 
+namespace {
+// Build the step table of the fused forward chain for (net, mode) and launch it.
+int launch_chain_fwd(const Ws& w, const Arena& A, int mode, const float* pts, const float* dirs, int64_t N, int S,
+                     float* raw, cudaStream_t st) {
+  const int64_t M = N * S;
+  const int T = (int)ceil_div(M, kTile);
+  ChainArgs c = {};
+  int n = 0;
+  auto add = [&](int pl, uint32_t a_off, int kind, uint32_t out_off, int out_ch, const Img* save, uint4* mask) {
+    ChainStep& s = c.step[n++];
+    const PackedDims pd = packed_dims(pl);
+    s.a_off = a_off; s.out_off = out_off; s.K = (uint16_t)pd.K; s.N = (uint16_t)pd.N; s.out_ch = (uint16_t)out_ch;
+    s.kind = (uint8_t)kind; s.w_bytes = (uint32_t)pd.K * pd.N * 2u; s.w_img = A.W(pl); s.bias = A.bias(pl);
+    s.gdst = save ? save->p : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u; s.mask = mask;
+  };
+  add(PL_T0, kRegX, CK_HIDDEN, kRegH, 128, &w.H[0], w.mask[0]);
+  for (int l = 1; l < 8; ++l)
+    add(PL_T0 + l, l == 4 ? kRegX : kRegH, CK_HIDDEN, kRegH, 128, &w.H[l], w.mask[l]);
+  if (mode == NEFES_MODE_SIGMA) {
+    add(PL_SIG, kRegH, CK_SIGMA, 0, 0, nullptr, nullptr);
+  } else {
+    add(PL_FS, kRegH, CK_FS, kRegH, 128, &w.FIN, nullptr);
+    if (mode == NEFES_MODE_FULL) {
+      add(PL_DT, kRegH, CK_HIDDEN, kRegH, 128, &w.DT, w.mask[8]);
+      add(PL_TE1, kRegH + 16384, CK_HIDDEN, kRegX, 64, &w.T2, w.mask[9]);        // t1 -> t2 (parked in the xyzPE slot)
+      add(PL_TE2, kRegX, CK_HIDDEN, kRegH + 16384, 64, &w.T3, w.mask[10]);       // t2 -> t3 (over t1)
+      add(PL_TH, kRegH + 16384, CK_HEADS, 0, 0, nullptr, nullptr);
+    } else {
+      add(PL_DIR, kRegH, CK_HIDDEN, kRegH, 64, &w.DT, w.mask[8]);
+    }
+    add(PL_RGB, kRegH, CK_RGB, 0, 0, nullptr, nullptr);
+  }
+  c.n_steps = n;
+  c.pts = pts; c.dirs = dirs; c.S = S; c.M = M; c.n_tiles = T;
+  c.raw = raw; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137); c.sig_col = 131;
+  c.x_img = w.X.p; c.d_img = (mode == NEFES_MODE_SIGMA) ? nullptr : w.DIRPE.p;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NEFES_CUDA(cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
+    attr_done = true;
+  }
+  const int n_pairs = (T + 1) / 2;
+  const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
+  chain_fwd_kernel<<<grid, kChainThreads, kChainSmem, st>>>(c);
+  NEFES_CHECK_LAUNCH("chain_fwd");
+  return NEFES_OK;
+}
+bool use_chain() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NEFES_CHAIN"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+}  // namespace
+
 int mlp_workspace_bf16(int net, int mode, int64_t M, int64_t N, int64_t* saved, int64_t* sf, int64_t* sb) {
   (void)net;
   const int64_t T = ceil_div(M, kTile);
@@ -788,6 +845,7 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
 
   prepack_kernel<<<256, 256, 0, st>>>(P, pack_src(net), A.ar, w.arena, fine ? 1 : 0);
   NEFES_CHECK_LAUNCH("prepack");
+  if (use_chain()) return launch_chain_fwd(w, A, mode, pts, dirs, N, S, raw, st);   // NEFES_CHAIN=0: layer-at-a-time
   encode_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(pts, dirs, S, M, Mp, w.X.p,
                                                                     mode == NEFES_MODE_SIGMA ? nullptr : w.DIRPE.p);
   NEFES_CHECK_LAUNCH("encode_images");
