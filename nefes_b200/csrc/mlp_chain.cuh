@@ -1,128 +1,239 @@
-// Fused forward layer chain of the NeFeS field (bf16 tensor path): one persistent kernel runs PE and ALL
-// layers of the MLP for a pair of 128-point tiles; activations never leave the SM between layers.
+// Fused layer chains of the NeFeS field (bf16 tensor path): one persistent kernel runs ALL layers of the MLP for a
+// pair of 128-point tiles; activations (forward) / data gradients (backward) never leave the SM between layers.
 //
-//   warp 0      weight producer: streams each layer's W image L2 -> shared (bulk copies, 2-slot ring)
-//   warp 1      MMA issuer: for every layer, tile 0 then tile 1 (tcgen05.mma M=128, accumulators in TMEM,
+//   warp 0      producer: streams each step's weight image L2 -> shared (bulk copies, 2-slot ring) and, in the
+//               backward chain, prefetches the head-gradient images of the tile pair several steps ahead
+//   warp 1      MMA issuer: for every step, tile 0 then tile 1 (tcgen05.mma M=128, fp32 accumulators in TMEM,
 //               256 columns per tile); the tensor pipe works on one tile while the other tile's epilogue runs
-//   warps 2-5   epilogue of tile 0, warps 6-9 epilogue of tile 1: positional encoding -> shared operand image;
-//               per layer TMEM -> registers -> bias / ReLU / bit-mask -> bf16 operand image of the NEXT layer in
-//               shared memory (in place) -> the same image is bulk-stored to HBM once for backward
+//   warps 2-5   epilogue of tile 0, warps 6-9 epilogue of tile 1.
+//     forward:  positional encoding -> operand image; per layer TMEM -> registers -> bias (packed fp32x2 add) ->
+//               ReLU fused into the bf16 pack -> operand image of the NEXT layer in shared memory (in place) and
+//               the same 16-byte words to HBM (saved for backward); the 137 fp32 outputs of a point are gathered
+//               in a row-major staging image and leave with two bulk stores per tile.
+//     backward: per layer TMEM -> registers -> bf16 pack -> ReLU mask taken from the SAVED activation (a > 0, one
+//               compare per bf16 pair) -> gradient image of the next (earlier) layer in shared memory and to HBM
+//               (operand of the weight-gradient kernel).
 //
-// Per-tile shared region (56 KB): [ xyzPE 16 KB | H 32 KB | dirPE 8 KB ] -- contiguous so the skip input
-// [xyzPE | h4] (K=192) and the direction input [final | dirPE] (K=160) are plain operand ranges.
-// Included by mlp_tc.cu (uses its helpers).
+// The chain is table-driven (ChainStep): operand offset inside the tile region, weight image, epilogue kind,
+// destination.  Included by mlp_tc.cu (uses its helpers).   script/models/nerfh_nff.py:525-576.
 #pragma once
 
 namespace nefes {
 
-enum { CK_HIDDEN = 0,   // bias + ReLU + mask -> image
-       CK_PLAIN = 1,    // bias -> image (no activation)
-       CK_FS = 2,       // bias -> image (128 ch: xyz_encoding_final) + column 128: softplus -> raw[:, sig_col]
-       CK_HEADS = 3,    // columns 0..4: sigmoid x3, softplus x2 -> raw[:, 132..136]
-       CK_SIGMA = 4,    // column 0: softplus -> raw[:, 0]                       (sigma-only mode)
-       CK_RGB = 5 };    // bias -> 131 fp32 columns -> raw[:, 0..130] (staged, coalesced)
+enum { CK_HIDDEN = 0,   // fwd: bias + ReLU -> image
+       CK_FS = 1,       // fwd: bias -> image (128 ch: xyz_encoding_final); column 128: softplus -> sigma (kept)
+       CK_HEADS = 2,    // fwd: columns 0..4: sigmoid x3, softplus x2 (kept in registers until CK_RGB)
+       CK_SIGMA = 3,    // fwd: column 0: softplus -> raw[:, 0]                       (sigma-only mode)
+       CK_RGB = 4,      // fwd: bias -> 131 fp32 columns; with the kept sigma / heads -> raw rows (staged, bulk store)
+       CK_DGRAD = 5 };  // bwd: optional ReLU mask from the saved activation -> image
 
+constexpr int kChainLoads = 3;
+struct ChainLoad {                 // one prefetch of a head-gradient image into the tile region (backward)
+  const uint8_t* src; uint32_t tile_stride, bytes, dst_off;
+  int8_t issue_step;               // producer issues it when it reaches this step ...
+  int8_t next_pair;                // ... for the NEXT pair (1) or the current one (0)
+  int8_t pad[2];
+};
 struct ChainStep {
-  uint32_t a_off;                // operand start inside the tile region (bytes)
-  uint32_t out_off;              // image destination inside the tile region (bytes)
+  uint32_t a_off;                  // A operand start inside the tile region (bytes)
+  uint32_t out_off;                // image destination inside the tile region (bytes)
   uint16_t K, N, out_ch;
-  uint8_t kind, pad;
-  uint32_t w_bytes;
-  const uint8_t* w_img;          // [K/8][N][8] bf16
-  const float* bias;             // [N]
-  uint8_t* gdst;                 // saved activation image (or null)
-  uint32_t g_tile_stride;
-  uint4* mask;                   // ReLU bit-mask destination (or null)
+  uint8_t kind;
+  int8_t wait_load;                // index of the ChainLoad the MMA of this step must wait for (-1: none)
+  uint32_t w_bytes, w_lbo;         // weight image: bytes to stream (compacted), LBO = bytes between 8-wide K chunks
+  uint32_t w_piece, w_src_stride;  // streamed as pieces of w_piece bytes, w_src_stride apart in the source image
+  const uint8_t* w_img;
+  const float* bias;               // fwd: [N]
+  uint8_t* gdst;                   // image saved to HBM (or null)
+  const uint8_t* act;              // bwd: saved activation image whose sign gates this gradient (or null)
+  uint32_t g_tile_stride, act_tile_stride;
 };
 constexpr int kChainMaxSteps = 14;
 struct ChainArgs {
   ChainStep step[kChainMaxSteps];
-  int n_steps;
+  ChainLoad load[kChainLoads];
+  int n_steps, n_loads;
   const float* pts; const float* dirs; int S; int64_t M; int n_tiles;
-  float* raw; int C; int sig_col;
-  uint8_t* x_img; uint8_t* d_img;            // saved xyzPE / dirPE images (wgrad operands)
+  float* raw; int C;
+  uint8_t* x_img; uint8_t* d_img;            // fwd: saved xyzPE / dirPE images (wgrad operands)
+  long long* dbg;                            // optional clock stamps of CTA 0 (NEFES_CHAIN_DBG)
+  int xflags;                                // timing experiments only (NEFES_CHAIN_X): 1 no saves, 2 no PE, 4 no raw store
 };
 
-constexpr uint32_t kRegX = 0, kRegH = 16384, kRegD = 49152, kRegBytes = 57344;
-constexpr uint32_t kChainWSlot = 49152;      // largest W image: 192 x 128 bf16
+// forward tile region: [ xyzPE 16 KB | H 32 KB | dirPE 8 KB ] -- contiguous so the skip input [xyzPE | h4] (K=192)
+// and the direction input [final | dirPE] (K=160) are plain operand ranges.
+constexpr uint32_t kRegX = 0, kRegH = 16384, kRegD = 49152;
+// backward tile region: P (36 KB) | Q (36 KB) | S (4 KB)
+constexpr uint32_t kRegP = 0, kRegQ = 36864, kRegS = 73728;
+constexpr uint32_t kFwdRegBytes = 57344, kBwdRegBytes = 77824;
+constexpr uint32_t kFwdWSlot = 49152;        // largest forward W image: 192 x 128 bf16
+constexpr uint32_t kBwdWSlot = 36864;        // largest backward WT image: 144 x 128 bf16
 constexpr int kChainThreads = 64 + 256;
 constexpr int kChainBiasStride = 160;        // floats per step in the shared bias table (N <= 160)
-constexpr uint32_t kChainSmem = 2 * kRegBytes + 2 * kChainWSlot + 10240;  // + bias table (14 x 160 floats)
+constexpr uint32_t kChainBiasBytes = kChainMaxSteps * kChainBiasStride * 4;
+constexpr uint32_t kFwdChainSmem = 2 * kFwdRegBytes + 2 * kFwdWSlot + kChainBiasBytes;
+constexpr uint32_t kBwdChainSmem = 2 * kBwdRegBytes + 2 * kBwdWSlot;
 
 __device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
 
-// 16 accumulator columns of one row -> two 8-channel chunks of the image at `dst`
+// (lo + blo, hi + bhi) as one packed fp32x2 add, then one cvt to a bf16 pair (ReLU folded into the cvt)
 template <bool RELU>
-__device__ __forceinline__ uint32_t chain_block(const uint32_t (&v)[16], const float* __restrict__ bias, uint8_t* __restrict__ dst,
-                                                uint8_t* __restrict__ gdst, int c0, int row) {
-  uint32_t bits = 0u;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int c = c0 + h * 8;
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + c);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float x[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      x[e] = __uint_as_float(v[h * 8 + e]) + bb[e];
-      if (RELU) {
-        const bool on = x[e] > 0.f;
-        x[e] = on ? x[e] : 0.f;
-        bits |= on ? (1u << (h * 8 + e)) : 0u;
-      }
-    }
-    uint4 pk;
-    pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]);
-    pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
-    *reinterpret_cast<uint4*>(dst + (c >> 3) * kChunkBytes + row * 16) = pk;
-    // saved for backward: same image layout in HBM; a warp's 32 rows x 16 B are one contiguous 512-byte store
-    if (gdst != nullptr) *reinterpret_cast<uint4*>(gdst + (c >> 3) * kChunkBytes + row * 16) = pk;
-  }
-  return bits;
+__device__ __forceinline__ uint32_t bias_pack(uint32_t lo, uint32_t hi, float blo, float bhi) {
+  uint32_t r;
+  if (RELU)
+    asm("{\n\t.reg .b64 a, b, c;\n\t.reg .f32 x, y;\n\t"
+        "mov.b64 a, {%1, %2};\n\tmov.b64 b, {%3, %4};\n\tadd.rn.f32x2 c, a, b;\n\tmov.b64 {x, y}, c;\n\t"
+        "cvt.rn.relu.bf16x2.f32 %0, y, x;\n\t}"
+        : "=r"(r) : "r"(lo), "r"(hi), "f"(blo), "f"(bhi));
+  else
+    asm("{\n\t.reg .b64 a, b, c;\n\t.reg .f32 x, y;\n\t"
+        "mov.b64 a, {%1, %2};\n\tmov.b64 b, {%3, %4};\n\tadd.rn.f32x2 c, a, b;\n\tmov.b64 {x, y}, c;\n\t"
+        "cvt.rn.bf16x2.f32 %0, y, x;\n\t}"
+        : "=r"(r) : "r"(lo), "r"(hi), "f"(blo), "f"(bhi));
+  return r;
 }
 
-__global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_kernel(const ChainArgs A) {
+// 32 accumulator columns [c0, c0+32) of one row -> four 8-channel chunks of the image (and of its HBM copy)
+template <bool RELU>
+__device__ __forceinline__ void fwd_cols32(const uint32_t (&v)[32], const float* __restrict__ bias, uint8_t* __restrict__ dst_row,
+                                           uint8_t* __restrict__ gdst_row, int c0) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + 8 * j);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 8 * j + 4);
+    uint4 pk;
+    pk.x = bias_pack<RELU>(v[8 * j + 0], v[8 * j + 1], b0.x, b0.y);
+    pk.y = bias_pack<RELU>(v[8 * j + 2], v[8 * j + 3], b0.z, b0.w);
+    pk.z = bias_pack<RELU>(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
+    pk.w = bias_pack<RELU>(v[8 * j + 6], v[8 * j + 7], b1.z, b1.w);
+    const int off = ((c0 >> 3) + j) * (int)kChunkBytes;
+    *reinterpret_cast<uint4*>(dst_row + off) = pk;
+    if (gdst_row != nullptr) *reinterpret_cast<uint4*>(gdst_row + off) = pk;   // a warp's 32 rows x 16 B = 512 contiguous bytes
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_mask(uint32_t lo, uint32_t hi, uint32_t act, bool gate) {
+  uint32_t p = pack_bf16(__uint_as_float(lo), __uint_as_float(hi));
+  if (gate) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&act);
+    p &= __hgt2_mask(a, __floats2bfloat162_rn(0.f, 0.f));
+  }
+  return p;
+}
+
+// positional encoding of one point -> bf16 chunks: [x, sin(2^l x), cos(2^l x)] with the base sin/cos from the accurate
+// sincosf and the octaves by the double-angle recurrence (error doubles per octave: <= 2^9 * 1e-7 = 5e-5, far below
+// the bf16 operand rounding of 4e-3).   script/models/nerfh_nff.py:241-270
+template <int FREQS, int CHUNKS>
+__device__ __forceinline__ void pe_row(const float* __restrict__ p3, bool ok, uint8_t* __restrict__ s_row, uint8_t* __restrict__ g_row) {
+  float e[CHUNKS * 8];
+#pragma unroll
+  for (int i = 0; i < CHUNKS * 8; ++i) e[i] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = ok ? p3[c] : 0.f;
+    e[c] = v;
+    float sn, cs;
+    sincosf(v, &sn, &cs);
+#pragma unroll
+    for (int l = 0; l < FREQS; ++l) {
+      e[3 + 6 * l + c] = ok ? sn : 0.f;
+      e[6 + 6 * l + c] = ok ? cs : 0.f;
+      const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
+      sn = s2; cs = c2;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CHUNKS; ++j) {
+    uint4 pk;
+    pk.x = pack_bf16(e[8 * j], e[8 * j + 1]); pk.y = pack_bf16(e[8 * j + 2], e[8 * j + 3]);
+    pk.z = pack_bf16(e[8 * j + 4], e[8 * j + 5]); pk.w = pack_bf16(e[8 * j + 6], e[8 * j + 7]);
+    *reinterpret_cast<uint4*>(s_row + j * kChunkBytes) = pk;
+    *reinterpret_cast<uint4*>(g_row + j * kChunkBytes) = pk;
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_wfull[2], bar_wempty[2], bar_act[2], bar_acc[2];
+  __shared__ uint64_t bar_wfull[2], bar_wempty[2], bar_act[2], bar_acc[2], bar_ld[2][kChainLoads];
   __shared__ uint32_t tmem_slot;
+  constexpr uint32_t kReg = BWD ? kBwdRegBytes : kFwdRegBytes;
+  constexpr uint32_t kWSlot = BWD ? kBwdWSlot : kFwdWSlot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* sW = smem + 2 * kRegBytes;
-  float* sBias = reinterpret_cast<float*>(smem + 2 * kRegBytes + 2 * kChainWSlot);   // [n_steps][...] packed below
+  uint8_t* sW = smem + 2 * kReg;
+  float* sBias = reinterpret_cast<float*>(smem + 2 * kReg + 2 * kWSlot);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1);
       mbar_init(&bar_act[i], 128); mbar_init(&bar_acc[i], 1);
+      for (int l = 0; l < kChainLoads; ++l) mbar_init(&bar_ld[i][l], 1);
     }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_slot);
-  // all biases of the chain -> shared
-  for (int s = 0; s < A.n_steps; ++s)
-    for (int i = threadIdx.x; i < A.step[s].N; i += kChainThreads) sBias[s * kChainBiasStride + i] = A.step[s].bias[i];
+  if (!BWD) {
+    for (int s = 0; s < A.n_steps; ++s)
+      for (int i = threadIdx.x; i < A.step[s].N; i += kChainThreads) sBias[s * kChainBiasStride + i] = A.step[s].bias[i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const int n_pairs = (A.n_tiles + 1) >> 1;
+  const bool dbg = A.dbg != nullptr && blockIdx.x == 0;
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t cnt = 0;
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-        for (int s = 0; s < A.n_steps; ++s, ++cnt) {
+      // ------------------------------- producer ---------------------------------------------------------------
+      uint32_t cnt = 0;                 // W ring position
+      uint32_t q = 0;                   // steps started so far (per tile the same; tile 1 may skip the last pair)
+      auto issue_load = [&](int li, int pair) {
+        const ChainLoad& L = A.load[li];
+        for (int g = 0; g < 2; ++g) {
+          const int tile = pair * 2 + g;
+          if (tile >= A.n_tiles) break;
+          mbar_arrive_expect_tx(&bar_ld[g][li], L.bytes);
+          bulk_g2s(smem + g * kReg + L.dst_off, L.src + (int64_t)tile * L.tile_stride, L.bytes, &bar_ld[g][li]);
+        }
+      };
+      if (BWD) {
+        for (int l = 0; l < A.n_loads; ++l)
+          if (A.load[l].issue_step >= 0 && A.load[l].next_pair && (int)blockIdx.x < n_pairs) issue_load(l, blockIdx.x);
+      }
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const bool valid1 = pair * 2 + 1 < A.n_tiles;
+        for (int s = 0; s < A.n_steps; ++s, ++cnt, ++q) {
           const int slot = cnt & 1;
           mbar_wait(&bar_wempty[slot], ((cnt >> 1) & 1) ^ 1);
           const uint32_t bytes = A.step[s].w_bytes;
           mbar_arrive_expect_tx(&bar_wfull[slot], bytes);
-          for (uint32_t off = 0; off < bytes; off += 16384u)
-            bulk_g2s(sW + slot * kChainWSlot + off, A.step[s].w_img + off, min(16384u, bytes - off), &bar_wfull[slot]);
+          const uint32_t piece = A.step[s].w_piece, sstride = A.step[s].w_src_stride;
+          const uint8_t* src = A.step[s].w_img;
+          for (uint32_t off = 0; off < bytes; off += piece, src += sstride)
+            bulk_g2s(sW + slot * kWSlot + off, src, min(piece, bytes - off), &bar_wfull[slot]);
+          if (BWD) {
+            for (int l = 0; l < A.n_loads; ++l) {
+              const ChainLoad& L = A.load[l];
+              if (L.issue_step != s) continue;
+              const int tp = L.next_pair ? pair + (int)gridDim.x : pair;
+              if (tp >= n_pairs) continue;
+              // the destination was last read by the MMAs of step s-1 of THIS pair: wait until they retired
+              if (q > 0) {
+                mbar_wait(&bar_acc[0], (q - 1) & 1);
+                if (valid1) mbar_wait(&bar_acc[1], (q - 1) & 1);
+              }
+              issue_load(l, tp);
+            }
+          }
         }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t cnt = 0, act_ph[2] = {0u, 0u};
+      // ------------------------------- MMA issuer ----------------------------------------------------------------
+      uint32_t cnt = 0, act_ph[2] = {0u, 0u}, ld_ph[2][kChainLoads] = {};
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         const bool valid1 = pair * 2 + 1 < A.n_tiles;
         for (int s = 0; s < A.n_steps; ++s, ++cnt) {
@@ -130,185 +241,179 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_kernel(const Chain
           const int slot = cnt & 1;
           mbar_wait(&bar_wfull[slot], (cnt >> 1) & 1);
           const uint32_t idesc = idesc_bf16(128, st.N, 0, 0);
-          const uint32_t w_lbo = (uint32_t)st.N * 16u;
-          const uint64_t db0 = smem_desc(smem_u32(sW + slot * kChainWSlot), w_lbo, 128);
+          const uint64_t db0 = smem_desc(smem_u32(sW + slot * kWSlot), st.w_lbo, 128);
           for (int g = 0; g < 2; ++g) {
             if (g == 1 && !valid1) break;
             mbar_wait(&bar_act[g], act_ph[g]);
             act_ph[g] ^= 1u;
+            if (BWD && st.wait_load >= 0) {
+              mbar_wait(&bar_ld[g][st.wait_load], ld_ph[g][st.wait_load]);
+              ld_ph[g][st.wait_load] ^= 1u;
+            }
             tc_fence_after();
-            const uint64_t da0 = smem_desc(smem_u32(smem + g * kRegBytes + st.a_off), kChunkBytes, 128);
+            const uint64_t da0 = smem_desc(smem_u32(smem + g * kReg + st.a_off), kChunkBytes, 128);
             const uint32_t d = tmem + g * 256;
             for (int k = 0; k < st.K / 16; ++k)
-              mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k * (2 * w_lbo >> 4)), idesc, k > 0);
+              mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k * (2 * st.w_lbo >> 4)), idesc, k > 0);
             mma_commit(&bar_acc[g]);
+            if (dbg && cnt < 64) A.dbg[cnt * 2 + g] = clock64();
           }
           mma_commit(&bar_wempty[slot]);
         }
       }
     }
   } else {
+    // --------------------------------- epilogue warps ----------------------------------------------------------------
     const int g = (warp - 2) >> 2;                    // tile of the pair this warp serves
     const int q = warp & 3;                           // TMEM lane quarter
     const int row = q * 32 + lane;
     const int gt = ((warp - 2) & 3) * 32 + lane;      // 0..127 inside the group
-    uint8_t* reg = smem + g * kRegBytes;
+    uint8_t* reg = smem + g * kReg;
     const uint32_t taddr = tmem + g * 256 + ((uint32_t)(q * 32) << 16);
     uint32_t acc_ph = 0u;
+    bool store_pending = false;
+    uint32_t ecnt = 0;
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int tile = pair * 2 + g;
       if (tile >= A.n_tiles) break;
       const int64_t grow = (int64_t)tile * kTile + row;
       const bool ok = grow < A.M;
-      // ---- positional encodings of this row -> operand images (also saved to HBM for wgrad) ------------------
-      // sin/cos of the base frequency with the accurate sincosf, higher octaves by the double-angle recurrence
-      // (error doubles per octave: <= 2^9 * 1e-7 = 5e-5, far below the bf16 operand rounding of 4e-3).
-      {
-        float e[64];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float v = ok ? A.pts[grow * 3 + c] : 0.f;
-          e[c] = v;
-          float sn, cs;
-          sincosf(v, &sn, &cs);
-#pragma unroll
-          for (int l = 0; l < kXyzFreqs; ++l) {
-            e[3 + 6 * l + c] = ok ? sn : 0.f;
-            e[6 + 6 * l + c] = ok ? cs : 0.f;
-            const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
-            sn = s2; cs = c2;
-          }
+      float kept[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sigma, transient rgb x3, transient sigma, beta
+      if (!BWD) {
+        if (store_pending) {                          // the raw staging of the previous tile lives in this region
+          if (gt == 0) bulk_wait_read<0>();
+          group_barrier(g);
+          store_pending = false;
         }
-        e[63] = 0.f;
-        uint8_t* gx = A.x_img + (int64_t)tile * (64 * 256) + row * 16;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 pk;
-          pk.x = pack_bf16(e[8 * j], e[8 * j + 1]); pk.y = pack_bf16(e[8 * j + 2], e[8 * j + 3]);
-          pk.z = pack_bf16(e[8 * j + 4], e[8 * j + 5]); pk.w = pack_bf16(e[8 * j + 6], e[8 * j + 7]);
-          *reinterpret_cast<uint4*>(reg + kRegX + j * kChunkBytes + row * 16) = pk;
-          *reinterpret_cast<uint4*>(gx + j * kChunkBytes) = pk;
-        }
+        if (!(A.xflags & 2)) pe_row<kXyzFreqs, 8>(A.pts + grow * 3, ok, reg + kRegX + row * 16, A.x_img + (int64_t)tile * (64 * 256) + row * 16);
+        if (A.d_img != nullptr && !(A.xflags & 2))
+          pe_row<kDirFreqs, 4>(A.dirs + (grow / A.S) * 3, ok, reg + kRegD + row * 16, A.d_img + (int64_t)tile * (32 * 256) + row * 16);
+        fence_async_smem();
       }
-      if (A.d_img != nullptr) {
-        float e[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float v = ok ? A.dirs[(grow / A.S) * 3 + c] : 0.f;
-          e[c] = v;
-          float sn, cs;
-          sincosf(v, &sn, &cs);
-#pragma unroll
-          for (int l = 0; l < kDirFreqs; ++l) {
-            e[3 + 6 * l + c] = ok ? sn : 0.f;
-            e[6 + 6 * l + c] = ok ? cs : 0.f;
-            const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
-            sn = s2; cs = c2;
-          }
-        }
-        uint8_t* gd = A.d_img + (int64_t)tile * (32 * 256) + row * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 pk;
-          pk.x = pack_bf16(e[8 * j], e[8 * j + 1]); pk.y = pack_bf16(e[8 * j + 2], e[8 * j + 3]);
-          pk.z = pack_bf16(e[8 * j + 4], e[8 * j + 5]); pk.w = pack_bf16(e[8 * j + 6], e[8 * j + 7]);
-          *reinterpret_cast<uint4*>(reg + kRegD + j * kChunkBytes + row * 16) = pk;
-          *reinterpret_cast<uint4*>(gd + j * kChunkBytes) = pk;
-        }
-      }
-      fence_async_smem();
-      mbar_arrive(&bar_act[g]);                        // operand of step 0 is ready
+      mbar_arrive(&bar_act[g]);                        // operand of step 0 is ready (bwd: it arrives by bulk copy)
 
-      for (int s = 0; s < A.n_steps; ++s) {
+      for (int s = 0; s < A.n_steps; ++s, ++ecnt) {
         const ChainStep& st = A.step[s];
         const float* bias = sBias + s * kChainBiasStride;
+        uint4 av[16];
+        if (BWD) {                                     // saved activation of this row: issue the loads before waiting
+          if (st.act != nullptr) {
+            const uint8_t* ap = st.act + (int64_t)tile * st.act_tile_stride + row * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j * 8 < st.out_ch) av[j] = __ldg(reinterpret_cast<const uint4*>(ap + j * kChunkBytes));
+          }
+        }
         mbar_wait(&bar_acc[g], acc_ph);
         acc_ph ^= 1u;
         tc_fence_after();
-        if (st.kind <= CK_FS) {
-          // the image is written in place: its last reader (the MMA that just completed) is done
-          uint8_t* dst = reg + st.out_off;
-          uint8_t* gdst = st.gdst ? st.gdst + (int64_t)tile * st.g_tile_stride : nullptr;
-          uint16_t* mrow = st.mask ? reinterpret_cast<uint16_t*>(st.mask + grow) : nullptr;
-          for (int b0 = 0; b0 < (st.out_ch >> 4); b0 += 4) {
-            uint32_t v0[16], v1[16], v2[16], v3[16];
-            tmem_ld16(taddr + b0 * 16, v0);
-            tmem_ld16(taddr + (b0 + 1) * 16, v1);
-            tmem_ld16(taddr + (b0 + 2) * 16, v2);
-            tmem_ld16(taddr + (b0 + 3) * 16, v3);
-            tmem_ld_wait();
-            uint32_t m0, m1, m2, m3;
-            if (st.kind == CK_HIDDEN) {
-              m0 = chain_block<true>(v0, bias, dst, gdst, b0 * 16, row);
-              m1 = chain_block<true>(v1, bias, dst, gdst, (b0 + 1) * 16, row);
-              m2 = chain_block<true>(v2, bias, dst, gdst, (b0 + 2) * 16, row);
-              m3 = chain_block<true>(v3, bias, dst, gdst, (b0 + 3) * 16, row);
-              if (mrow != nullptr) *reinterpret_cast<uint2*>(mrow + b0) = make_uint2(m0 | (m1 << 16), m2 | (m3 << 16));
-            } else {
-              chain_block<false>(v0, bias, dst, gdst, b0 * 16, row);
-              chain_block<false>(v1, bias, dst, gdst, (b0 + 1) * 16, row);
-              chain_block<false>(v2, bias, dst, gdst, (b0 + 2) * 16, row);
-              chain_block<false>(v3, bias, dst, gdst, (b0 + 3) * 16, row);
+        if (dbg && gt == 0 && ecnt < 64) A.dbg[128 + ecnt * 4 + g * 2] = clock64();
+        if (BWD) {
+          uint8_t* dst_row = reg + st.out_off + row * 16;
+          uint8_t* gdst_row = (st.gdst && !(A.xflags & 1)) ? st.gdst + (int64_t)tile * st.g_tile_stride + row * 16 : nullptr;
+          const bool gate = st.act != nullptr;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            if (b * 32 < st.out_ch) {
+              uint32_t v[32];
+              tmem_ld32(taddr + b * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 a = av[b * 4 + j];
+                uint4 pk;
+                pk.x = pack_mask(v[8 * j + 0], v[8 * j + 1], a.x, gate);
+                pk.y = pack_mask(v[8 * j + 2], v[8 * j + 3], a.y, gate);
+                pk.z = pack_mask(v[8 * j + 4], v[8 * j + 5], a.z, gate);
+                pk.w = pack_mask(v[8 * j + 6], v[8 * j + 7], a.w, gate);
+                const int off = (b * 4 + j) * (int)kChunkBytes;
+                *reinterpret_cast<uint4*>(dst_row + off) = pk;
+                if (gdst_row != nullptr) *reinterpret_cast<uint4*>(gdst_row + off) = pk;
+              }
             }
+          }
+        } else if (st.kind == CK_HIDDEN || st.kind == CK_FS) {
+          // the image is written in place: its last reader (the MMA that just completed) is done
+          uint8_t* dst_row = reg + st.out_off + row * 16;
+          uint8_t* gdst_row = (st.gdst && !(A.xflags & 1)) ? st.gdst + (int64_t)tile * st.g_tile_stride + row * 16 : nullptr;
+          for (int b = 0; b * 32 < st.out_ch; ++b) {
+            uint32_t v[32];
+            tmem_ld32(taddr + b * 32, v);
+            tmem_ld_wait();
+            if (st.kind == CK_HIDDEN) fwd_cols32<true>(v, bias, dst_row, gdst_row, b * 32);
+            else fwd_cols32<false>(v, bias, dst_row, gdst_row, b * 32);
           }
           if (st.kind == CK_FS) {
             uint32_t v[16];
             tmem_ld16(taddr + 128, v);
             tmem_ld_wait();
-            if (ok) A.raw[grow * A.C + A.sig_col] = softplus_f(__uint_as_float(v[0]) + bias[128]);
+            kept[0] = softplus_f(__uint_as_float(v[0]) + bias[128]);
           }
-          tc_fence_before();
-          fence_async_smem();
         } else if (st.kind == CK_HEADS || st.kind == CK_SIGMA) {
           uint32_t v[16];
           tmem_ld16(taddr, v);
           tmem_ld_wait();
-          if (ok) {
-            if (st.kind == CK_SIGMA) {
-              A.raw[grow * A.C] = softplus_f(__uint_as_float(v[0]) + bias[0]);
-            } else {
+          if (st.kind == CK_SIGMA) {
+            if (ok) A.raw[grow] = softplus_f(__uint_as_float(v[0]) + bias[0]);
+          } else {
 #pragma unroll
-              for (int e = 0; e < 5; ++e) {
-                const float x = __uint_as_float(v[e]) + bias[e];
-                A.raw[grow * A.C + 132 + e] = e < 3 ? sigmoid_f(x) : softplus_f(x);
-              }
+            for (int e = 0; e < 5; ++e) {
+              const float x = __uint_as_float(v[e]) + bias[e];
+              kept[1 + e] = e < 3 ? sigmoid_f(x) : softplus_f(x);
             }
           }
-          tc_fence_before();
-        } else {   // CK_RGB: 131 fp32 columns, staged through the (now dead) tile region in two halves of 66 columns
-          group_barrier(g);
+        } else if (!(A.xflags & 4)) {   // CK_RGB: the whole fp32 row block [64 rows][C] staged in the (now dead) tile region, one bulk store per half
           float* stage = reinterpret_cast<float*>(reg);
-          constexpr int kHalf = 66, kPitch = 67;
+          const int C = A.C;
+          const int64_t row0 = (int64_t)tile * kTile;
+          const int64_t n_valid = (A.M - row0) < (int64_t)kTile ? (A.M - row0) : (int64_t)kTile;
+          const bool bulk_ok = ((n_valid < 64 ? n_valid : 64) * C) % 4 == 0 && ((n_valid > 64 ? n_valid - 64 : 0) * C) % 4 == 0;
 #pragma unroll 1
           for (int hf = 0; hf < 2; ++hf) {
-            const int c_lo = hf * kHalf, c_hi = hf == 0 ? kHalf : kHeadCh;
+            if (hf == 1) {                            // staging is reused: the first bulk store must have read it
+              if (gt == 0) bulk_wait_read<0>();
+              group_barrier(g);
+            }
+            if ((q >> 1) == hf) {
+              float* srow = stage + (row - hf * 64) * C;
 #pragma unroll 1
-            for (int b = (c_lo >> 4); b * 16 < c_hi; ++b) {
-              uint32_t v[16];
-              tmem_ld16(taddr + b * 16, v);
-              tmem_ld_wait();
+              for (int b = 0; b < 9; ++b) {
+                uint32_t v[16];
+                tmem_ld16(taddr + b * 16, v);
+                tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int c = b * 16 + e;
-                if (c >= c_lo && c < c_hi) stage[row * kPitch + (c - c_lo)] = __uint_as_float(v[e]) + bias[c];
+                for (int e = 0; e < 16; ++e) {
+                  const int c = b * 16 + e;
+                  if (c < kHeadCh) srow[c] = __uint_as_float(v[e]) + bias[c];
+                }
+              }
+              srow[131] = kept[0];
+              if (C == 137) {
+#pragma unroll
+                for (int e = 0; e < 5; ++e) srow[132 + e] = kept[1 + e];
               }
             }
+            fence_async_smem();
             group_barrier(g);
-            const int ncol = c_hi - c_lo;
-            for (int rr = (warp - 2) & 3; rr < kTile; rr += 4) {
-              const int64_t gr = (int64_t)tile * kTile + rr;
-              if (gr < A.M)
-                for (int c = lane; c < ncol; c += 32) A.raw[gr * A.C + c_lo + c] = stage[rr * kPitch + c];
+            const int64_t nv = n_valid - hf * 64 < 64 ? n_valid - hf * 64 : 64;
+            if (nv > 0) {
+              float* gdst = A.raw + (row0 + hf * 64) * C;
+              if (bulk_ok) {
+                if (gt == 0) { bulk_s2g(gdst, stage, (uint32_t)(nv * C * 4)); bulk_commit(); }
+              } else {
+                for (int i = gt; i < (int)(nv * C); i += 128) gdst[i] = stage[i];
+              }
             }
-            group_barrier(g);
           }
-          tc_fence_before();
+          store_pending = true;
         }
+        tc_fence_before();
+        fence_async_smem();
+        if (dbg && gt == 0 && ecnt < 64) A.dbg[128 + ecnt * 4 + g * 2 + 1] = clock64();
         if (s + 1 < A.n_steps) mbar_arrive(&bar_act[g]);   // operand of the next step is ready, accumulator drained
       }
     }
+    if (!BWD && gt == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();

@@ -770,6 +770,38 @@ struct Arena {
 }  // namespace
 
 namespace {
+long long* chain_dbg_buf() {
+  static long long* d = nullptr;
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("NEFES_CHAIN_DBG"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (on && d == nullptr) { cudaMalloc(&d, 512 * sizeof(long long)); }
+  return on ? d : nullptr;
+}
+void chain_dbg_dump(const char* what, const ChainArgs& c, cudaStream_t st) {
+  if (c.dbg == nullptr) return;
+  static int dumps = 0;
+  if (dumps >= 6) return;
+  ++dumps;
+  cudaStreamSynchronize(st);
+  long long h[512];
+  cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+  const long long t0 = h[0];
+  fprintf(stderr, "[chain dbg] %s: n_steps=%d tiles=%d\n", what, c.n_steps, c.n_tiles);
+  for (int i = 0; i < 2 * c.n_steps && i < 64; ++i)
+    fprintf(stderr, "  seq %2d step %2d | mma commit t0 %8lld t1 %8lld | epi0 ready %8lld done %8lld | epi1 ready %8lld done %8lld\n", i,
+            i % c.n_steps, h[i * 2] - t0, h[i * 2 + 1] - t0, h[128 + i * 4] - t0, h[128 + i * 4 + 1] - t0,
+            h[128 + i * 4 + 2] - t0, h[128 + i * 4 + 3] - t0);
+}
+
+// weight image streamed in pieces: the whole image, or rows [row0, row0 + 128) of every 8-wide chunk (compacted)
+void set_weights(ChainStep& s, const uint8_t* img, int chunks, int rows, int row0, int take_rows) {
+  s.w_img = img + (int64_t)row0 * 16;
+  s.w_lbo = (uint32_t)take_rows * 16u;
+  s.w_bytes = (uint32_t)chunks * take_rows * 16u;
+  if (take_rows == rows) { s.w_piece = 16384u; s.w_src_stride = 16384u; }
+  else { s.w_piece = (uint32_t)take_rows * 16u; s.w_src_stride = (uint32_t)rows * 16u; }
+}
+
 // Build the step table of the fused forward chain for (net, mode) and launch it.
 int launch_chain_fwd(const Ws& w, const Arena& A, int mode, const float* pts, const float* dirs, int64_t N, int S,
                      float* raw, cudaStream_t st) {
@@ -777,43 +809,111 @@ int launch_chain_fwd(const Ws& w, const Arena& A, int mode, const float* pts, co
   const int T = (int)ceil_div(M, kTile);
   ChainArgs c = {};
   int n = 0;
-  auto add = [&](int pl, uint32_t a_off, int kind, uint32_t out_off, int out_ch, const Img* save, uint4* mask) {
+  auto add = [&](int pl, uint32_t a_off, int kind, uint32_t out_off, int out_ch, const Img* save) {
     ChainStep& s = c.step[n++];
     const PackedDims pd = packed_dims(pl);
     s.a_off = a_off; s.out_off = out_off; s.K = (uint16_t)pd.K; s.N = (uint16_t)pd.N; s.out_ch = (uint16_t)out_ch;
-    s.kind = (uint8_t)kind; s.w_bytes = (uint32_t)pd.K * pd.N * 2u; s.w_img = A.W(pl); s.bias = A.bias(pl);
-    s.gdst = save ? save->p : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u; s.mask = mask;
+    s.kind = (uint8_t)kind; s.wait_load = -1; s.bias = A.bias(pl);
+    set_weights(s, A.W(pl), pd.K / 8, pd.N, 0, pd.N);
+    s.gdst = save ? save->p : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u;
   };
-  add(PL_T0, kRegX, CK_HIDDEN, kRegH, 128, &w.H[0], w.mask[0]);
-  for (int l = 1; l < 8; ++l)
-    add(PL_T0 + l, l == 4 ? kRegX : kRegH, CK_HIDDEN, kRegH, 128, &w.H[l], w.mask[l]);
+  add(PL_T0, kRegX, CK_HIDDEN, kRegH, 128, &w.H[0]);
+  for (int l = 1; l < 8; ++l) add(PL_T0 + l, l == 4 ? kRegX : kRegH, CK_HIDDEN, kRegH, 128, &w.H[l]);
   if (mode == NEFES_MODE_SIGMA) {
-    add(PL_SIG, kRegH, CK_SIGMA, 0, 0, nullptr, nullptr);
+    add(PL_SIG, kRegH, CK_SIGMA, 0, 0, nullptr);
   } else {
-    add(PL_FS, kRegH, CK_FS, kRegH, 128, &w.FIN, nullptr);
+    add(PL_FS, kRegH, CK_FS, kRegH, 128, &w.FIN);
     if (mode == NEFES_MODE_FULL) {
-      add(PL_DT, kRegH, CK_HIDDEN, kRegH, 128, &w.DT, w.mask[8]);
-      add(PL_TE1, kRegH + 16384, CK_HIDDEN, kRegX, 64, &w.T2, w.mask[9]);        // t1 -> t2 (parked in the xyzPE slot)
-      add(PL_TE2, kRegX, CK_HIDDEN, kRegH + 16384, 64, &w.T3, w.mask[10]);       // t2 -> t3 (over t1)
-      add(PL_TH, kRegH + 16384, CK_HEADS, 0, 0, nullptr, nullptr);
+      add(PL_DT, kRegH, CK_HIDDEN, kRegH, 128, &w.DT);
+      add(PL_TE1, kRegH + 16384, CK_HIDDEN, kRegX, 64, &w.T2);        // t1 -> t2 (parked in the xyzPE slot)
+      add(PL_TE2, kRegX, CK_HIDDEN, kRegH + 16384, 64, &w.T3);        // t2 -> t3 (over t1)
+      add(PL_TH, kRegH + 16384, CK_HEADS, 0, 0, nullptr);
     } else {
-      add(PL_DIR, kRegH, CK_HIDDEN, kRegH, 64, &w.DT, w.mask[8]);
+      add(PL_DIR, kRegH, CK_HIDDEN, kRegH, 64, &w.DT);
     }
-    add(PL_RGB, kRegH, CK_RGB, 0, 0, nullptr, nullptr);
+    add(PL_RGB, kRegH, CK_RGB, 0, 0, nullptr);
   }
   c.n_steps = n;
   c.pts = pts; c.dirs = dirs; c.S = S; c.M = M; c.n_tiles = T;
-  c.raw = raw; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137); c.sig_col = 131;
+  c.raw = raw; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
   c.x_img = w.X.p; c.d_img = (mode == NEFES_MODE_SIGMA) ? nullptr : w.DIRPE.p;
+  c.dbg = chain_dbg_buf();
+  { const char* e = getenv("NEFES_CHAIN_X"); c.xflags = e ? atoi(e) : 0; }
   static bool attr_done = false;
   if (!attr_done) {
-    NEFES_CUDA(cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
+    NEFES_CUDA(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdChainSmem));
     attr_done = true;
   }
   const int n_pairs = (T + 1) / 2;
   const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
-  chain_fwd_kernel<<<grid, kChainThreads, kChainSmem, st>>>(c);
+  chain_kernel<false><<<grid, kChainThreads, kFwdChainSmem, st>>>(c);
   NEFES_CHECK_LAUNCH("chain_fwd");
+  chain_dbg_dump("fwd", c, st);
+  return NEFES_OK;
+}
+
+// Fused data-gradient chain: head-gradient images in, the gradient image of every layer's pre-activation out
+// (operands of the weight-gradient kernel); ReLU masks come from the saved activations.
+int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_t M, cudaStream_t st) {
+  const int T = (int)ceil_div(M, kTile);
+  ChainArgs c = {};
+  int n = 0;
+  // D[pts, n_in] = G[pts, K = out channels] * W: B operand = WT image [K/8][in rows][8], rows [row0, row0 + n_in)
+  auto add = [&](int pl, int k_ch, int row0, int n_in, uint32_t a_off, uint32_t out_off, const Img* act, int act_ch0,
+                 const Img* save, int save_ch0, int wait_load) {
+    ChainStep& s = c.step[n++];
+    const PackedDims pd = packed_dims(pl);
+    s.a_off = a_off; s.out_off = out_off; s.K = (uint16_t)k_ch; s.N = (uint16_t)n_in; s.out_ch = (uint16_t)n_in;
+    s.kind = CK_DGRAD; s.wait_load = (int8_t)wait_load; s.bias = nullptr;
+    set_weights(s, A.WT(pl), k_ch / 8, pd.K, row0, n_in);
+    s.act = act ? act->p + (int64_t)act_ch0 * 256 : nullptr; s.act_tile_stride = act ? (uint32_t)act->tile_stride() : 0u;
+    s.gdst = save ? save->p + (int64_t)save_ch0 * 256 : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u;
+  };
+  auto load = [&](int idx, const Img& img, int ch0, int nch, uint32_t dst_off, int issue_step, int next_pair) {
+    ChainLoad& L = c.load[idx];
+    L.src = img.p + (int64_t)ch0 * 256; L.tile_stride = (uint32_t)img.tile_stride(); L.bytes = (uint32_t)nch * 256u;
+    L.dst_off = dst_off; L.issue_step = (int8_t)issue_step; L.next_pair = (int8_t)next_pair;
+  };
+  enum { LD_RGB = 0, LD_TH = 1, LD_SIG = 2 };
+  if (mode == NEFES_MODE_SIGMA) {
+    add(PL_SIG, 16, 0, 128, kRegS, kRegQ, &w.H[7], 0, &b.G[7], 0, LD_SIG);
+    load(LD_SIG, b.GSIG, 0, 16, kRegS, 1, 1);
+    c.n_loads = 3;
+  } else {
+    add(PL_RGB, 144, 0, 64, kRegP, kRegQ, &w.DT, 0, &b.GDT, 0, LD_RGB);
+    if (mode == NEFES_MODE_FULL) {
+      add(PL_TH, 16, 0, 64, kRegS, kRegP, &w.T3, 0, &b.GT3, 0, LD_TH);
+      add(PL_TE2, 64, 0, 64, kRegP, kRegP + 16384, &w.T2, 0, &b.GT2, 0, -1);
+      add(PL_TE1, 64, 0, 64, kRegP + 16384, kRegQ + 16384, &w.DT, 64, &b.GDT, 64, -1);
+      add(PL_DT, 128, 0, 128, kRegQ, kRegP, nullptr, 0, &b.GFS, 0, -1);
+      load(LD_TH, b.GTH, 0, 16, kRegS, 2, 1);
+    } else {
+      add(PL_DIR, 64, 0, 128, kRegQ, kRegP, nullptr, 0, &b.GFS, 0, -1);
+    }
+    const int fs_step = n;
+    add(PL_FS, 144, 0, 128, kRegP, kRegQ, &w.H[7], 0, &b.G[7], 0, LD_SIG);
+    load(LD_RGB, b.GRGB, 0, 144, kRegP, fs_step + 1, 1);          // P is free once the FS MMAs retired
+    load(LD_SIG, b.GFS, 128, 16, kRegP + 32768, 1, 0);            // P[32K:36K] is free once the RGB MMAs retired
+    c.n_loads = 3;
+  }
+  for (int l = 7; l >= 1; --l)   // G[l] = grad wrt pre-activation of trunk layer l  ->  G[l-1]
+    add(PL_T0 + l, 128, l == 4 ? 64 : 0, 128, kRegQ, kRegQ, &w.H[l - 1], 0, &b.G[l - 1], 0, -1);
+  c.n_steps = n;
+  c.M = M; c.n_tiles = T;
+  c.dbg = chain_dbg_buf();
+  { const char* e = getenv("NEFES_CHAIN_X"); c.xflags = e ? atoi(e) : 0; }
+  for (int l = 0; l < kChainLoads; ++l)
+    if (c.load[l].bytes == 0) c.load[l].issue_step = -1;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NEFES_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdChainSmem));
+    attr_done = true;
+  }
+  const int n_pairs = (T + 1) / 2;
+  const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
+  chain_kernel<true><<<grid, kChainThreads, kBwdChainSmem, st>>>(c);
+  NEFES_CHECK_LAUNCH("chain_bwd");
+  chain_dbg_dump("bwd", c, st);
   return NEFES_OK;
 }
 bool use_chain() {
@@ -915,6 +1015,9 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
       raw, d_raw, C, M, Mp, b.GRGB.p, b.GTH.p, gsig_img.p, gsig_img.tile_stride(), mode == NEFES_MODE_SIGMA ? 0 : 16);
   NEFES_CHECK_LAUNCH("head_grad_images");
 
+  if (use_chain()) {
+    TRY(launch_chain_bwd(w, b, A, mode, M, st));
+  } else {
   // dA[pts, Kin] = G[pts, Nout] * W  (B operand = WT image rows [row0, row0 + n_out_cols))
   auto dgrad = [&](int pl, ASrc gsrc, int g_ch, int row0, int n_cols, uint8_t* out, int64_t out_stride, int out_ch,
                    const uint4* mask, int mask_shift) {
@@ -942,6 +1045,8 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   for (int l = 7; l >= 1; --l)   // G[l] = grad wrt pre-activation of trunk layer l  ->  G[l-1]
     TRY(dgrad(PL_T0 + l, src_of(b.G[l]), 128, l == 4 ? 64 : 0, 128, b.G[l - 1].p, b.G[l - 1].tile_stride(), 128,
               w.mask[l - 1], 0));
+
+  }
 
   // ---- gradients to the inputs (pose refinement): fp32 out of the GEMM, then the SIMT PE backward ------
   if (d_pts != nullptr) {        // d xyzPE = G5 W_T4[:, :63] + G1 W_T0 as ONE GEMM over the concatenated K = [G5 | G1]
