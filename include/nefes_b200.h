@@ -56,6 +56,11 @@ enum {
   NEFES_PREC_FP32 = 0,             /* SIMT fp32 FMA -- the 1e-3 parity path                 */
   NEFES_PREC_BF16 = 1              /* tcgen05 bf16 operands, fp32 TMEM accumulators         */
 };
+/* memory layout of the per-point network output `raw` (M points x C channels, fp32) */
+enum {
+  NEFES_RAW_ROWS = 0,              /* [M][C]: the reference's raw[N,S,C]                     */
+  NEFES_RAW_TILES = 1              /* [ceil(M/128)][C][128]: engine-internal, see nefes_mlp_fwd_tiles */
+};
 
 #define NEFES_MAX_LAYERS 18
 typedef struct {
@@ -164,6 +169,17 @@ int nefes_mlp_workspace(int net, int mode, int prec, int64_t M, int64_t N,
 int nefes_mlp_fwd(const float* params, int net, int mode, int prec, const float* pts,
                   const float* dirs, int64_t N, int S, float* raw, void* saved, void* scratch,
                   void* stream);
+/* Same, with raw in the engine's tile-major layout: blocks of 128 consecutive points, each [C][128] fp32
+ * (raw_tiles[(m/128)*C*128 + c*128 + m%128]); the buffer holds ceil(M/128)*C*128 floats.  This is the layout the
+ * fused chain writes with coalesced stores and nefes_composite_*_tiles reads; it never crosses the reference-facing
+ * Python surface (run_network_NeRFH_NFF / raw2outputs_NeRFH_NFF speak [N,S,C]).  bf16 precision only. */
+int nefes_mlp_fwd_tiles(const float* params, int net, int mode, int prec, const float* pts,
+                        const float* dirs, int64_t N, int S, float* raw_tiles, void* saved, void* scratch,
+                        void* stream);
+int nefes_mlp_bwd_tiles(const float* params, int net, int mode, int prec, const float* pts,
+                        const float* dirs, int64_t N, int S, const float* raw_tiles, const float* d_raw_tiles,
+                        const void* saved, void* scratch, float* d_params, float* d_pts, float* d_dirs,
+                        void* stream);
 /* d_params (flat, same layout as params) is ACCUMULATED into (caller zero-fills) or NULL
  * (frozen weights: refinement); d_pts [M,3] / d_dirs [N,3] are overwritten, or NULL. */
 int nefes_mlp_bwd(const float* params, int net, int mode, int prec, const float* pts,
@@ -202,6 +218,12 @@ typedef struct {
 } nefes_comp_grad_t;
 int nefes_composite_bwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
                         int mode, const nefes_comp_grad_t* g_host, float* d_raw, void* stream);
+/* The same two operators on tile-major raw / d_raw blocks (NEFES_RAW_TILES, see nefes_mlp_fwd_tiles); S must divide
+ * 128 so that a ray never straddles a tile (64 coarse / 128 fine samples on every reference config). */
+int nefes_composite_fwd_tiles(const float* raw_tiles, const float* z_vals, const float* noise, int N, int S,
+                              int mode, float beta_min, const nefes_comp_out_t* out_host, void* stream);
+int nefes_composite_bwd_tiles(const float* raw_tiles, const float* z_vals, const float* noise, int N, int S,
+                              int mode, const nefes_comp_grad_t* g_host, float* d_raw_tiles, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Caller-side helpers on the "next" rows of SURVEY 8f that the training step needs resident.

@@ -69,8 +69,12 @@ _SIGS = {
     "nefes_mlp_workspace": (i32, [i32, i32, i32, i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "nefes_mlp_fwd": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp]),
     "nefes_mlp_bwd": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "nefes_mlp_fwd_tiles": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp]),
+    "nefes_mlp_bwd_tiles": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nefes_composite_fwd": (i32, [vp, vp, vp, i32, i32, i32, f32, C.POINTER(CompOut), vp]),
     "nefes_composite_bwd": (i32, [vp, vp, vp, i32, i32, i32, C.POINTER(CompGrad), vp, vp]),
+    "nefes_composite_fwd_tiles": (i32, [vp, vp, vp, i32, i32, i32, f32, C.POINTER(CompOut), vp]),
+    "nefes_composite_bwd_tiles": (i32, [vp, vp, vp, i32, i32, i32, C.POINTER(CompGrad), vp, vp]),
     "nefes_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]),
 }
 

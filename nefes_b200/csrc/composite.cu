@@ -3,6 +3,9 @@
 // backward.  One CTA per ray.  Phase 1: one thread per sample -- alphas, transmittance as a
 // warp-shuffle product scan in fp64 (torch's CPU cumprod accumulates in fp64), weights.
 // Phase 2: one thread per channel -- coalesced sweep over the ray's [S, C] block of `raw`.
+// TILES variants read / write the engine's tile-major raw blocks [C][128] (nefes_mlp_fwd_tiles): element (sample s,
+// channel c) of a ray sits at  tile*C*128 + c*128 + row0 + s, so phase 2 runs one WARP per channel with the lanes on
+// consecutive samples (128-byte coalesced) and a shuffle reduction.
 #include "common.cuh"
 
 namespace nefes {
@@ -76,7 +79,7 @@ struct Samp {
 };
 
 template <int MODE>
-__device__ __forceinline__ Samp sample_terms(const float* __restrict__ row, const float* __restrict__ zr,
+__device__ __forceinline__ Samp sample_terms(const float* __restrict__ row, int cs, const float* __restrict__ zr,
                                              const float* __restrict__ noise_r, int s, int S, Scan& sc) {
   constexpr bool TR = (MODE == NEFES_COMP_TRANSIENT || MODE == NEFES_COMP_TRANSIENT_STATIC_ONLY);
   Samp q = {};
@@ -85,8 +88,8 @@ __device__ __forceinline__ Samp sample_terms(const float* __restrict__ row, cons
   if (ok) {
     q.z = zr[s];
     q.delta = (s + 1 < S) ? __fsub_rn(zr[s + 1], q.z) : kLastDelta;
-    sig_s = row[Chan<MODE>::SIG];
-    if (TR) sig_t = row[135];
+    sig_s = row[Chan<MODE>::SIG * cs];
+    if (TR) sig_t = row[135 * cs];
     if (!TR && noise_r != nullptr) sig_s = __fadd_rn(sig_s, noise_r[s]);
   }
   if (TR) {
@@ -102,7 +105,7 @@ __device__ __forceinline__ Samp sample_terms(const float* __restrict__ row, cons
   return q;
 }
 
-template <int MODE>
+template <int MODE, bool TILES>
 __global__ void composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                                      const float* __restrict__ noise, int S, float beta_min,
                                      nefes_comp_out_t o) {
@@ -111,9 +114,11 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw, const float*
   __shared__ Scan sc;
   __shared__ float s_ws[kMaxS], s_wt[kMaxS];
   const int r = blockIdx.x, t = threadIdx.x;
-  const float* rr = raw + (int64_t)r * S * C;
+  // element (sample s, channel c) = rr[s * rs + c * cs]
+  const int rs = TILES ? 1 : C, cs = TILES ? 128 : 1;
+  const float* rr = TILES ? raw + ((int64_t)r * S / 128) * C * 128 + ((int64_t)r * S) % 128 : raw + (int64_t)r * S * C;
   const float* zr = z + (int64_t)r * S;
-  const Samp q = sample_terms<MODE>(rr + (int64_t)t * C, zr, noise ? noise + (int64_t)r * S : nullptr, t, S, sc);
+  const Samp q = sample_terms<MODE>(rr + (int64_t)t * rs, cs, zr, noise ? noise + (int64_t)r * S : nullptr, t, S, sc);
   const bool ok = t < S;
   const float w = q.a * q.T;                                 // combined weights (nerfh_nff.py:77)
   float w_static, w_out;
@@ -125,7 +130,7 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw, const float*
     s_ws[t] = w_static;
     s_wt[t] = w_t;
     o.weights[(int64_t)r * S + t] = w_out;
-    if (TR && o.tsig != nullptr) o.tsig[(int64_t)r * S + t] = rr[(int64_t)t * C + 135];
+    if (TR && o.tsig != nullptr) o.tsig[(int64_t)r * S + t] = rr[(int64_t)t * rs + 135 * cs];
   }
   const float acc = block_total(ok ? w : 0.f, sc);           // acc_map = sum of combined weights
   if (t == 0) o.acc[r] = acc;
@@ -134,13 +139,31 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw, const float*
   const float depth = block_total(ok ? w_out * q.z : 0.f, sc);
   const float wsum = (MODE == NEFES_COMP_TRANSIENT_STATIC_ONLY) ? block_total(ok ? w_out : 0.f, sc) : acc;
   float beta = 0.f;
-  if (MODE == NEFES_COMP_TRANSIENT) beta = block_total(ok ? w_t * rr[(int64_t)t * C + 136] : 0.f, sc) + beta_min;
+  if (MODE == NEFES_COMP_TRANSIENT) beta = block_total(ok ? w_t * rr[(int64_t)t * rs + 136 * cs] : 0.f, sc) + beta_min;
   if (t == 0) {
     o.depth[r] = depth;
     o.disp[r] = 1.f / fmaxf(1e-10f, depth / wsum);
     o.beta[r] = beta;
   }
   __syncthreads();                                           // s_ws / s_wt visible
+  if (TILES) {
+    const int lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    for (int c = warp; c < kHeadCh; c += nw) {
+      const float* col = rr + (int64_t)c * 128;
+      float v = 0.f;
+      for (int s2 = lane; s2 < S; s2 += 32) v += s_ws[s2] * col[s2];
+      if (MODE == NEFES_COMP_TRANSIENT && c < 3) {
+        const float* colt = rr + (int64_t)(132 + c) * 128;
+        for (int s2 = lane; s2 < S; s2 += 32) v += s_wt[s2] * colt[s2];
+      }
+      v = warp_sum(v);
+      if (lane == 0) {
+        if (c < 3) o.rgb[(int64_t)r * 3 + c] = v;
+        else o.feat[(int64_t)r * kFeat + (c - 3)] = v;
+      }
+    }
+    return;
+  }
   for (int c = t; c < kHeadCh; c += blockDim.x) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int s = 0;
@@ -162,7 +185,7 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw, const float*
   }
 }
 
-template <int MODE>
+template <int MODE, bool TILES>
 __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                                      const float* __restrict__ noise, int S, nefes_comp_grad_t g,
                                      float* __restrict__ d_raw) {
@@ -171,10 +194,12 @@ __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float*
   __shared__ float s_ws[kMaxS], s_wt[kMaxS], s_dsig[kMaxS], s_dsigt[kMaxS], s_dbeta[kMaxS];
   __shared__ float s_grgb[3];
   const int r = blockIdx.x, t = threadIdx.x;
-  const float* rr = raw + (int64_t)r * S * C;
+  const int rs = TILES ? 1 : C, cs = TILES ? 128 : 1;
+  const int64_t roff = TILES ? ((int64_t)r * S / 128) * C * 128 + ((int64_t)r * S) % 128 : (int64_t)r * S * C;
+  const float* rr = raw + roff;
   const float* zr = z + (int64_t)r * S;
-  const float* row = rr + (int64_t)t * C;
-  const Samp q = sample_terms<MODE>(row, zr, noise ? noise + (int64_t)r * S : nullptr, t, S, sc);
+  const float* row = rr + (int64_t)t * rs;
+  const Samp q = sample_terms<MODE>(row, cs, zr, noise ? noise + (int64_t)r * S : nullptr, t, S, sc);
   const bool ok = t < S;
   if (t < 3) s_grgb[t] = g.rgb ? g.rgb[(int64_t)r * 3 + t] : 0.f;
 
@@ -207,9 +232,9 @@ __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float*
     float G_static = 0.f, G_t = 0.f, G_w = 0.f;              // d/d w_static, d/d w_t, d/d w (combined)
     const float gb = (MODE == NEFES_COMP_TRANSIENT && g.beta) ? g.beta[r] : 0.f;
     if (ok && MODE != NEFES_COMP_SIGMA) {
-      G_static = s_grgb[0] * row[0] + s_grgb[1] * row[1] + s_grgb[2] * row[2];
+      G_static = s_grgb[0] * row[0] + s_grgb[1] * row[cs] + s_grgb[2] * row[2 * cs];
       if (MODE == NEFES_COMP_TRANSIENT)
-        G_t = s_grgb[0] * row[132] + s_grgb[1] * row[133] + s_grgb[2] * row[134] + gb * row[136];
+        G_t = s_grgb[0] * row[132 * cs] + s_grgb[1] * row[133 * cs] + s_grgb[2] * row[134 * cs] + gb * row[136 * cs];
     }
     if (ok) {
       const float g_out = g_depth * q.z + g_wsum + gw_out;   // on w_out
@@ -241,9 +266,29 @@ __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float*
     s_ws[t] = w_static; s_wt[t] = w_t; s_dsig[t] = dsig; s_dsigt[t] = dsigt; s_dbeta[t] = dbeta;
   }
   __syncthreads();
-  float* dr = d_raw + (int64_t)r * S * C;
+  float* dr = d_raw + roff;
   if (MODE == NEFES_COMP_SIGMA) {
     if (ok) dr[t] = dsig;
+    return;
+  }
+  if (TILES) {
+    const int lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    for (int c = warp; c < C; c += nw) {
+      float gsel = 0.f;
+      if (c < 3) gsel = s_grgb[c];
+      else if (c < kHeadCh) gsel = g.feat ? g.feat[(int64_t)r * kFeat + (c - 3)] : 0.f;
+      else if (c >= 132 && c < 135) gsel = s_grgb[c - 132];
+      float* col = dr + (int64_t)c * 128;
+      for (int s2 = lane; s2 < S; s2 += 32) {
+        float v;
+        if (c < kHeadCh) v = gsel * s_ws[s2];
+        else if (c == 131) v = s_dsig[s2];
+        else if (c < 135) v = gsel * s_wt[s2];
+        else if (c == 135) v = s_dsigt[s2];
+        else v = s_dbeta[s2];
+        col[s2] = v;
+      }
+    }
     return;
   }
   for (int c = t; c < C; c += blockDim.x) {
@@ -274,45 +319,68 @@ static int comp_check(const char* who, const float* raw, const float* z, int N, 
   return NEFES_OK;
 }
 
-int nefes_composite_fwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
-                        int mode, float beta_min, const nefes_comp_out_t* out_host, void* stream) {
-  if (int e = comp_check("nefes_composite_fwd", raw, z_vals, N, S, mode)) return e;
+}  // extern "C"
+
+template <bool TILES>
+static int comp_fwd_launch(const char* who, const float* raw, const float* z_vals, const float* noise, int N, int S, int mode,
+                           float beta_min, const nefes_comp_out_t* out_host, void* stream) {
+  if (int e = comp_check(who, raw, z_vals, N, S, mode)) return e;
   if (N == 0) return NEFES_OK;
-  NEFES_REQUIRE(out_host && out_host->acc && out_host->weights, NEFES_EINVAL,
-                "nefes_composite_fwd: acc and weights outputs are required");
+  NEFES_REQUIRE(out_host && out_host->acc && out_host->weights, NEFES_EINVAL, "%s: acc and weights outputs are required", who);
   if (mode != NEFES_COMP_SIGMA)
     NEFES_REQUIRE(out_host->rgb && out_host->feat && out_host->disp && out_host->depth && out_host->beta,
-                  NEFES_EINVAL, "nefes_composite_fwd: missing output pointer");
-  if (N == 0) return NEFES_OK;
-  const int threads = (int)nefes::round_up(S > 160 ? S : (mode == NEFES_COMP_SIGMA ? S : 160), 32);
+                  NEFES_EINVAL, "%s: missing output pointer", who);
+  NEFES_REQUIRE(!TILES || 128 % S == 0, NEFES_EINVAL, "%s: tile-major raw needs S to divide 128 (S=%d)", who, S);
+  const int threads = (int)nefes::round_up(S > 160 ? S : (mode == NEFES_COMP_SIGMA ? S : (TILES ? 256 : 160)), 32);
   cudaStream_t st = (cudaStream_t)stream;
   nefes_comp_out_t o = *out_host;
   switch (mode) {
-    case NEFES_COMP_SIGMA: nefes::composite_fwd_kernel<NEFES_COMP_SIGMA><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
-    case NEFES_COMP_STATIC: nefes::composite_fwd_kernel<NEFES_COMP_STATIC><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
-    case NEFES_COMP_TRANSIENT: nefes::composite_fwd_kernel<NEFES_COMP_TRANSIENT><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
-    default: nefes::composite_fwd_kernel<NEFES_COMP_TRANSIENT_STATIC_ONLY><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
+    case NEFES_COMP_SIGMA: nefes::composite_fwd_kernel<NEFES_COMP_SIGMA, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
+    case NEFES_COMP_STATIC: nefes::composite_fwd_kernel<NEFES_COMP_STATIC, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
+    case NEFES_COMP_TRANSIENT: nefes::composite_fwd_kernel<NEFES_COMP_TRANSIENT, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
+    default: nefes::composite_fwd_kernel<NEFES_COMP_TRANSIENT_STATIC_ONLY, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
   }
-  NEFES_CHECK_LAUNCH("composite_fwd");
+  NEFES_CHECK_LAUNCH(who);
   return NEFES_OK;
 }
 
-int nefes_composite_bwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
-                        int mode, const nefes_comp_grad_t* g_host, float* d_raw, void* stream) {
-  if (int e = comp_check("nefes_composite_bwd", raw, z_vals, N, S, mode)) return e;
+template <bool TILES>
+static int comp_bwd_launch(const char* who, const float* raw, const float* z_vals, const float* noise, int N, int S, int mode,
+                           const nefes_comp_grad_t* g_host, float* d_raw, void* stream) {
+  if (int e = comp_check(who, raw, z_vals, N, S, mode)) return e;
   if (N == 0) return NEFES_OK;
-  NEFES_REQUIRE(g_host && d_raw, NEFES_EINVAL, "nefes_composite_bwd: null pointer");
-  const int threads = (int)nefes::round_up(S > 160 ? S : (mode == NEFES_COMP_SIGMA ? S : 160), 32);
+  NEFES_REQUIRE(g_host && d_raw, NEFES_EINVAL, "%s: null pointer", who);
+  NEFES_REQUIRE(!TILES || 128 % S == 0, NEFES_EINVAL, "%s: tile-major raw needs S to divide 128 (S=%d)", who, S);
+  const int threads = (int)nefes::round_up(S > 160 ? S : (mode == NEFES_COMP_SIGMA ? S : (TILES ? 256 : 160)), 32);
   cudaStream_t st = (cudaStream_t)stream;
   nefes_comp_grad_t g = *g_host;
   switch (mode) {
-    case NEFES_COMP_SIGMA: nefes::composite_bwd_kernel<NEFES_COMP_SIGMA><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
-    case NEFES_COMP_STATIC: nefes::composite_bwd_kernel<NEFES_COMP_STATIC><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
-    case NEFES_COMP_TRANSIENT: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
-    default: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT_STATIC_ONLY><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
+    case NEFES_COMP_SIGMA: nefes::composite_bwd_kernel<NEFES_COMP_SIGMA, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
+    case NEFES_COMP_STATIC: nefes::composite_bwd_kernel<NEFES_COMP_STATIC, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
+    case NEFES_COMP_TRANSIENT: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
+    default: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT_STATIC_ONLY, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
   }
-  NEFES_CHECK_LAUNCH("composite_bwd");
+  NEFES_CHECK_LAUNCH(who);
   return NEFES_OK;
+}
+
+extern "C" {
+
+int nefes_composite_fwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
+                        int mode, float beta_min, const nefes_comp_out_t* out_host, void* stream) {
+  return comp_fwd_launch<false>("nefes_composite_fwd", raw, z_vals, noise, N, S, mode, beta_min, out_host, stream);
+}
+int nefes_composite_fwd_tiles(const float* raw_tiles, const float* z_vals, const float* noise, int N, int S,
+                              int mode, float beta_min, const nefes_comp_out_t* out_host, void* stream) {
+  return comp_fwd_launch<true>("nefes_composite_fwd_tiles", raw_tiles, z_vals, noise, N, S, mode, beta_min, out_host, stream);
+}
+int nefes_composite_bwd(const float* raw, const float* z_vals, const float* noise, int N, int S,
+                        int mode, const nefes_comp_grad_t* g_host, float* d_raw, void* stream) {
+  return comp_bwd_launch<false>("nefes_composite_bwd", raw, z_vals, noise, N, S, mode, g_host, d_raw, stream);
+}
+int nefes_composite_bwd_tiles(const float* raw_tiles, const float* z_vals, const float* noise, int N, int S,
+                              int mode, const nefes_comp_grad_t* g_host, float* d_raw_tiles, void* stream) {
+  return comp_bwd_launch<true>("nefes_composite_bwd_tiles", raw_tiles, z_vals, noise, N, S, mode, g_host, d_raw_tiles, stream);
 }
 
 }  // extern "C"

@@ -6,9 +6,9 @@ int mlp_fwd_fp32(const float*, int, int, const float*, const float*, int64_t, in
 int mlp_bwd_fp32(const float*, int, int, const float*, const float*, int64_t, int, const float*, const float*,
                  const void*, void*, float*, float*, float*, cudaStream_t);
 int mlp_workspace_fp32(int, int64_t, int64_t, int64_t*, int64_t*, int64_t*);
-int mlp_fwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, float*, void*, void*, cudaStream_t);
+int mlp_fwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, float*, void*, void*, int, cudaStream_t);
 int mlp_bwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, const float*, const float*,
-                 const void*, void*, float*, float*, float*, cudaStream_t);
+                 const void*, void*, float*, float*, float*, int, cudaStream_t);
 int mlp_workspace_bf16(int, int, int64_t, int64_t, int64_t*, int64_t*, int64_t*);
 
 // torch.optim.Adam semantics (amsgrad=False, weight_decay=0, maximize=False)
@@ -50,33 +50,59 @@ int nefes_mlp_workspace(int net, int mode, int prec, int64_t M, int64_t N, int64
   return nefes::mlp_workspace_fp32(mode, M, N, saved_bytes_host, scratch_fwd_bytes_host, scratch_bwd_bytes_host);
 }
 
-int nefes_mlp_fwd(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
-                  int64_t N, int S, float* raw, void* saved, void* scratch, void* stream) {
-  if (int e = nefes::check_mlp("nefes_mlp_fwd", net, mode, prec, N, S)) return e;
-  NEFES_REQUIRE(params && pts && raw && saved, NEFES_EINVAL, "nefes_mlp_fwd: null pointer");
-  NEFES_REQUIRE(mode == NEFES_MODE_SIGMA || (dirs && scratch), NEFES_EINVAL, "nefes_mlp_fwd: dirs/scratch required");
-  NEFES_REQUIRE(((uintptr_t)saved & 15) == 0 && ((uintptr_t)scratch & 15) == 0, NEFES_EALIGN,
-                "nefes_mlp_fwd: workspaces must be 16-byte aligned");
+static int mlp_fwd_any(const char* who, int layout, const float* params, int net, int mode, int prec, const float* pts,
+                       const float* dirs, int64_t N, int S, float* raw, void* saved, void* scratch, void* stream) {
+  if (int e = nefes::check_mlp(who, net, mode, prec, N, S)) return e;
+  NEFES_REQUIRE(params && pts && raw && saved, NEFES_EINVAL, "%s: null pointer", who);
+  NEFES_REQUIRE(mode == NEFES_MODE_SIGMA || (dirs && scratch), NEFES_EINVAL, "%s: dirs/scratch required", who);
+  NEFES_REQUIRE(((uintptr_t)saved & 15) == 0 && ((uintptr_t)scratch & 15) == 0 && ((uintptr_t)raw & 15) == 0, NEFES_EALIGN,
+                "%s: raw and workspaces must be 16-byte aligned", who);
+  NEFES_REQUIRE(layout == NEFES_RAW_ROWS || prec == NEFES_PREC_BF16, NEFES_EINVAL,
+                "%s: the tile-major raw layout belongs to the bf16 tensor path", who);
   if (N == 0) return NEFES_OK;
   if (prec == NEFES_PREC_BF16)
-    return nefes::mlp_fwd_bf16(params, net, mode, pts, dirs, N, S, raw, saved, scratch, (cudaStream_t)stream);
+    return nefes::mlp_fwd_bf16(params, net, mode, pts, dirs, N, S, raw, saved, scratch, layout, (cudaStream_t)stream);
   return nefes::mlp_fwd_fp32(params, net, mode, pts, dirs, N, S, raw, saved, scratch, (cudaStream_t)stream);
 }
 
-int nefes_mlp_bwd(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
-                  int64_t N, int S, const float* raw, const float* d_raw, const void* saved, void* scratch,
-                  float* d_params, float* d_pts, float* d_dirs, void* stream) {
-  if (int e = nefes::check_mlp("nefes_mlp_bwd", net, mode, prec, N, S)) return e;
-  NEFES_REQUIRE(params && pts && raw && d_raw && saved && scratch, NEFES_EINVAL, "nefes_mlp_bwd: null pointer");
-  NEFES_REQUIRE(mode == NEFES_MODE_SIGMA || dirs, NEFES_EINVAL, "nefes_mlp_bwd: dirs required");
+static int mlp_bwd_any(const char* who, int layout, const float* params, int net, int mode, int prec, const float* pts,
+                       const float* dirs, int64_t N, int S, const float* raw, const float* d_raw, const void* saved,
+                       void* scratch, float* d_params, float* d_pts, float* d_dirs, void* stream) {
+  if (int e = nefes::check_mlp(who, net, mode, prec, N, S)) return e;
+  NEFES_REQUIRE(params && pts && raw && d_raw && saved && scratch, NEFES_EINVAL, "%s: null pointer", who);
+  NEFES_REQUIRE(mode == NEFES_MODE_SIGMA || dirs, NEFES_EINVAL, "%s: dirs required", who);
   NEFES_REQUIRE(((uintptr_t)saved & 15) == 0 && ((uintptr_t)scratch & 15) == 0, NEFES_EALIGN,
-                "nefes_mlp_bwd: workspaces must be 16-byte aligned");
+                "%s: workspaces must be 16-byte aligned", who);
+  NEFES_REQUIRE(layout == NEFES_RAW_ROWS || prec == NEFES_PREC_BF16, NEFES_EINVAL,
+                "%s: the tile-major raw layout belongs to the bf16 tensor path", who);
   if (N == 0) return NEFES_OK;
   if (prec == NEFES_PREC_BF16)
     return nefes::mlp_bwd_bf16(params, net, mode, pts, dirs, N, S, raw, d_raw, saved, scratch, d_params, d_pts,
-                               d_dirs, (cudaStream_t)stream);
+                               d_dirs, layout, (cudaStream_t)stream);
   return nefes::mlp_bwd_fp32(params, net, mode, pts, dirs, N, S, raw, d_raw, saved, scratch, d_params, d_pts,
                              d_dirs, (cudaStream_t)stream);
+}
+
+int nefes_mlp_fwd(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
+                  int64_t N, int S, float* raw, void* saved, void* scratch, void* stream) {
+  return mlp_fwd_any("nefes_mlp_fwd", NEFES_RAW_ROWS, params, net, mode, prec, pts, dirs, N, S, raw, saved, scratch, stream);
+}
+int nefes_mlp_fwd_tiles(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
+                        int64_t N, int S, float* raw_tiles, void* saved, void* scratch, void* stream) {
+  return mlp_fwd_any("nefes_mlp_fwd_tiles", NEFES_RAW_TILES, params, net, mode, prec, pts, dirs, N, S, raw_tiles, saved,
+                     scratch, stream);
+}
+int nefes_mlp_bwd(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
+                  int64_t N, int S, const float* raw, const float* d_raw, const void* saved, void* scratch,
+                  float* d_params, float* d_pts, float* d_dirs, void* stream) {
+  return mlp_bwd_any("nefes_mlp_bwd", NEFES_RAW_ROWS, params, net, mode, prec, pts, dirs, N, S, raw, d_raw, saved, scratch,
+                     d_params, d_pts, d_dirs, stream);
+}
+int nefes_mlp_bwd_tiles(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
+                        int64_t N, int S, const float* raw_tiles, const float* d_raw_tiles, const void* saved,
+                        void* scratch, float* d_params, float* d_pts, float* d_dirs, void* stream) {
+  return mlp_bwd_any("nefes_mlp_bwd_tiles", NEFES_RAW_TILES, params, net, mode, prec, pts, dirs, N, S, raw_tiles,
+                     d_raw_tiles, saved, scratch, d_params, d_pts, d_dirs, stream);
 }
 
 int nefes_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

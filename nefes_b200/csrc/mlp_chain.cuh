@@ -1,18 +1,20 @@
 // Fused layer chains of the NeFeS field (bf16 tensor path): one persistent kernel runs ALL layers of the MLP for a
 // pair of 128-point tiles; activations (forward) / data gradients (backward) never leave the SM between layers.
 //
-//   warp 0      producer: streams each step's weight image L2 -> shared (bulk copies, 2-slot ring) and, in the
-//               backward chain, prefetches the head-gradient images of the tile pair several steps ahead
+//   warp 0      producer: streams each step's weight image L2 -> shared (bulk copies, 2-slot ring) and prefetches the
+//               per-tile operand images (forward: xyz / direction encodings; backward: head-gradient images) for the
+//               NEXT tile pair as soon as their slot of the tile region is dead
 //   warp 1      MMA issuer: for every step, tile 0 then tile 1 (tcgen05.mma M=128, fp32 accumulators in TMEM,
 //               256 columns per tile); the tensor pipe works on one tile while the other tile's epilogue runs
-//   warps 2-5   epilogue of tile 0, warps 6-9 epilogue of tile 1.
-//     forward:  positional encoding -> operand image; per layer TMEM -> registers -> bias (packed fp32x2 add) ->
-//               ReLU fused into the bf16 pack -> operand image of the NEXT layer in shared memory (in place) and
-//               the same 16-byte words to HBM (saved for backward); the 137 fp32 outputs of a point are gathered
-//               in a row-major staging image and leave with two bulk stores per tile.
-//     backward: per layer TMEM -> registers -> bf16 pack -> ReLU mask taken from the SAVED activation (a > 0, one
-//               compare per bf16 pair) -> gradient image of the next (earlier) layer in shared memory and to HBM
-//               (operand of the weight-gradient kernel).
+//   warps 2-9   epilogue of tile 0, warps 10-17 epilogue of tile 1: a warp owns 32 points (its TMEM lane quarter) x
+//               one half of the output columns, so every scheduler has four epilogue warps to hide tcgen05.ld / LDS
+//               latency behind each other.
+//     forward:  TMEM -> registers -> bias (packed fp32x2 add) -> ReLU fused into the bf16 pack -> operand image of
+//               the NEXT layer in shared memory (in place) and the same 16-byte words to HBM (saved for backward);
+//               the fp32 outputs go straight to the tile-major raw block [C][128] (128-byte coalesced stores).
+//     backward: TMEM -> registers -> bf16 pack -> ReLU mask taken from the SAVED activation (a > 0, one compare per
+//               bf16 pair) -> gradient image of the next (earlier) layer in shared memory and to HBM (operand of the
+//               weight-gradient kernel).
 //
 // The chain is table-driven (ChainStep): operand offset inside the tile region, weight image, epilogue kind,
 // destination.  Included by mlp_tc.cu (uses its helpers).   script/models/nerfh_nff.py:525-576.
@@ -21,14 +23,14 @@
 namespace nefes {
 
 enum { CK_HIDDEN = 0,   // fwd: bias + ReLU -> image
-       CK_FS = 1,       // fwd: bias -> image (128 ch: xyz_encoding_final); column 128: softplus -> sigma (kept)
-       CK_HEADS = 2,    // fwd: columns 0..4: sigmoid x3, softplus x2 (kept in registers until CK_RGB)
-       CK_SIGMA = 3,    // fwd: column 0: softplus -> raw[:, 0]                       (sigma-only mode)
-       CK_RGB = 4,      // fwd: bias -> 131 fp32 columns; with the kept sigma / heads -> raw rows (staged, bulk store)
+       CK_FS = 1,       // fwd: bias -> image (128 ch: xyz_encoding_final); column 128: softplus -> raw[131]
+       CK_HEADS = 2,    // fwd: columns 0..4: sigmoid x3, softplus x2 -> raw[132..136]
+       CK_SIGMA = 3,    // fwd: column 0: softplus -> raw[0]                          (sigma-only mode)
+       CK_RGB = 4,      // fwd: bias -> 131 fp32 columns -> raw[0..130]
        CK_DGRAD = 5 };  // bwd: optional ReLU mask from the saved activation -> image
 
 constexpr int kChainLoads = 3;
-struct ChainLoad {                 // one prefetch of a head-gradient image into the tile region (backward)
+struct ChainLoad {                 // one prefetch of a per-tile operand image into the tile region
   const uint8_t* src; uint32_t tile_stride, bytes, dst_off;
   int8_t issue_step;               // producer issues it when it reaches this step ...
   int8_t next_pair;                // ... for the NEXT pair (1) or the current one (0)
@@ -40,6 +42,7 @@ struct ChainStep {
   uint16_t K, N, out_ch;
   uint8_t kind;
   int8_t wait_load;                // index of the ChainLoad the MMA of this step must wait for (-1: none)
+  int8_t wait_load2, pad8;
   uint32_t w_bytes, w_lbo;         // weight image: bytes to stream (compacted), LBO = bytes between 8-wide K chunks
   uint32_t w_piece, w_src_stride;  // streamed as pieces of w_piece bytes, w_src_stride apart in the source image
   const uint8_t* w_img;
@@ -53,9 +56,8 @@ struct ChainArgs {
   ChainStep step[kChainMaxSteps];
   ChainLoad load[kChainLoads];
   int n_steps, n_loads;
-  const float* pts; const float* dirs; int S; int64_t M; int n_tiles;
-  float* raw; int C;
-  uint8_t* x_img; uint8_t* d_img;            // fwd: saved xyzPE / dirPE images (wgrad operands)
+  int64_t M; int n_tiles;
+  float* raw; int C;                         // fwd: tile-major output blocks [n_tiles][C][128] fp32
   long long* dbg;                            // optional clock stamps of CTA 0 (NEFES_CHAIN_DBG)
   int xflags;                                // timing experiments only (NEFES_CHAIN_X): 1 no saves, 2 no PE, 4 no raw store
 };
@@ -68,13 +70,14 @@ constexpr uint32_t kRegP = 0, kRegQ = 36864, kRegS = 73728;
 constexpr uint32_t kFwdRegBytes = 57344, kBwdRegBytes = 77824;
 constexpr uint32_t kFwdWSlot = 49152;        // largest forward W image: 192 x 128 bf16
 constexpr uint32_t kBwdWSlot = 36864;        // largest backward WT image: 144 x 128 bf16
-constexpr int kChainThreads = 64 + 256;
+constexpr int kChainEpiWarps = 8;             // per tile
+constexpr int kChainThreads = 64 + 2 * kChainEpiWarps * 32;
 constexpr int kChainBiasStride = 160;        // floats per step in the shared bias table (N <= 160)
 constexpr uint32_t kChainBiasBytes = kChainMaxSteps * kChainBiasStride * 4;
 constexpr uint32_t kFwdChainSmem = 2 * kFwdRegBytes + 2 * kFwdWSlot + kChainBiasBytes;
 constexpr uint32_t kBwdChainSmem = 2 * kBwdRegBytes + 2 * kBwdWSlot;
 
-__device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+__device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
 
 // (lo + blo, hi + bhi) as one packed fp32x2 add, then one cvt to a bf16 pair (ReLU folded into the cvt)
 template <bool RELU>
@@ -121,38 +124,6 @@ __device__ __forceinline__ uint32_t pack_mask(uint32_t lo, uint32_t hi, uint32_t
   return p;
 }
 
-// positional encoding of one point -> bf16 chunks: [x, sin(2^l x), cos(2^l x)] with the base sin/cos from the accurate
-// sincosf and the octaves by the double-angle recurrence (error doubles per octave: <= 2^9 * 1e-7 = 5e-5, far below
-// the bf16 operand rounding of 4e-3).   script/models/nerfh_nff.py:241-270
-template <int FREQS, int CHUNKS>
-__device__ __forceinline__ void pe_row(const float* __restrict__ p3, bool ok, uint8_t* __restrict__ s_row, uint8_t* __restrict__ g_row) {
-  float e[CHUNKS * 8];
-#pragma unroll
-  for (int i = 0; i < CHUNKS * 8; ++i) e[i] = 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float v = ok ? p3[c] : 0.f;
-    e[c] = v;
-    float sn, cs;
-    sincosf(v, &sn, &cs);
-#pragma unroll
-    for (int l = 0; l < FREQS; ++l) {
-      e[3 + 6 * l + c] = ok ? sn : 0.f;
-      e[6 + 6 * l + c] = ok ? cs : 0.f;
-      const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
-      sn = s2; cs = c2;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < CHUNKS; ++j) {
-    uint4 pk;
-    pk.x = pack_bf16(e[8 * j], e[8 * j + 1]); pk.y = pack_bf16(e[8 * j + 2], e[8 * j + 3]);
-    pk.z = pack_bf16(e[8 * j + 4], e[8 * j + 5]); pk.w = pack_bf16(e[8 * j + 6], e[8 * j + 7]);
-    *reinterpret_cast<uint4*>(s_row + j * kChunkBytes) = pk;
-    *reinterpret_cast<uint4*>(g_row + j * kChunkBytes) = pk;
-  }
-}
-
 template <bool BWD>
 __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -167,7 +138,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1);
-      mbar_init(&bar_act[i], 128); mbar_init(&bar_acc[i], 1);
+      mbar_init(&bar_act[i], kChainEpiWarps * 32); mbar_init(&bar_acc[i], 1);
       for (int l = 0; l < kChainLoads; ++l) mbar_init(&bar_ld[i][l], 1);
     }
     fence_mbar_init();
@@ -187,8 +158,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------- producer ---------------------------------------------------------------
-      uint32_t cnt = 0;                 // W ring position
-      uint32_t q = 0;                   // steps started so far (per tile the same; tile 1 may skip the last pair)
+      uint32_t cnt = 0;                 // W ring position == steps started so far
       auto issue_load = [&](int li, int pair) {
         const ChainLoad& L = A.load[li];
         for (int g = 0; g < 2; ++g) {
@@ -198,13 +168,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
           bulk_g2s(smem + g * kReg + L.dst_off, L.src + (int64_t)tile * L.tile_stride, L.bytes, &bar_ld[g][li]);
         }
       };
-      if (BWD) {
-        for (int l = 0; l < A.n_loads; ++l)
-          if (A.load[l].issue_step >= 0 && A.load[l].next_pair && (int)blockIdx.x < n_pairs) issue_load(l, blockIdx.x);
-      }
+      for (int l = 0; l < A.n_loads; ++l)
+        if (A.load[l].issue_step >= 0 && A.load[l].next_pair && (int)blockIdx.x < n_pairs) issue_load(l, blockIdx.x);
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         const bool valid1 = pair * 2 + 1 < A.n_tiles;
-        for (int s = 0; s < A.n_steps; ++s, ++cnt, ++q) {
+        for (int s = 0; s < A.n_steps; ++s, ++cnt) {
           const int slot = cnt & 1;
           mbar_wait(&bar_wempty[slot], ((cnt >> 1) & 1) ^ 1);
           const uint32_t bytes = A.step[s].w_bytes;
@@ -213,19 +181,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
           const uint8_t* src = A.step[s].w_img;
           for (uint32_t off = 0; off < bytes; off += piece, src += sstride)
             bulk_g2s(sW + slot * kWSlot + off, src, min(piece, bytes - off), &bar_wfull[slot]);
-          if (BWD) {
-            for (int l = 0; l < A.n_loads; ++l) {
-              const ChainLoad& L = A.load[l];
-              if (L.issue_step != s) continue;
-              const int tp = L.next_pair ? pair + (int)gridDim.x : pair;
-              if (tp >= n_pairs) continue;
-              // the destination was last read by the MMAs of step s-1 of THIS pair: wait until they retired
-              if (q > 0) {
-                mbar_wait(&bar_acc[0], (q - 1) & 1);
-                if (valid1) mbar_wait(&bar_acc[1], (q - 1) & 1);
-              }
-              issue_load(l, tp);
+          for (int l = 0; l < A.n_loads; ++l) {
+            const ChainLoad& L = A.load[l];
+            if (L.issue_step != s) continue;
+            const int tp = L.next_pair ? pair + (int)gridDim.x : pair;
+            if (tp >= n_pairs) continue;
+            // the destination was last read by the MMAs of step s-1 of THIS pair: wait until they retired
+            if (cnt > 0) {
+              mbar_wait(&bar_acc[0], (cnt - 1) & 1);
+              if (valid1) mbar_wait(&bar_acc[1], (cnt - 1) & 1);
             }
+            issue_load(l, tp);
           }
         }
       }
@@ -240,23 +206,29 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
           const ChainStep& st = A.step[s];
           const int slot = cnt & 1;
           mbar_wait(&bar_wfull[slot], (cnt >> 1) & 1);
+          if (dbg && cnt < 32) A.dbg[cnt * 48] = clock64();
           const uint32_t idesc = idesc_bf16(128, st.N, 0, 0);
           const uint64_t db0 = smem_desc(smem_u32(sW + slot * kWSlot), st.w_lbo, 128);
           for (int g = 0; g < 2; ++g) {
             if (g == 1 && !valid1) break;
             mbar_wait(&bar_act[g], act_ph[g]);
             act_ph[g] ^= 1u;
-            if (BWD && st.wait_load >= 0) {
+            if (st.wait_load >= 0) {
               mbar_wait(&bar_ld[g][st.wait_load], ld_ph[g][st.wait_load]);
               ld_ph[g][st.wait_load] ^= 1u;
             }
+            if (st.wait_load2 >= 0) {
+              mbar_wait(&bar_ld[g][st.wait_load2], ld_ph[g][st.wait_load2]);
+              ld_ph[g][st.wait_load2] ^= 1u;
+            }
             tc_fence_after();
+            if (dbg && cnt < 32) A.dbg[cnt * 48 + 1 + g] = clock64();
             const uint64_t da0 = smem_desc(smem_u32(smem + g * kReg + st.a_off), kChunkBytes, 128);
             const uint32_t d = tmem + g * 256;
             for (int k = 0; k < st.K / 16; ++k)
               mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k * (2 * st.w_lbo >> 4)), idesc, k > 0);
             mma_commit(&bar_acc[g]);
-            if (dbg && cnt < 64) A.dbg[cnt * 2 + g] = clock64();
+            if (dbg && cnt < 32) A.dbg[cnt * 48 + 3 + g] = clock64();
           }
           mma_commit(&bar_wempty[slot]);
         }
@@ -264,156 +236,126 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
     }
   } else {
     // --------------------------------- epilogue warps ----------------------------------------------------------------
-    const int g = (warp - 2) >> 2;                    // tile of the pair this warp serves
+    const int ew = warp - 2;                          // 0..15
+    const int g = ew >> 3;                            // tile of the pair this warp serves
+    const int half = (ew >> 2) & 1;                   // which half of the output columns
     const int q = warp & 3;                           // TMEM lane quarter
     const int row = q * 32 + lane;
-    const int gt = ((warp - 2) & 3) * 32 + lane;      // 0..127 inside the group
+    const int gt = (ew & 7) * 32 + lane;              // 0..255 inside the group
     uint8_t* reg = smem + g * kReg;
     const uint32_t taddr = tmem + g * 256 + ((uint32_t)(q * 32) << 16);
     uint32_t acc_ph = 0u;
-    bool store_pending = false;
     uint32_t ecnt = 0;
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int tile = pair * 2 + g;
       if (tile >= A.n_tiles) break;
       const int64_t grow = (int64_t)tile * kTile + row;
       const bool ok = grow < A.M;
-      float kept[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sigma, transient rgb x3, transient sigma, beta
-      if (!BWD) {
-        if (store_pending) {                          // the raw staging of the previous tile lives in this region
-          if (gt == 0) bulk_wait_read<0>();
-          group_barrier(g);
-          store_pending = false;
-        }
-        if (!(A.xflags & 2)) pe_row<kXyzFreqs, 8>(A.pts + grow * 3, ok, reg + kRegX + row * 16, A.x_img + (int64_t)tile * (64 * 256) + row * 16);
-        if (A.d_img != nullptr && !(A.xflags & 2))
-          pe_row<kDirFreqs, 4>(A.dirs + (grow / A.S) * 3, ok, reg + kRegD + row * 16, A.d_img + (int64_t)tile * (32 * 256) + row * 16);
-        fence_async_smem();
-      }
-      mbar_arrive(&bar_act[g]);                        // operand of step 0 is ready (bwd: it arrives by bulk copy)
+      float* rawt = BWD ? nullptr : A.raw + (int64_t)tile * A.C * kTile + row;   // + c * 128
+      mbar_arrive(&bar_act[g]);                        // step 0: its operand arrives by bulk copy
 
       for (int s = 0; s < A.n_steps; ++s, ++ecnt) {
         const ChainStep& st = A.step[s];
         const float* bias = sBias + s * kChainBiasStride;
-        uint4 av[16];
+        const int ncol = st.out_ch >> 1;               // image columns of this warp: [c_base, c_base + ncol), 32 or 64
+        const int c_base = half * ncol;
+        uint4 av[8];
         if (BWD) {                                     // saved activation of this row: issue the loads before waiting
           if (st.act != nullptr) {
-            const uint8_t* ap = st.act + (int64_t)tile * st.act_tile_stride + row * 16;
+            const uint8_t* ap = st.act + (int64_t)tile * st.act_tile_stride + (c_base >> 3) * kChunkBytes + row * 16;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j * 8 < st.out_ch) av[j] = __ldg(reinterpret_cast<const uint4*>(ap + j * kChunkBytes));
+            for (int j = 0; j < 8; ++j)
+              if (j * 8 < ncol) av[j] = __ldg(reinterpret_cast<const uint4*>(ap + j * kChunkBytes));
           }
         }
         mbar_wait(&bar_acc[g], acc_ph);
         acc_ph ^= 1u;
         tc_fence_after();
-        if (dbg && gt == 0 && ecnt < 64) A.dbg[128 + ecnt * 4 + g * 2] = clock64();
-        if (BWD) {
-          uint8_t* dst_row = reg + st.out_off + row * 16;
-          uint8_t* gdst_row = (st.gdst && !(A.xflags & 1)) ? st.gdst + (int64_t)tile * st.g_tile_stride + row * 16 : nullptr;
-          const bool gate = st.act != nullptr;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            if (b * 32 < st.out_ch) {
-              uint32_t v[32];
-              tmem_ld32(taddr + b * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 a = av[b * 4 + j];
-                uint4 pk;
-                pk.x = pack_mask(v[8 * j + 0], v[8 * j + 1], a.x, gate);
-                pk.y = pack_mask(v[8 * j + 2], v[8 * j + 3], a.y, gate);
-                pk.z = pack_mask(v[8 * j + 4], v[8 * j + 5], a.z, gate);
-                pk.w = pack_mask(v[8 * j + 6], v[8 * j + 7], a.w, gate);
-                const int off = (b * 4 + j) * (int)kChunkBytes;
-                *reinterpret_cast<uint4*>(dst_row + off) = pk;
-                if (gdst_row != nullptr) *reinterpret_cast<uint4*>(gdst_row + off) = pk;
-              }
-            }
-          }
-        } else if (st.kind == CK_HIDDEN || st.kind == CK_FS) {
+        if (dbg && lane == 0 && ecnt < 32) A.dbg[ecnt * 48 + 8 + ew] = clock64();
+        if (BWD || st.kind == CK_HIDDEN || st.kind == CK_FS) {
           // the image is written in place: its last reader (the MMA that just completed) is done
           uint8_t* dst_row = reg + st.out_off + row * 16;
           uint8_t* gdst_row = (st.gdst && !(A.xflags & 1)) ? st.gdst + (int64_t)tile * st.g_tile_stride + row * 16 : nullptr;
-          for (int b = 0; b * 32 < st.out_ch; ++b) {
-            uint32_t v[32];
-            tmem_ld32(taddr + b * 32, v);
-            tmem_ld_wait();
-            if (st.kind == CK_HIDDEN) fwd_cols32<true>(v, bias, dst_row, gdst_row, b * 32);
-            else fwd_cols32<false>(v, bias, dst_row, gdst_row, b * 32);
-          }
-          if (st.kind == CK_FS) {
-            uint32_t v[16];
-            tmem_ld16(taddr + 128, v);
-            tmem_ld_wait();
-            kept[0] = softplus_f(__uint_as_float(v[0]) + bias[128]);
-          }
-        } else if (st.kind == CK_HEADS || st.kind == CK_SIGMA) {
-          uint32_t v[16];
-          tmem_ld16(taddr, v);
-          tmem_ld_wait();
-          if (st.kind == CK_SIGMA) {
-            if (ok) A.raw[grow] = softplus_f(__uint_as_float(v[0]) + bias[0]);
-          } else {
+          if (BWD) {
+            const bool gate = st.act != nullptr;
 #pragma unroll
-            for (int e = 0; e < 5; ++e) {
-              const float x = __uint_as_float(v[e]) + bias[e];
-              kept[1 + e] = e < 3 ? sigmoid_f(x) : softplus_f(x);
-            }
-          }
-        } else if (!(A.xflags & 4)) {   // CK_RGB: the whole fp32 row block [64 rows][C] staged in the (now dead) tile region, one bulk store per half
-          float* stage = reinterpret_cast<float*>(reg);
-          const int C = A.C;
-          const int64_t row0 = (int64_t)tile * kTile;
-          const int64_t n_valid = (A.M - row0) < (int64_t)kTile ? (A.M - row0) : (int64_t)kTile;
-          const bool bulk_ok = ((n_valid < 64 ? n_valid : 64) * C) % 4 == 0 && ((n_valid > 64 ? n_valid - 64 : 0) * C) % 4 == 0;
-#pragma unroll 1
-          for (int hf = 0; hf < 2; ++hf) {
-            if (hf == 1) {                            // staging is reused: the first bulk store must have read it
-              if (gt == 0) bulk_wait_read<0>();
-              group_barrier(g);
-            }
-            if ((q >> 1) == hf) {
-              float* srow = stage + (row - hf * 64) * C;
-#pragma unroll 1
-              for (int b = 0; b < 9; ++b) {
-                uint32_t v[16];
-                tmem_ld16(taddr + b * 16, v);
+            for (int h2 = 0; h2 < 2; ++h2) {
+              if (h2 * 32 < ncol) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c_base + h2 * 32, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const int c = b * 16 + e;
-                  if (c < kHeadCh) srow[c] = __uint_as_float(v[e]) + bias[c];
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 a = av[h2 * 4 + j];
+                  uint4 pk;
+                  pk.x = pack_mask(v[8 * j + 0], v[8 * j + 1], a.x, gate);
+                  pk.y = pack_mask(v[8 * j + 2], v[8 * j + 3], a.y, gate);
+                  pk.z = pack_mask(v[8 * j + 4], v[8 * j + 5], a.z, gate);
+                  pk.w = pack_mask(v[8 * j + 6], v[8 * j + 7], a.w, gate);
+                  const int off = ((c_base >> 3) + h2 * 4 + j) * (int)kChunkBytes;
+                  *reinterpret_cast<uint4*>(dst_row + off) = pk;
+                  if (gdst_row != nullptr) *reinterpret_cast<uint4*>(gdst_row + off) = pk;
                 }
               }
-              srow[131] = kept[0];
-              if (C == 137) {
-#pragma unroll
-                for (int e = 0; e < 5; ++e) srow[132 + e] = kept[1 + e];
-              }
             }
-            fence_async_smem();
-            group_barrier(g);
-            const int64_t nv = n_valid - hf * 64 < 64 ? n_valid - hf * 64 : 64;
-            if (nv > 0) {
-              float* gdst = A.raw + (row0 + hf * 64) * C;
-              if (bulk_ok) {
-                if (gt == 0) { bulk_s2g(gdst, stage, (uint32_t)(nv * C * 4)); bulk_commit(); }
+          } else {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(taddr + c_base, v0);
+            if (ncol == 64) tmem_ld32(taddr + c_base + 32, v1);
+            tmem_ld_wait();
+            if (st.kind == CK_HIDDEN) {
+            fwd_cols32<true>(v0, bias, dst_row, gdst_row, c_base);
+            if (ncol == 64) fwd_cols32<true>(v1, bias, dst_row, gdst_row, c_base + 32);
+          } else {
+            fwd_cols32<false>(v0, bias, dst_row, gdst_row, c_base);
+            if (ncol == 64) fwd_cols32<false>(v1, bias, dst_row, gdst_row, c_base + 32);
+            if (half == 1) {                           // sigma pre-activation rides in column 128 of this GEMM
+              uint32_t v[16];
+              tmem_ld16(taddr + 128, v);
+              tmem_ld_wait();
+              if (ok) rawt[131 * kTile] = softplus_f(__uint_as_float(v[0]) + bias[128]);
+            }
+          }
+          }
+        } else if (st.kind == CK_HEADS || st.kind == CK_SIGMA) {
+          if (half == 0) {
+            uint32_t v[16];
+            tmem_ld16(taddr, v);
+            tmem_ld_wait();
+            if (ok) {
+              if (st.kind == CK_SIGMA) {
+                rawt[0] = softplus_f(__uint_as_float(v[0]) + bias[0]);
               } else {
-                for (int i = gt; i < (int)(nv * C); i += 128) gdst[i] = stage[i];
+#pragma unroll
+                for (int e = 0; e < 5; ++e) {
+                  const float x = __uint_as_float(v[e]) + bias[e];
+                  rawt[(132 + e) * kTile] = e < 3 ? sigmoid_f(x) : softplus_f(x);
+                }
               }
             }
           }
-          store_pending = true;
+        } else if (!(A.xflags & 4)) {   // CK_RGB: 131 fp32 columns; half 0 -> [0, 80), half 1 -> [80, 131)
+          const int cb = half * 80;
+          const int nblk = half == 0 ? 5 : 4;          // 16-column blocks; the last one of half 1 is cut at 131
+#pragma unroll 1
+          for (int b2 = 0; b2 < nblk; ++b2) {
+            uint32_t v[16];
+            tmem_ld16(taddr + cb + b2 * 16, v);
+            tmem_ld_wait();
+            const int c0 = cb + b2 * 16;
+            if (ok) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (c0 + e < kHeadCh) rawt[(c0 + e) * kTile] = __uint_as_float(v[e]) + bias[c0 + e];
+            }
+          }
         }
         tc_fence_before();
         fence_async_smem();
-        if (dbg && gt == 0 && ecnt < 64) A.dbg[128 + ecnt * 4 + g * 2 + 1] = clock64();
+        if (dbg && lane == 0 && ecnt < 32) A.dbg[ecnt * 48 + 24 + ew] = clock64();
         if (s + 1 < A.n_steps) mbar_arrive(&bar_act[g]);   // operand of the next step is ready, accumulator drained
       }
     }
-    if (!BWD && gt == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();

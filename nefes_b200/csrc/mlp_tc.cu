@@ -458,7 +458,39 @@ __global__ void prepack_kernel(const float* __restrict__ P, PackSrc ps, PackedAr
   }
 }
 
-// pts [M,3] -> X image (64 ch: PE 63 + 0); dirs [N,3] -> DIRPE image (32 ch: PE 27 + 0 x5), one thread per point
+// positional encoding of one point -> bf16 chunks: [x, sin(2^l x), cos(2^l x)] with the base sin/cos from the accurate
+// sincosf and the octaves by the double-angle recurrence (error doubles per octave: <= 2^9 * 1e-7 = 5e-5, far below
+// the bf16 operand rounding of 4e-3).   script/models/nerfh_nff.py:241-270
+template <int FREQS, int CHUNKS>
+__device__ __forceinline__ void pe_row(const float* __restrict__ p3, bool ok, uint8_t* __restrict__ g_row) {
+  float e[CHUNKS * 8];
+#pragma unroll
+  for (int i = 0; i < CHUNKS * 8; ++i) e[i] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = ok ? p3[c] : 0.f;
+    e[c] = v;
+    float sn, cs;
+    sincosf(v, &sn, &cs);
+#pragma unroll
+    for (int l = 0; l < FREQS; ++l) {
+      e[3 + 6 * l + c] = ok ? sn : 0.f;
+      e[6 + 6 * l + c] = ok ? cs : 0.f;
+      const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
+      sn = s2; cs = c2;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CHUNKS; ++j) {
+    uint4 pk;
+    pk.x = pack_bf16(e[8 * j], e[8 * j + 1]); pk.y = pack_bf16(e[8 * j + 2], e[8 * j + 3]);
+    pk.z = pack_bf16(e[8 * j + 4], e[8 * j + 5]); pk.w = pack_bf16(e[8 * j + 6], e[8 * j + 7]);
+    *reinterpret_cast<uint4*>(g_row + j * kChunkBytes) = pk;
+  }
+}
+
+// pts [M,3] -> X image (64 ch: PE 63 + 0); dirs [N,3] -> DIRPE image (32 ch: PE 27 + 0 x5), one thread per point.
+// The images are the first operands of the forward chain AND operands of the weight-gradient kernel.
 __global__ void encode_images_kernel(const float* __restrict__ pts, const float* __restrict__ dirs, int S, int64_t M,
                                      int64_t Mp, uint8_t* __restrict__ ximg, uint8_t* __restrict__ dimg) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,79 +498,41 @@ __global__ void encode_images_kernel(const float* __restrict__ pts, const float*
   const int64_t tile = m / kTile;
   const int row = (int)(m % kTile);
   const bool ok = m < M;
-  {
-    float e[64];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float v = ok ? pts[m * 3 + c] : 0.f;
-      e[c] = v;
-      float f = 1.f;
-#pragma unroll
-      for (int l = 0; l < kXyzFreqs; ++l, f *= 2.f) {
-        float s, co;
-        sincosf(v * f, &s, &co);
-        e[3 + 6 * l + c] = ok ? s : 0.f;
-        e[6 + 6 * l + c] = ok ? co : 0.f;
-      }
-    }
-    e[63] = 0.f;
-    uint8_t* base = ximg + tile * (64 * 256) + row * 16;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint4 pk;
-      pk.x = pack_bf16(e[8 * j], e[8 * j + 1]); pk.y = pack_bf16(e[8 * j + 2], e[8 * j + 3]);
-      pk.z = pack_bf16(e[8 * j + 4], e[8 * j + 5]); pk.w = pack_bf16(e[8 * j + 6], e[8 * j + 7]);
-      *reinterpret_cast<uint4*>(base + j * kChunkBytes) = pk;
-    }
-  }
-  if (dimg != nullptr) {
-    float e[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) e[i] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float v = ok ? dirs[(m / S) * 3 + c] : 0.f;
-      e[c] = v;
-      float f = 1.f;
-#pragma unroll
-      for (int l = 0; l < kDirFreqs; ++l, f *= 2.f) {
-        float s, co;
-        sincosf(v * f, &s, &co);
-        e[3 + 6 * l + c] = ok ? s : 0.f;
-        e[6 + 6 * l + c] = ok ? co : 0.f;
-      }
-    }
-    uint8_t* base = dimg + tile * (32 * 256) + row * 16;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 pk;
-      pk.x = pack_bf16(e[8 * j], e[8 * j + 1]); pk.y = pack_bf16(e[8 * j + 2], e[8 * j + 3]);
-      pk.z = pack_bf16(e[8 * j + 4], e[8 * j + 5]); pk.w = pack_bf16(e[8 * j + 6], e[8 * j + 7]);
-      *reinterpret_cast<uint4*>(base + j * kChunkBytes) = pk;
-    }
-  }
+  pe_row<kXyzFreqs, 8>(pts + (ok ? m : 0) * 3, ok, ximg + tile * (64 * 256) + row * 16);
+  if (dimg != nullptr) pe_row<kDirFreqs, 4>(dirs + (ok ? m / S : 0) * 3, ok, dimg + tile * (32 * 256) + row * 16);
 }
 
-// d_raw (fp32, row-major) -> gradient images of the head pre-activations.
+// tile-major raw blocks [T][C][128] <-> row-major [M][C]   (public row-major API of the field query)
+__global__ void tiles_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t M, int C) {
+  const int64_t tile = blockIdx.x;
+  const int64_t n_valid = min((int64_t)kTile, M - tile * kTile);
+  const float* s = src + tile * C * kTile;
+  float* d = dst + tile * kTile * C;
+  for (int i = threadIdx.x; i < (int)n_valid * C; i += blockDim.x) d[i] = s[(i % C) * kTile + i / C];
+}
+
+// d_raw (fp32) -> gradient images of the head pre-activations.  Element (row r of tile t, column c) of raw / d_raw sits
+// at  t*C*128 + r*rs + c*cs : row-major rs = C, cs = 1; tile-major rs = 1, cs = 128 (then every load is coalesced).
 //   C == 137: GRGB (144 ch), GTH (16 ch), sigma grad into channel 128 of GFS (chunks 16,17)
 //   C == 132: GRGB, GFS chunks 16,17            C == 1: GSIG (16 ch)
-__global__ void head_grad_images_kernel(const float* __restrict__ raw, const float* __restrict__ d_raw, int C, int64_t M,
-                                        int64_t Mp, uint8_t* __restrict__ grgb, uint8_t* __restrict__ gth,
+__global__ void head_grad_images_kernel(const float* __restrict__ raw, const float* __restrict__ d_raw, int C, int rs, int cs,
+                                        int64_t M, int64_t Mp, uint8_t* __restrict__ grgb, uint8_t* __restrict__ gth,
                                         uint8_t* __restrict__ gfs, int64_t gfs_tile_stride, int gfs_chunk0) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Mp) return;
   const int64_t tile = m / kTile;
   const int row = (int)(m % kTile);
   const bool ok = m < M;
-  const float* y = raw + m * C;
-  const float* gd = d_raw + m * C;
+  const int64_t base = ok ? tile * C * kTile + (int64_t)row * rs : 0;
+  const float* y = raw + base;
+  const float* gd = d_raw + base;
   const int sig_col = (C == 1) ? 0 : 131;
-  const float dsig = ok ? gd[sig_col] * (1.f - expf(-y[sig_col])) : 0.f;
+  const float dsig = ok ? gd[(int64_t)sig_col * cs] * (1.f - expf(-y[(int64_t)sig_col * cs])) : 0.f;
   {  // sigma pre-activation gradient: channel 0 of a 16-channel group, rest zero
-    uint8_t* base = gfs + tile * gfs_tile_stride + (int64_t)gfs_chunk0 * kChunkBytes + row * 16;
+    uint8_t* base_s = gfs + tile * gfs_tile_stride + (int64_t)gfs_chunk0 * kChunkBytes + row * 16;
     uint4 pk = make_uint4(pack_bf16(dsig, 0.f), 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(base) = pk;
-    *reinterpret_cast<uint4*>(base + kChunkBytes) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(base_s) = pk;
+    *reinterpret_cast<uint4*>(base_s + kChunkBytes) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (C == 1) return;
   uint8_t* rb = grgb + tile * (144 * 256) + row * 16;
@@ -547,7 +541,7 @@ __global__ void head_grad_images_kernel(const float* __restrict__ raw, const flo
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int c = 8 * j + q;
-      e[q] = (ok && c < kHeadCh) ? gd[c] : 0.f;
+      e[q] = (ok && c < kHeadCh) ? gd[(int64_t)c * cs] : 0.f;
     }
     uint4 pk;
     pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
@@ -557,9 +551,9 @@ __global__ void head_grad_images_kernel(const float* __restrict__ raw, const flo
     float e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (ok) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) e[c] = gd[132 + c] * y[132 + c] * (1.f - y[132 + c]);
-      e[3] = gd[135] * (1.f - expf(-y[135]));
-      e[4] = gd[136] * (1.f - expf(-y[136]));
+      for (int c = 0; c < 3; ++c) { const float yc = y[(int64_t)(132 + c) * cs]; e[c] = gd[(int64_t)(132 + c) * cs] * yc * (1.f - yc); }
+      e[3] = gd[(int64_t)135 * cs] * (1.f - expf(-y[(int64_t)135 * cs]));
+      e[4] = gd[(int64_t)136 * cs] * (1.f - expf(-y[(int64_t)136 * cs]));
     }
     uint8_t* tb = gth + tile * (16 * 256) + row * 16;
     uint4 pk;
@@ -613,7 +607,6 @@ struct Img { uint8_t* p; int ch; int64_t tile_stride() const { return (int64_t)c
 struct Ws {             // saved-for-backward (forward writes, backward reads)
   uint8_t* arena;
   Img X, DIRPE, H[8], FIN, DT, T2, T3;
-  uint4* mask[11];      // 0..7: h1..h8, 8: DT, 9: t2, 10: t3
   int64_t bytes;
 };
 struct WsB {            // backward scratch
@@ -632,17 +625,11 @@ Ws carve_ws(void* base, int64_t T, int mode) {
   w.arena = take(packed_arena().bytes);
   w.X = img(64);
   for (int l = 0; l < 8; ++l) w.H[l] = img(128);
-  for (int l = 0; l < 8; ++l) w.mask[l] = (uint4*)take(T * kTile * 16);
   if (mode != NEFES_MODE_SIGMA) {
     w.DIRPE = img(32);
     w.FIN = img(128);
     w.DT = img(mode == NEFES_MODE_FULL ? 128 : 64);
-    w.mask[8] = (uint4*)take(T * kTile * 16);
-    if (mode == NEFES_MODE_FULL) {
-      w.T2 = img(64); w.T3 = img(64);
-      w.mask[9] = (uint4*)take(T * kTile * 16);
-      w.mask[10] = (uint4*)take(T * kTile * 16);
-    }
+    if (mode == NEFES_MODE_FULL) { w.T2 = img(64); w.T3 = img(64); }
   }
   w.bytes = (int64_t)(p - (uint8_t*)base);
   return w;
@@ -774,7 +761,7 @@ long long* chain_dbg_buf() {
   static long long* d = nullptr;
   static int on = -1;
   if (on < 0) { const char* e = getenv("NEFES_CHAIN_DBG"); on = (e && e[0] == '1') ? 1 : 0; }
-  if (on && d == nullptr) { cudaMalloc(&d, 512 * sizeof(long long)); }
+  if (on && d == nullptr) { cudaMalloc(&d, 2048 * sizeof(long long)); }
   return on ? d : nullptr;
 }
 void chain_dbg_dump(const char* what, const ChainArgs& c, cudaStream_t st) {
@@ -783,14 +770,22 @@ void chain_dbg_dump(const char* what, const ChainArgs& c, cudaStream_t st) {
   if (dumps >= 6) return;
   ++dumps;
   cudaStreamSynchronize(st);
-  long long h[512];
+  static long long h[2048];
   cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost);
   const long long t0 = h[0];
-  fprintf(stderr, "[chain dbg] %s: n_steps=%d tiles=%d\n", what, c.n_steps, c.n_tiles);
-  for (int i = 0; i < 2 * c.n_steps && i < 64; ++i)
-    fprintf(stderr, "  seq %2d step %2d | mma commit t0 %8lld t1 %8lld | epi0 ready %8lld done %8lld | epi1 ready %8lld done %8lld\n", i,
-            i % c.n_steps, h[i * 2] - t0, h[i * 2 + 1] - t0, h[128 + i * 4] - t0, h[128 + i * 4 + 1] - t0,
-            h[128 + i * 4 + 2] - t0, h[128 + i * 4 + 3] - t0);
+  fprintf(stderr, "[chain dbg] %s: n_steps=%d tiles=%d  (cycles since the first weight tile landed)\n", what, c.n_steps, c.n_tiles);
+  for (int i = 0; i < 2 * c.n_steps && i < 32; ++i) {
+    const long long* r = h + i * 48;
+    long long lo[2] = {1ll << 62, 1ll << 62}, hi[2] = {0, 0}, rd[2] = {0, 0};
+    for (int w = 0; w < 16; ++w) {
+      lo[w >> 3] = r[24 + w] < lo[w >> 3] ? r[24 + w] : lo[w >> 3];
+      hi[w >> 3] = r[24 + w] > hi[w >> 3] ? r[24 + w] : hi[w >> 3];
+      rd[w >> 3] = r[8 + w] > rd[w >> 3] ? r[8 + w] : rd[w >> 3];
+    }
+    fprintf(stderr, "  seq %2d step %2d | W ok %7lld | t0: A ok %7lld commit %7lld | t1: A ok %7lld commit %7lld | epi0 ready %7lld done %7lld..%7lld | epi1 ready %7lld done %7lld..%7lld\n",
+            i, i % c.n_steps, r[0] - t0, r[1] - t0, r[3] - t0, r[2] - t0, r[4] - t0, rd[0] - t0, lo[0] - t0, hi[0] - t0,
+            rd[1] - t0, lo[1] - t0, hi[1] - t0);
+  }
 }
 
 // weight image streamed in pieces: the whole image, or rows [row0, row0 + 128) of every 8-wide chunk (compacted)
@@ -802,41 +797,50 @@ void set_weights(ChainStep& s, const uint8_t* img, int chunks, int rows, int row
   else { s.w_piece = (uint32_t)take_rows * 16u; s.w_src_stride = (uint32_t)rows * 16u; }
 }
 
-// Build the step table of the fused forward chain for (net, mode) and launch it.
-int launch_chain_fwd(const Ws& w, const Arena& A, int mode, const float* pts, const float* dirs, int64_t N, int S,
-                     float* raw, cudaStream_t st) {
-  const int64_t M = N * S;
+// Build the step table of the fused forward chain for (net, mode) and launch it.  raw_t: tile-major [T][C][128].
+int launch_chain_fwd(const Ws& w, const Arena& A, int mode, int64_t M, float* raw_t, cudaStream_t st) {
   const int T = (int)ceil_div(M, kTile);
   ChainArgs c = {};
   int n = 0;
-  auto add = [&](int pl, uint32_t a_off, int kind, uint32_t out_off, int out_ch, const Img* save) {
+  enum { LD_X = 0, LD_D = 1 };
+  auto add = [&](int pl, uint32_t a_off, int kind, uint32_t out_off, int out_ch, const Img* save, int wait_load) {
     ChainStep& s = c.step[n++];
     const PackedDims pd = packed_dims(pl);
     s.a_off = a_off; s.out_off = out_off; s.K = (uint16_t)pd.K; s.N = (uint16_t)pd.N; s.out_ch = (uint16_t)out_ch;
-    s.kind = (uint8_t)kind; s.wait_load = -1; s.bias = A.bias(pl);
+    s.kind = (uint8_t)kind; s.wait_load = (int8_t)wait_load; s.wait_load2 = -1; s.bias = A.bias(pl);
     set_weights(s, A.W(pl), pd.K / 8, pd.N, 0, pd.N);
     s.gdst = save ? save->p : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u;
   };
-  add(PL_T0, kRegX, CK_HIDDEN, kRegH, 128, &w.H[0]);
-  for (int l = 1; l < 8; ++l) add(PL_T0 + l, l == 4 ? kRegX : kRegH, CK_HIDDEN, kRegH, 128, &w.H[l]);
+  auto load = [&](int idx, const Img& img, uint32_t dst_off, int issue_step) {
+    ChainLoad& L = c.load[idx];
+    L.src = img.p; L.tile_stride = (uint32_t)img.tile_stride(); L.bytes = (uint32_t)img.ch * 256u;
+    L.dst_off = dst_off; L.issue_step = (int8_t)issue_step; L.next_pair = 1;
+  };
+  add(PL_T0, kRegX, CK_HIDDEN, kRegH, 128, &w.H[0], LD_X);
+  for (int l = 1; l < 8; ++l) add(PL_T0 + l, l == 4 ? kRegX : kRegH, CK_HIDDEN, kRegH, 128, &w.H[l], -1);
+  for (int l = 0; l < kChainLoads; ++l) c.load[l].issue_step = -1;
   if (mode == NEFES_MODE_SIGMA) {
-    add(PL_SIG, kRegH, CK_SIGMA, 0, 0, nullptr);
+    add(PL_SIG, kRegH, CK_SIGMA, 0, 0, nullptr, -1);
+    load(LD_X, w.X, kRegX, 5);                                    // the xyz slot is dead once the skip layer retired
   } else {
-    add(PL_FS, kRegH, CK_FS, kRegH, 128, &w.FIN);
+    add(PL_FS, kRegH, CK_FS, kRegH, 128, &w.FIN, -1);
     if (mode == NEFES_MODE_FULL) {
-      add(PL_DT, kRegH, CK_HIDDEN, kRegH, 128, &w.DT);
-      add(PL_TE1, kRegH + 16384, CK_HIDDEN, kRegX, 64, &w.T2);        // t1 -> t2 (parked in the xyzPE slot)
-      add(PL_TE2, kRegX, CK_HIDDEN, kRegH + 16384, 64, &w.T3);        // t2 -> t3 (over t1)
-      add(PL_TH, kRegH + 16384, CK_HEADS, 0, 0, nullptr);
+      add(PL_DT, kRegH, CK_HIDDEN, kRegH, 128, &w.DT, LD_D);
+      add(PL_TE1, kRegH + 16384, CK_HIDDEN, kRegX, 64, &w.T2, -1);        // t1 -> t2 (parked in the xyzPE slot)
+      add(PL_TE2, kRegX, CK_HIDDEN, kRegH + 16384, 64, &w.T3, -1);        // t2 -> t3 (over t1)
+      add(PL_TH, kRegH + 16384, CK_HEADS, 0, 0, nullptr, -1);
+      load(LD_X, w.X, kRegX, 12);                                 // ... here only after t2 was consumed
+      load(LD_D, w.DIRPE, kRegD, 10);
     } else {
-      add(PL_DIR, kRegH, CK_HIDDEN, kRegH, 64, &w.DT);
+      add(PL_DIR, kRegH, CK_HIDDEN, kRegH, 64, &w.DT, LD_D);
+      load(LD_X, w.X, kRegX, 5);
+      load(LD_D, w.DIRPE, kRegD, 10);
     }
-    add(PL_RGB, kRegH, CK_RGB, 0, 0, nullptr);
+    add(PL_RGB, kRegH, CK_RGB, 0, 0, nullptr, -1);
   }
-  c.n_steps = n;
-  c.pts = pts; c.dirs = dirs; c.S = S; c.M = M; c.n_tiles = T;
-  c.raw = raw; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
-  c.x_img = w.X.p; c.d_img = (mode == NEFES_MODE_SIGMA) ? nullptr : w.DIRPE.p;
+  c.n_steps = n; c.n_loads = kChainLoads;
+  c.M = M; c.n_tiles = T;
+  c.raw = raw_t; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
   c.dbg = chain_dbg_buf();
   { const char* e = getenv("NEFES_CHAIN_X"); c.xflags = e ? atoi(e) : 0; }
   static bool attr_done = false;
@@ -864,7 +868,7 @@ int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_
     ChainStep& s = c.step[n++];
     const PackedDims pd = packed_dims(pl);
     s.a_off = a_off; s.out_off = out_off; s.K = (uint16_t)k_ch; s.N = (uint16_t)n_in; s.out_ch = (uint16_t)n_in;
-    s.kind = CK_DGRAD; s.wait_load = (int8_t)wait_load; s.bias = nullptr;
+    s.kind = CK_DGRAD; s.wait_load = (int8_t)wait_load; s.wait_load2 = -1; s.bias = nullptr;
     set_weights(s, A.WT(pl), k_ch / 8, pd.K, row0, n_in);
     s.act = act ? act->p + (int64_t)act_ch0 * 256 : nullptr; s.act_tile_stride = act ? (uint32_t)act->tile_stride() : 0u;
     s.gdst = save ? save->p + (int64_t)save_ch0 * 256 : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u;
@@ -916,25 +920,20 @@ int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_
   chain_dbg_dump("bwd", c, st);
   return NEFES_OK;
 }
-bool use_chain() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("NEFES_CHAIN"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
 }  // namespace
 
 int mlp_workspace_bf16(int net, int mode, int64_t M, int64_t N, int64_t* saved, int64_t* sf, int64_t* sb) {
   (void)net;
   const int64_t T = ceil_div(M, kTile);
+  const int C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
   *saved = carve_ws(nullptr, T, mode).bytes + 1024;
-  *sf = 1024;
+  *sf = T * C * kTile * 4 + 1024;                  // tile-major raw block when the caller wants rows
   *sb = carve_wsb(nullptr, T, mode, N).bytes + 1024;
   return NEFES_OK;
 }
 
 int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const float* dirs, int64_t N, int S, float* raw,
-                 void* saved, void* scratch, cudaStream_t st) {
-  (void)scratch;
+                 void* saved, void* scratch, int layout, cudaStream_t st) {
   const int64_t M = N * S;
   const int T = (int)ceil_div(M, kTile);
   const int64_t Mp = (int64_t)T * kTile;
@@ -945,62 +944,22 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
 
   prepack_kernel<<<256, 256, 0, st>>>(P, pack_src(net), A.ar, w.arena, fine ? 1 : 0);
   NEFES_CHECK_LAUNCH("prepack");
-  if (use_chain()) return launch_chain_fwd(w, A, mode, pts, dirs, N, S, raw, st);   // NEFES_CHAIN=0: layer-at-a-time
   encode_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(pts, dirs, S, M, Mp, w.X.p,
                                                                     mode == NEFES_MODE_SIGMA ? nullptr : w.DIRPE.p);
   NEFES_CHECK_LAUNCH("encode_images");
-
-  auto hidden = [&](int pl, ASrc a0, const ASrc* a1, Img out, uint4* mask) {
-    GemmDesc d;
-    const PackedDims pd = packed_dims(pl);
-    d.a[0] = a0; if (a1) { d.a[1] = *a1; d.n_src = 2; }
-    d.K = pd.K; d.N = pd.N; d.w_img = A.W(pl); d.w_rows = pd.N; d.bias = A.bias(pl);
-    d.out_img = out.p; d.out_tile_stride = out.tile_stride(); d.out_ch = out.ch; d.relu = 1; d.mask_out = mask;
-    return launch_tile_gemm(d, T, M, st, "fwd hidden layer");
-  };
-  TRY(hidden(PL_T0, src_of(w.X), nullptr, w.H[0], w.mask[0]));
-  for (int l = 1; l < 8; ++l) {
-    if (l == 4) { ASrc h4 = src_of(w.H[3]); TRY(hidden(PL_T4, src_of(w.X), &h4, w.H[4], w.mask[4])); }
-    else TRY(hidden(PL_T0 + l, src_of(w.H[l - 1]), nullptr, w.H[l], w.mask[l]));
-  }
-  if (mode == NEFES_MODE_SIGMA) {
-    GemmDesc d;
-    d.a[0] = src_of(w.H[7]); d.K = 128; d.N = 16; d.w_img = A.W(PL_SIG); d.w_rows = 16; d.bias = A.bias(PL_SIG);
-    d.raw = raw; d.raw_ld = 1; d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = 1; d.raw_act = RAW_ACT_SOFTPLUS;
-    return launch_tile_gemm(d, T, M, st, "fwd sigma head");
-  }
-  {  // final (128, no activation) + sigma (softplus -> raw[:,131])
-    GemmDesc d;
-    d.a[0] = src_of(w.H[7]); d.K = 128; d.N = 144; d.w_img = A.W(PL_FS); d.w_rows = 144; d.bias = A.bias(PL_FS);
-    d.out_img = w.FIN.p; d.out_tile_stride = w.FIN.tile_stride(); d.out_ch = 128; d.relu = 0;
-    d.raw = raw; d.raw_ld = C; d.raw_col0 = 131; d.d_col0 = 128; d.raw_ncol = 1; d.raw_act = RAW_ACT_SOFTPLUS;
-    TRY(launch_tile_gemm(d, T, M, st, "fwd final+sigma"));
-  }
-  {  // [final | dirPE] -> dir hidden (+ transient hidden 0)
-    const int pl = (mode == NEFES_MODE_FULL) ? PL_DT : PL_DIR;
-    ASrc dp = src_of(w.DIRPE);
-    TRY(hidden(pl, src_of(w.FIN), &dp, w.DT, w.mask[8]));
-  }
-  {  // rgb + feature head (131, no activation) -> raw[:, 0:131]
-    GemmDesc d;
-    d.a[0] = src_of(w.DT, 0, 64); d.K = 64; d.N = 144; d.w_img = A.W(PL_RGB); d.w_rows = 144; d.bias = A.bias(PL_RGB);
-    d.raw = raw; d.raw_ld = C; d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = kHeadCh; d.raw_act = RAW_ACT_NONE;
-    TRY(launch_tile_gemm(d, T, M, st, "fwd rgb head"));
-  }
-  if (mode == NEFES_MODE_FULL) {
-    TRY(hidden(PL_TE1, src_of(w.DT, 64, 64), nullptr, w.T2, w.mask[9]));
-    TRY(hidden(PL_TE2, src_of(w.T2), nullptr, w.T3, w.mask[10]));
-    GemmDesc d;
-    d.a[0] = src_of(w.T3); d.K = 64; d.N = 16; d.w_img = A.W(PL_TH); d.w_rows = 16; d.bias = A.bias(PL_TH);
-    d.raw = raw; d.raw_ld = C; d.raw_col0 = 132; d.d_col0 = 0; d.raw_ncol = 5; d.raw_act = RAW_ACT_THEADS;
-    TRY(launch_tile_gemm(d, T, M, st, "fwd transient heads"));
+  const bool direct = (layout == NEFES_RAW_TILES) || C == 1;      // C == 1: the two layouts coincide
+  float* raw_t = direct ? raw : reinterpret_cast<float*>(scratch);
+  TRY(launch_chain_fwd(w, A, mode, M, raw_t, st));
+  if (!direct) {
+    tiles_to_rows_kernel<<<T, 256, 0, st>>>(raw_t, raw, M, C);
+    NEFES_CHECK_LAUNCH("tiles_to_rows");
   }
   return NEFES_OK;
 }
 
 int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const float* dirs, int64_t N, int S,
                  const float* raw, const float* d_raw, const void* saved, void* scratch, float* dP, float* d_pts,
-                 float* d_dirs, cudaStream_t st) {
+                 float* d_dirs, int layout, cudaStream_t st) {
   (void)P;
   const int64_t M = N * S;
   const int T = (int)ceil_div(M, kTile);
@@ -1011,42 +970,12 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   Arena A = {w.arena, packed_arena()};
 
   const Img& gsig_img = (mode == NEFES_MODE_SIGMA) ? b.GSIG : b.GFS;
+  const bool tiles = layout == NEFES_RAW_TILES;
   head_grad_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(
-      raw, d_raw, C, M, Mp, b.GRGB.p, b.GTH.p, gsig_img.p, gsig_img.tile_stride(), mode == NEFES_MODE_SIGMA ? 0 : 16);
+      raw, d_raw, C, tiles ? 1 : C, tiles ? kTile : 1, M, Mp, b.GRGB.p, b.GTH.p, gsig_img.p, gsig_img.tile_stride(),
+      mode == NEFES_MODE_SIGMA ? 0 : 16);
   NEFES_CHECK_LAUNCH("head_grad_images");
-
-  if (use_chain()) {
-    TRY(launch_chain_bwd(w, b, A, mode, M, st));
-  } else {
-  // dA[pts, Kin] = G[pts, Nout] * W  (B operand = WT image rows [row0, row0 + n_out_cols))
-  auto dgrad = [&](int pl, ASrc gsrc, int g_ch, int row0, int n_cols, uint8_t* out, int64_t out_stride, int out_ch,
-                   const uint4* mask, int mask_shift) {
-    GemmDesc d;
-    const PackedDims pd = packed_dims(pl);
-    d.a[0] = gsrc; d.K = g_ch; d.N = n_cols; d.w_img = A.WT(pl); d.w_rows = pd.K; d.w_row0 = row0;
-    d.out_img = out; d.out_tile_stride = out_stride; d.out_ch = out_ch; d.relu = 0; d.mask_in = mask; d.mask_shift = mask_shift;
-    return launch_tile_gemm(d, T, M, st, "dgrad");
-  };
-
-  if (mode != NEFES_MODE_SIGMA) {
-    const int dt_ch = w.DT.ch;
-    if (mode == NEFES_MODE_FULL) {
-      TRY(dgrad(PL_TH, src_of(b.GTH), 16, 0, 64, b.GT3.p, b.GT3.tile_stride(), 64, w.mask[10], 0));
-      TRY(dgrad(PL_TE2, src_of(b.GT3), 64, 0, 64, b.GT2.p, b.GT2.tile_stride(), 64, w.mask[9], 0));
-      TRY(dgrad(PL_TE1, src_of(b.GT2), 64, 0, 64, b.GDT.p + 64 * 256, b.GDT.tile_stride(), 64, w.mask[8], 64));
-    }
-    TRY(dgrad(PL_RGB, src_of(b.GRGB), 144, 0, 64, b.GDT.p, b.GDT.tile_stride(), 64, w.mask[8], 0));
-    TRY(dgrad(mode == NEFES_MODE_FULL ? PL_DT : PL_DIR, src_of(b.GDT), dt_ch, 0, 128, b.GFS.p, b.GFS.tile_stride(), 128,
-              nullptr, 0));
-    TRY(dgrad(PL_FS, src_of(b.GFS), 144, 0, 128, b.G[7].p, b.G[7].tile_stride(), 128, w.mask[7], 0));
-  } else {
-    TRY(dgrad(PL_SIG, src_of(b.GSIG), 16, 0, 128, b.G[7].p, b.G[7].tile_stride(), 128, w.mask[7], 0));
-  }
-  for (int l = 7; l >= 1; --l)   // G[l] = grad wrt pre-activation of trunk layer l  ->  G[l-1]
-    TRY(dgrad(PL_T0 + l, src_of(b.G[l]), 128, l == 4 ? 64 : 0, 128, b.G[l - 1].p, b.G[l - 1].tile_stride(), 128,
-              w.mask[l - 1], 0));
-
-  }
+  TRY(launch_chain_bwd(w, b, A, mode, M, st));
 
   // ---- gradients to the inputs (pose refinement): fp32 out of the GEMM, then the SIMT PE backward ------
   if (d_pts != nullptr) {        // d xyzPE = G5 W_T4[:, :63] + G1 W_T0 as ONE GEMM over the concatenated K = [G5 | G1]

@@ -69,8 +69,12 @@ def run_network_NeRFH_NFF(inputs, viewdirs, ts, fn, embed_fn=None, embeddirs_fn=
     rays_per_chunk = max(1, int(netchunk) // n_samples)
     if n_rays <= rays_per_chunk:
         return fn.query(inputs, viewdirs, mode)
+    if (rays_per_chunk * n_samples) % 128:                    # keep chunk boundaries on tile boundaries
+        rays_per_chunk = max(1, rays_per_chunk - rays_per_chunk % 128)
     outs = [fn.query(inputs[i:i + rays_per_chunk], None if viewdirs is None else viewdirs[i:i + rays_per_chunk], mode)
             for i in range(0, n_rays, rays_per_chunk)]
+    if isinstance(outs[0], ops.TiledRaw):
+        return ops.TiledRaw.cat(outs)
     return torch.cat(outs, 0)
 
 

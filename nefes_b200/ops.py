@@ -174,11 +174,60 @@ def encode_pe(x, n_freqs):
 # ------------------------------------------------------------------------------------------------
 # K5 field query (PE + MLP)
 # ------------------------------------------------------------------------------------------------
-class _FieldQuery(Function):
-    """pts [N,S,3], dirs [N,3] (or None for MODE_SIGMA), flat params -> raw [N,S,C]."""
+class TiledRaw:
+    """raw [N,S,C] held in the engine's tile-major layout: `t` is [ceil(N*S/128), C, 128] fp32 (blocks of 128
+    consecutive points, channel-major inside a block -- what the fused MLP chain writes with coalesced stores and the
+    compositing kernels read).  Stays inside render_rays; `.rows()` gives the reference's [N,S,C] tensor."""
+
+    def __init__(self, t, N, S, C_):
+        self.t, self.N, self.S, self.C = t, N, S, C_
+
+    @property
+    def shape(self):
+        return torch.Size((self.N, self.S, self.C))
+
+    @property
+    def device(self):
+        return self.t.device
+
+    def rows(self):
+        M = self.N * self.S
+        return self.t.permute(0, 2, 1).reshape(-1, self.C)[:M].reshape(self.N, self.S, self.C)
 
     @staticmethod
-    def forward(ctx, pts, dirs, flat, net, mode, prec):
+    def cat(parts):
+        if any((p.N * p.S) % 128 for p in parts[:-1]):
+            raise RuntimeError("nefes_b200: netchunk must cut the rays at multiples of 128 points")
+        return TiledRaw(torch.cat([p.t for p in parts], 0), sum(p.N for p in parts), parts[0].S, parts[0].C)
+
+
+_tiled_depth = 0
+
+
+class tiled_raw:
+    """Context manager used by render_rays: field queries issued inside return TiledRaw where the engine can
+    (bf16 path, samples per ray dividing 128), so raw never takes the row-major detour between the MLP and the
+    compositing kernels."""
+
+    def __enter__(self):
+        global _tiled_depth
+        _tiled_depth += 1
+
+    def __exit__(self, *a):
+        global _tiled_depth
+        _tiled_depth -= 1
+
+
+def want_tiled(prec, mode, S):
+    return _tiled_depth > 0 and prec == L.PREC_BF16 and mode != L.MODE_SIGMA and 128 % int(S) == 0
+
+
+class _FieldQuery(Function):
+    """pts [N,S,3], dirs [N,3] (or None for MODE_SIGMA), flat params -> raw [N,S,C]
+    (tiled=True: the tile-major block tensor [T,C,128] of TiledRaw)."""
+
+    @staticmethod
+    def forward(ctx, pts, dirs, flat, net, mode, prec, tiled):
         L.need_cuda(pts, dirs, flat)
         pts_c = L.f32c(pts)
         N, S = pts_c.shape[0], pts_c.shape[1]
@@ -192,20 +241,20 @@ class _FieldQuery(Function):
         sv, sf, _ = L.mlp_workspace(net, mode, prec, N * S, N)
         saved = _buf(sv, dev)
         scratch = _buf(sf, dev)
-        raw = torch.empty(N, S, Cc, device=dev)
+        raw = torch.empty((N * S + 127) // 128, Cc, 128, device=dev) if tiled else torch.empty(N, S, Cc, device=dev)
+        fn = L.lib().nefes_mlp_fwd_tiles if tiled else L.lib().nefes_mlp_fwd
         with torch.cuda.device(dev), _Timed("mlp_fwd"):
-            L.check(L.lib().nefes_mlp_fwd(L.ptr(flat_c), net, mode, prec, L.ptr(pts_c), L.ptr(dirs_c), N, S,
-                                          L.ptr(raw), L.ptr(saved), L.ptr(scratch), L.stream_of(pts_c)),
-                    "nefes_mlp_fwd")
+            L.check(fn(L.ptr(flat_c), net, mode, prec, L.ptr(pts_c), L.ptr(dirs_c), N, S,
+                       L.ptr(raw), L.ptr(saved), L.ptr(scratch), L.stream_of(pts_c)), "nefes_mlp_fwd")
         if need_bwd:
             ctx.save_for_backward(pts_c, dirs_c, flat_c, raw, saved)
-            ctx.meta = (net, mode, prec, N, S, tuple(pts.shape), None if dirs is None else tuple(dirs.shape))
+            ctx.meta = (net, mode, prec, N, S, tuple(pts.shape), None if dirs is None else tuple(dirs.shape), tiled)
         return raw
 
     @staticmethod
     def backward(ctx, d_raw):
         pts_c, dirs_c, flat_c, raw, saved = ctx.saved_tensors
-        net, mode, prec, N, S, pshape, dshape = ctx.meta
+        net, mode, prec, N, S, pshape, dshape, tiled = ctx.meta
         dev = pts_c.device
         d_raw = L.f32c(d_raw)
         need_p, need_d, need_w = ctx.needs_input_grad[:3]
@@ -214,16 +263,21 @@ class _FieldQuery(Function):
         d_flat = torch.zeros_like(flat_c) if need_w else None
         _, _, sb = L.mlp_workspace(net, mode, prec, N * S, N)
         scratch = _buf(sb, dev)
+        fn = L.lib().nefes_mlp_bwd_tiles if tiled else L.lib().nefes_mlp_bwd
         with torch.cuda.device(dev), _Timed("mlp_bwd"):
-            L.check(L.lib().nefes_mlp_bwd(L.ptr(flat_c), net, mode, prec, L.ptr(pts_c), L.ptr(dirs_c), N, S,
-                                          L.ptr(raw), L.ptr(d_raw), L.ptr(saved), L.ptr(scratch), L.ptr(d_flat),
-                                          L.ptr(d_pts), L.ptr(d_dirs), L.stream_of(pts_c)), "nefes_mlp_bwd")
+            L.check(fn(L.ptr(flat_c), net, mode, prec, L.ptr(pts_c), L.ptr(dirs_c), N, S,
+                       L.ptr(raw), L.ptr(d_raw), L.ptr(saved), L.ptr(scratch), L.ptr(d_flat),
+                       L.ptr(d_pts), L.ptr(d_dirs), L.stream_of(pts_c)), "nefes_mlp_bwd")
         return (d_pts.reshape(pshape) if d_pts is not None else None,
-                d_dirs.reshape(dshape) if d_dirs is not None else None, d_flat, None, None, None)
+                d_dirs.reshape(dshape) if d_dirs is not None else None, d_flat, None, None, None, None)
 
 
 def field_query(pts, dirs, flat, net, mode, prec=L.PREC_FP32):
-    return _FieldQuery.apply(pts, dirs, flat, int(net), int(mode), int(prec))
+    """-> raw [N,S,C]; inside a `tiled_raw()` block (render_rays) a TiledRaw where the engine supports it."""
+    if want_tiled(prec, mode, pts.shape[1]):
+        t = _FieldQuery.apply(pts, dirs, flat, int(net), int(mode), int(prec), True)
+        return TiledRaw(t, pts.shape[0], pts.shape[1], L.RAW_CH[mode])
+    return _FieldQuery.apply(pts, dirs, flat, int(net), int(mode), int(prec), False)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -235,7 +289,7 @@ class _Composite(Function):
     backward kernel instead of through a dense zero-filled slice gradient."""
 
     @staticmethod
-    def forward(ctx, raw, z, noise, mode, beta_min):
+    def forward(ctx, raw, z, noise, mode, beta_min, tiled):
         L.need_cuda(raw, z, noise)
         raw_c, z_c, noise_c = L.f32c(raw), L.f32c(z), L.f32c(noise)
         N, S = z_c.shape
@@ -253,12 +307,12 @@ class _Composite(Function):
                 tsig = torch.empty(N, S, device=dev)
         out = L.CompOut(L.ptr(rgb), L.ptr(feat), L.ptr(disp), L.ptr(acc), L.ptr(weights), L.ptr(depth), L.ptr(beta),
                         L.ptr(tsig))
+        fn = L.lib().nefes_composite_fwd_tiles if tiled else L.lib().nefes_composite_fwd
         with torch.cuda.device(dev):
-            L.check(L.lib().nefes_composite_fwd(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode,
-                                                float(beta_min), C.byref(out), L.stream_of(raw_c)),
-                    "nefes_composite_fwd")
+            L.check(fn(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode,
+                       float(beta_min), C.byref(out), L.stream_of(raw_c)), "nefes_composite_fwd")
         ctx.save_for_backward(raw_c, z_c, noise_c)
-        ctx.meta = (mode, N, S, tuple(raw.shape))
+        ctx.meta = (mode, N, S, tuple(raw.shape), tiled)
         if mode == L.COMP_SIGMA:
             return acc, weights
         if tsig is None:
@@ -268,7 +322,7 @@ class _Composite(Function):
     @staticmethod
     def backward(ctx, *grads):
         raw_c, z_c, noise_c = ctx.saved_tensors
-        mode, N, S, rshape = ctx.meta
+        mode, N, S, rshape, tiled = ctx.meta
         if mode == L.COMP_SIGMA:
             g_acc, g_w = grads
             g = dict(acc=g_acc, weights=g_w)
@@ -277,14 +331,17 @@ class _Composite(Function):
         g = {k: L.f32c(v) for k, v in g.items() if v is not None}
         gs = L.CompGrad(*[L.ptr(g.get(k)) for k in ("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig")])
         d_raw = torch.empty_like(raw_c)
+        fn = L.lib().nefes_composite_bwd_tiles if tiled else L.lib().nefes_composite_bwd
         with torch.cuda.device(raw_c.device):
-            L.check(L.lib().nefes_composite_bwd(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode, C.byref(gs),
-                                                L.ptr(d_raw), L.stream_of(raw_c)), "nefes_composite_bwd")
-        return d_raw.reshape(rshape), None, None, None, None
+            L.check(fn(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode, C.byref(gs),
+                       L.ptr(d_raw), L.stream_of(raw_c)), "nefes_composite_bwd")
+        return d_raw.reshape(rshape), None, None, None, None, None
 
 
 def composite(raw, z, noise, mode, beta_min=0.1):
-    return _Composite.apply(raw, z, noise, int(mode), float(beta_min))
+    if isinstance(raw, TiledRaw):
+        return _Composite.apply(raw.t, z, noise, int(mode), float(beta_min), True)
+    return _Composite.apply(raw, z, noise, int(mode), float(beta_min), False)
 
 
 # ------------------------------------------------------------------------------------------------
