@@ -168,6 +168,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
           bulk_g2s(smem + g * kReg + L.dst_off, L.src + (int64_t)tile * L.tile_stride, L.bytes, &bar_ld[g][li]);
         }
       };
+      // loads whose issue point is step s: their destination was last read by the MMAs of step s-1 of this pair
+      auto do_loads = [&](int s, int pair, bool valid1) {
+        for (int l = 0; l < A.n_loads; ++l) {
+          const ChainLoad& L = A.load[l];
+          if (L.issue_step != s) continue;
+          const int tp = L.next_pair ? pair + (int)gridDim.x : pair;
+          if (tp >= n_pairs) continue;
+          if (cnt > 0) {
+            mbar_wait(&bar_acc[0], (cnt - 1) & 1);
+            if (valid1) mbar_wait(&bar_acc[1], (cnt - 1) & 1);
+          }
+          issue_load(l, tp);
+        }
+      };
       for (int l = 0; l < A.n_loads; ++l)
         if (A.load[l].issue_step >= 0 && A.load[l].next_pair && (int)blockIdx.x < n_pairs) issue_load(l, blockIdx.x);
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -181,18 +195,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
           const uint8_t* src = A.step[s].w_img;
           for (uint32_t off = 0; off < bytes; off += piece, src += sstride)
             bulk_g2s(sW + slot * kWSlot + off, src, min(piece, bytes - off), &bar_wfull[slot]);
-          for (int l = 0; l < A.n_loads; ++l) {
-            const ChainLoad& L = A.load[l];
-            if (L.issue_step != s) continue;
-            const int tp = L.next_pair ? pair + (int)gridDim.x : pair;
-            if (tp >= n_pairs) continue;
-            // the destination was last read by the MMAs of step s-1 of THIS pair: wait until they retired
-            if (cnt > 0) {
-              mbar_wait(&bar_acc[0], (cnt - 1) & 1);
-              if (valid1) mbar_wait(&bar_acc[1], (cnt - 1) & 1);
-            }
-            issue_load(l, tp);
-          }
+          // slots that only die with the last step of the previous pair: after this pair's first weights are on the way
+          if (s == 0 && pair != (int)blockIdx.x) do_loads(A.n_steps, pair - (int)gridDim.x, true);
+          do_loads(s, pair, valid1);
         }
       }
     }

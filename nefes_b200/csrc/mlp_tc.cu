@@ -287,6 +287,7 @@ struct WgradJob {
   ASrc g; int g_ch;                // gradient image (MN = output channel)
   ASrc a[2]; int n_src; int a_ch;  // activation image(s) (MN = input channel)
   int pl;                          // packed layer (scatter map)
+  int no_bias;                     // 1: the bias gradient of this layer is owned by another kernel
   int64_t cost_begin;              // prefix sum of tiles*bytes_per_tile over jobs
   uint32_t tile_bytes;
 };
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
                 const int64_t idx = packed_weight_index(w.ps, J.pl, n, c0 + e);
                 if (idx >= 0) atomicAdd(w.d_flat + idx, __uint_as_float(v[e]));
               }
-            } else {
+            } else if (!J.no_bias) {
               const int64_t idx = packed_bias_index(w.ps, J.pl, n);
               if (idx >= 0) atomicAdd(w.d_flat + idx, __uint_as_float(v[0]));
             }
@@ -576,6 +577,7 @@ __global__ void ray_reduce_kernel(const float* __restrict__ src, int ld, int nco
 
 }  // namespace nefes
 #include "mlp_chain.cuh"
+#include "mlp_trunk_bwd.cuh"
 extern "C" int nefes_encode_pe_bwd(const float*, const float*, int, int64_t, int, float*, void*);
 namespace nefes {
 
@@ -858,7 +860,7 @@ int launch_chain_fwd(const Ws& w, const Arena& A, int mode, int64_t M, float* ra
 
 // Fused data-gradient chain: head-gradient images in, the gradient image of every layer's pre-activation out
 // (operands of the weight-gradient kernel); ReLU masks come from the saved activations.
-int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_t M, cudaStream_t st) {
+int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_t M, bool with_trunk, cudaStream_t st) {
   const int T = (int)ceil_div(M, kTile);
   ChainArgs c = {};
   int n = 0;
@@ -900,8 +902,9 @@ int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_
     load(LD_SIG, b.GFS, 128, 16, kRegP + 32768, 1, 0);            // P[32K:36K] is free once the RGB MMAs retired
     c.n_loads = 3;
   }
-  for (int l = 7; l >= 1; --l)   // G[l] = grad wrt pre-activation of trunk layer l  ->  G[l-1]
-    add(PL_T0 + l, 128, l == 4 ? 64 : 0, 128, kRegQ, kRegQ, &w.H[l - 1], 0, &b.G[l - 1], 0, -1);
+  if (with_trunk)
+    for (int l = 7; l >= 1; --l)   // G[l] = grad wrt pre-activation of trunk layer l  ->  G[l-1]
+      add(PL_T0 + l, 128, l == 4 ? 64 : 0, 128, kRegQ, kRegQ, &w.H[l - 1], 0, &b.G[l - 1], 0, -1);
   c.n_steps = n;
   c.M = M; c.n_tiles = T;
   c.dbg = chain_dbg_buf();
@@ -918,6 +921,40 @@ int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_
   chain_kernel<true><<<grid, kChainThreads, kBwdChainSmem, st>>>(c);
   NEFES_CHECK_LAUNCH("chain_bwd");
   chain_dbg_dump("bwd", c, st);
+  return NEFES_OK;
+}
+}  // namespace
+
+namespace {
+// Fused data + weight gradients of the eight trunk layers: four launches of two layers each (mlp_trunk_bwd.cuh).
+int launch_trunk_bwd(const Ws& w, const WsB& b, const Arena& A, int net, int64_t M, float* dP, cudaStream_t st) {
+  const int T = (int)ceil_div(M, kTile);
+  static bool attr_done = false;
+  if (!attr_done) {
+    NEFES_CUDA(cudaFuncSetAttribute(trunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrunkSmem));
+    attr_done = true;
+  }
+  const int grid = T < num_sms() ? T : num_sms();
+  for (int grp = 0; grp < 4; ++grp) {
+    const int l0 = 7 - 2 * grp, l1 = l0 - 1;        // layers of this launch: T_l0 then T_l1
+    TrunkArgs t = {};
+    t.g_in = b.G[l0].p; t.g_in_tile_stride = (uint32_t)b.G[l0].tile_stride();
+    for (int j = 0; j < 2; ++j) {
+      const int l = j == 0 ? l0 : l1;
+      TrunkStep& s = t.step[j];
+      const PackedDims pd = packed_dims(PL_T0 + l);
+      s.wt_img = A.WT(PL_T0 + l); s.wt_rows = (uint32_t)pd.K; s.wt_row0 = l == 4 ? 64u : 0u;
+      s.has_dgrad = l > 0;
+      const Img& act = l > 0 ? w.H[l - 1] : w.X;
+      s.act = act.p; s.act_tile_stride = (uint32_t)act.tile_stride(); s.act_ch = act.ch;
+      s.pl = PL_T0 + l; s.k_off = l == 4 ? 64 : 0; s.bias = 1;
+      if (l == 5) { s.g_save = b.G[4].p; s.g_save_tile_stride = (uint32_t)b.G[4].tile_stride(); }   // operand of the T4 xyz-part job
+    }
+    if (l1 > 0) { t.g_out = b.G[l1 - 1].p; t.g_out_tile_stride = (uint32_t)b.G[l1 - 1].tile_stride(); }
+    t.n_tiles = T; t.ps = pack_src(net); t.d_flat = dP;
+    trunk_bwd_kernel<<<grid, kTrunkThreads, kTrunkSmem, st>>>(t);
+    NEFES_CHECK_LAUNCH("trunk_bwd");
+  }
   return NEFES_OK;
 }
 }  // namespace
@@ -975,7 +1012,11 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
       raw, d_raw, C, tiles ? 1 : C, tiles ? kTile : 1, M, Mp, b.GRGB.p, b.GTH.p, gsig_img.p, gsig_img.tile_stride(),
       mode == NEFES_MODE_SIGMA ? 0 : 16);
   NEFES_CHECK_LAUNCH("head_grad_images");
-  TRY(launch_chain_bwd(w, b, A, mode, M, st));
+  // training (weight gradients, no gradient to the sample positions): the trunk runs as fused dgrad+wgrad launches and
+  // the chain stops at G[7]; otherwise (pose refinement) the chain runs all layers and keeps every gradient image
+  const bool fused_trunk = dP != nullptr && d_pts == nullptr && getenv("NEFES_NO_FUSED_TRUNK") == nullptr;
+  TRY(launch_chain_bwd(w, b, A, mode, M, !fused_trunk, st));
+  if (fused_trunk) TRY(launch_trunk_bwd(w, b, A, net, M, dP, st));
 
   // ---- gradients to the inputs (pose refinement): fp32 out of the GEMM, then the SIMT PE backward ------
   if (d_pts != nullptr) {        // d xyzPE = G5 W_T4[:, :63] + G1 W_T0 as ONE GEMM over the concatenated K = [G5 | G1]
@@ -1004,8 +1045,9 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   WgradArgs wa = {};
   int nj = 0;
   uint32_t max_tile_bytes = 0;
-  auto job = [&](int pl, const Img& gimg, int g_ch0, int g_ch, ASrc a0, const ASrc* a1) {
+  auto job = [&](int pl, const Img& gimg, int g_ch0, int g_ch, ASrc a0, const ASrc* a1, int no_bias = 0) {
     WgradJob& J = wa.job[nj++];
+    J.no_bias = no_bias;
     J.g = src_of(gimg, g_ch0, g_ch); J.g_ch = g_ch;
     J.a[0] = a0; J.n_src = 1; J.a_ch = (int)(a0.bytes / 256);
     if (a1) { J.a[1] = *a1; J.n_src = 2; J.a_ch += (int)(a1->bytes / 256); }
@@ -1026,11 +1068,15 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   } else {
     job(PL_SIG, b.GSIG, 0, 16, src_of(w.H[7]), nullptr);
   }
-  for (int l = 7; l >= 1; --l) {
-    if (l == 4) { ASrc h = src_of(w.H[3]); job(PL_T4, b.G[4], 0, 128, src_of(w.X), &h); }
-    else job(PL_T0 + l, b.G[l], 0, 128, src_of(w.H[l - 1]), nullptr);
+  if (fused_trunk) {
+    job(PL_T4, b.G[4], 0, 128, src_of(w.X), nullptr, 1);      // xyz columns of the skip layer (its h columns and bias: trunk launch)
+  } else {
+    for (int l = 7; l >= 1; --l) {
+      if (l == 4) { ASrc h = src_of(w.H[3]); job(PL_T4, b.G[4], 0, 128, src_of(w.X), &h); }
+      else job(PL_T0 + l, b.G[l], 0, 128, src_of(w.H[l - 1]), nullptr);
+    }
+    job(PL_T0, b.G[0], 0, 128, src_of(w.X), nullptr);
   }
-  job(PL_T0, b.G[0], 0, 128, src_of(w.X), nullptr);
   wa.n_jobs = nj;
   int64_t cost = 0;
   for (int j = 0; j < nj; ++j) { wa.job[j].cost_begin = cost; cost += (int64_t)T * wa.job[j].tile_bytes; }

@@ -166,15 +166,16 @@ def test_positional_encoding(nb):
     for L_ in (10, 4):
         xg = x.to(DEV).requires_grad_(True)
         e = ops.encode_pe(xg, L_)
-        xr = x.clone().requires_grad_(True)
+        xr = x.clone().double().requires_grad_(True)
         er = O.freq_encode(xr, L_)
-        # |arg| reaches 2^9*4 rad: fp32 argument spacing is 2.4e-4 there, both sides evaluate sin of the
-        # same rounded argument; libm differences are a few ulp.
-        assert float((e.detach().cpu() - er.detach()).abs().max()) < 2e-6
+        # |arg| reaches 2^9*4 rad: fp32 argument spacing is 2.4e-4 there; the oracle evaluates sin/cos of the SAME fp32
+        # argument (x * 2^l is exact) in fp64 -- the host's vectorised fp32 sinf is itself only accurate to 1e-4 at
+        # such arguments on some CPUs, so it cannot be the yardstick for the device's full-range sincosf.
+        assert float((e.detach().cpu().double() - er.detach()).abs().max()) < 2e-6
         k = torch.randn(er.shape, generator=gen)
         (e * k.to(DEV)).sum().backward()
-        (er * k).sum().backward()
-        assert rel_err(xg.grad, xr.grad) < 1e-5
+        (er * k.double()).sum().backward()
+        assert rel_err(xg.grad, xr.grad.float()) < 1e-5
 
 
 CASES = {

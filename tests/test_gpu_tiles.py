@@ -48,6 +48,9 @@ def test_tiled_query_and_composite_match_rows(n_rays, S, net):
     for name, x, y in zip(names, a, b):
         if name in ("raw", "weights"):
             assert torch.equal(x, y), name
-        else:   # reductions run in a different order (thread-per-channel vs warp-per-channel, atomics)
+        else:
+            # forward reductions run in a different order (thread-per-channel vs warp-per-channel): 1e-6 relative; the
+            # gradients are then re-rounded to bf16 images, where a 1-ulp input change is a 4e-3 output change
+            tol = 1e-2 if name.startswith("d_") else 2e-5
             scale = float(x.abs().max()) + 1e-12
-            assert float((x - y).abs().max()) <= 2e-4 * scale, (name, float((x - y).abs().max()), scale)
+            assert float((x - y).abs().max()) <= tol * scale, (name, float((x - y).abs().max()), scale)
