@@ -27,7 +27,8 @@ enum { CK_HIDDEN = 0,   // fwd: bias + ReLU -> image
        CK_HEADS = 2,    // fwd: columns 0..4: sigmoid x3, softplus x2 -> raw[132..136]
        CK_SIGMA = 3,    // fwd: column 0: softplus -> raw[0]                          (sigma-only mode)
        CK_RGB = 4,      // fwd: bias -> 131 fp32 columns -> raw[0..130]
-       CK_DGRAD = 5 };  // bwd: optional ReLU mask from the saved activation -> image
+       CK_DGRAD = 5,    // bwd: optional ReLU mask from the saved activation -> image
+       CK_NONE = 6 };   // first K-slice of a layer whose weights do not fit one ring slot: the next step accumulates on top
 
 constexpr int kChainLoads = 3;
 struct ChainLoad {                 // one prefetch of a per-tile operand image into the tile region
@@ -42,7 +43,9 @@ struct ChainStep {
   uint16_t K, N, out_ch;
   uint8_t kind;
   int8_t wait_load;                // index of the ChainLoad the MMA of this step must wait for (-1: none)
-  int8_t wait_load2, pad8;
+  int8_t wait_load2;
+  int8_t acc0;                     // 1: accumulate onto the previous step's partial sums (second K-slice)
+  uint16_t bias_off, pad16;        // fwd: offset of this step's biases in the shared bias table (floats)
   uint32_t w_bytes, w_lbo;         // weight image: bytes to stream (compacted), LBO = bytes between 8-wide K chunks
   uint32_t w_piece, w_src_stride;  // streamed as pieces of w_piece bytes, w_src_stride apart in the source image
   const uint8_t* w_img;
@@ -51,7 +54,7 @@ struct ChainStep {
   const uint8_t* act;              // bwd: saved activation image whose sign gates this gradient (or null)
   uint32_t g_tile_stride, act_tile_stride;
 };
-constexpr int kChainMaxSteps = 14;
+constexpr int kChainMaxSteps = 16;
 struct ChainArgs {
   ChainStep step[kChainMaxSteps];
   ChainLoad load[kChainLoads];
@@ -68,14 +71,14 @@ constexpr uint32_t kRegX = 0, kRegH = 16384, kRegD = 49152;
 // backward tile region: P (36 KB) | Q (36 KB) | S (4 KB)
 constexpr uint32_t kRegP = 0, kRegQ = 36864, kRegS = 73728;
 constexpr uint32_t kFwdRegBytes = 57344, kBwdRegBytes = 77824;
-constexpr uint32_t kFwdWSlot = 49152;        // largest forward W image: 192 x 128 bf16
+constexpr uint32_t kFwdWSlot = 49152;        // largest forward W image: 192 x 128 bf16 (a layer whose image is larger is split in two K-slices)
 constexpr uint32_t kBwdWSlot = 36864;        // largest backward WT image: 144 x 128 bf16
+constexpr int kFwdSlots = 2, kBwdSlots = 2;  // depth of the weight ring (measured: a third slot + split layers buys nothing)
 constexpr int kChainEpiWarps = 8;             // per tile
 constexpr int kChainThreads = 64 + 2 * kChainEpiWarps * 32;
-constexpr int kChainBiasStride = 160;        // floats per step in the shared bias table (N <= 160)
-constexpr uint32_t kChainBiasBytes = kChainMaxSteps * kChainBiasStride * 4;
-constexpr uint32_t kFwdChainSmem = 2 * kFwdRegBytes + 2 * kFwdWSlot + kChainBiasBytes;
-constexpr uint32_t kBwdChainSmem = 2 * kBwdRegBytes + 2 * kBwdWSlot;
+constexpr uint32_t kChainBiasBytes = 6400;   // shared bias table: sum of the layer widths of one chain (<= 1600 floats)
+constexpr uint32_t kFwdChainSmem = 2 * kFwdRegBytes + kFwdSlots * kFwdWSlot + kChainBiasBytes;
+constexpr uint32_t kBwdChainSmem = 2 * kBwdRegBytes + kBwdSlots * kBwdWSlot;
 
 __device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
 
@@ -126,18 +129,19 @@ __device__ __forceinline__ uint32_t pack_mask(uint32_t lo, uint32_t hi, uint32_t
 
 template <bool BWD>
 __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs A) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_wfull[2], bar_wempty[2], bar_act[2], bar_acc[2], bar_ld[2][kChainLoads];
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar_wfull[3], bar_wempty[3], bar_act[2], bar_acc[2], bar_ld[2][kChainLoads];
   __shared__ uint32_t tmem_slot;
   constexpr uint32_t kReg = BWD ? kBwdRegBytes : kFwdRegBytes;
   constexpr uint32_t kWSlot = BWD ? kBwdWSlot : kFwdWSlot;
+  constexpr int kSlots = BWD ? kBwdSlots : kFwdSlots;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* sW = smem + 2 * kReg;
-  float* sBias = reinterpret_cast<float*>(smem + 2 * kReg + 2 * kWSlot);
+  float* sBias = reinterpret_cast<float*>(smem + 2 * kReg + kSlots * kWSlot);
 
   if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1);
       mbar_init(&bar_act[i], kChainEpiWarps * 32); mbar_init(&bar_acc[i], 1);
       for (int l = 0; l < kChainLoads; ++l) mbar_init(&bar_ld[i][l], 1);
     }
@@ -146,7 +150,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
   if (warp == 1) tmem_alloc<512>(&tmem_slot);
   if (!BWD) {
     for (int s = 0; s < A.n_steps; ++s)
-      for (int i = threadIdx.x; i < A.step[s].N; i += kChainThreads) sBias[s * kChainBiasStride + i] = A.step[s].bias[i];
+      if (A.step[s].bias != nullptr)
+        for (int i = threadIdx.x; i < A.step[s].N; i += kChainThreads) sBias[A.step[s].bias_off + i] = A.step[s].bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -168,27 +173,26 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
           bulk_g2s(smem + g * kReg + L.dst_off, L.src + (int64_t)tile * L.tile_stride, L.bytes, &bar_ld[g][li]);
         }
       };
-      // loads whose issue point is step s: their destination was last read by the MMAs of step s-1 of this pair
-      auto do_loads = [&](int s, int pair, bool valid1) {
+      // loads whose issue point is step s: their destination was last read by the MMAs of step s-1 (both tiles).  That is
+      // exactly what releases the weight slot of step s-1, and the producer follows those phases one by one (it never
+      // lags a phase behind, so the parity wait cannot alias -- unlike a wait on the per-tile accumulator barriers, which
+      // may be several phases ahead of the producer).
+      auto do_loads = [&](int s, int pair) {
         for (int l = 0; l < A.n_loads; ++l) {
           const ChainLoad& L = A.load[l];
           if (L.issue_step != s) continue;
           const int tp = L.next_pair ? pair + (int)gridDim.x : pair;
           if (tp >= n_pairs) continue;
-          if (cnt > 0) {
-            mbar_wait(&bar_acc[0], (cnt - 1) & 1);
-            if (valid1) mbar_wait(&bar_acc[1], (cnt - 1) & 1);
-          }
+          if (cnt > 0) mbar_wait(&bar_wempty[(cnt - 1) % kSlots], ((cnt - 1) / kSlots) & 1);
           issue_load(l, tp);
         }
       };
       for (int l = 0; l < A.n_loads; ++l)
         if (A.load[l].issue_step >= 0 && A.load[l].next_pair && (int)blockIdx.x < n_pairs) issue_load(l, blockIdx.x);
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const bool valid1 = pair * 2 + 1 < A.n_tiles;
         for (int s = 0; s < A.n_steps; ++s, ++cnt) {
-          const int slot = cnt & 1;
-          mbar_wait(&bar_wempty[slot], ((cnt >> 1) & 1) ^ 1);
+          const int slot = cnt % kSlots;
+          mbar_wait(&bar_wempty[slot], ((cnt / kSlots) & 1) ^ 1);
           const uint32_t bytes = A.step[s].w_bytes;
           mbar_arrive_expect_tx(&bar_wfull[slot], bytes);
           const uint32_t piece = A.step[s].w_piece, sstride = A.step[s].w_src_stride;
@@ -196,8 +200,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
           for (uint32_t off = 0; off < bytes; off += piece, src += sstride)
             bulk_g2s(sW + slot * kWSlot + off, src, min(piece, bytes - off), &bar_wfull[slot]);
           // slots that only die with the last step of the previous pair: after this pair's first weights are on the way
-          if (s == 0 && pair != (int)blockIdx.x) do_loads(A.n_steps, pair - (int)gridDim.x, true);
-          do_loads(s, pair, valid1);
+          if (s == 0 && pair != (int)blockIdx.x) do_loads(A.n_steps, pair - (int)gridDim.x);
+          do_loads(s, pair);
         }
       }
     }
@@ -209,8 +213,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
         const bool valid1 = pair * 2 + 1 < A.n_tiles;
         for (int s = 0; s < A.n_steps; ++s, ++cnt) {
           const ChainStep& st = A.step[s];
-          const int slot = cnt & 1;
-          mbar_wait(&bar_wfull[slot], (cnt >> 1) & 1);
+          const int slot = cnt % kSlots;
+          mbar_wait(&bar_wfull[slot], (cnt / kSlots) & 1);
           if (dbg && cnt < 32) A.dbg[cnt * 48] = clock64();
           const uint32_t idesc = idesc_bf16(128, st.N, 0, 0);
           const uint64_t db0 = smem_desc(smem_u32(sW + slot * kWSlot), st.w_lbo, 128);
@@ -231,7 +235,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
             const uint64_t da0 = smem_desc(smem_u32(smem + g * kReg + st.a_off), kChunkBytes, 128);
             const uint32_t d = tmem + g * 256;
             for (int k = 0; k < st.K / 16; ++k)
-              mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k * (2 * st.w_lbo >> 4)), idesc, k > 0);
+              mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k * (2 * st.w_lbo >> 4)), idesc,
+                     (k > 0 || st.acc0) ? 1u : 0u);
             mma_commit(&bar_acc[g]);
             if (dbg && cnt < 32) A.dbg[cnt * 48 + 3 + g] = clock64();
           }
@@ -251,6 +256,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
     const uint32_t taddr = tmem + g * 256 + ((uint32_t)(q * 32) << 16);
     uint32_t acc_ph = 0u;
     uint32_t ecnt = 0;
+    bool store_pending = false;                       // a bulk store of this group may still be reading the tile region
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int tile = pair * 2 + g;
       if (tile >= A.n_tiles) break;
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
 
       for (int s = 0; s < A.n_steps; ++s, ++ecnt) {
         const ChainStep& st = A.step[s];
-        const float* bias = sBias + s * kChainBiasStride;
+        const float* bias = sBias + st.bias_off;
         const int ncol = st.out_ch >> 1;               // image columns of this warp: [c_base, c_base + ncol), 32 or 64
         const int c_base = half * ncol;
         uint4 av[8];
@@ -277,10 +283,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
         acc_ph ^= 1u;
         tc_fence_after();
         if (dbg && lane == 0 && ecnt < 32) A.dbg[ecnt * 48 + 8 + ew] = clock64();
-        if (BWD || st.kind == CK_HIDDEN || st.kind == CK_FS) {
+        if (!BWD && store_pending) {                   // forward saves leave by bulk store: it must have read its image
+          if (gt == 0) bulk_wait_read<0>();            // before anything below may overwrite the region
+          group_barrier(g);
+          store_pending = false;
+        }
+        if (!BWD && st.kind == CK_NONE) {
+          // partial sums stay in TMEM; nothing to do
+        } else if (BWD || st.kind == CK_HIDDEN || st.kind == CK_FS) {
           // the image is written in place: its last reader (the MMA that just completed) is done
           uint8_t* dst_row = reg + st.out_off + row * 16;
-          uint8_t* gdst_row = (st.gdst && !(A.xflags & 1)) ? st.gdst + (int64_t)tile * st.g_tile_stride + row * 16 : nullptr;
+          uint8_t* gdst_row = ((BWD || (A.xflags & 8)) && st.gdst && !(A.xflags & 1)) ? st.gdst + (int64_t)tile * st.g_tile_stride + row * 16 : nullptr;
           if (BWD) {
             const bool gate = st.act != nullptr;
 #pragma unroll
@@ -357,10 +370,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
         }
         tc_fence_before();
         fence_async_smem();
+        if (!BWD && st.gdst != nullptr && !(A.xflags & 9)) {   // saved for backward: the image just written, one bulk store
+          group_barrier(g);
+          if (gt == 0) {
+            bulk_s2g(st.gdst + (int64_t)tile * st.g_tile_stride, reg + st.out_off, (uint32_t)st.out_ch * 256u);
+            bulk_commit();
+          }
+          store_pending = true;
+        }
         if (dbg && lane == 0 && ecnt < 32) A.dbg[ecnt * 48 + 24 + ew] = clock64();
         if (s + 1 < A.n_steps) mbar_arrive(&bar_act[g]);   // operand of the next step is ready, accumulator drained
       }
     }
+    if (!BWD && gt == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();

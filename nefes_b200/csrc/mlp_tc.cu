@@ -116,7 +116,7 @@ __device__ __forceinline__ void epi_block(const TileGemmArgs& g, const uint32_t 
 
 template <int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1) tile_gemm_kernel(const TileGemmArgs g) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_w, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -301,7 +301,7 @@ struct WgradArgs {
 
 constexpr int kWgradMaxStages = 4;
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs w) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_full[kWgradMaxStages], bar_empty[kWgradMaxStages], bar_done;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -803,43 +803,67 @@ void set_weights(ChainStep& s, const uint8_t* img, int chunks, int rows, int row
 int launch_chain_fwd(const Ws& w, const Arena& A, int mode, int64_t M, float* raw_t, cudaStream_t st) {
   const int T = (int)ceil_div(M, kTile);
   ChainArgs c = {};
-  int n = 0;
+  int n = 0, bias_floats = 0;
   enum { LD_X = 0, LD_D = 1 };
-  auto add = [&](int pl, uint32_t a_off, int kind, uint32_t out_off, int out_ch, const Img* save, int wait_load) {
-    ChainStep& s = c.step[n++];
+  // one layer = one step, or two when its weight image exceeds a ring slot: K-slice [0, k_split) without epilogue
+  // (CK_NONE), then [k_split, K) accumulating on top.  a_off2: operand offset of the second slice.
+  auto add = [&](int pl, uint32_t a_off, int kind, uint32_t out_off, int out_ch, const Img* save, int wait_load,
+                 int k_split = 0, uint32_t a_off2 = 0, int wait_load_b = -1) {
     const PackedDims pd = packed_dims(pl);
-    s.a_off = a_off; s.out_off = out_off; s.K = (uint16_t)pd.K; s.N = (uint16_t)pd.N; s.out_ch = (uint16_t)out_ch;
-    s.kind = (uint8_t)kind; s.wait_load = (int8_t)wait_load; s.wait_load2 = -1; s.bias = A.bias(pl);
-    set_weights(s, A.W(pl), pd.K / 8, pd.N, 0, pd.N);
-    s.gdst = save ? save->p : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u;
+    const int boff = bias_floats;
+    bias_floats += (pd.N + 3) & ~3;
+    for (int part = 0; part < (k_split ? 2 : 1); ++part) {
+      ChainStep& s = c.step[n++];
+      const int k0 = part == 0 ? 0 : k_split, k1 = (k_split && part == 0) ? k_split : pd.K;
+      s.a_off = part == 0 ? a_off : a_off2; s.out_off = out_off; s.K = (uint16_t)(k1 - k0); s.N = (uint16_t)pd.N;
+      s.out_ch = (uint16_t)out_ch; s.wait_load2 = -1; s.acc0 = (int8_t)part;
+      const bool last = !k_split || part == 1;
+      s.kind = (uint8_t)(last ? kind : CK_NONE);
+      s.wait_load = (int8_t)(part == 0 ? wait_load : wait_load_b);
+      s.bias = last ? A.bias(pl) : nullptr; s.bias_off = (uint16_t)boff;
+      set_weights(s, A.W(pl) + (int64_t)(k0 / 8) * pd.N * 16, (k1 - k0) / 8, pd.N, 0, pd.N);
+      s.gdst = (save && last) ? save->p : nullptr; s.g_tile_stride = (save && last) ? (uint32_t)save->tile_stride() : 0u;
+    }
   };
   auto load = [&](int idx, const Img& img, uint32_t dst_off, int issue_step) {
     ChainLoad& L = c.load[idx];
     L.src = img.p; L.tile_stride = (uint32_t)img.tile_stride(); L.bytes = (uint32_t)img.ch * 256u;
     L.dst_off = dst_off; L.issue_step = (int8_t)issue_step; L.next_pair = 1;
   };
-  add(PL_T0, kRegX, CK_HIDDEN, kRegH, 128, &w.H[0], LD_X);
-  for (int l = 1; l < 8; ++l) add(PL_T0 + l, l == 4 ? kRegX : kRegH, CK_HIDDEN, kRegH, 128, &w.H[l], -1);
   for (int l = 0; l < kChainLoads; ++l) c.load[l].issue_step = -1;
+  add(PL_T0, kRegX, CK_HIDDEN, kRegH, 128, &w.H[0], LD_X);
+  for (int l = 1; l < 8; ++l) {
+    const uint32_t kbytes = (uint32_t)packed_dims(PL_T0 + l).K * packed_dims(PL_T0 + l).N * 2u;
+    if (l == 4 && kbytes > kFwdWSlot) add(PL_T4, kRegX, CK_HIDDEN, kRegH, 128, &w.H[4], -1, 64, kRegH);   // xyz slice, then h slice
+    else add(PL_T0 + l, l == 4 ? kRegX : kRegH, CK_HIDDEN, kRegH, 128, &w.H[l], -1);
+  }
+  const int x_dead = n;                                            // first step after the skip layer retired
   if (mode == NEFES_MODE_SIGMA) {
     add(PL_SIG, kRegH, CK_SIGMA, 0, 0, nullptr, -1);
-    load(LD_X, w.X, kRegX, 5);                                    // the xyz slot is dead once the skip layer retired
+    load(LD_X, w.X, kRegX, x_dead);
   } else {
     add(PL_FS, kRegH, CK_FS, kRegH, 128, &w.FIN, -1);
     if (mode == NEFES_MODE_FULL) {
-      add(PL_DT, kRegH, CK_HIDDEN, kRegH, 128, &w.DT, LD_D);
+      if ((uint32_t)packed_dims(PL_DT).K * packed_dims(PL_DT).N * 2u > kFwdWSlot)
+        add(PL_DT, kRegH, CK_HIDDEN, kRegH, 128, &w.DT, -1, 128, kRegD, LD_D);   // [final | dirPE]: final slice, then dirPE slice
+      else
+        add(PL_DT, kRegH, CK_HIDDEN, kRegH, 128, &w.DT, LD_D);
+      load(LD_D, w.DIRPE, kRegD, n);
       add(PL_TE1, kRegH + 16384, CK_HIDDEN, kRegX, 64, &w.T2, -1);        // t1 -> t2 (parked in the xyzPE slot)
       add(PL_TE2, kRegX, CK_HIDDEN, kRegH + 16384, 64, &w.T3, -1);        // t2 -> t3 (over t1)
       add(PL_TH, kRegH + 16384, CK_HEADS, 0, 0, nullptr, -1);
-      load(LD_X, w.X, kRegX, 12);                                 // ... here only after t2 was consumed
-      load(LD_D, w.DIRPE, kRegD, 10);
+      // the xyz slot held t2: free once the MMAs of the heads step retired (its epilogue waited for t2's bulk store)
+      load(LD_X, w.X, kRegX, n);
     } else {
       add(PL_DIR, kRegH, CK_HIDDEN, kRegH, 64, &w.DT, LD_D);
-      load(LD_X, w.X, kRegX, 5);
-      load(LD_D, w.DIRPE, kRegD, 10);
+      load(LD_X, w.X, kRegX, x_dead);
+      load(LD_D, w.DIRPE, kRegD, n);
     }
     add(PL_RGB, kRegH, CK_RGB, 0, 0, nullptr, -1);
   }
+  NEFES_REQUIRE(n <= kChainMaxSteps && bias_floats * 4 <= (int)kChainBiasBytes, NEFES_EINVAL, "chain_fwd: step table overflow");
+  for (int i = 0; i < n; ++i)
+    NEFES_REQUIRE(c.step[i].w_bytes <= kFwdWSlot, NEFES_EINVAL, "chain_fwd: weight slice of step %d exceeds the ring slot", i);
   c.n_steps = n; c.n_loads = kChainLoads;
   c.M = M; c.n_tiles = T;
   c.raw = raw_t; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
@@ -870,7 +894,7 @@ int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_
     ChainStep& s = c.step[n++];
     const PackedDims pd = packed_dims(pl);
     s.a_off = a_off; s.out_off = out_off; s.K = (uint16_t)k_ch; s.N = (uint16_t)n_in; s.out_ch = (uint16_t)n_in;
-    s.kind = CK_DGRAD; s.wait_load = (int8_t)wait_load; s.wait_load2 = -1; s.bias = nullptr;
+    s.kind = CK_DGRAD; s.wait_load = (int8_t)wait_load; s.wait_load2 = -1; s.acc0 = 0; s.bias = nullptr; s.bias_off = 0;
     set_weights(s, A.WT(pl), k_ch / 8, pd.K, row0, n_in);
     s.act = act ? act->p + (int64_t)act_ch0 * 256 : nullptr; s.act_tile_stride = act ? (uint32_t)act->tile_stride() : 0u;
     s.gdst = save ? save->p + (int64_t)save_ch0 * 256 : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u;

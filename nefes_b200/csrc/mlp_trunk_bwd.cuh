@@ -50,7 +50,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const TrunkArgs T) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_w, bar_gin[2], bar_afull[2], bar_afree[2], bar_acc, bar_gmid, bar_gout, bar_done;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
