@@ -4,8 +4,10 @@
 //   warp 0      producer: streams each step's weight image L2 -> shared (bulk copies, 2-slot ring) and prefetches the
 //               per-tile operand images (forward: xyz / direction encodings; backward: head-gradient images) for the
 //               NEXT tile pair as soon as their slot of the tile region is dead
-//   warp 1      MMA issuer: for every step, tile 0 then tile 1 (tcgen05.mma M=128, fp32 accumulators in TMEM,
-//               256 columns per tile); the tensor pipe works on one tile while the other tile's epilogue runs
+//   warp 1, 18  MMA issuers, one per tile of the pair (tcgen05.mma M=128, fp32 accumulators in TMEM, 256 columns per
+//               tile).  One thread per tile because every barrier wait / commit costs the issuing thread 200-300 cycles:
+//               with a single issuer those latencies of the two tiles add up and the tensor pipe idles half the time;
+//               with two, the pipe works on one tile while the other tile's issuer waits and its epilogue runs
 //   warps 2-9   epilogue of tile 0, warps 10-17 epilogue of tile 1: a warp owns 32 points (its TMEM lane quarter) x
 //               one half of the output columns, so every scheduler has four epilogue warps to hide tcgen05.ld / LDS
 //               latency behind each other.
@@ -75,7 +77,7 @@ constexpr uint32_t kFwdWSlot = 49152;        // largest forward W image: 192 x 1
 constexpr uint32_t kBwdWSlot = 36864;        // largest backward WT image: 144 x 128 bf16
 constexpr int kFwdSlots = 2, kBwdSlots = 2;  // depth of the weight ring (measured: a third slot + split layers buys nothing)
 constexpr int kChainEpiWarps = 8;             // per tile
-constexpr int kChainThreads = 64 + 2 * kChainEpiWarps * 32;
+constexpr int kChainThreads = 64 + 2 * kChainEpiWarps * 32 + 32;   // + a second MMA-issuer warp (tile 1)
 constexpr uint32_t kChainBiasBytes = 6400;   // shared bias table: sum of the layer widths of one chain (<= 1600 floats)
 constexpr uint32_t kFwdChainSmem = 2 * kFwdRegBytes + kFwdSlots * kFwdWSlot + kChainBiasBytes;
 constexpr uint32_t kBwdChainSmem = 2 * kBwdRegBytes + kBwdSlots * kBwdWSlot;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
   float* sBias = reinterpret_cast<float*>(smem + 2 * kReg + kSlots * kWSlot);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 2); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_act[i], kChainEpiWarps * 32); mbar_init(&bar_acc[i], 1);
       for (int l = 0; l < kChainLoads; ++l) mbar_init(&bar_ld[i][l], 1);
@@ -205,30 +207,30 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2 + 2 * kChainEpiWarps) {
     if (lane == 0) {
-      // ------------------------------- MMA issuer ----------------------------------------------------------------
-      uint32_t cnt = 0, act_ph[2] = {0u, 0u}, ld_ph[2][kChainLoads] = {};
+      // ------------------------------- MMA issuer of tile g --------------------------------------------------------
+      const int g = warp == 1 ? 0 : 1;
+      uint32_t cnt = 0, act_ph = 0u, ld_ph[kChainLoads] = {};
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const bool valid1 = pair * 2 + 1 < A.n_tiles;
+        const bool valid = pair * 2 + g < A.n_tiles;
         for (int s = 0; s < A.n_steps; ++s, ++cnt) {
           const ChainStep& st = A.step[s];
           const int slot = cnt % kSlots;
           mbar_wait(&bar_wfull[slot], (cnt / kSlots) & 1);
-          if (dbg && cnt < 32) A.dbg[cnt * 48] = clock64();
-          const uint32_t idesc = idesc_bf16(128, st.N, 0, 0);
-          const uint64_t db0 = smem_desc(smem_u32(sW + slot * kWSlot), st.w_lbo, 128);
-          for (int g = 0; g < 2; ++g) {
-            if (g == 1 && !valid1) break;
-            mbar_wait(&bar_act[g], act_ph[g]);
-            act_ph[g] ^= 1u;
+          if (dbg && g == 0 && cnt < 32) A.dbg[cnt * 48] = clock64();
+          if (valid) {
+            const uint32_t idesc = idesc_bf16(128, st.N, 0, 0);
+            const uint64_t db0 = smem_desc(smem_u32(sW + slot * kWSlot), st.w_lbo, 128);
+            mbar_wait(&bar_act[g], act_ph);
+            act_ph ^= 1u;
             if (st.wait_load >= 0) {
-              mbar_wait(&bar_ld[g][st.wait_load], ld_ph[g][st.wait_load]);
-              ld_ph[g][st.wait_load] ^= 1u;
+              mbar_wait(&bar_ld[g][st.wait_load], ld_ph[st.wait_load]);
+              ld_ph[st.wait_load] ^= 1u;
             }
             if (st.wait_load2 >= 0) {
-              mbar_wait(&bar_ld[g][st.wait_load2], ld_ph[g][st.wait_load2]);
-              ld_ph[g][st.wait_load2] ^= 1u;
+              mbar_wait(&bar_ld[g][st.wait_load2], ld_ph[st.wait_load2]);
+              ld_ph[st.wait_load2] ^= 1u;
             }
             tc_fence_after();
             if (dbg && cnt < 32) A.dbg[cnt * 48 + 1 + g] = clock64();
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
             mma_commit(&bar_acc[g]);
             if (dbg && cnt < 32) A.dbg[cnt * 48 + 3 + g] = clock64();
           }
-          mma_commit(&bar_wempty[slot]);
+          mma_commit(&bar_wempty[slot]);       // the slot is free once BOTH tiles' MMAs retired (count 2)
         }
       }
     }

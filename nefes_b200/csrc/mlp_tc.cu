@@ -463,10 +463,11 @@ __global__ void prepack_kernel(const float* __restrict__ P, PackSrc ps, PackedAr
 // sincosf and the octaves by the double-angle recurrence (error doubles per octave: <= 2^9 * 1e-7 = 5e-5, far below
 // the bf16 operand rounding of 4e-3).   script/models/nerfh_nff.py:241-270
 template <int FREQS, int CHUNKS>
-__device__ __forceinline__ void pe_row(const float* __restrict__ p3, bool ok, uint8_t* __restrict__ g_row) {
+__device__ __forceinline__ void pe_row(const float* __restrict__ p3, bool ok, uint8_t* __restrict__ g_row, float last_ch) {
   float e[CHUNKS * 8];
 #pragma unroll
   for (int i = 0; i < CHUNKS * 8; ++i) e[i] = 0.f;
+  e[CHUNKS * 8 - 1] = last_ch;       // padding channel (its weights are zero); 1 makes it a bias-gradient carrier
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float v = ok ? p3[c] : 0.f;
@@ -499,8 +500,9 @@ __global__ void encode_images_kernel(const float* __restrict__ pts, const float*
   const int64_t tile = m / kTile;
   const int row = (int)(m % kTile);
   const bool ok = m < M;
-  pe_row<kXyzFreqs, 8>(pts + (ok ? m : 0) * 3, ok, ximg + tile * (64 * 256) + row * 16);
-  if (dimg != nullptr) pe_row<kDirFreqs, 4>(dirs + (ok ? m / S : 0) * 3, ok, dimg + tile * (32 * 256) + row * 16);
+  pe_row<kXyzFreqs, 8>(pts + (ok ? m : 0) * 3, ok, ximg + tile * (64 * 256) + row * 16, 0.f);
+  // channel 31 of the direction image = 1: its column of the [dir | tenc0] weight gradient is that layer's bias gradient
+  if (dimg != nullptr) pe_row<kDirFreqs, 4>(dirs + (ok ? m / S : 0) * 3, ok, dimg + tile * (32 * 256) + row * 16, 1.f);
 }
 
 // tile-major raw blocks [T][C][128] <-> row-major [M][C]   (public row-major API of the field query)
@@ -518,9 +520,10 @@ __global__ void tiles_to_rows_kernel(const float* __restrict__ src, float* __res
 //   C == 132: GRGB, GFS chunks 16,17            C == 1: GSIG (16 ch)
 __global__ void head_grad_images_kernel(const float* __restrict__ raw, const float* __restrict__ d_raw, int C, int rs, int cs,
                                         int64_t M, int64_t Mp, uint8_t* __restrict__ grgb, uint8_t* __restrict__ gth,
-                                        uint8_t* __restrict__ gfs, int64_t gfs_tile_stride, int gfs_chunk0) {
+                                        uint8_t* __restrict__ gfs, int64_t gfs_tile_stride, int gfs_chunk0,
+                                        float* __restrict__ d_sig_bias) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= Mp) return;
+  if (m >= Mp) return;                               // Mp is a multiple of the block size: whole blocks leave together
   const int64_t tile = m / kTile;
   const int row = (int)(m % kTile);
   const bool ok = m < M;
@@ -529,6 +532,13 @@ __global__ void head_grad_images_kernel(const float* __restrict__ raw, const flo
   const float* gd = d_raw + base;
   const int sig_col = (C == 1) ? 0 : 131;
   const float dsig = ok ? gd[(int64_t)sig_col * cs] * (1.f - expf(-y[(int64_t)sig_col * cs])) : 0.f;
+  if (d_sig_bias != nullptr) {                       // bias gradient of the sigma head = sum of its pre-activation gradients
+    __shared__ float s_part[4];
+    const float ws = warp_sum(__bfloat162float(__float2bfloat16(dsig)));     // the value the tensor path sees
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ws;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(d_sig_bias, s_part[0] + s_part[1] + s_part[2] + s_part[3]);
+  }
   {  // sigma pre-activation gradient: channel 0 of a 16-channel group, rest zero
     uint8_t* base_s = gfs + tile * gfs_tile_stride + (int64_t)gfs_chunk0 * kChunkBytes + row * 16;
     uint4 pk = make_uint4(pack_bf16(dsig, 0.f), 0u, 0u, 0u);
@@ -578,6 +588,7 @@ __global__ void ray_reduce_kernel(const float* __restrict__ src, int ld, int nco
 }  // namespace nefes
 #include "mlp_chain.cuh"
 #include "mlp_trunk_bwd.cuh"
+#include "mlp_fused_bwd.cuh"
 extern "C" int nefes_encode_pe_bwd(const float*, const float*, int, int64_t, int, float*, void*);
 namespace nefes {
 
@@ -983,6 +994,268 @@ int launch_trunk_bwd(const Ws& w, const WsB& b, const Arena& A, int net, int64_t
 }
 }  // namespace
 
+namespace {
+// ---- program builder for fused_bwd_kernel (mlp_fused_bwd.cuh) ------------------------------------------------------
+struct FusedBuilder {
+  FusedArgs a = {};
+  int np = 0, nm = 0, ne = 0, nbar = 0;
+  uint32_t smem = 0;
+  uint32_t alloc(uint32_t bytes) { const uint32_t o = smem; smem += (bytes + 127u) & ~127u; return o; }
+  int bar(int count) { a.bar_count[nbar] = (uint16_t)count; return nbar++; }
+  // producer
+  void p_wait(int b, int flags = 0) { FProdOp& o = a.prod[np++]; o.kind = FO_WAIT; o.bar = (uint8_t)b; o.flags = (uint8_t)flags; }
+  void p_load(int b, const uint8_t* src, uint32_t tile_stride, uint32_t bytes, uint32_t off, int next) {
+    FProdOp& o = a.prod[np++]; o.kind = FO_LOAD; o.bar = (uint8_t)b; o.next = (uint8_t)next; o.src = src; o.tile_stride = tile_stride;
+    o.bytes = bytes; o.smem_off = off;
+  }
+  void p_store(uint8_t* dst, uint32_t tile_stride, uint32_t bytes, uint32_t off) {
+    FProdOp& o = a.prod[np++]; o.kind = FO_STORE; o.dst = dst; o.tile_stride = tile_stride; o.bytes = bytes; o.smem_off = off;
+  }
+  void p_arrive(int b) { FProdOp& o = a.prod[np++]; o.kind = FO_ARRIVE; o.bar = (uint8_t)b; }
+  // MMA issuer
+  void m_wait(int b, int flags = 0) { FMmaOp& o = a.mma[nm++]; o.kind = FO_WAIT; o.bar = (uint8_t)b; o.flags = (uint8_t)flags; }
+  void m_commit(int b) { FMmaOp& o = a.mma[nm++]; o.kind = FO_COMMIT; o.bar = (uint8_t)b; }
+  // data gradient: acc[128 pts, n] = G[pts, k_ch] (K-major image at g_off) * WT (image [k_ch/8][wt_rows][8] at w_off)
+  void m_dgrad(uint32_t g_off, int k_ch, uint32_t w_off, int wt_rows, int n, int col) {
+    FMmaOp& o = a.mma[nm++]; o.kind = FO_MMA; o.accmode = FA_FRESH; o.ksteps = (uint8_t)(k_ch / 16);
+    o.a_off = g_off; o.a_lbo = 128; o.a_sbo = 8; o.a_adv = 256;
+    o.b_off = w_off; o.b_lbo = (uint16_t)wt_rows; o.b_sbo = 8; o.b_adv = (uint16_t)(2 * wt_rows);
+    o.tmem_col = (uint16_t)col; o.idesc = idesc_bf16(128, n, 0, 0);
+  }
+  // weight gradient: D[128 rows of the image at a_off, n channels of the image at b_off] += A^T B over the 128 points
+  void m_wgrad(uint32_t a_off, uint32_t b_off, int n, int col) {
+    FMmaOp& o = a.mma[nm++]; o.kind = FO_MMA; o.accmode = FA_LAUNCH; o.ksteps = 8;
+    o.a_off = a_off; o.a_lbo = 8; o.a_sbo = 128; o.a_adv = 16;
+    o.b_off = b_off; o.b_lbo = 8; o.b_sbo = 128; o.b_adv = 16;
+    o.tmem_col = (uint16_t)col; o.idesc = idesc_bf16(128, n, 1, 1);
+  }
+  // epilogue
+  void e_wait(int b, int flags = 0) { FEpiOp& o = a.epi[ne++]; o.kind = FO_WAIT; o.bar = (uint8_t)b; o.flags = (uint8_t)flags; }
+  void e_arrive(int b) { FEpiOp& o = a.epi[ne++]; o.kind = FO_ARRIVE; o.bar = (uint8_t)b; }
+  void e_epi(int col, int n, bool mask, uint32_t mask_off, uint32_t out_off) {
+    FEpiOp& o = a.epi[ne++]; o.kind = FO_EPI; o.acc_col = (uint16_t)col; o.n = (uint16_t)n; o.has_mask = mask ? 1 : 0;
+    o.mask_off = mask_off; o.out_off = out_off;
+  }
+  void flush(int col, int n_cols, int pl, int m0, int k_off, int kind) {
+    FFlush& f = a.flush[a.n_flush++]; f.tmem_col = (uint16_t)col; f.n_cols = (uint16_t)n_cols; f.pl = (int16_t)pl; f.m0 = (int16_t)m0;
+    f.k_off = (int16_t)k_off; f.kind = (uint8_t)kind;
+  }
+  void ones(uint32_t off) { a.ones_off[a.n_ones++] = off; }
+  // weight image, rows [row0, row0 + take) of every chunk compacted, loaded once
+  void p_weights(int b, const uint8_t* img, int chunks, int rows, int row0, int take, uint32_t off, int* n_loads) {
+    if (take == rows) {
+      const uint32_t bytes = (uint32_t)chunks * rows * 16u;
+      for (uint32_t o = 0; o < bytes; o += 16384u) { p_load(b, img + o, 0, bytes - o < 16384u ? bytes - o : 16384u, off + o, 2); ++*n_loads; }
+    } else {
+      for (int c = 0; c < chunks; ++c) { p_load(b, img + ((int64_t)c * rows + row0) * 16, 0, (uint32_t)take * 16u, off + (uint32_t)c * take * 16u, 2); ++*n_loads; }
+    }
+  }
+  int finish(int n_tiles, int net, float* dP, const char* what) {
+    NEFES_REQUIRE(np < kFMaxProd && nm < kFMaxMma && ne < kFMaxEpi && a.n_flush <= kFMaxFlush && nbar <= kFMaxBars && a.n_ones <= 4,
+                  NEFES_EINVAL, "%s: program table overflow (%d %d %d %d %d)", what, np, nm, ne, a.n_flush, nbar);
+    a.prod[np].kind = FO_END; a.mma[nm].kind = FO_END; a.epi[ne].kind = FO_END;
+    a.n_tiles = n_tiles; a.ps = pack_src(net); a.d_flat = dP;
+    return NEFES_OK;
+  }
+};
+
+int launch_fused(FusedBuilder& B, int n_tiles, cudaStream_t st, const char* what) {
+  static uint32_t attr_bytes = 0;
+  NEFES_REQUIRE(B.smem <= 228000u, NEFES_EINVAL, "%s: shared memory plan exceeds the SM (%u B)", what, B.smem);
+  if (B.smem > attr_bytes) {
+    NEFES_CUDA(cudaFuncSetAttribute(fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+    attr_bytes = B.smem;
+  }
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  B.a.dbg = chain_dbg_buf();
+  if (B.a.dbg) cudaMemsetAsync(B.a.dbg, 0, 2048 * sizeof(long long), st);
+  fused_bwd_kernel<<<grid, kFusedThreads, B.smem, st>>>(B.a);
+  NEFES_CHECK_LAUNCH(what);
+  if (B.a.dbg) {
+    static int dumps = 0;
+    if (dumps++ < 4) {
+      cudaStreamSynchronize(st);
+      static long long h[2048];
+      cudaMemcpy(h, B.a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      const long long t0 = h[(1 * 4 + 0) * 48 + 0];
+      static const char* kn[] = {"END", "WAIT", "LOAD", "STORE", "ARRIVE", "MMA", "COMMIT", "EPI"};
+      fprintf(stderr, "[fused dbg] %s  (cycles since the MMA issuer's first op)\n", what);
+      for (int it = 1; it < 3; ++it) {
+        fprintf(stderr, " tile %d producer:", it);
+        for (int i = 0; i < 48 && B.a.prod[i].kind != FO_END; ++i) fprintf(stderr, " %s%d@%lld", kn[B.a.prod[i].kind], B.a.prod[i].bar, h[(0 * 4 + it) * 48 + i] - t0);
+        fprintf(stderr, "\n tile %d mma:", it);
+        for (int i = 0; i < 48 && B.a.mma[i].kind != FO_END; ++i) fprintf(stderr, " %s%d@%lld", kn[B.a.mma[i].kind], B.a.mma[i].bar, h[(1 * 4 + it) * 48 + i] - t0);
+        fprintf(stderr, "\n tile %d epi:", it);
+        for (int i = 0; i < 48 && B.a.epi[i].kind != FO_END; ++i) fprintf(stderr, " %s%d@%lld", kn[B.a.epi[i].kind], B.a.epi[i].bar, h[(2 * 4 + it) * 48 + i] - t0);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+  return NEFES_OK;
+}
+
+// Head group 1: rgb+feature head, and (fine net) the transient heads and the two transient hidden layers.
+//   in : GRGB (144 ch), GTH (16 ch) gradient images; saved DT (dir | tenc0 hidden), T3, T2
+//   out: GDT (gradient wrt the pre-activations of [dir | tenc0]) -> HBM, operand of head group 2
+int launch_heads1(const Ws& w, const WsB& b, const Arena& A, int net, int mode, int64_t M, float* dP, cudaStream_t st) {
+  const int T = (int)ceil_div(M, kTile);
+  const bool fine = mode == NEFES_MODE_FULL;
+  FusedBuilder B;
+  const uint32_t W0 = B.alloc(18 * 64 * 16), W1 = B.alloc(2 * 64 * 16), W2 = B.alloc(8 * 64 * 16), W3 = B.alloc(8 * 64 * 16);
+  const uint32_t G0 = B.alloc(36864), G1 = B.alloc(4096), G2 = B.alloc(16384), G3 = B.alloc(16384), G4 = B.alloc(32768);
+  const uint32_t Adir = B.alloc(20480), Atenc = B.alloc(20480), At3 = B.alloc(20480), At2 = B.alloc(20480);
+  B.ones(Adir + 16384);
+  if (fine) { B.ones(Atenc + 16384); B.ones(At3 + 16384); B.ones(At2 + 16384); }
+  int n_w = 0;
+  const int bW = B.bar(0);
+  B.p_weights(bW, A.WT(PL_RGB), 18, 64, 0, 64, W0, &n_w);
+  if (fine) {
+    B.p_weights(bW, A.WT(PL_TH), 2, 64, 0, 64, W1, &n_w);
+    B.p_weights(bW, A.WT(PL_TE2), 8, 64, 0, 64, W2, &n_w);
+    B.p_weights(bW, A.WT(PL_TE1), 8, 64, 0, 64, W3, &n_w);
+  }
+  B.a.bar_count[bW] = (uint16_t)n_w;
+  const int L_GRGB = B.bar(1), L_DIR = B.bar(1), ACC0 = B.bar(1), E0 = B.bar(256), D0 = B.bar(1), OUTFREE = B.bar(1);
+  int L_GTH = -1, L_TENC = -1, L_T3 = -1, L_T2 = -1, ACC1 = -1, ACC2 = -1, ACC3 = -1, E1 = -1, E2 = -1, E3 = -1, D1 = -1, D2 = -1, D3 = -1;
+  if (fine) {
+    L_GTH = B.bar(1); L_TENC = B.bar(1); L_T3 = B.bar(1); L_T2 = B.bar(1);
+    ACC1 = B.bar(1); ACC2 = B.bar(1); ACC3 = B.bar(1); E1 = B.bar(256); E2 = B.bar(256); E3 = B.bar(256);
+    D1 = B.bar(1); D2 = B.bar(1); D3 = B.bar(1);
+  }
+  const int Elast = fine ? E3 : E0;
+  const uint32_t dt_stride = (uint32_t)w.DT.tile_stride();
+  // ---- producer
+  B.p_load(L_GRGB, b.GRGB.p, (uint32_t)b.GRGB.tile_stride(), 36864, G0, 1);
+  B.p_load(L_DIR, w.DT.p, dt_stride, 16384, Adir, 1);
+  if (fine) {
+    B.p_load(L_GTH, b.GTH.p, (uint32_t)b.GTH.tile_stride(), 4096, G1, 1);
+    B.p_load(L_TENC, w.DT.p + 64 * 256, dt_stride, 16384, Atenc, 1);
+    B.p_load(L_T3, w.T3.p, (uint32_t)w.T3.tile_stride(), 16384, At3, 1);
+    B.p_load(L_T2, w.T2.p, (uint32_t)w.T2.tile_stride(), 16384, At2, 1);
+  }
+  // (the loads above run for the first tile before the loop; inside the loop each one refills its slot for tile it+1
+  //  right after the waits that precede it in program order)
+  {
+    FusedBuilder P;   // reorder: waits first, then the matching load -- rebuild the producer program
+    P = B; P.np = 0;
+    auto reload = [&](int idx) { P.a.prod[P.np++] = B.a.prod[idx]; };
+    int li = 0;
+    for (; B.a.prod[li].kind == FO_LOAD && B.a.prod[li].next == 2; ++li) reload(li);      // once-loads (weights)
+    const int iGRGB = li, iDIR = li + 1, iGTH = li + 2, iTENC = li + 3, iT3 = li + 4, iT2 = li + 5;
+    P.p_wait(D0); reload(iGRGB);
+    P.p_wait(E0); reload(iDIR);
+    if (fine) {
+      P.p_wait(D1); reload(iGTH);
+      P.p_wait(E1); reload(iT3);
+      P.p_wait(D2); P.p_wait(E2); reload(iT2);
+      P.p_wait(D3); P.p_wait(E3); reload(iTENC);
+    }
+    P.p_store(b.GDT.p, (uint32_t)b.GDT.tile_stride(), fine ? 32768u : 16384u, G4);
+    P.p_arrive(OUTFREE);
+    B = P;
+  }
+  // ---- MMA issuer
+  B.m_wait(bW, FW_ONCE);
+  B.m_wait(L_GRGB); B.m_wait(Elast, FW_PREV);
+  B.m_dgrad(G0, 144, W0, 64, 64, 0); B.m_commit(ACC0);
+  B.m_wait(L_DIR);
+  B.m_wgrad(G0, Adir, 80, 64); B.m_wgrad(G0 + 32768, Adir, 80, 144); B.m_commit(D0);
+  if (fine) {
+    B.m_wait(L_GTH); B.m_wait(E0);
+    B.m_dgrad(G1, 16, W1, 64, 64, 0); B.m_commit(ACC1);
+    B.m_wait(L_T3);
+    B.m_wgrad(G1, At3, 80, 224); B.m_commit(D1);
+    B.m_wait(E1);
+    B.m_dgrad(G2, 64, W2, 64, 64, 0); B.m_commit(ACC2);
+    B.m_wait(L_T2);
+    B.m_wgrad(G2, At2, 80, 304); B.m_commit(D2);
+    B.m_wait(E2);
+    B.m_dgrad(G3, 64, W3, 64, 64, 0); B.m_commit(ACC3);
+    B.m_wait(L_TENC);
+    B.m_wgrad(G3, Atenc, 80, 384); B.m_commit(D3);
+  }
+  // ---- epilogue
+  B.e_wait(ACC0); B.e_wait(L_DIR); B.e_wait(OUTFREE, FW_PREV); B.e_epi(0, 64, true, Adir, G4); B.e_arrive(E0);
+  if (fine) {
+    B.e_wait(ACC1); B.e_wait(L_T3); B.e_epi(0, 64, true, At3, G2); B.e_arrive(E1);
+    B.e_wait(ACC2); B.e_wait(L_T2); B.e_epi(0, 64, true, At2, G3); B.e_arrive(E2);
+    B.e_wait(ACC3); B.e_wait(L_TENC); B.e_epi(0, 64, true, Atenc, G4 + 16384); B.e_arrive(E3);
+  }
+  // ---- flush
+  B.flush(64, 64, PL_RGB, 0, 0, FF_W); B.flush(128, 16, PL_RGB, 0, 0, FF_BIAS);
+  B.flush(144, 64, PL_RGB, 128, 0, FF_W); B.flush(208, 16, PL_RGB, 128, 0, FF_BIAS);
+  if (fine) {
+    B.flush(224, 64, PL_TH, 0, 0, FF_W); B.flush(288, 16, PL_TH, 0, 0, FF_BIAS);
+    B.flush(304, 64, PL_TE2, 0, 0, FF_W); B.flush(368, 16, PL_TE2, 0, 0, FF_BIAS);
+    B.flush(384, 64, PL_TE1, 0, 0, FF_W); B.flush(448, 16, PL_TE1, 0, 0, FF_BIAS);
+  }
+  TRY(B.finish(T, net, dP, "heads1"));
+  return launch_fused(B, T, st, "fused_bwd heads1");
+}
+
+// Head group 2: [dir | tenc0] layer (input [final | dirPE]) and final+sigma layer (input h8).
+//   in : GDT (from group 1), sigma gradient chunk (GFS image channels 128..143); saved FIN, DIRPE, H[7]
+//   out: G[7] (gradient wrt the pre-activation of the last trunk layer) -> HBM, operand of the trunk launches
+int launch_heads2(const Ws& w, const WsB& b, const Arena& A, int net, int mode, int64_t M, float* dP, cudaStream_t st) {
+  const int T = (int)ceil_div(M, kTile);
+  const bool fine = mode == NEFES_MODE_FULL;
+  const int pl_dt = fine ? PL_DT : PL_DIR;
+  const int dt_ch = fine ? 128 : 64;
+  FusedBuilder B;
+  const uint32_t W0 = B.alloc((uint32_t)(dt_ch / 8) * 128 * 16), W1 = B.alloc(18 * 128 * 16);
+  const uint32_t G0 = B.alloc(32768), G1 = B.alloc(36864), A0 = B.alloc(40960), A1 = B.alloc(36864);
+  B.ones(A1 + 32768);
+  int n_w = 0;
+  const int bW = B.bar(0);
+  B.p_weights(bW, A.WT(pl_dt), dt_ch / 8, 160, 0, 128, W0, &n_w);
+  B.p_weights(bW, A.WT(PL_FS), 18, 128, 0, 128, W1, &n_w);
+  B.a.bar_count[bW] = (uint16_t)n_w;
+  const int L_GDT = B.bar(1), L_GSIG = B.bar(1), L_A0 = B.bar(2), L_H7 = B.bar(1);
+  const int ACC0 = B.bar(1), ACC1 = B.bar(1), E0 = B.bar(256), E1 = B.bar(256), D0 = B.bar(1), D1 = B.bar(1);
+  const uint32_t gdt_bytes = (uint32_t)dt_ch * 256u;
+  // ---- producer: first-tile loads, then per tile
+  B.p_load(L_GDT, b.GDT.p, (uint32_t)b.GDT.tile_stride(), gdt_bytes, G0, 1);
+  B.p_load(L_GSIG, b.GFS.p + 128 * 256, (uint32_t)b.GFS.tile_stride(), 4096, G1 + 32768, 1);
+  B.p_load(L_A0, w.FIN.p, (uint32_t)w.FIN.tile_stride(), 32768, A0, 1);
+  B.p_load(L_A0, w.DIRPE.p, (uint32_t)w.DIRPE.tile_stride(), 8192, A0 + 32768, 1);
+  B.p_load(L_H7, w.H[7].p, (uint32_t)w.H[7].tile_stride(), 32768, A1, 1);
+  {
+    FusedBuilder P;
+    P = B; P.np = 0;
+    auto reload = [&](int idx) { P.a.prod[P.np++] = B.a.prod[idx]; };
+    int li = 0;
+    for (; B.a.prod[li].kind == FO_LOAD && B.a.prod[li].next == 2; ++li) reload(li);
+    const int iGDT = li, iGSIG = li + 1, iFIN = li + 2, iDIRPE = li + 3, iH7 = li + 4;
+    P.p_wait(D0); reload(iFIN); reload(iDIRPE);
+    P.p_wait(D1); P.p_wait(E1); reload(iH7); reload(iGSIG);
+    P.p_store(b.G[7].p, (uint32_t)b.G[7].tile_stride(), 32768, G0);
+    reload(iGDT);
+    B = P;
+  }
+  // ---- MMA issuer
+  B.m_wait(bW, FW_ONCE);
+  B.m_wait(L_GDT); B.m_wait(E1, FW_PREV);
+  B.m_dgrad(G0, dt_ch, W0, 128, 128, 0); B.m_commit(ACC0);
+  B.m_wait(L_A0);
+  B.m_wgrad(G0, A0, 160, 128); B.m_commit(D0);
+  B.m_wait(E0); B.m_wait(L_GSIG);
+  B.m_dgrad(G1, 144, W1, 128, 128, 0); B.m_commit(ACC1);
+  B.m_wait(L_H7);
+  B.m_wgrad(G1, A1, 144, 288);
+  B.m_wgrad(A1, G1 + 32768, 16, 432);                 // sigma row, transposed: D[h8 channel, 0] = sum_p h8[p, ch] * gsig[p]
+  B.m_commit(D1);
+  // ---- epilogue
+  B.e_wait(ACC0); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);
+  B.e_wait(ACC1); B.e_wait(L_H7); B.e_epi(0, 128, true, A1, G0); B.e_arrive(E1);
+  // ---- flush: the dirPE image carries a constant 1 in its last padding channel (column 128 + 31): bias of [dir | tenc0]
+  B.flush(128, 160, pl_dt, 0, 0, FF_W); B.flush(128 + 144, 16, pl_dt, 0, 15, FF_BIAS);
+  B.flush(288, 128, PL_FS, 0, 0, FF_W); B.flush(288 + 128, 16, PL_FS, 0, 0, FF_BIAS);
+  B.flush(432, 16, PL_FS, 128, 0, FF_WT);
+  TRY(B.finish(T, net, dP, "heads2"));
+  return launch_fused(B, T, st, "fused_bwd heads2");
+}
+}  // namespace
+
 int mlp_workspace_bf16(int net, int mode, int64_t M, int64_t N, int64_t* saved, int64_t* sf, int64_t* sb) {
   (void)net;
   const int64_t T = ceil_div(M, kTile);
@@ -1032,14 +1305,22 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
 
   const Img& gsig_img = (mode == NEFES_MODE_SIGMA) ? b.GSIG : b.GFS;
   const bool tiles = layout == NEFES_RAW_TILES;
+  // training (weight gradients, no gradient to the sample positions): fused data+weight-gradient launches -- two for
+  // the heads, four for the trunk; otherwise (pose refinement) the data-gradient chain runs all layers and keeps every
+  // gradient image for the input-gradient GEMMs
+  const bool fused_trunk = dP != nullptr && d_pts == nullptr && getenv("NEFES_NO_FUSED_TRUNK") == nullptr;
+  // (measured: a gain for the fine net's six head layers, none for the coarse net's three)
+  const bool fused_heads = fused_trunk && mode == NEFES_MODE_FULL && getenv("NEFES_NO_FUSED_HEADS") == nullptr;
   head_grad_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(
       raw, d_raw, C, tiles ? 1 : C, tiles ? kTile : 1, M, Mp, b.GRGB.p, b.GTH.p, gsig_img.p, gsig_img.tile_stride(),
-      mode == NEFES_MODE_SIGMA ? 0 : 16);
+      mode == NEFES_MODE_SIGMA ? 0 : 16, fused_heads ? dP + layout_for(net).b[L_SIGMA] : nullptr);
   NEFES_CHECK_LAUNCH("head_grad_images");
-  // training (weight gradients, no gradient to the sample positions): the trunk runs as fused dgrad+wgrad launches and
-  // the chain stops at G[7]; otherwise (pose refinement) the chain runs all layers and keeps every gradient image
-  const bool fused_trunk = dP != nullptr && d_pts == nullptr && getenv("NEFES_NO_FUSED_TRUNK") == nullptr;
-  TRY(launch_chain_bwd(w, b, A, mode, M, !fused_trunk, st));
+  if (fused_heads) {
+    TRY(launch_heads1(w, b, A, net, mode, M, dP, st));
+    TRY(launch_heads2(w, b, A, net, mode, M, dP, st));
+  } else {
+    TRY(launch_chain_bwd(w, b, A, mode, M, !fused_trunk, st));
+  }
   if (fused_trunk) TRY(launch_trunk_bwd(w, b, A, net, M, dP, st));
 
   // ---- gradients to the inputs (pose refinement): fp32 out of the GEMM, then the SIMT PE backward ------
@@ -1079,12 +1360,14 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
     J.tile_bytes = (uint32_t)(J.g_ch + J.a_ch) * 256u;
     if (J.tile_bytes > max_tile_bytes) max_tile_bytes = J.tile_bytes;
   };
-  if (mode == NEFES_MODE_FULL) {
+  if (mode == NEFES_MODE_FULL && !fused_heads) {
     job(PL_TH, b.GTH, 0, 16, src_of(w.T3), nullptr);
     job(PL_TE2, b.GT3, 0, 64, src_of(w.T2), nullptr);
     job(PL_TE1, b.GT2, 0, 64, src_of(w.DT, 64, 64), nullptr);
   }
-  if (mode != NEFES_MODE_SIGMA) {
+  if (fused_heads) {
+    // every head layer was handled by the fused launches
+  } else if (mode != NEFES_MODE_SIGMA) {
     ASrc dp = src_of(w.DIRPE);
     job(PL_RGB, b.GRGB, 0, 144, src_of(w.DT, 0, 64), nullptr);
     job(mode == NEFES_MODE_FULL ? PL_DT : PL_DIR, b.GDT, 0, w.DT.ch, src_of(w.FIN), &dp);
