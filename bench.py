@@ -36,6 +36,9 @@ RAYS = N_IMAGES * N_RAND
 # algorithmic MLP work per ray, SURVEY.md 8d: fwd 68.32 MFLOP, fwd+bwd 204.96 MFLOP (train mode)
 MLP_FLOP_PER_RAY_FWD_BWD = 204.96e6
 METRIC = "NeFeS rays/sec (fwd+bwd, 64+64 samples)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at the bench shape, from the `ncu --set full` captures
+# summarised in profiles/ (fine net, 6144 rays x 128 samples); per-launch like roofline.achieved
+NCU_TRAFFIC = {"chain_fwd_fine": 2.738e9}
 
 
 def nerfw_loss(ret, target, lambda_u=0.01):
@@ -181,6 +184,7 @@ def run_engine(a):
         step(b)
     barrier()
     ops.PROFILE = []
+    _lib.lib().nefes_prof_enable(1)                 # CUDA events around every hot launch, on the launching stream
     l0 = _lib.lib().nefes_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -192,6 +196,11 @@ def run_engine(a):
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = int(_lib.lib().nefes_launch_count() - l0)
     prof, ops.PROFILE = ops.PROFILE, None
+    import ctypes
+    buf = ctypes.create_string_buffer(1 << 16)
+    _lib.check(_lib.lib().nefes_prof_report(buf, len(buf)), "nefes_prof_report")
+    _lib.lib().nefes_prof_enable(0)
+    kern = json.loads(buf.value.decode())
     mlp_ms = sum(s.elapsed_time(e) for _, s, e in prof) / a.steps
     value = world * RAYS * a.steps / (ms / 1e3)
 
@@ -210,6 +219,15 @@ def run_engine(a):
 
     tf_peak, hbm_peak, which = measured_peaks()
     achieved = MLP_FLOP_PER_RAY_FWD_BWD * RAYS / (mlp_ms / 1e3) / 1e12
+    # per-kernel table: achieved = algorithmic bytes (flops) of the launches / their measured duration
+    table = {}
+    for tag, k in kern.items():
+        if k["ms"] <= 0:
+            continue
+        table[tag] = {"launches_per_step": k["launches"] / a.steps, "ms_per_step": k["ms"] / a.steps,
+                      "GB_per_s": k["alg_bytes"] / k["ms"] / 1e6, "TFLOP_per_s": k["alg_flops"] / k["ms"] / 1e9,
+                      "hbm_frac": k["alg_bytes"] / k["ms"] / 1e6 / hbm_peak, "tensor_frac": k["alg_flops"] / k["ms"] / 1e9 / tf_peak}
+    top = max(table, key=lambda t: table[t]["ms_per_step"]) if table else None
     out = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -223,10 +241,17 @@ def run_engine(a):
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "field MLP (K5) forward+backward, all launches of one step",
-                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                     "traffic": None, "peak_source": which, "ms_per_step_in_kernel": mlp_ms,
-                     "share_of_step": mlp_ms / (ms / a.steps)},
+        # dominant kernel of the step (largest share of device time).  Every MLP kernel of this design streams saved
+        # activation / gradient images through HBM and is bounded by it, hence bound = hbm;
+        # `traffic` is dram read+write of one launch from the committed ncu capture (profiles/), null if not captured.
+        "roofline": ({"bound": "hbm", "kernel": top, "achieved": table[top]["GB_per_s"], "peak": hbm_peak, "unit": "GB/s",
+                      "frac": table[top]["hbm_frac"], "traffic": NCU_TRAFFIC.get(top), "peak_source": which,
+                      "ms_per_step_in_kernel": table[top]["ms_per_step"],
+                      "share_of_step": table[top]["ms_per_step"] / (ms / a.steps)} if top else None),
+        "kernels": table,
+        "mlp_tensor": {"what": "field MLP (K5) forward+backward, all launches of one step, against the tensor roofline",
+                       "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                       "ms_per_step": mlp_ms, "share_of_step": mlp_ms / (ms / a.steps)},
         "clocks": clk.summary(),
         "final_loss": losses[-1] if losses else None,
     }

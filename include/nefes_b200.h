@@ -38,6 +38,11 @@ int nefes_version(void);
 const char* nefes_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t nefes_launch_count(void);
+/* Optional per-kernel timing for roofline reports: while enabled, the hot launches are bracketed by CUDA events on their
+ * own stream and tagged with their algorithmic bytes / flops; the report is a JSON object
+ * {tag: {launches, ms, alg_bytes, alg_flops}} (synchronises the device).  Off by default (no overhead). */
+int nefes_prof_enable(int on);
+int nefes_prof_report(char* buf, int cap);
 
 /* ------------------------------------------------------------------------------------------
  * Field (MLP) description.  Architecture is the one every reference config uses:

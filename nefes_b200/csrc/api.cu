@@ -2,6 +2,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <map>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -17,6 +20,24 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+struct ProfRec { const char* tag; cudaEvent_t e0, e1; double bytes, flops; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+void prof_begin(const char* tag, cudaStream_t st, double alg_bytes, double alg_flops) {
+  if (!g_prof_on) return;
+  ProfRec r = {tag, nullptr, nullptr, alg_bytes, alg_flops};
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().e1, st);
+}
 
 namespace {
 struct Row { Layer id; const char* name; int out, in; bool fine_only; };
@@ -79,6 +100,39 @@ extern "C" {
 int nefes_version(void) { return NEFES_VERSION; }
 const char* nefes_last_error(void) { return nefes::g_err; }
 int64_t nefes_launch_count(void) { return nefes::g_launches.load(); }
+
+int nefes_prof_enable(int on) {
+  for (auto& r : nefes::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  nefes::g_prof.clear();
+  nefes::g_prof_on = on != 0;
+  return NEFES_OK;
+}
+
+int nefes_prof_report(char* buf, int cap) {
+  NEFES_REQUIRE(buf != nullptr && cap > 2, NEFES_EINVAL, "nefes_prof_report: bad buffer");
+  cudaDeviceSynchronize();
+  struct Agg { int n = 0; double ms = 0, bytes = 0, flops = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : nefes::g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    Agg& a = agg[r.tag];
+    a.n += 1; a.ms += ms; a.bytes += r.bytes; a.flops += r.flops;
+  }
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s\"%s\": {\"launches\": %d, \"ms\": %.6f, \"alg_bytes\": %.0f, \"alg_flops\": %.0f}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  NEFES_REQUIRE((int)out.size() + 1 <= cap, NEFES_EINVAL, "nefes_prof_report: buffer too small (%d needed)", (int)out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return NEFES_OK;
+}
 
 int nefes_param_layout(int net, nefes_layout_t* out_host) {
   NEFES_REQUIRE(out_host != nullptr, NEFES_EINVAL, "nefes_param_layout: null output");

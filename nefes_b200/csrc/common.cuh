@@ -10,6 +10,10 @@ namespace nefes {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// optional per-kernel timing (nefes_prof_enable): CUDA events on the launching stream around a launch, together with
+// the launch's ALGORITHMIC bytes and flops, so a roofline fraction can be reported per kernel (bench.py)
+void prof_begin(const char* tag, cudaStream_t st, double alg_bytes, double alg_flops);
+void prof_end(cudaStream_t st);
 
 #define NEFES_REQUIRE(cond, code, ...)                 \
   do {                                                 \

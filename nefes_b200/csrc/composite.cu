@@ -334,12 +334,18 @@ static int comp_fwd_launch(const char* who, const float* raw, const float* z_val
   const int threads = (int)nefes::round_up(S > 160 ? S : (mode == NEFES_COMP_SIGMA ? S : (TILES ? 256 : 160)), 32);
   cudaStream_t st = (cudaStream_t)stream;
   nefes_comp_out_t o = *out_host;
+  {
+    const int C = mode == NEFES_COMP_SIGMA ? 1 : (mode == NEFES_COMP_STATIC ? 132 : 137);
+    nefes::prof_begin(mode == NEFES_COMP_STATIC ? "composite_fwd_coarse" : (mode == NEFES_COMP_SIGMA ? "composite_fwd_sigma" : "composite_fwd_fine"), st,
+                      (double)N * (4.0 * S * C + 4.0 * S * 3 + 4.0 * 140), 0.0);
+  }
   switch (mode) {
     case NEFES_COMP_SIGMA: nefes::composite_fwd_kernel<NEFES_COMP_SIGMA, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
     case NEFES_COMP_STATIC: nefes::composite_fwd_kernel<NEFES_COMP_STATIC, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
     case NEFES_COMP_TRANSIENT: nefes::composite_fwd_kernel<NEFES_COMP_TRANSIENT, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
     default: nefes::composite_fwd_kernel<NEFES_COMP_TRANSIENT_STATIC_ONLY, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, beta_min, o); break;
   }
+  nefes::prof_end(st);
   NEFES_CHECK_LAUNCH(who);
   return NEFES_OK;
 }
@@ -354,12 +360,18 @@ static int comp_bwd_launch(const char* who, const float* raw, const float* z_val
   const int threads = (int)nefes::round_up(S > 160 ? S : (mode == NEFES_COMP_SIGMA ? S : (TILES ? 256 : 160)), 32);
   cudaStream_t st = (cudaStream_t)stream;
   nefes_comp_grad_t g = *g_host;
+  {
+    const int C = mode == NEFES_COMP_SIGMA ? 1 : (mode == NEFES_COMP_STATIC ? 132 : 137);
+    nefes::prof_begin(mode == NEFES_COMP_STATIC ? "composite_bwd_coarse" : (mode == NEFES_COMP_SIGMA ? "composite_bwd_sigma" : "composite_bwd_fine"), st,
+                      (double)N * (8.0 * S * C + 4.0 * S * 3 + 4.0 * 140), 0.0);   // raw in, d_raw out
+  }
   switch (mode) {
     case NEFES_COMP_SIGMA: nefes::composite_bwd_kernel<NEFES_COMP_SIGMA, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
     case NEFES_COMP_STATIC: nefes::composite_bwd_kernel<NEFES_COMP_STATIC, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
     case NEFES_COMP_TRANSIENT: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
     default: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT_STATIC_ONLY, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
   }
+  nefes::prof_end(st);
   NEFES_CHECK_LAUNCH(who);
   return NEFES_OK;
 }

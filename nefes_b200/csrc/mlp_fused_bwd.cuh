@@ -5,8 +5,13 @@
 // programs over a per-tile set of mbarriers, every one of which completes exactly ONE phase per tile:
 //
 //   producer (1 thread)      WAIT bar | LOAD image -> smem (bulk copy, completes on bar) | STORE smem -> image | ARRIVE bar
-//   MMA issuer (1 thread)    WAIT bar | MMA group (descriptors relative to the smem base, fresh / per-launch accumulate)
-//                            | COMMIT bar (tcgen05.commit: all MMAs issued so far retired)
+//   MMA issuers (2 threads)  WAIT bar | MMA group (descriptors relative to the smem base, fresh / per-launch accumulate)
+//                            | COMMIT bar (tcgen05.commit: all MMAs issued so far BY THIS THREAD retired).
+//                            Thread 0 issues the data-gradient GEMMs (the serial chain layer -> epilogue -> layer), thread 1
+//                            the weight-gradient GEMMs (independent accumulators): every wait / commit costs its thread
+//                            200-400 cycles, and with one issuer those latencies were 60 % of the tile time.  Completion
+//                            order ACROSS the two threads is not defined, so every buffer hand-over between the two
+//                            streams is an explicit barrier in the programs.
 //   epilogue (256 threads)   WAIT bar | EPI: TMEM acc -> ReLU mask from a saved activation image in smem (a > 0) -> bf16
 //                            gradient image in smem (operand of the next layer) | ARRIVE bar
 //
@@ -47,10 +52,10 @@ struct FEpiOp {
 struct FFlush {
   uint16_t tmem_col, n_cols; int16_t pl, m0, k_off; uint8_t kind, pad;
 };
-constexpr int kFMaxProd = 44, kFMaxMma = 44, kFMaxEpi = 20, kFMaxFlush = 12, kFMaxBars = 32;
+constexpr int kFMaxProd = 44, kFMaxMma = 28, kFMaxEpi = 28, kFMaxFlush = 12, kFMaxBars = 32;
 struct FusedArgs {
   FProdOp prod[kFMaxProd];
-  FMmaOp mma[kFMaxMma];
+  FMmaOp mma[2][kFMaxMma];
   FEpiOp epi[kFMaxEpi];
   FFlush flush[kFMaxFlush];
   uint16_t bar_count[kFMaxBars];            // arrival count of every barrier (0: unused)
@@ -60,7 +65,7 @@ struct FusedArgs {
   PackSrc ps; float* d_flat;
   long long* dbg;                           // optional clock stamps of CTA 0: [role 0..2][tile 0..3][op 0..47]
 };
-constexpr int kFusedThreads = 64 + 256;
+constexpr int kFusedThreads = 64 + 256 + 32;     // producer, dgrad issuer, 8 epilogue warps, wgrad issuer
 #ifdef NEFES_FUSED_DBG
 constexpr bool kFusedDbg = true;
 #else
@@ -75,16 +80,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
   // the three programs are interpreted from shared memory: a dynamically indexed read of the kernel-parameter bank costs
   // a constant-cache miss (~300 cycles) per op field once the table exceeds the cache, which dominated the tile time
   __shared__ FProdOp s_prod[kFMaxProd];
-  __shared__ FMmaOp s_mma[kFMaxMma];
+  __shared__ FMmaOp s_mma[2][kFMaxMma];
   __shared__ FEpiOp s_epi[kFMaxEpi];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < kFMaxProd; i += kFusedThreads) s_prod[i] = F.prod[i];
-  for (int i = threadIdx.x; i < kFMaxMma; i += kFusedThreads) s_mma[i] = F.mma[i];
+  for (int i = threadIdx.x; i < 2 * kFMaxMma; i += kFusedThreads) s_mma[i / kFMaxMma][i % kFMaxMma] = F.mma[i / kFMaxMma][i % kFMaxMma];
   for (int i = threadIdx.x; i < kFMaxEpi; i += kFusedThreads) s_epi[i] = F.epi[i];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kFMaxBars; ++i) mbar_init(&bars[i], F.bar_count[i] ? F.bar_count[i] : 1);
-    mbar_init(&bar_done, 1);
+    mbar_init(&bar_done, 2);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_slot);
@@ -138,12 +143,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
       }
       bulk_wait_all();
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
     if (lane == 0 && n_my > 0) {
-      // ------------------------------- MMA issuer ----------------------------------------------------------------------
+      // ------------------------------- MMA issuers: warp 1 data gradients, warp 10 weight gradients ----------------------
+      const FMmaOp* prog = s_mma[warp == 1 ? 0 : 1];
       for (int it = 0; it < n_my; ++it) {
-        for (int i = 0; s_mma[i].kind != FO_END; ++i) {
-          const FMmaOp& o = s_mma[i];
+        for (int i = 0; prog[i].kind != FO_END; ++i) {
+          const FMmaOp& o = prog[i];
           if (o.kind == FO_WAIT) {
             if (o.flags & FW_PREV) { if (it > 0) mbar_wait(&bars[o.bar], (it - 1) & 1); }
             else if (o.flags & FW_ONCE) { if (it == 0) mbar_wait(&bars[o.bar], 0); }
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           } else if (o.kind == FO_COMMIT) {
             mma_commit(&bars[o.bar]);
           }
-          if (kFusedDbg && F.dbg != nullptr && blockIdx.x == 0 && it < 4 && i < 48) F.dbg[(1 * 4 + it) * 48 + i] = clock64();
+          if (kFusedDbg && F.dbg != nullptr && blockIdx.x == 0 && warp == 1 && it < 4 && i < 48) F.dbg[(1 * 4 + it) * 48 + i] = clock64();
         }
       }
       mma_commit(&bar_done);

@@ -887,7 +887,16 @@ int launch_chain_fwd(const Ws& w, const Arena& A, int mode, int64_t M, float* ra
   }
   const int n_pairs = (T + 1) / 2;
   const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
+  {
+    // algorithmic HBM bytes per point: encodings in, every saved activation image out (bf16), raw out (fp32); flops: 2 x MACs
+    const double save_ch = (mode == NEFES_MODE_SIGMA) ? 8 * 128 : (mode == NEFES_MODE_STATIC ? 8 * 128 + 128 + 64 : 8 * 128 + 128 + 128 + 64 + 64);
+    const double in_ch = (mode == NEFES_MODE_SIGMA) ? 64 : 96;
+    const double macs = (mode == NEFES_MODE_SIGMA) ? 130944 : (mode == NEFES_MODE_STATIC ? 165632 : 184064);
+    prof_begin(mode == NEFES_MODE_FULL ? "chain_fwd_fine" : (mode == NEFES_MODE_STATIC ? "chain_fwd_coarse" : "chain_fwd_sigma"), st,
+               (double)M * (2.0 * (save_ch + in_ch) + 4.0 * c.C), (double)M * 2.0 * macs);
+  }
   chain_kernel<false><<<grid, kChainThreads, kFwdChainSmem, st>>>(c);
+  prof_end(st);
   NEFES_CHECK_LAUNCH("chain_fwd");
   chain_dbg_dump("fwd", c, st);
   return NEFES_OK;
@@ -953,7 +962,14 @@ int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_
   }
   const int n_pairs = (T + 1) / 2;
   const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
+  {
+    double ch = 0, macs = 0;     // channels moved per point: operand loads + mask activations + saved gradient images
+    for (int i = 0; i < n; ++i) { ch += (c.step[i].act ? c.step[i].out_ch : 0) + (c.step[i].gdst ? c.step[i].out_ch : 0); macs += (double)c.step[i].K * c.step[i].N; }
+    for (int l = 0; l < kChainLoads; ++l) ch += c.load[l].bytes / 256.0;
+    prof_begin(with_trunk ? "chain_bwd_full" : "chain_bwd_heads", st, (double)M * 2.0 * ch, (double)M * 2.0 * macs);
+  }
   chain_kernel<true><<<grid, kChainThreads, kBwdChainSmem, st>>>(c);
+  prof_end(st);
   NEFES_CHECK_LAUNCH("chain_bwd");
   chain_dbg_dump("bwd", c, st);
   return NEFES_OK;
@@ -987,7 +1003,14 @@ int launch_trunk_bwd(const Ws& w, const WsB& b, const Arena& A, int net, int64_t
     }
     if (l1 > 0) { t.g_out = b.G[l1 - 1].p; t.g_out_tile_stride = (uint32_t)b.G[l1 - 1].tile_stride(); }
     t.n_tiles = T; t.ps = pack_src(net); t.d_flat = dP;
+    {
+      double ch = 128 + t.step[0].act_ch + t.step[1].act_ch + (t.g_out ? 128 : 0) + (t.step[0].g_save ? 128 : 0);
+      double macs = 0;
+      for (int j = 0; j < 2; ++j) macs += (t.step[j].has_dgrad ? 128.0 * 128 : 0) + 128.0 * t.step[j].act_ch;
+      prof_begin("trunk_bwd", st, (double)M * 2.0 * ch, (double)M * 2.0 * macs);
+    }
     trunk_bwd_kernel<<<grid, kTrunkThreads, kTrunkSmem, st>>>(t);
+    prof_end(st);
     NEFES_CHECK_LAUNCH("trunk_bwd");
   }
   return NEFES_OK;
@@ -998,7 +1021,7 @@ namespace {
 // ---- program builder for fused_bwd_kernel (mlp_fused_bwd.cuh) ------------------------------------------------------
 struct FusedBuilder {
   FusedArgs a = {};
-  int np = 0, nm = 0, ne = 0, nbar = 0;
+  int np = 0, nm[2] = {0, 0}, ne = 0, nbar = 0, mp = 0;   // mp: MMA program being written (0 dgrad thread, 1 wgrad thread)
   uint32_t smem = 0;
   uint32_t alloc(uint32_t bytes) { const uint32_t o = smem; smem += (bytes + 127u) & ~127u; return o; }
   int bar(int count) { a.bar_count[nbar] = (uint16_t)count; return nbar++; }
@@ -1013,18 +1036,18 @@ struct FusedBuilder {
   }
   void p_arrive(int b) { FProdOp& o = a.prod[np++]; o.kind = FO_ARRIVE; o.bar = (uint8_t)b; }
   // MMA issuer
-  void m_wait(int b, int flags = 0) { FMmaOp& o = a.mma[nm++]; o.kind = FO_WAIT; o.bar = (uint8_t)b; o.flags = (uint8_t)flags; }
-  void m_commit(int b) { FMmaOp& o = a.mma[nm++]; o.kind = FO_COMMIT; o.bar = (uint8_t)b; }
+  void m_wait(int b, int flags = 0) { FMmaOp& o = a.mma[mp][nm[mp]++]; o.kind = FO_WAIT; o.bar = (uint8_t)b; o.flags = (uint8_t)flags; }
+  void m_commit(int b) { FMmaOp& o = a.mma[mp][nm[mp]++]; o.kind = FO_COMMIT; o.bar = (uint8_t)b; }
   // data gradient: acc[128 pts, n] = G[pts, k_ch] (K-major image at g_off) * WT (image [k_ch/8][wt_rows][8] at w_off)
   void m_dgrad(uint32_t g_off, int k_ch, uint32_t w_off, int wt_rows, int n, int col) {
-    FMmaOp& o = a.mma[nm++]; o.kind = FO_MMA; o.accmode = FA_FRESH; o.ksteps = (uint8_t)(k_ch / 16);
+    FMmaOp& o = a.mma[mp][nm[mp]++]; o.kind = FO_MMA; o.accmode = FA_FRESH; o.ksteps = (uint8_t)(k_ch / 16);
     o.a_off = g_off; o.a_lbo = 128; o.a_sbo = 8; o.a_adv = 256;
     o.b_off = w_off; o.b_lbo = (uint16_t)wt_rows; o.b_sbo = 8; o.b_adv = (uint16_t)(2 * wt_rows);
     o.tmem_col = (uint16_t)col; o.idesc = idesc_bf16(128, n, 0, 0);
   }
   // weight gradient: D[128 rows of the image at a_off, n channels of the image at b_off] += A^T B over the 128 points
   void m_wgrad(uint32_t a_off, uint32_t b_off, int n, int col) {
-    FMmaOp& o = a.mma[nm++]; o.kind = FO_MMA; o.accmode = FA_LAUNCH; o.ksteps = 8;
+    FMmaOp& o = a.mma[mp][nm[mp]++]; o.kind = FO_MMA; o.accmode = FA_LAUNCH; o.ksteps = 8;
     o.a_off = a_off; o.a_lbo = 8; o.a_sbo = 128; o.a_adv = 16;
     o.b_off = b_off; o.b_lbo = 8; o.b_sbo = 128; o.b_adv = 16;
     o.tmem_col = (uint16_t)col; o.idesc = idesc_bf16(128, n, 1, 1);
@@ -1051,9 +1074,10 @@ struct FusedBuilder {
     }
   }
   int finish(int n_tiles, int net, float* dP, const char* what) {
-    NEFES_REQUIRE(np < kFMaxProd && nm < kFMaxMma && ne < kFMaxEpi && a.n_flush <= kFMaxFlush && nbar <= kFMaxBars && a.n_ones <= 4,
-                  NEFES_EINVAL, "%s: program table overflow (%d %d %d %d %d)", what, np, nm, ne, a.n_flush, nbar);
-    a.prod[np].kind = FO_END; a.mma[nm].kind = FO_END; a.epi[ne].kind = FO_END;
+    NEFES_REQUIRE(np < kFMaxProd && nm[0] < kFMaxMma && nm[1] < kFMaxMma && ne < kFMaxEpi && a.n_flush <= kFMaxFlush &&
+                  nbar <= kFMaxBars && a.n_ones <= 4,
+                  NEFES_EINVAL, "%s: program table overflow (%d %d %d %d %d %d)", what, np, nm[0], nm[1], ne, a.n_flush, nbar);
+    a.prod[np].kind = FO_END; a.mma[0][nm[0]].kind = FO_END; a.mma[1][nm[1]].kind = FO_END; a.epi[ne].kind = FO_END;
     a.n_tiles = n_tiles; a.ps = pack_src(net); a.d_flat = dP;
     return NEFES_OK;
   }
@@ -1069,7 +1093,16 @@ int launch_fused(FusedBuilder& B, int n_tiles, cudaStream_t st, const char* what
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   B.a.dbg = chain_dbg_buf();
   if (B.a.dbg) cudaMemsetAsync(B.a.dbg, 0, 2048 * sizeof(long long), st);
+  {
+    double bytes = 0, macs = 0;  // per tile: every per-tile load and store; MACs of every MMA group
+    for (int i = 0; i < B.np; ++i) if ((B.a.prod[i].kind == FO_LOAD && B.a.prod[i].next != 2) || B.a.prod[i].kind == FO_STORE) bytes += B.a.prod[i].bytes;
+    for (int t = 0; t < 2; ++t)
+      for (int i = 0; i < B.nm[t]; ++i)
+        if (B.a.mma[t][i].kind == FO_MMA) macs += 128.0 * (((B.a.mma[t][i].idesc >> 17) & 0x3F) * 8) * B.a.mma[t][i].ksteps * 16;
+    prof_begin(what, st, bytes * n_tiles, 2.0 * macs * n_tiles);
+  }
   fused_bwd_kernel<<<grid, kFusedThreads, B.smem, st>>>(B.a);
+  prof_end(st);
   NEFES_CHECK_LAUNCH(what);
   if (B.a.dbg) {
     static int dumps = 0;
@@ -1084,7 +1117,7 @@ int launch_fused(FusedBuilder& B, int n_tiles, cudaStream_t st, const char* what
         fprintf(stderr, " tile %d producer:", it);
         for (int i = 0; i < 48 && B.a.prod[i].kind != FO_END; ++i) fprintf(stderr, " %s%d@%lld", kn[B.a.prod[i].kind], B.a.prod[i].bar, h[(0 * 4 + it) * 48 + i] - t0);
         fprintf(stderr, "\n tile %d mma:", it);
-        for (int i = 0; i < 48 && B.a.mma[i].kind != FO_END; ++i) fprintf(stderr, " %s%d@%lld", kn[B.a.mma[i].kind], B.a.mma[i].bar, h[(1 * 4 + it) * 48 + i] - t0);
+        for (int i = 0; i < 48 && B.a.mma[0][i].kind != FO_END; ++i) fprintf(stderr, " %s%d@%lld", kn[B.a.mma[0][i].kind], B.a.mma[0][i].bar, h[(1 * 4 + it) * 48 + i] - t0);
         fprintf(stderr, "\n tile %d epi:", it);
         for (int i = 0; i < 48 && B.a.epi[i].kind != FO_END; ++i) fprintf(stderr, " %s%d@%lld", kn[B.a.epi[i].kind], B.a.epi[i].bar, h[(2 * 4 + it) * 48 + i] - t0);
         fprintf(stderr, "\n");
@@ -1142,11 +1175,9 @@ int launch_heads1(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
     int li = 0;
     for (; B.a.prod[li].kind == FO_LOAD && B.a.prod[li].next == 2; ++li) reload(li);      // once-loads (weights)
     const int iGRGB = li, iDIR = li + 1, iGTH = li + 2, iTENC = li + 3, iT3 = li + 4, iT2 = li + 5;
-    P.p_wait(D0); reload(iGRGB);
-    P.p_wait(E0); reload(iDIR);
+    P.p_wait(D0); P.p_wait(E0); reload(iGRGB); reload(iDIR);       // D: weight-gradient reads done, E: data-gradient + mask reads done
     if (fine) {
-      P.p_wait(D1); reload(iGTH);
-      P.p_wait(E1); reload(iT3);
+      P.p_wait(D1); P.p_wait(E1); reload(iGTH); reload(iT3);
       P.p_wait(D2); P.p_wait(E2); reload(iT2);
       P.p_wait(D3); P.p_wait(E3); reload(iTENC);
     }
@@ -1154,31 +1185,36 @@ int launch_heads1(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
     P.p_arrive(OUTFREE);
     B = P;
   }
-  // ---- MMA issuer
+  // ---- data-gradient issuer: the serial chain  RGB -> (fine) TH -> TE2 -> TE1
+  B.mp = 0;
   B.m_wait(bW, FW_ONCE);
-  B.m_wait(L_GRGB); B.m_wait(Elast, FW_PREV);
+  B.m_wait(L_GRGB); B.m_wait(Elast, FW_PREV);                 // accumulator drained by the last epilogue of the previous tile
   B.m_dgrad(G0, 144, W0, 64, 64, 0); B.m_commit(ACC0);
-  B.m_wait(L_DIR);
-  B.m_wgrad(G0, Adir, 80, 64); B.m_wgrad(G0 + 32768, Adir, 80, 144); B.m_commit(D0);
   if (fine) {
     B.m_wait(L_GTH); B.m_wait(E0);
     B.m_dgrad(G1, 16, W1, 64, 64, 0); B.m_commit(ACC1);
-    B.m_wait(L_T3);
-    B.m_wgrad(G1, At3, 80, 224); B.m_commit(D1);
     B.m_wait(E1);
     B.m_dgrad(G2, 64, W2, 64, 64, 0); B.m_commit(ACC2);
-    B.m_wait(L_T2);
-    B.m_wgrad(G2, At2, 80, 304); B.m_commit(D2);
     B.m_wait(E2);
     B.m_dgrad(G3, 64, W3, 64, 64, 0); B.m_commit(ACC3);
-    B.m_wait(L_TENC);
+  }
+  // ---- weight-gradient issuer (own accumulators; its operands are handed over by explicit barriers)
+  B.mp = 1;
+  B.m_wait(L_GRGB); B.m_wait(L_DIR);
+  B.m_wgrad(G0, Adir, 80, 64); B.m_wgrad(G0 + 32768, Adir, 80, 144); B.m_commit(D0);
+  if (fine) {
+    B.m_wait(L_GTH); B.m_wait(L_T3);
+    B.m_wgrad(G1, At3, 80, 224); B.m_commit(D1);
+    B.m_wait(E1); B.m_wait(L_T2);                              // GT3 written by epilogue 1
+    B.m_wgrad(G2, At2, 80, 304); B.m_commit(D2);
+    B.m_wait(E2); B.m_wait(L_TENC);                            // GT2 written by epilogue 2
     B.m_wgrad(G3, Atenc, 80, 384); B.m_commit(D3);
   }
-  // ---- epilogue
+  // ---- epilogue (a gradient image may be overwritten only when BOTH streams finished reading its previous content)
   B.e_wait(ACC0); B.e_wait(L_DIR); B.e_wait(OUTFREE, FW_PREV); B.e_epi(0, 64, true, Adir, G4); B.e_arrive(E0);
   if (fine) {
-    B.e_wait(ACC1); B.e_wait(L_T3); B.e_epi(0, 64, true, At3, G2); B.e_arrive(E1);
-    B.e_wait(ACC2); B.e_wait(L_T2); B.e_epi(0, 64, true, At2, G3); B.e_arrive(E2);
+    B.e_wait(ACC1); B.e_wait(L_T3); B.e_wait(D2, FW_PREV); B.e_epi(0, 64, true, At3, G2); B.e_arrive(E1);
+    B.e_wait(ACC2); B.e_wait(L_T2); B.e_wait(D3, FW_PREV); B.e_epi(0, 64, true, At2, G3); B.e_arrive(E2);
     B.e_wait(ACC3); B.e_wait(L_TENC); B.e_epi(0, 64, true, Atenc, G4 + 16384); B.e_arrive(E3);
   }
   // ---- flush
@@ -1232,21 +1268,24 @@ int launch_heads2(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
     reload(iGDT);
     B = P;
   }
-  // ---- MMA issuer
+  // ---- data-gradient issuer
+  B.mp = 0;
   B.m_wait(bW, FW_ONCE);
   B.m_wait(L_GDT); B.m_wait(E1, FW_PREV);
   B.m_dgrad(G0, dt_ch, W0, 128, 128, 0); B.m_commit(ACC0);
-  B.m_wait(L_A0);
-  B.m_wgrad(G0, A0, 160, 128); B.m_commit(D0);
   B.m_wait(E0); B.m_wait(L_GSIG);
   B.m_dgrad(G1, 144, W1, 128, 128, 0); B.m_commit(ACC1);
-  B.m_wait(L_H7);
+  // ---- weight-gradient issuer
+  B.mp = 1;
+  B.m_wait(L_GDT); B.m_wait(L_A0);
+  B.m_wgrad(G0, A0, 160, 128); B.m_commit(D0);
+  B.m_wait(E0); B.m_wait(L_GSIG); B.m_wait(L_H7);
   B.m_wgrad(G1, A1, 144, 288);
   B.m_wgrad(A1, G1 + 32768, 16, 432);                 // sigma row, transposed: D[h8 channel, 0] = sum_p h8[p, ch] * gsig[p]
   B.m_commit(D1);
   // ---- epilogue
-  B.e_wait(ACC0); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);
-  B.e_wait(ACC1); B.e_wait(L_H7); B.e_epi(0, 128, true, A1, G0); B.e_arrive(E1);
+  B.e_wait(ACC0); B.e_wait(D1, FW_PREV); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);        // gFIN over the previous gFS
+  B.e_wait(ACC1); B.e_wait(L_H7); B.e_wait(D0); B.e_epi(0, 128, true, A1, G0); B.e_arrive(E1); // G7 over GDT (read by D0)
   // ---- flush: the dirPE image carries a constant 1 in its last padding channel (column 128 + 31): bias of [dir | tenc0]
   B.flush(128, 160, pl_dt, 0, 0, FF_W); B.flush(128 + 144, 16, pl_dt, 0, 15, FF_BIAS);
   B.flush(288, 128, PL_FS, 0, 0, FF_W); B.flush(288 + 128, 16, PL_FS, 0, 0, FF_BIAS);
@@ -1311,9 +1350,11 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   const bool fused_trunk = dP != nullptr && d_pts == nullptr && getenv("NEFES_NO_FUSED_TRUNK") == nullptr;
   // (measured: a gain for the fine net's six head layers, none for the coarse net's three)
   const bool fused_heads = fused_trunk && mode == NEFES_MODE_FULL && getenv("NEFES_NO_FUSED_HEADS") == nullptr;
+  prof_begin("head_grad_images", st, (double)M * (4.0 * C + 4.0 * (C == 137 ? 6 : 1) + 2.0 * (C == 1 ? 16 : (C == 137 ? 176 : 160))), 0.0);
   head_grad_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(
       raw, d_raw, C, tiles ? 1 : C, tiles ? kTile : 1, M, Mp, b.GRGB.p, b.GTH.p, gsig_img.p, gsig_img.tile_stride(),
       mode == NEFES_MODE_SIGMA ? 0 : 16, fused_heads ? dP + layout_for(net).b[L_SIGMA] : nullptr);
+  prof_end(st);
   NEFES_CHECK_LAUNCH("head_grad_images");
   if (fused_heads) {
     TRY(launch_heads1(w, b, A, net, mode, M, dP, st));
@@ -1403,7 +1444,13 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   }
   int grid = num_sms();
   if (grid > T * nj) grid = T * nj;
+  {
+    double macs = 0;
+    for (int j = 0; j < nj; ++j) macs += (double)wa.job[j].g_ch * wa.job[j].a_ch;
+    prof_begin("wgrad", st, (double)cost, (double)M * 2.0 * macs);
+  }
   wgrad_kernel<<<grid, kThreads, smem, st>>>(wa);
+  prof_end(st);
   NEFES_CHECK_LAUNCH("wgrad");
   return NEFES_OK;
 }
