@@ -52,7 +52,7 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1387.4), d.get("hbm_gbs", 6553.3), "measured (MEASURED_PEAKS.json, sustained bf16)"
+        return d.get("bf16_tflops_sustained", 1387.4), d.get("hbm_gbs", 6553.3), "measured (MEASURED_PEAKS.json: copy bandwidth, sustained bf16 GEMM)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
@@ -147,6 +147,8 @@ def run_engine(a):
               use_viewdirs=True, white_bkgd=False, args=Args(), ndc=False, lindisp=False, near=NEAR, far=FAR,
               perturb=1., raw_noise_std=0., test_time=False, retraw=True)
 
+    loss_fn = nb.NerfWLoss(coef=1, lambda_u=0.01)                                # losses.py:96-132 on two kernels
+
     def step(b):
         """b: dict of DEVICE tensors.  One optimiser step, returns the loss tensor."""
         ro, rd = nb.get_rays_batch(H, W, FOCAL, b["pose"])                      # [4,60,80,3]
@@ -154,7 +156,8 @@ def run_engine(a):
         rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, b["idx"][..., None].expand(-1, -1, 3)).reshape(-1, 3)
         hist = b["hist"][:, None, :].expand(-1, N_RAND, -1).reshape(-1, 10)
         rgb, disp, acc, ex = nb.render(H, W, FOCAL, chunk=32768, rays=(ro, rd), img_idx=hist, **kw)
-        loss = nerfw_loss(dict(rgb_map=rgb, **ex), b["target"])
+        loss = loss_fn({"rgb_coarse": ex["rgb0"], "rgb_fine": rgb, "beta": ex["beta"],
+                        "transient_sigmas": ex["transient_sigmas"]}, b["target"])
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:
@@ -227,7 +230,8 @@ def run_engine(a):
         table[tag] = {"launches_per_step": k["launches"] / a.steps, "ms_per_step": k["ms"] / a.steps,
                       "GB_per_s": k["alg_bytes"] / k["ms"] / 1e6, "TFLOP_per_s": k["alg_flops"] / k["ms"] / 1e9,
                       "hbm_frac": k["alg_bytes"] / k["ms"] / 1e6 / hbm_peak, "tensor_frac": k["alg_flops"] / k["ms"] / 1e9 / tf_peak}
-    top = max(table, key=lambda t: table[t]["ms_per_step"]) if table else None
+    # dominant kernel = the single launch that takes longest (a tag that launches 8 small kernels does not outrank it)
+    top = max(table, key=lambda t: table[t]["ms_per_step"] / table[t]["launches_per_step"]) if table else None
     out = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -246,6 +250,7 @@ def run_engine(a):
         # `traffic` is dram read+write of one launch from the committed ncu capture (profiles/), null if not captured.
         "roofline": ({"bound": "hbm", "kernel": top, "achieved": table[top]["GB_per_s"], "peak": hbm_peak, "unit": "GB/s",
                       "frac": table[top]["hbm_frac"], "traffic": NCU_TRAFFIC.get(top), "peak_source": which,
+                      "ms_per_launch": table[top]["ms_per_step"] / table[top]["launches_per_step"],
                       "ms_per_step_in_kernel": table[top]["ms_per_step"],
                       "share_of_step": table[top]["ms_per_step"] / (ms / a.steps)} if top else None),
         "kernels": table,

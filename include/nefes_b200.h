@@ -239,6 +239,18 @@ int nefes_adam_step(float* params, const float* grads, float* exp_avg, float* ex
                     int64_t n, float lr, float beta1, float beta2, float eps, int step,
                     float grad_scale, void* stream);
 
+/* NeRF-W colour loss of the stage-1 step (script/models/losses.py:96-132, NerfWLoss with the transient head):
+ *   loss = coef * (0.5 mean((rgb_coarse-t)^2) + mean((rgb_fine-t)^2 / (2 beta^2)) + 3 + mean(log beta)
+ *                  + lambda_u mean(transient_sigmas))
+ * rgb_* / target [N,3], beta [N], transient_sigmas [N,S]; scratch8: 8 floats of device scratch; loss: 1 float.
+ * bwd: d_loss is the upstream cotangent of the scalar (device pointer); the four gradients are overwritten. */
+int nefes_nerfw_loss_fwd(const float* rgb_coarse, const float* rgb_fine, const float* beta, const float* transient_sigmas,
+                         const float* target, int64_t N, int S, float coef, float lambda_u, float* scratch8, float* loss,
+                         void* stream);
+int nefes_nerfw_loss_bwd(const float* rgb_coarse, const float* rgb_fine, const float* beta, const float* target,
+                         const float* d_loss, int64_t N, int S, float coef, float lambda_u, float* d_rgb_coarse,
+                         float* d_rgb_fine, float* d_beta, float* d_transient_sigmas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

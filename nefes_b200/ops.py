@@ -290,6 +290,7 @@ class _Composite(Function):
 
     @staticmethod
     def forward(ctx, raw, z, noise, mode, beta_min, tiled):
+        ctx.set_materialize_grads(False)             # unused outputs arrive as None, not as zero-filled tensors
         L.need_cuda(raw, z, noise)
         raw_c, z_c, noise_c = L.f32c(raw), L.f32c(z), L.f32c(noise)
         N, S = z_c.shape
