@@ -185,6 +185,14 @@ int nefes_mlp_bwd_tiles(const float* params, int net, int mode, int prec, const 
                         const float* dirs, int64_t N, int S, const float* raw_tiles, const float* d_raw_tiles,
                         const void* saved, void* scratch, float* d_params, float* d_pts, float* d_dirs,
                         void* stream);
+/* Backward from the COMPACT cotangent of raw that nefes_composite_bwd_compact writes ([N][5][S] fp32: static weight,
+ * transient weight, d sigma, d transient sigma, d beta per sample) plus the per-ray cotangents of the composited rgb
+ * [N,3] and feature [N,128] (either may be NULL = zero): d_raw[s, c] = weight[s] * g_ray[c] for the 134 colour / feature
+ * channels, so the 137-channel fp32 block never exists in HBM.  Tile-major raw, bf16 path, colour modes. */
+int nefes_mlp_bwd_compact(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
+                          int64_t N, int S, const float* raw_tiles, const float* compact, const float* g_rgb,
+                          const float* g_feat, const void* saved, void* scratch, float* d_params, float* d_pts,
+                          float* d_dirs, void* stream);
 /* d_params (flat, same layout as params) is ACCUMULATED into (caller zero-fills) or NULL
  * (frozen weights: refinement); d_pts [M,3] / d_dirs [N,3] are overwritten, or NULL. */
 int nefes_mlp_bwd(const float* params, int net, int mode, int prec, const float* pts,
@@ -229,6 +237,9 @@ int nefes_composite_fwd_tiles(const float* raw_tiles, const float* z_vals, const
                               int mode, float beta_min, const nefes_comp_out_t* out_host, void* stream);
 int nefes_composite_bwd_tiles(const float* raw_tiles, const float* z_vals, const float* noise, int N, int S,
                               int mode, const nefes_comp_grad_t* g_host, float* d_raw_tiles, void* stream);
+/* ... writing the compact cotangent [N][5][S] consumed by nefes_mlp_bwd_compact instead of d_raw */
+int nefes_composite_bwd_compact(const float* raw_tiles, const float* z_vals, const float* noise, int N, int S,
+                                int mode, const nefes_comp_grad_t* g_host, float* compact, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Caller-side helpers on the "next" rows of SURVEY 8f that the training step needs resident.

@@ -188,7 +188,7 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw, const float*
 template <int MODE, bool TILES>
 __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                                      const float* __restrict__ noise, int S, nefes_comp_grad_t g,
-                                     float* __restrict__ d_raw) {
+                                     float* __restrict__ d_raw, float* __restrict__ compact) {
   constexpr int C = Chan<MODE>::C;
   __shared__ Scan sc;
   __shared__ float s_ws[kMaxS], s_wt[kMaxS], s_dsig[kMaxS], s_dsigt[kMaxS], s_dbeta[kMaxS];
@@ -261,6 +261,16 @@ __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float*
     }
     if ((MODE == NEFES_COMP_TRANSIENT || MODE == NEFES_COMP_TRANSIENT_STATIC_ONLY) && ok && g.tsig)
       dsigt += g.tsig[(int64_t)r * S + t];
+  }
+  if (compact != nullptr) {
+    // compact form of d_raw [ray][5][S]: d_raw[s, c] is rank one in (sample, channel) for the 131 + 3 colour / feature
+    // channels -- (static weight | transient weight) x (cotangent of the ray's rgb / feature) -- so only the two weight
+    // vectors and the three per-sample scalar gradients leave this kernel; the field backward rebuilds the columns
+    if (ok) {
+      float* cr = compact + (int64_t)r * 5 * S + t;
+      cr[0] = w_static; cr[S] = w_t; cr[2 * S] = dsig; cr[3 * S] = dsigt; cr[4 * S] = dbeta;
+    }
+    return;
   }
   if (ok) {
     s_ws[t] = w_static; s_wt[t] = w_t; s_dsig[t] = dsig; s_dsigt[t] = dsigt; s_dbeta[t] = dbeta;
@@ -352,10 +362,10 @@ static int comp_fwd_launch(const char* who, const float* raw, const float* z_val
 
 template <bool TILES>
 static int comp_bwd_launch(const char* who, const float* raw, const float* z_vals, const float* noise, int N, int S, int mode,
-                           const nefes_comp_grad_t* g_host, float* d_raw, void* stream) {
+                           const nefes_comp_grad_t* g_host, float* d_raw, void* stream, float* compact = nullptr) {
   if (int e = comp_check(who, raw, z_vals, N, S, mode)) return e;
   if (N == 0) return NEFES_OK;
-  NEFES_REQUIRE(g_host && d_raw, NEFES_EINVAL, "%s: null pointer", who);
+  NEFES_REQUIRE(g_host && (d_raw || compact), NEFES_EINVAL, "%s: null pointer", who);
   NEFES_REQUIRE(!TILES || 128 % S == 0, NEFES_EINVAL, "%s: tile-major raw needs S to divide 128 (S=%d)", who, S);
   const int threads = (int)nefes::round_up(S > 160 ? S : (mode == NEFES_COMP_SIGMA ? S : (TILES ? 256 : 160)), 32);
   cudaStream_t st = (cudaStream_t)stream;
@@ -363,13 +373,13 @@ static int comp_bwd_launch(const char* who, const float* raw, const float* z_val
   {
     const int C = mode == NEFES_COMP_SIGMA ? 1 : (mode == NEFES_COMP_STATIC ? 132 : 137);
     nefes::prof_begin(mode == NEFES_COMP_STATIC ? "composite_bwd_coarse" : (mode == NEFES_COMP_SIGMA ? "composite_bwd_sigma" : "composite_bwd_fine"), st,
-                      (double)N * (8.0 * S * C + 4.0 * S * 3 + 4.0 * 140), 0.0);   // raw in, d_raw out
+                      (double)N * ((compact ? 4.0 * S * 8 : 8.0 * S * C) + 4.0 * S * 3 + 4.0 * 140), 0.0);   // raw in, d_raw out
   }
   switch (mode) {
-    case NEFES_COMP_SIGMA: nefes::composite_bwd_kernel<NEFES_COMP_SIGMA, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
-    case NEFES_COMP_STATIC: nefes::composite_bwd_kernel<NEFES_COMP_STATIC, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
-    case NEFES_COMP_TRANSIENT: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
-    default: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT_STATIC_ONLY, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw); break;
+    case NEFES_COMP_SIGMA: nefes::composite_bwd_kernel<NEFES_COMP_SIGMA, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw, compact); break;
+    case NEFES_COMP_STATIC: nefes::composite_bwd_kernel<NEFES_COMP_STATIC, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw, compact); break;
+    case NEFES_COMP_TRANSIENT: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw, compact); break;
+    default: nefes::composite_bwd_kernel<NEFES_COMP_TRANSIENT_STATIC_ONLY, TILES><<<N, threads, 0, st>>>(raw, z_vals, noise, S, g, d_raw, compact); break;
   }
   nefes::prof_end(st);
   NEFES_CHECK_LAUNCH(who);
@@ -393,6 +403,12 @@ int nefes_composite_bwd(const float* raw, const float* z_vals, const float* nois
 int nefes_composite_bwd_tiles(const float* raw_tiles, const float* z_vals, const float* noise, int N, int S,
                               int mode, const nefes_comp_grad_t* g_host, float* d_raw_tiles, void* stream) {
   return comp_bwd_launch<true>("nefes_composite_bwd_tiles", raw_tiles, z_vals, noise, N, S, mode, g_host, d_raw_tiles, stream);
+}
+
+int nefes_composite_bwd_compact(const float* raw_tiles, const float* z_vals, const float* noise, int N, int S,
+                                int mode, const nefes_comp_grad_t* g_host, float* compact, void* stream) {
+  NEFES_REQUIRE(compact != nullptr && mode != NEFES_COMP_SIGMA, NEFES_EINVAL, "nefes_composite_bwd_compact: bad arguments");
+  return comp_bwd_launch<true>("nefes_composite_bwd_compact", raw_tiles, z_vals, noise, N, S, mode, g_host, nullptr, stream, compact);
 }
 
 }  // extern "C"

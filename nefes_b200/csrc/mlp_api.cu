@@ -8,7 +8,7 @@ int mlp_bwd_fp32(const float*, int, int, const float*, const float*, int64_t, in
 int mlp_workspace_fp32(int, int64_t, int64_t, int64_t*, int64_t*, int64_t*);
 int mlp_fwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, float*, void*, void*, int, cudaStream_t);
 int mlp_bwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, const float*, const float*,
-                 const void*, void*, float*, float*, float*, int, cudaStream_t);
+                 const void*, void*, float*, float*, float*, int, cudaStream_t, const float*, const float*, const float*);
 int mlp_workspace_bf16(int, int, int64_t, int64_t, int64_t*, int64_t*, int64_t*);
 
 // torch.optim.Adam semantics (amsgrad=False, weight_decay=0, maximize=False)
@@ -67,9 +67,10 @@ static int mlp_fwd_any(const char* who, int layout, const float* params, int net
 
 static int mlp_bwd_any(const char* who, int layout, const float* params, int net, int mode, int prec, const float* pts,
                        const float* dirs, int64_t N, int S, const float* raw, const float* d_raw, const void* saved,
-                       void* scratch, float* d_params, float* d_pts, float* d_dirs, void* stream) {
+                       void* scratch, float* d_params, float* d_pts, float* d_dirs, void* stream,
+                       const float* compact = nullptr, const float* g_rgb = nullptr, const float* g_feat = nullptr) {
   if (int e = nefes::check_mlp(who, net, mode, prec, N, S)) return e;
-  NEFES_REQUIRE(params && pts && raw && d_raw && saved && scratch, NEFES_EINVAL, "%s: null pointer", who);
+  NEFES_REQUIRE(params && pts && raw && (d_raw || compact) && saved && scratch, NEFES_EINVAL, "%s: null pointer", who);
   NEFES_REQUIRE(mode == NEFES_MODE_SIGMA || dirs, NEFES_EINVAL, "%s: dirs required", who);
   NEFES_REQUIRE(((uintptr_t)saved & 15) == 0 && ((uintptr_t)scratch & 15) == 0, NEFES_EALIGN,
                 "%s: workspaces must be 16-byte aligned", who);
@@ -78,7 +79,7 @@ static int mlp_bwd_any(const char* who, int layout, const float* params, int net
   if (N == 0) return NEFES_OK;
   if (prec == NEFES_PREC_BF16)
     return nefes::mlp_bwd_bf16(params, net, mode, pts, dirs, N, S, raw, d_raw, saved, scratch, d_params, d_pts,
-                               d_dirs, layout, (cudaStream_t)stream);
+                               d_dirs, layout, (cudaStream_t)stream, compact, g_rgb, g_feat);
   return nefes::mlp_bwd_fp32(params, net, mode, pts, dirs, N, S, raw, d_raw, saved, scratch, d_params, d_pts,
                              d_dirs, (cudaStream_t)stream);
 }
@@ -103,6 +104,16 @@ int nefes_mlp_bwd_tiles(const float* params, int net, int mode, int prec, const 
                         void* scratch, float* d_params, float* d_pts, float* d_dirs, void* stream) {
   return mlp_bwd_any("nefes_mlp_bwd_tiles", NEFES_RAW_TILES, params, net, mode, prec, pts, dirs, N, S, raw_tiles,
                      d_raw_tiles, saved, scratch, d_params, d_pts, d_dirs, stream);
+}
+
+int nefes_mlp_bwd_compact(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
+                          int64_t N, int S, const float* raw_tiles, const float* compact, const float* g_rgb,
+                          const float* g_feat, const void* saved, void* scratch, float* d_params, float* d_pts,
+                          float* d_dirs, void* stream) {
+  NEFES_REQUIRE(compact != nullptr && mode != NEFES_MODE_SIGMA && prec == NEFES_PREC_BF16, NEFES_EINVAL,
+                "nefes_mlp_bwd_compact: needs the compact cotangent, a colour mode and the bf16 path");
+  return mlp_bwd_any("nefes_mlp_bwd_compact", NEFES_RAW_TILES, params, net, mode, prec, pts, dirs, N, S, raw_tiles, nullptr,
+                     saved, scratch, d_params, d_pts, d_dirs, stream, compact, g_rgb, g_feat);
 }
 
 int nefes_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

@@ -521,7 +521,8 @@ __global__ void tiles_to_rows_kernel(const float* __restrict__ src, float* __res
 __global__ void head_grad_images_kernel(const float* __restrict__ raw, const float* __restrict__ d_raw, int C, int rs, int cs,
                                         int64_t M, int64_t Mp, uint8_t* __restrict__ grgb, uint8_t* __restrict__ gth,
                                         uint8_t* __restrict__ gfs, int64_t gfs_tile_stride, int gfs_chunk0,
-                                        float* __restrict__ d_sig_bias) {
+                                        float* __restrict__ d_sig_bias, const float* __restrict__ compact,
+                                        const float* __restrict__ g_rgb, const float* __restrict__ g_feat, int S) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Mp) return;                               // Mp is a multiple of the block size: whole blocks leave together
   const int64_t tile = m / kTile;
@@ -531,7 +532,27 @@ __global__ void head_grad_images_kernel(const float* __restrict__ raw, const flo
   const float* y = raw + base;
   const float* gd = d_raw + base;
   const int sig_col = (C == 1) ? 0 : 131;
-  const float dsig = ok ? gd[(int64_t)sig_col * cs] * (1.f - expf(-y[(int64_t)sig_col * cs])) : 0.f;
+  // compact cotangent (nefes_composite_bwd_compact): d_raw[m, c] = w_s[m] * g_ray[c] (c < 131), w_t[m] * g_rgb (132..134),
+  // and three per-sample scalars -- rebuilt here instead of being read back from a 137-channel fp32 block
+  float w_s = 0.f, w_t = 0.f, c_dsig = 0.f, c_dsigt = 0.f, c_dbeta = 0.f;
+  const float* gf = nullptr;
+  float grgb3[3] = {0.f, 0.f, 0.f};
+  if (compact != nullptr && ok) {
+    const int64_t ray = m / S;
+    const float* cr = compact + ray * 5 * S + (m % S);
+    w_s = cr[0]; w_t = cr[S]; c_dsig = cr[2 * S]; c_dsigt = cr[3 * S]; c_dbeta = cr[4 * S];
+    if (g_feat != nullptr) gf = g_feat + ray * kFeat;
+    if (g_rgb != nullptr) { grgb3[0] = g_rgb[ray * 3]; grgb3[1] = g_rgb[ray * 3 + 1]; grgb3[2] = g_rgb[ray * 3 + 2]; }
+  }
+  auto gval = [&](int c) -> float {              // cotangent of raw[m, c]
+    if (compact == nullptr) return gd[(int64_t)c * cs];
+    if (c < 3) return grgb3[c] * w_s;
+    if (c < kHeadCh) return gf ? gf[c - 3] * w_s : 0.f;
+    if (c == 131) return c_dsig;
+    if (c < 135) return grgb3[c - 132] * w_t;
+    return c == 135 ? c_dsigt : c_dbeta;
+  };
+  const float dsig = ok ? gval(sig_col) * (1.f - expf(-y[(int64_t)sig_col * cs])) : 0.f;
   if (d_sig_bias != nullptr) {                       // bias gradient of the sigma head = sum of its pre-activation gradients
     __shared__ float s_part[4];
     const float ws = warp_sum(__bfloat162float(__float2bfloat16(dsig)));     // the value the tensor path sees
@@ -552,7 +573,7 @@ __global__ void head_grad_images_kernel(const float* __restrict__ raw, const flo
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int c = 8 * j + q;
-      e[q] = (ok && c < kHeadCh) ? gd[(int64_t)c * cs] : 0.f;
+      e[q] = (ok && c < kHeadCh) ? gval(c) : 0.f;
     }
     uint4 pk;
     pk.x = pack_bf16(e[0], e[1]); pk.y = pack_bf16(e[2], e[3]); pk.z = pack_bf16(e[4], e[5]); pk.w = pack_bf16(e[6], e[7]);
@@ -562,9 +583,9 @@ __global__ void head_grad_images_kernel(const float* __restrict__ raw, const flo
     float e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (ok) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { const float yc = y[(int64_t)(132 + c) * cs]; e[c] = gd[(int64_t)(132 + c) * cs] * yc * (1.f - yc); }
-      e[3] = gd[(int64_t)135 * cs] * (1.f - expf(-y[(int64_t)135 * cs]));
-      e[4] = gd[(int64_t)136 * cs] * (1.f - expf(-y[(int64_t)136 * cs]));
+      for (int c = 0; c < 3; ++c) { const float yc = y[(int64_t)(132 + c) * cs]; e[c] = gval(132 + c) * yc * (1.f - yc); }
+      e[3] = gval(135) * (1.f - expf(-y[(int64_t)135 * cs]));
+      e[4] = gval(136) * (1.f - expf(-y[(int64_t)136 * cs]));
     }
     uint8_t* tb = gth + tile * (16 * 256) + row * 16;
     uint4 pk;
@@ -1332,7 +1353,7 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
 
 int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const float* dirs, int64_t N, int S,
                  const float* raw, const float* d_raw, const void* saved, void* scratch, float* dP, float* d_pts,
-                 float* d_dirs, int layout, cudaStream_t st) {
+                 float* d_dirs, int layout, cudaStream_t st, const float* compact, const float* g_rgb, const float* g_feat) {
   (void)P;
   const int64_t M = N * S;
   const int T = (int)ceil_div(M, kTile);
@@ -1350,10 +1371,10 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   const bool fused_trunk = dP != nullptr && d_pts == nullptr && getenv("NEFES_NO_FUSED_TRUNK") == nullptr;
   // (measured: a gain for the fine net's six head layers, none for the coarse net's three)
   const bool fused_heads = fused_trunk && mode == NEFES_MODE_FULL && getenv("NEFES_NO_FUSED_HEADS") == nullptr;
-  prof_begin("head_grad_images", st, (double)M * (4.0 * C + 4.0 * (C == 137 ? 6 : 1) + 2.0 * (C == 1 ? 16 : (C == 137 ? 176 : 160))), 0.0);
+  prof_begin("head_grad_images", st, (double)M * ((compact ? 20.0 : 4.0 * C) + 4.0 * (C == 137 ? 6 : 1) + 2.0 * (C == 1 ? 16 : (C == 137 ? 176 : 160))), 0.0);
   head_grad_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(
       raw, d_raw, C, tiles ? 1 : C, tiles ? kTile : 1, M, Mp, b.GRGB.p, b.GTH.p, gsig_img.p, gsig_img.tile_stride(),
-      mode == NEFES_MODE_SIGMA ? 0 : 16, fused_heads ? dP + layout_for(net).b[L_SIGMA] : nullptr);
+      mode == NEFES_MODE_SIGMA ? 0 : 16, fused_heads ? dP + layout_for(net).b[L_SIGMA] : nullptr, compact, g_rgb, g_feat, S);
   prof_end(st);
   NEFES_CHECK_LAUNCH("head_grad_images");
   if (fused_heads) {

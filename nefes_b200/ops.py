@@ -181,6 +181,10 @@ class TiledRaw:
 
     def __init__(self, t, N, S, C_):
         self.t, self.N, self.S, self.C = t, N, S, C_
+        # set by render_rays, the only consumer of its own raw: the compositing backward may then hand the field backward
+        # the COMPACT cotangent (weights x per-ray cotangents) instead of a [T,C,128] fp32 block
+        self.private = False
+        self.single = True                           # produced by ONE field query (its autograd node owns `t`)
 
     @property
     def shape(self):
@@ -198,10 +202,14 @@ class TiledRaw:
     def cat(parts):
         if any((p.N * p.S) % 128 for p in parts[:-1]):
             raise RuntimeError("nefes_b200: netchunk must cut the rays at multiples of 128 points")
-        return TiledRaw(torch.cat([p.t for p in parts], 0), sum(p.N for p in parts), parts[0].S, parts[0].C)
+        out = TiledRaw(torch.cat([p.t for p in parts], 0), sum(p.N for p in parts), parts[0].S, parts[0].C)
+        out.single = False
+        return out
 
 
 _tiled_depth = 0
+# compact cotangents in flight between _Composite.backward and _FieldQuery.backward, keyed by raw's storage address
+_COMPACT = {}
 
 
 class tiled_raw:
@@ -256,7 +264,9 @@ class _FieldQuery(Function):
         pts_c, dirs_c, flat_c, raw, saved = ctx.saved_tensors
         net, mode, prec, N, S, pshape, dshape, tiled = ctx.meta
         dev = pts_c.device
-        d_raw = L.f32c(d_raw)
+        compact = _COMPACT.pop(raw.data_ptr(), None) if tiled else None
+        if compact is None:
+            d_raw = L.f32c(d_raw)
         need_p, need_d, need_w = ctx.needs_input_grad[:3]
         d_pts = torch.empty_like(pts_c) if need_p else None
         d_dirs = torch.empty_like(dirs_c) if (need_d and dirs_c is not None) else None
@@ -265,9 +275,16 @@ class _FieldQuery(Function):
         scratch = _buf(sb, dev)
         fn = L.lib().nefes_mlp_bwd_tiles if tiled else L.lib().nefes_mlp_bwd
         with torch.cuda.device(dev), _Timed("mlp_bwd"):
-            L.check(fn(L.ptr(flat_c), net, mode, prec, L.ptr(pts_c), L.ptr(dirs_c), N, S,
-                       L.ptr(raw), L.ptr(d_raw), L.ptr(saved), L.ptr(scratch), L.ptr(d_flat),
-                       L.ptr(d_pts), L.ptr(d_dirs), L.stream_of(pts_c)), "nefes_mlp_bwd")
+            if compact is not None:
+                cg, g_rgb, g_feat = compact
+                L.check(L.lib().nefes_mlp_bwd_compact(L.ptr(flat_c), net, mode, prec, L.ptr(pts_c), L.ptr(dirs_c), N, S,
+                                                      L.ptr(raw), L.ptr(cg), L.ptr(g_rgb), L.ptr(g_feat), L.ptr(saved),
+                                                      L.ptr(scratch), L.ptr(d_flat), L.ptr(d_pts), L.ptr(d_dirs),
+                                                      L.stream_of(pts_c)), "nefes_mlp_bwd_compact")
+            else:
+                L.check(fn(L.ptr(flat_c), net, mode, prec, L.ptr(pts_c), L.ptr(dirs_c), N, S,
+                           L.ptr(raw), L.ptr(d_raw), L.ptr(saved), L.ptr(scratch), L.ptr(d_flat),
+                           L.ptr(d_pts), L.ptr(d_dirs), L.stream_of(pts_c)), "nefes_mlp_bwd")
         return (d_pts.reshape(pshape) if d_pts is not None else None,
                 d_dirs.reshape(dshape) if d_dirs is not None else None, d_flat, None, None, None, None)
 
@@ -289,7 +306,7 @@ class _Composite(Function):
     backward kernel instead of through a dense zero-filled slice gradient."""
 
     @staticmethod
-    def forward(ctx, raw, z, noise, mode, beta_min, tiled):
+    def forward(ctx, raw, z, noise, mode, beta_min, tiled, compact=False):
         ctx.set_materialize_grads(False)             # unused outputs arrive as None, not as zero-filled tensors
         L.need_cuda(raw, z, noise)
         raw_c, z_c, noise_c = L.f32c(raw), L.f32c(z), L.f32c(noise)
@@ -313,7 +330,7 @@ class _Composite(Function):
             L.check(fn(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode,
                        float(beta_min), C.byref(out), L.stream_of(raw_c)), "nefes_composite_fwd")
         ctx.save_for_backward(raw_c, z_c, noise_c)
-        ctx.meta = (mode, N, S, tuple(raw.shape), tiled)
+        ctx.meta = (mode, N, S, tuple(raw.shape), tiled, bool(compact) and tiled and mode != L.COMP_SIGMA)
         if mode == L.COMP_SIGMA:
             return acc, weights
         if tsig is None:
@@ -323,7 +340,7 @@ class _Composite(Function):
     @staticmethod
     def backward(ctx, *grads):
         raw_c, z_c, noise_c = ctx.saved_tensors
-        mode, N, S, rshape, tiled = ctx.meta
+        mode, N, S, rshape, tiled, compact = ctx.meta
         if mode == L.COMP_SIGMA:
             g_acc, g_w = grads
             g = dict(acc=g_acc, weights=g_w)
@@ -331,18 +348,27 @@ class _Composite(Function):
             g = dict(zip(("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig"), grads))
         g = {k: L.f32c(v) for k, v in g.items() if v is not None}
         gs = L.CompGrad(*[L.ptr(g.get(k)) for k in ("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig")])
+        if compact:
+            # the field backward picks the compact cotangent up by raw's address; what autograd carries is a placeholder
+            # of the right shape that is never read (a 0-dim tensor expanded, no memory, no kernel)
+            cg = torch.empty(N, 5, S, device=raw_c.device)
+            with torch.cuda.device(raw_c.device):
+                L.check(L.lib().nefes_composite_bwd_compact(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode, C.byref(gs),
+                                                            L.ptr(cg), L.stream_of(raw_c)), "nefes_composite_bwd_compact")
+            _COMPACT[raw_c.data_ptr()] = (cg, g.get("rgb"), g.get("feat"))
+            return cg.new_zeros(()).expand(rshape), None, None, None, None, None, None
         d_raw = torch.empty_like(raw_c)
         fn = L.lib().nefes_composite_bwd_tiles if tiled else L.lib().nefes_composite_bwd
         with torch.cuda.device(raw_c.device):
             L.check(fn(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode, C.byref(gs),
                        L.ptr(d_raw), L.stream_of(raw_c)), "nefes_composite_bwd")
-        return d_raw.reshape(rshape), None, None, None, None, None
+        return d_raw.reshape(rshape), None, None, None, None, None, None
 
 
 def composite(raw, z, noise, mode, beta_min=0.1):
     if isinstance(raw, TiledRaw):
-        return _Composite.apply(raw.t, z, noise, int(mode), float(beta_min), True)
-    return _Composite.apply(raw, z, noise, int(mode), float(beta_min), False)
+        return _Composite.apply(raw.t, z, noise, int(mode), float(beta_min), True, raw.private)
+    return _Composite.apply(raw, z, noise, int(mode), float(beta_min), False, False)
 
 
 # ------------------------------------------------------------------------------------------------

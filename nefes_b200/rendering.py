@@ -59,6 +59,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     store_rgb = N_importance == 0
     with ops.tiled_raw():
         raw = network_query_fn(pts, viewdirs, None, network_fn, 'coarse', False, test_time=test_time, store_rgb=store_rgb)
+    if isinstance(raw, ops.TiledRaw):
+        raw.private = raw.single                     # consumed by the compositing below and by nothing else
     if noise is None and raw_noise_std > 0. and not (test_time and not store_rgb):
         noise = torch.randn(N_rays, N_samples, device=dev) * raw_noise_std        # nerfh_nff.py:67
     rgb_map, feat_map, disp_map, acc_map, weights, depth_map, _, _ = raw2outputs_NeRFH_NFF(
@@ -88,6 +90,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         with ops.tiled_raw():
             raw = network_query_fn(pts, viewdirs, img_idxs, network_fine, 'fine', output_transient,
                                    test_time=test_time, store_rgb=store_rgb)
+        if isinstance(raw, ops.TiledRaw):
+            raw.private = raw.single
         rgb_map, feat_map, disp_map, acc_map, weights, depth_map, transient_sigmas, beta = raw2outputs_NeRFH_NFF(
             raw, z_vals, raw_noise_std=raw_noise_std, output_transient=output_transient,
             beta_min=network_fine.beta_min, white_bkgd=white_bkgd, test_time=test_time, typ="fine",

@@ -79,3 +79,35 @@ def test_nerfw_loss_matches_torch_expression():
     assert abs(float(le) - float(lr)) <= 2e-6 * abs(float(lr))
     for a, b in zip(ge, gr):
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12
+
+
+def test_render_gradients_do_not_depend_on_netchunk():
+    """netchunk splits the field query into several launches (TiledRaw.cat): the compact-cotangent shortcut must step
+    aside there and the weight gradients must match the single-launch render."""
+    import nefes_b200 as nb
+    c, f = _nets()
+    H, W, focal = 60, 80, 65.688
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 384
+    ro = torch.zeros(n, 3, device="cuda")
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda", generator=g), dim=-1)
+    t_rand, u = torch.rand(n, 64, device="cuda", generator=g), torch.rand(n, 64, device="cuda", generator=g)
+
+    def run(netchunk):
+        class Args:
+            nerfh_nff, use_fine_only, NeRFW, transient_at_test = True, False, True, True
+        Args.netchunk = netchunk
+        q = lambda i, v, ts, fn, typ, ot, test_time, store_rgb: nb.run_network_NeRFH_NFF(
+            i, v, ts, fn, typ=typ, output_transient=ot, netchunk=Args.netchunk, test_time=test_time, store_rgb=store_rgb)
+        c.zero_grad(); f.zero_grad()
+        rgb, disp, acc, ex = nb.render(H, W, focal, rays=(ro, rd), img_idx=torch.zeros(1, 10), near=0., far=4., ndc=False,
+                                       use_viewdirs=True, network_query_fn=q, N_samples=64, N_importance=64, network_fn=c,
+                                       network_fine=f, perturb=1., raw_noise_std=0., test_time=False, args=Args(),
+                                       t_rand=t_rand, u=u)
+        (rgb.sum() + (ex["feat_map"] ** 2).sum() + ex["rgb0"].sum() + ex["beta"].sum()).backward()
+        return rgb.detach(), ex["feat_map"].detach(), c.flat.grad.clone(), f.flat.grad.clone()
+
+    a, b = run(1 << 21), run(128 * 64)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for x, y in zip(a[2:], b[2:]):
+        assert float((x - y).abs().max()) <= 1e-2 * float(x.abs().max())
