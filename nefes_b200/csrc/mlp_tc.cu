@@ -608,6 +608,7 @@ __global__ void ray_reduce_kernel(const float* __restrict__ src, int ld, int nco
 
 }  // namespace nefes
 #include "mlp_chain.cuh"
+#include "mlp_chain_ts.cuh"
 #include "mlp_trunk_bwd.cuh"
 #include "mlp_fused_bwd.cuh"
 extern "C" int nefes_encode_pe_bwd(const float*, const float*, int, int64_t, int, float*, void*);
@@ -920,6 +921,63 @@ int launch_chain_fwd(const Ws& w, const Arena& A, int mode, int64_t M, float* ra
   prof_end(st);
   NEFES_CHECK_LAUNCH("chain_fwd");
   chain_dbg_dump("fwd", c, st);
+  return NEFES_OK;
+}
+
+// The same forward chain with the activations in tensor memory (mlp_chain_ts.cuh): step operands are TMEM columns.
+int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float* raw_t, cudaStream_t st) {
+  const int T = (int)ceil_div(M, kTile);
+  TsArgs c = {};
+  int n = 0, bias_floats = 0;
+  auto add = [&](int pl, uint32_t a_col, int kind, uint32_t out_col, int out_ch, const Img* save) {
+    ChainStep& s = c.step[n++];
+    const PackedDims pd = packed_dims(pl);
+    s.a_off = a_col; s.out_off = out_col; s.K = (uint16_t)pd.K; s.N = (uint16_t)pd.N; s.out_ch = (uint16_t)out_ch;
+    s.kind = (uint8_t)kind; s.wait_load = -1; s.wait_load2 = -1; s.acc0 = 0;
+    s.bias = A.bias(pl); s.bias_off = (uint16_t)bias_floats;
+    bias_floats += (pd.N + 3) & ~3;
+    set_weights(s, A.W(pl), pd.K / 8, pd.N, 0, pd.N);
+    s.gdst = save ? save->p : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u;
+  };
+  add(PL_T0, kTsX, CK_HIDDEN, kTsH, 128, &w.H[0]);
+  for (int l = 1; l < 8; ++l) add(PL_T0 + l, l == 4 ? kTsX : kTsH, CK_HIDDEN, kTsH, 128, &w.H[l]);
+  if (mode == NEFES_MODE_SIGMA) {
+    add(PL_SIG, kTsH, CK_SIGMA, 0, 0, nullptr);
+  } else {
+    add(PL_FS, kTsH, CK_FS, kTsH, 128, &w.FIN);
+    if (mode == NEFES_MODE_FULL) {
+      add(PL_DT, kTsH, CK_HIDDEN, kTsH, 128, &w.DT);                 // [final | dirPE] = columns 176..255
+      add(PL_TE1, kTsH + 32, CK_HIDDEN, kTsX, 64, &w.T2);            // t1 (channels 64..127) -> t2, parked in the xyzPE columns
+      add(PL_TE2, kTsX, CK_HIDDEN, kTsH + 32, 64, &w.T3);            // t2 -> t3 (over t1)
+      add(PL_TH, kTsH + 32, CK_HEADS, 0, 0, nullptr);
+    } else {
+      add(PL_DIR, kTsH, CK_HIDDEN, kTsH, 64, &w.DT);
+    }
+    add(PL_RGB, kTsH, CK_RGB, 0, 0, nullptr);
+  }
+  NEFES_REQUIRE(n <= kChainMaxSteps && bias_floats * 4 <= (int)kChainBiasBytes, NEFES_EINVAL, "chain_fwd_ts: step table overflow");
+  for (int i = 0; i < n; ++i)
+    NEFES_REQUIRE(c.step[i].w_bytes <= kTsWSlot, NEFES_EINVAL, "chain_fwd_ts: weight image of step %d exceeds the ring slot", i);
+  c.n_steps = n; c.M = M; c.n_tiles = T;
+  c.raw = raw_t; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
+  c.x_img = w.X.p; c.d_img = (mode == NEFES_MODE_SIGMA) ? nullptr : w.DIRPE.p;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NEFES_CUDA(cudaFuncSetAttribute(chain_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmem));
+    attr_done = true;
+  }
+  const int n_pairs = (T + 1) / 2;
+  const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
+  {
+    const double save_ch = (mode == NEFES_MODE_SIGMA) ? 8 * 128 : (mode == NEFES_MODE_STATIC ? 8 * 128 + 128 + 64 : 8 * 128 + 128 + 128 + 64 + 64);
+    const double in_ch = (mode == NEFES_MODE_SIGMA) ? 64 : 96;
+    const double macs = (mode == NEFES_MODE_SIGMA) ? 130944 : (mode == NEFES_MODE_STATIC ? 165632 : 184064);
+    prof_begin(mode == NEFES_MODE_FULL ? "chain_fwd_fine" : (mode == NEFES_MODE_STATIC ? "chain_fwd_coarse" : "chain_fwd_sigma"), st,
+               (double)M * (2.0 * (save_ch + in_ch) + 4.0 * c.C), (double)M * 2.0 * macs);
+  }
+  chain_fwd_ts_kernel<<<grid, kChainThreads, kTsSmem, st>>>(c);
+  prof_end(st);
+  NEFES_CHECK_LAUNCH("chain_fwd_ts");
   return NEFES_OK;
 }
 
@@ -1343,7 +1401,11 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   NEFES_CHECK_LAUNCH("encode_images");
   const bool direct = (layout == NEFES_RAW_TILES) || C == 1;      // C == 1: the two layouts coincide
   float* raw_t = direct ? raw : reinterpret_cast<float*>(scratch);
-  TRY(launch_chain_fwd(w, A, mode, M, raw_t, st));
+  // NEFES_FWD_TS=1: activations in tensor memory (mlp_chain_ts.cuh).  Measured equal to the shared-memory-operand chain
+  // within 2 % at the bench shape (both sit on the same HBM write stream), so the older, longer-validated one is the default.
+  static const bool fwd_ts = getenv("NEFES_FWD_TS") != nullptr;
+  if (fwd_ts) TRY(launch_chain_fwd_ts(w, A, mode, M, raw_t, st));
+  else TRY(launch_chain_fwd(w, A, mode, M, raw_t, st));
   if (!direct) {
     tiles_to_rows_kernel<<<T, 256, 0, st>>>(raw_t, raw, M, C);
     NEFES_CHECK_LAUNCH("tiles_to_rows");
@@ -1370,7 +1432,8 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   // gradient image for the input-gradient GEMMs
   const bool fused_trunk = dP != nullptr && d_pts == nullptr && getenv("NEFES_NO_FUSED_TRUNK") == nullptr;
   // (measured: a gain for the fine net's six head layers, none for the coarse net's three)
-  const bool fused_heads = fused_trunk && mode == NEFES_MODE_FULL && getenv("NEFES_NO_FUSED_HEADS") == nullptr;
+  const bool fused_heads = fused_trunk && (mode == NEFES_MODE_FULL || (mode == NEFES_MODE_STATIC && getenv("NEFES_FUSED_HEADS_COARSE") != nullptr)) &&
+                           getenv("NEFES_NO_FUSED_HEADS") == nullptr;
   prof_begin("head_grad_images", st, (double)M * ((compact ? 20.0 : 4.0 * C) + 4.0 * (C == 137 ? 6 : 1) + 2.0 * (C == 1 ? 16 : (C == 137 ? 176 : 160))), 0.0);
   head_grad_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(
       raw, d_raw, C, tiles ? 1 : C, tiles ? kTile : 1, M, Mp, b.GRGB.p, b.GTH.p, gsig_img.p, gsig_img.tile_stride(),
