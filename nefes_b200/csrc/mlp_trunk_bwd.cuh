@@ -42,7 +42,7 @@ constexpr uint32_t kTrOffG = 65536;                 // 3 x 32 KB gradient images
 constexpr uint32_t kTrOffA = kTrOffG + 3 * 32768;   // 2 x 32 KB activation images
 constexpr uint32_t kTrOffOnes = kTrOffA + 2 * 32768;
 constexpr uint32_t kTrunkSmem = kTrOffOnes + 2048;
-constexpr int kTrunkThreads = 64 + 256;
+constexpr int kTrunkThreads = 64 + 256 + 32;     // producer, dgrad issuer, 8 epilogue warps, wgrad issuer
 constexpr uint32_t kTrAcc = 0, kTrDW0 = 128, kTrDB0 = 256, kTrDW1 = 272, kTrDB1 = 400;   // TMEM columns
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const Trunk
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_gin[i], 1); mbar_init(&bar_afull[i], 1); mbar_init(&bar_afree[i], 257); }
-    mbar_init(&bar_acc, 1); mbar_init(&bar_gmid, 256); mbar_init(&bar_gout, 256); mbar_init(&bar_done, 1);
+    mbar_init(&bar_acc, 1); mbar_init(&bar_gmid, 256); mbar_init(&bar_gout, 256); mbar_init(&bar_done, 2);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_slot);
@@ -140,49 +140,63 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const Trunk
     }
   } else if (warp == 1) {
     if (lane == 0 && n_my > 0) {
-      // ------------------------------- MMA issuer ----------------------------------------------------------------------
+      // ------------------------------- MMA issuer 1: the data-gradient GEMMs (the serial chain) -------------------------
+      // Two issuer threads because every barrier wait / commit costs its thread 200-400 cycles: the weight-gradient
+      // GEMMs (own accumulators) are issued by warp 10.  Completion order ACROSS the two threads is not defined, so
+      // every buffer hand-over between the two streams is an explicit barrier.
       const uint32_t idesc_d = idesc_bf16(128, 128, 0, 0);
+      if (T.step[0].has_dgrad || T.step[1].has_dgrad) mbar_wait(&bar_w, 0);
+      for (int it = 0; it < n_my; ++it) {
+        for (int j = 0; j < (two ? 2 : 1); ++j) {
+          const TrunkStep& s = T.step[j];
+          if (!s.has_dgrad) continue;
+          const uint32_t gs = smem_u32(smem + kTrOffG + (j == 0 ? (it & 1) : 2) * 32768);
+          if (j == 0) {
+            mbar_wait(&bar_gin[it & 1], (it >> 1) & 1);
+            // accumulator drained by the last epilogue of the previous tile
+            if (it >= 1) mbar_wait(has_out ? &bar_gout : &bar_gmid, (it - 1) & 1);
+          } else {
+            mbar_wait(&bar_gmid, it & 1);                                 // G_mid written, accumulator drained
+          }
+          tc_fence_after();
+          const uint64_t da0 = smem_desc(gs, kChunkBytes, 128);
+          const uint64_t db0 = smem_desc(smem_u32(smem + kTrOffWT + j * 32768), kChunkBytes, 128);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            mma_ss(tmem + kTrAcc, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), idesc_d, k > 0);
+          mma_commit(&bar_acc);
+        }
+      }
+      mma_commit(&bar_done);
+    }
+  } else if (warp == 10) {
+    if (lane == 0 && n_my > 0) {
+      // ------------------------------- MMA issuer 2: the weight- and bias-gradient GEMMs -----------------------------------
       const uint32_t idesc_b = idesc_bf16(128, 16, 1, 1);
       const uint32_t ones = smem_u32(smem + kTrOffOnes);
-      if (T.step[0].has_dgrad || T.step[1].has_dgrad) mbar_wait(&bar_w, 0);
       for (int it = 0; it < n_my; ++it) {
         for (int j = 0; j < (two ? 2 : 1); ++j) {
           const TrunkStep& s = T.step[j];
           const uint32_t gs = smem_u32(smem + kTrOffG + (j == 0 ? (it & 1) : 2) * 32768);
           const uint32_t as = smem_u32(smem + kTrOffA + j * 32768);
-          if (j == 0) {
-            mbar_wait(&bar_gin[it & 1], (it >> 1) & 1);
-            if (it >= 1 && has_out) mbar_wait(&bar_gout, (it - 1) & 1);   // accumulator drained by epilogue 1 of the previous tile
-          } else {
-            mbar_wait(&bar_gmid, it & 1);                                 // G_mid written, accumulator drained
-          }
-          tc_fence_after();
-          if (s.has_dgrad) {
-            const uint64_t da0 = smem_desc(gs, kChunkBytes, 128);
-            const uint64_t db0 = smem_desc(smem_u32(smem + kTrOffWT + j * 32768), kChunkBytes, 128);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              mma_ss(tmem + kTrAcc, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), idesc_d, k > 0);
-            mma_commit(&bar_acc);
-          }
+          if (j == 0) mbar_wait(&bar_gin[it & 1], (it >> 1) & 1);
+          else mbar_wait(&bar_gmid, it & 1);                              // its gradient operand was written by epilogue 0
           mbar_wait(&bar_afull[j], it & 1);
           tc_fence_after();
-          {
-            const uint32_t idesc_w = idesc_bf16(128, s.act_ch, 1, 1);
-            const uint64_t da0 = smem_desc(gs, 128, kChunkBytes);
-            const uint64_t db0 = smem_desc(as, 128, kChunkBytes);
-            const uint64_t do0 = smem_desc(ones, 128, 0);
-            const uint32_t dw = tmem + (j == 0 ? kTrDW0 : kTrDW1), dbias = tmem + (j == 0 ? kTrDB0 : kTrDB1);
+          const uint32_t idesc_w = idesc_bf16(128, s.act_ch, 1, 1);
+          const uint64_t da0 = smem_desc(gs, 128, kChunkBytes);
+          const uint64_t db0 = smem_desc(as, 128, kChunkBytes);
+          const uint64_t do0 = smem_desc(ones, 128, 0);
+          const uint32_t dw = tmem + (j == 0 ? kTrDW0 : kTrDW1), dbias = tmem + (j == 0 ? kTrDB0 : kTrDB1);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)                   // 16 points per MMA: +256 B in both images
-              mma_ss(dw, da0 + (uint64_t)(k * 16), db0 + (uint64_t)(k * 16), idesc_w, (it > 0 || k > 0) ? 1u : 0u);
-            if (s.bias) {
+          for (int k = 0; k < 8; ++k)                   // 16 points per MMA: +256 B in both images
+            mma_ss(dw, da0 + (uint64_t)(k * 16), db0 + (uint64_t)(k * 16), idesc_w, (it > 0 || k > 0) ? 1u : 0u);
+          if (s.bias) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                mma_ss(dbias, da0 + (uint64_t)(k * 16), do0 + (uint64_t)(k * 16), idesc_b, (it > 0 || k > 0) ? 1u : 0u);
-            }
-            mma_commit(&bar_afree[j]);                    // + 256 epilogue arrivals: the activation slot may be refilled
+            for (int k = 0; k < 8; ++k)
+              mma_ss(dbias, da0 + (uint64_t)(k * 16), do0 + (uint64_t)(k * 16), idesc_b, (it > 0 || k > 0) ? 1u : 0u);
           }
+          mma_commit(&bar_afree[j]);                    // + 256 epilogue arrivals: the activation slot may be refilled
         }
       }
       mma_commit(&bar_done);
@@ -203,6 +217,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const Trunk
           mbar_wait(&bar_afull[j], it & 1);           // the mask comes from the activation image
           mbar_wait(&bar_acc, acc_ph);
           acc_ph ^= 1u;
+          // the destination image must be dead in BOTH MMA streams: G_mid was read by the weight-gradient GEMMs of step 1
+          // of the previous tile, G_out lands on G_in, read by those of step 0 of this tile
+          if (j == 0) { if (it > 0 && two) mbar_wait(&bar_afree[1], (it - 1) & 1); }
+          else mbar_wait(&bar_afree[0], it & 1);
           tc_fence_after();
           // input activation of layer j: channels [act_ch - 128, act_ch) of the slot gate the 128 gradient columns
           const uint8_t* a_row = smem + kTrOffA + j * 32768 + (uint32_t)(s.act_ch - 128) * 256u + (half * 8) * kChunkBytes + row * 16;
