@@ -249,6 +249,11 @@ int nefes_composite_bwd_compact(const float* raw_tiles, const float* z_vals, con
 int nefes_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                     int64_t n, float lr, float beta1, float beta2, float eps, int step,
                     float grad_scale, void* stream);
+/* The same update with the per-step state on the device -- state2[0] = step count (float, incremented by the call),
+ * state2[1] = learning rate -- so a CUDA graph that captured one training step replays with the right bias
+ * correction and a schedule the host can change by writing state2[1]. */
+int nefes_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        float* state2, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* NeRF-W colour loss of the stage-1 step (script/models/losses.py:96-132, NerfWLoss with the transient head):
  *   loss = coef * (0.5 mean((rgb_coarse-t)^2) + mean((rgb_fine-t)^2 / (2 beta^2)) + 3 + mean(log beta)

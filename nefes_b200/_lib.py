@@ -77,6 +77,7 @@ _SIGS = {
     "nefes_composite_bwd_tiles": (i32, [vp, vp, vp, i32, i32, i32, C.POINTER(CompGrad), vp, vp]),
     "nefes_composite_bwd_compact": (i32, [vp, vp, vp, i32, i32, i32, C.POINTER(CompGrad), vp, vp]),
     "nefes_mlp_bwd_compact": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "nefes_adam_step_dev": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, vp]),
     "nefes_nerfw_loss_fwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp]),
     "nefes_nerfw_loss_bwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, vp]),
     "nefes_prof_enable": (i32, [i32]),

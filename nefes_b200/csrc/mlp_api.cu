@@ -26,6 +26,26 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// The same step with the state that changes from step to step read from DEVICE memory, so that a captured CUDA graph of
+// a whole training step replays correctly: state[0] = step count (incremented by adam_tick_kernel right before this
+// launch), state[1] = learning rate.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, const float* __restrict__ state, float b1, float b2,
+                                float eps, float gscale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = state[0], lr = state[1];
+  const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+__global__ void adam_tick_kernel(float* state) { state[0] += 1.f; }
+
 static int check_mlp(const char* who, int net, int mode, int prec, int64_t N, int S) {
   NEFES_REQUIRE(net == NEFES_NET_COARSE || net == NEFES_NET_FINE, NEFES_EINVAL, "%s: bad net %d", who, net);
   NEFES_REQUIRE(mode >= NEFES_MODE_SIGMA && mode <= NEFES_MODE_FULL, NEFES_EINVAL, "%s: bad mode %d", who, mode);
@@ -126,6 +146,18 @@ int nefes_adam_step(float* params, const float* grads, float* exp_avg, float* ex
   nefes::adam_kernel<<<(unsigned)nefes::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
       params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
   NEFES_CHECK_LAUNCH("adam");
+  return NEFES_OK;
+}
+
+int nefes_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        float* state2, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  NEFES_REQUIRE(params && grads && exp_avg && exp_avg_sq && state2, NEFES_EINVAL, "nefes_adam_step_dev: null pointer");
+  NEFES_REQUIRE(n >= 0, NEFES_EINVAL, "nefes_adam_step_dev: bad n");
+  if (n == 0) return NEFES_OK;
+  nefes::adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state2);
+  nefes::adam_dev_kernel<<<(unsigned)nefes::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, exp_avg, exp_avg_sq, n, state2, beta1, beta2, eps, grad_scale);
+  NEFES_CHECK_LAUNCH("adam_dev");
   return NEFES_OK;
 }
 

@@ -285,16 +285,24 @@ class FlatAdam(torch.optim.Optimizer):
                 if p.grad is None:
                     continue
                 st = self.state[p]
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
+                    raise RuntimeError("nefes_b200.FlatAdam: parameters must be contiguous fp32 CUDA tensors")
                 if not st:
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
-                st["step"] += 1
-                if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous():
-                    ops.adam_step(p, p.grad, st["exp_avg"], st["exp_avg_sq"], group["lr"], group["betas"][0],
-                                  group["betas"][1], group["eps"], st["step"], grad_scale)
-                else:
-                    raise RuntimeError("nefes_b200.FlatAdam: parameters must be contiguous fp32 CUDA tensors")
+                    # (step count, lr) live on the device so that a captured CUDA graph of the step replays correctly
+                    st["dev"] = torch.tensor([0.0, float(group["lr"])], device=p.device)
+                    st["lr_host"] = float(group["lr"])
+                capturing = torch.cuda.is_current_stream_capturing()
+                if float(group["lr"]) != st["lr_host"]:
+                    if capturing:
+                        raise RuntimeError("nefes_b200.FlatAdam: change the learning rate outside graph capture")
+                    st["dev"][1] = float(group["lr"])
+                    st["lr_host"] = float(group["lr"])
+                st["step"] += 1                                  # host mirror (replays of a graph do not pass here)
+                ops.adam_step_dev(p, p.grad, st["exp_avg"], st["exp_avg_sq"], st["dev"], group["betas"][0],
+                                  group["betas"][1], group["eps"], grad_scale)
 
 
 def create_nerf(args, device=None):

@@ -379,3 +379,11 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     L.need_cuda(p, g, m, v)
     L.check(L.lib().nefes_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, beta1, beta2, eps,
                                     int(step), grad_scale, L.stream_of(p)), "nefes_adam_step")
+
+
+@torch.no_grad()
+def adam_step_dev(p, g, m, v, state2, beta1, beta2, eps, grad_scale=1.0):
+    """Adam with (step count, lr) in the 2-float device tensor `state2`: safe inside a captured CUDA graph."""
+    L.need_cuda(p, g, m, v, state2)
+    L.check(L.lib().nefes_adam_step_dev(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), L.ptr(state2), beta1, beta2,
+                                        eps, grad_scale, L.stream_of(p)), "nefes_adam_step_dev")
