@@ -1341,10 +1341,13 @@ int launch_heads2(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
     int li = 0;
     for (; B.a.prod[li].kind == FO_LOAD && B.a.prod[li].next == 2; ++li) reload(li);
     const int iGDT = li, iGSIG = li + 1, iFIN = li + 2, iDIRPE = li + 3, iH7 = li + 4;
-    P.p_wait(D0); reload(iFIN); reload(iDIRPE);
+    // G7 (output) is written over the [final | dirPE] slot A0, which only the weight-gradient GEMM of the first layer
+    // reads: the gradient input slot G0 is then free early in the tile and the NEXT tile's GDT -- the head of the
+    // serial data-gradient chain -- is prefetched; what waits for the store is A0, needed only by the weight-gradient stream
+    P.p_wait(D0); P.p_wait(E0); reload(iGDT);
     P.p_wait(D1); P.p_wait(E1); reload(iH7); reload(iGSIG);
-    P.p_store(b.G[7].p, (uint32_t)b.G[7].tile_stride(), 32768, G0);
-    reload(iGDT);
+    P.p_store(b.G[7].p, (uint32_t)b.G[7].tile_stride(), 32768, A0);
+    reload(iFIN); reload(iDIRPE);
     B = P;
   }
   // ---- data-gradient issuer
@@ -1364,7 +1367,7 @@ int launch_heads2(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
   B.m_commit(D1);
   // ---- epilogue
   B.e_wait(ACC0); B.e_wait(D1, FW_PREV); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);        // gFIN over the previous gFS
-  B.e_wait(ACC1); B.e_wait(L_H7); B.e_wait(D0); B.e_epi(0, 128, true, A1, G0); B.e_arrive(E1); // G7 over GDT (read by D0)
+  B.e_wait(ACC1); B.e_wait(L_H7); B.e_wait(D0); B.e_epi(0, 128, true, A1, A0); B.e_arrive(E1); // G7 over [final|dirPE] (read by D0)
   // ---- flush: the dirPE image carries a constant 1 in its last padding channel (column 128 + 31): bias of [dir | tenc0]
   B.flush(128, 160, pl_dt, 0, 0, FF_W); B.flush(128 + 144, 16, pl_dt, 0, 15, FF_BIAS);
   B.flush(288, 128, PL_FS, 0, 0, FF_W); B.flush(288 + 128, 16, PL_FS, 0, 0, FF_BIAS);
