@@ -130,8 +130,11 @@ def run_engine(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout at levels VERSION and WARN unless a debug file is named (honoured only
+        # above VERSION): stdout carries ONE JSON line, so send NCCL's output to stderr
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout; stdout carries ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
     _lib.lib()
@@ -307,7 +310,16 @@ def run_engine(a):
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a process group whose collectives were captured into a CUDA graph does not always tear down cleanly
+        # (observed: destroy_process_group / interpreter exit hanging after the result was printed): release the graph,
+        # drain the device, meet once more, and leave without running the teardown
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def side_measurements(a, nb, step, coarse, fine, resident, kw, dev):
