@@ -983,7 +983,8 @@ int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float*
 
 // Fused data-gradient chain: head-gradient images in, the gradient image of every layer's pre-activation out
 // (operands of the weight-gradient kernel); ReLU masks come from the saved activations.
-int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_t M, bool with_trunk, cudaStream_t st) {
+int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_t M, bool with_trunk, bool need_wgrad_images,
+                     cudaStream_t st) {
   const int T = (int)ceil_div(M, kTile);
   ChainArgs c = {};
   int n = 0;
@@ -996,6 +997,9 @@ int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_
     s.kind = CK_DGRAD; s.wait_load = (int8_t)wait_load; s.wait_load2 = -1; s.acc0 = 0; s.bias = nullptr; s.bias_off = 0;
     set_weights(s, A.WT(pl), k_ch / 8, pd.K, row0, n_in);
     s.act = act ? act->p + (int64_t)act_ch0 * 256 : nullptr; s.act_tile_stride = act ? (uint32_t)act->tile_stride() : 0u;
+    // a gradient image leaves the SM only if somebody reads it: the weight-gradient kernel (training), or the input-
+    // gradient GEMMs of the refinement path (G[4] and G[0] for the xyz encoding, GDT for the direction encoding)
+    if (save != nullptr && !need_wgrad_images && save != &b.G[4] && save != &b.G[0] && save != &b.GDT) save = nullptr;
     s.gdst = save ? save->p + (int64_t)save_ch0 * 256 : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u;
   };
   auto load = [&](int idx, const Img& img, int ch0, int nch, uint32_t dst_off, int issue_step, int next_pair) {
@@ -1447,7 +1451,7 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
     TRY(launch_heads1(w, b, A, net, mode, M, dP, st));
     TRY(launch_heads2(w, b, A, net, mode, M, dP, st));
   } else {
-    TRY(launch_chain_bwd(w, b, A, mode, M, !fused_trunk, st));
+    TRY(launch_chain_bwd(w, b, A, mode, M, !fused_trunk, dP != nullptr, st));
   }
   if (fused_trunk) TRY(launch_trunk_bwd(w, b, A, net, M, dP, st));
 
