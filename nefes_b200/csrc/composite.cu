@@ -148,6 +148,54 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw, const float*
   __syncthreads();                                           // s_ws / s_wt visible
   if (TILES) {
     const int lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    if (S == 128 || S == 64) {
+      // warp per channel, lane owns S/32 CONSECUTIVE samples (one 16- or 8-byte load per channel), eight channels in
+      // flight per warp: the plain one-channel-at-a-time loop keeps ~1 load per warp outstanding and is latency-bound
+      // at 1.6 TB/s (profiles/); the loads of a batch are independent and overlap
+      const int spl = S >> 5;
+      float w[4] = {0.f, 0.f, 0.f, 0.f}, wt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < spl) { w[i] = s_ws[lane * spl + i]; wt[i] = s_wt[lane * spl + i]; }
+      const float* base = rr + lane * spl;
+      for (int c0 = warp * 8; c0 < kHeadCh + 3; c0 += nw * 8) {      // virtual channels 131..133: transient colour
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = c0 + u;
+          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool live = c < kHeadCh || (MODE == NEFES_COMP_TRANSIENT && c < kHeadCh + 3);
+          if (live) {
+            const float* col = base + (int64_t)(c < kHeadCh ? c : c + 1) * 128;       // 131..133 -> raw channels 132..134
+            if (spl == 4) x[u] = *reinterpret_cast<const float4*>(col);
+            else { const float2 y = *reinterpret_cast<const float2*>(col); x[u].x = y.x; x[u].y = y.y; }
+          }
+        }
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool tr = (c0 + u) >= kHeadCh;
+          v[u] = (tr ? wt[0] : w[0]) * x[u].x + (tr ? wt[1] : w[1]) * x[u].y + (tr ? wt[2] : w[2]) * x[u].z + (tr ? wt[3] : w[3]) * x[u].w;
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o2);
+        }
+        if (lane < 8) {
+          float val = v[0];
+#pragma unroll
+          for (int u = 1; u < 8; ++u) if (lane == u) val = v[u];
+          const int c = c0 + lane;
+          if (c < 3) s_ws[kMaxS - 8 + c] = val;       // static colour: the transient part is added below
+          else if (c < kHeadCh) o.feat[(int64_t)r * kFeat + (c - 3)] = val;
+          else if (MODE == NEFES_COMP_TRANSIENT && c < kHeadCh + 3) s_wt[kMaxS - 8 + (c - kHeadCh)] = val;
+        }
+      }
+      __syncthreads();
+      if (t < 3) o.rgb[(int64_t)r * 3 + t] = s_ws[kMaxS - 8 + t] + (MODE == NEFES_COMP_TRANSIENT ? s_wt[kMaxS - 8 + t] : 0.f);
+      return;
+    }
     for (int c = warp; c < kHeadCh; c += nw) {
       const float* col = rr + (int64_t)c * 128;
       float v = 0.f;
