@@ -132,7 +132,7 @@ __device__ __forceinline__ uint32_t pack_mask(uint32_t lo, uint32_t hi, uint32_t
 template <bool BWD>
 __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs A) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_wfull[3], bar_wempty[3], bar_act[2], bar_acc[2], bar_ld[2][kChainLoads];
+  __shared__ uint64_t bar_wfull[3], bar_wempty[3], bar_act[2], bar_acc[2], bar_ld[2][kChainLoads], bar_stag;
   __shared__ uint32_t tmem_slot;
   constexpr uint32_t kReg = BWD ? kBwdRegBytes : kFwdRegBytes;
   constexpr uint32_t kWSlot = BWD ? kBwdWSlot : kFwdWSlot;
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 2); }
+    mbar_init(&bar_stag, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_act[i], kChainEpiWarps * 32); mbar_init(&bar_acc[i], 1);
       for (int l = 0; l < kChainLoads; ++l) mbar_init(&bar_ld[i][l], 1);
@@ -240,6 +241,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
               mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k * (2 * st.w_lbo >> 4)), idesc,
                      (k > 0 || st.acc0) ? 1u : 0u);
             mma_commit(&bar_acc[g]);
+            // anti-phase the two tiles: tile 1 starts a pair only when tile 0's first layer has retired, so that from then
+            // on one tile is in its epilogue while the other owns the tensor pipe (left alone, the two tiles fall into
+            // lock-step -- both in MMA, then both in epilogue -- and every step costs MMA + epilogue instead of the larger)
+            if (g == 0 && s == 0) mma_commit(&bar_stag);
             if (dbg && cnt < 32) A.dbg[cnt * 48 + 3 + g] = clock64();
           }
           mma_commit(&bar_wempty[slot]);       // the slot is free once BOTH tiles' MMAs retired (count 2)
@@ -257,11 +262,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
     uint8_t* reg = smem + g * kReg;
     const uint32_t taddr = tmem + g * 256 + ((uint32_t)(q * 32) << 16);
     uint32_t acc_ph = 0u;
-    uint32_t ecnt = 0;
+    uint32_t ecnt = 0, pair_it = 0;
     bool store_pending = false;                       // a bulk store of this group may still be reading the tile region
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_it) {
       const int tile = pair * 2 + g;
       if (tile >= A.n_tiles) break;
+      if (g == 1) mbar_wait(&bar_stag, pair_it & 1);   // start half a period after tile 0 (see the MMA issuer)
       const int64_t grow = (int64_t)tile * kTile + row;
       const bool ok = grow < A.M;
       float* rawt = BWD ? nullptr : A.raw + (int64_t)tile * A.C * kTile + row;   // + c * 128
