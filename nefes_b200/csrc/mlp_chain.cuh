@@ -101,22 +101,29 @@ __device__ __forceinline__ uint32_t bias_pack(uint32_t lo, uint32_t hi, float bl
   return r;
 }
 
-// 32 accumulator columns [c0, c0+32) of one row -> four 8-channel chunks of the image (and of its HBM copy)
+// 32 accumulator columns [c0, c0+32) of one row -> four 8-channel chunks of the image (and of its HBM copy).
+// All eight bias vectors are loaded BEFORE the first image store: the compiler will not move a shared-memory load above
+// a shared-memory store (possible alias), and a load -> add -> pack -> store chain per chunk exposes the LDS latency
+// four times per call with only two epilogue warps per scheduler to cover it.
 template <bool RELU>
 __device__ __forceinline__ void fwd_cols32(const uint32_t (&v)[32], const float* __restrict__ bias, uint8_t* __restrict__ dst_row,
                                            uint8_t* __restrict__ gdst_row, int c0) {
+  float4 b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = *reinterpret_cast<const float4*>(bias + c0 + 4 * j);
+  uint4 pk[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + 8 * j);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 8 * j + 4);
-    uint4 pk;
-    pk.x = bias_pack<RELU>(v[8 * j + 0], v[8 * j + 1], b0.x, b0.y);
-    pk.y = bias_pack<RELU>(v[8 * j + 2], v[8 * j + 3], b0.z, b0.w);
-    pk.z = bias_pack<RELU>(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
-    pk.w = bias_pack<RELU>(v[8 * j + 6], v[8 * j + 7], b1.z, b1.w);
+    pk[j].x = bias_pack<RELU>(v[8 * j + 0], v[8 * j + 1], b[2 * j].x, b[2 * j].y);
+    pk[j].y = bias_pack<RELU>(v[8 * j + 2], v[8 * j + 3], b[2 * j].z, b[2 * j].w);
+    pk[j].z = bias_pack<RELU>(v[8 * j + 4], v[8 * j + 5], b[2 * j + 1].x, b[2 * j + 1].y);
+    pk[j].w = bias_pack<RELU>(v[8 * j + 6], v[8 * j + 7], b[2 * j + 1].z, b[2 * j + 1].w);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
     const int off = ((c0 >> 3) + j) * (int)kChunkBytes;
-    *reinterpret_cast<uint4*>(dst_row + off) = pk;
-    if (gdst_row != nullptr) *reinterpret_cast<uint4*>(gdst_row + off) = pk;   // a warp's 32 rows x 16 B = 512 contiguous bytes
+    *reinterpret_cast<uint4*>(dst_row + off) = pk[j];
+    if (gdst_row != nullptr) *reinterpret_cast<uint4*>(gdst_row + off) = pk[j];   // a warp's 32 rows x 16 B = 512 contiguous bytes
   }
 }
 
@@ -197,11 +204,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
           const int slot = cnt % kSlots;
           mbar_wait(&bar_wempty[slot], ((cnt / kSlots) & 1) ^ 1);
           const uint32_t bytes = A.step[s].w_bytes;
-          mbar_arrive_expect_tx(&bar_wfull[slot], bytes);
-          const uint32_t piece = A.step[s].w_piece, sstride = A.step[s].w_src_stride;
-          const uint8_t* src = A.step[s].w_img;
-          for (uint32_t off = 0; off < bytes; off += piece, src += sstride)
-            bulk_g2s(sW + slot * kWSlot + off, src, min(piece, bytes - off), &bar_wfull[slot]);
+          if ((A.xflags & 16) && cnt >= 2u * A.n_steps) {   // timing experiment: no weight traffic after the first pairs
+            mbar_arrive(&bar_wfull[slot]);
+          } else {
+            mbar_arrive_expect_tx(&bar_wfull[slot], bytes);
+            const uint32_t piece = A.step[s].w_piece, sstride = A.step[s].w_src_stride;
+            const uint8_t* src = A.step[s].w_img;
+            for (uint32_t off = 0; off < bytes; off += piece, src += sstride)
+              bulk_g2s(sW + slot * kWSlot + off, src, min(piece, bytes - off), &bar_wfull[slot]);
+          }
           // slots that only die with the last step of the previous pair: after this pair's first weights are on the way
           if (s == 0 && pair != (int)blockIdx.x) do_loads(A.n_steps, pair - (int)gridDim.x);
           do_loads(s, pair);
@@ -329,6 +340,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
             tmem_ld32(taddr + c_base, v0);
             if (ncol == 64) tmem_ld32(taddr + c_base + 32, v1);
             tmem_ld_wait();
+            if (dbg && lane == 0 && ew == 0 && ecnt < 32) A.dbg[1600 + ecnt * 4 + 0] = clock64();
             if (st.kind == CK_HIDDEN) {
             fwd_cols32<true>(v0, bias, dst_row, gdst_row, c_base);
             if (ncol == 64) fwd_cols32<true>(v1, bias, dst_row, gdst_row, c_base + 32);
@@ -376,10 +388,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
             }
           }
         }
+        if (dbg && lane == 0 && ew == 0 && ecnt < 32) A.dbg[1600 + ecnt * 4 + 1] = clock64();
         tc_fence_before();
         fence_async_smem();
+        if (dbg && lane == 0 && ew == 0 && ecnt < 32) A.dbg[1600 + ecnt * 4 + 2] = clock64();
         if (!BWD && st.gdst != nullptr && !(A.xflags & 9)) {   // saved for backward: the image just written, one bulk store
           group_barrier(g);
+          if (dbg && lane == 0 && ew == 0 && ecnt < 32) A.dbg[1600 + ecnt * 4 + 3] = clock64();
           if (gt == 0) {
             bulk_s2g(st.gdst + (int64_t)tile * st.g_tile_stride, reg + st.out_off, (uint32_t)st.out_ch * 256u);
             bulk_commit();

@@ -27,6 +27,8 @@ struct TsArgs {
   float* raw; int C;
   const uint8_t* x_img; const uint8_t* d_img;     // encodings (bf16 images) written by encode_images_kernel
   int x_dead_step;                                // the xyzPE columns may be refilled once this step's MMAs retired
+  long long* dbg;                                 // optional clock stamps of CTA 0 (NEFES_CHAIN_DBG)
+  int xflags;                                     // timing experiments (NEFES_CHAIN_X): 1 no saves
 };
 
 __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts_kernel(const __grid_constant__ TsArgs A) {
@@ -85,10 +87,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts_kernel(const __
             mbar_wait(&bar_act[g], act_ph);
             act_ph ^= 1u;
             tc_fence_after();
+            if (A.dbg && blockIdx.x == 0 && cnt < 32) A.dbg[cnt * 16 + g * 2] = clock64();
             const uint32_t d = tmem + g * 256, a0 = tmem + g * 256 + st.a_off;
             for (int k = 0; k < st.K / 16; ++k)
               mma_ts(d, a0 + k * 8, db0 + (uint64_t)(k * (2 * st.w_lbo >> 4)), idesc, k > 0 ? 1u : 0u);
             mma_commit(&bar_acc[g]);
+            if (A.dbg && blockIdx.x == 0 && cnt < 32) A.dbg[cnt * 16 + g * 2 + 1] = clock64();
           }
           mma_commit(&bar_wempty[slot]);
         }
@@ -101,7 +105,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts_kernel(const __
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t tbase = tmem + g * 256 + ((uint32_t)(q * 32) << 16);     // this thread's TMEM lane, tile g
-    uint32_t acc_ph = 0u;
+    uint32_t acc_ph = 0u, ecnt = 0;
+    const bool dbg = A.dbg != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
     uint4 xv[4], dv[2];
     auto fetch_inputs = [&](int tile) {             // this row's halves of the encoding images -> registers
       const uint8_t* xp = A.x_img + (int64_t)tile * (64 * 256) + (half * 4) * kChunkBytes + row * 16;
@@ -139,23 +144,25 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts_kernel(const __
       mbar_arrive(&bar_act[g]);
       const int next_tile = (pair + (int)gridDim.x) * 2 + g;
 
-      for (int s = 0; s < n_steps; ++s) {
+      for (int s = 0; s < n_steps; ++s, ++ecnt) {
         const ChainStep& st = s_step[s];
         const float* bias = sBias + st.bias_off;
         if (s == n_steps - 1 && next_tile < A.n_tiles) fetch_inputs(next_tile);   // overlap with the last epilogue
         mbar_wait(&bar_acc[g], acc_ph);
         acc_ph ^= 1u;
         tc_fence_after();
+        if (dbg && ecnt < 32) A.dbg[ecnt * 16 + 4] = clock64();
         if (st.kind == CK_HIDDEN || st.kind == CK_FS) {
           const int ncol = st.out_ch >> 1;             // accumulator columns of this warp: 32 or 64
           const int c_base = half * ncol;
-          uint8_t* gdst_row = st.gdst ? st.gdst + (int64_t)tile * st.g_tile_stride + (c_base >> 3) * kChunkBytes + row * 16 : nullptr;
+          uint8_t* gdst_row = (st.gdst && !(A.xflags & 1)) ? st.gdst + (int64_t)tile * st.g_tile_stride + (c_base >> 3) * kChunkBytes + row * 16 : nullptr;
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             if (h2 * 32 < ncol) {
               uint32_t v[32], w[16];
               tmem_ld32(tbase + c_base + h2 * 32, v);
               tmem_ld_wait();
+              if (dbg && ecnt < 32) A.dbg[ecnt * 16 + 5 + h2 * 2] = clock64();
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 b0 = *reinterpret_cast<const float4*>(bias + c_base + h2 * 32 + 8 * j);
@@ -176,6 +183,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts_kernel(const __
               }
               // the operand of the next layer: packed pairs back into this row's lane (its last reader, the MMA, is done)
               tmem_st16(tbase + st.out_off + (c_base >> 1) + h2 * 16, w);
+              if (dbg && ecnt < 32) A.dbg[ecnt * 16 + 6 + h2 * 2] = clock64();
             }
           }
           if (st.kind == CK_FS && half == 1) {         // sigma pre-activation rides in column 128 of this GEMM
@@ -219,6 +227,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts_kernel(const __
           }
         }
         tc_fence_before();
+        if (dbg && ecnt < 32) A.dbg[ecnt * 16 + 9] = clock64();
         if (s + 1 < n_steps) mbar_arrive(&bar_act[g]);
       }
     }

@@ -817,6 +817,8 @@ void chain_dbg_dump(const char* what, const ChainArgs& c, cudaStream_t st) {
       hi[w >> 3] = r[24 + w] > hi[w >> 3] ? r[24 + w] : hi[w >> 3];
       rd[w >> 3] = r[8 + w] > rd[w >> 3] ? r[8 + w] : rd[w >> 3];
     }
+    fprintf(stderr, "  [epi warp 0: ready %lld | tmem loaded +%lld | computed+stored +%lld | fenced +%lld | group barrier +%lld]\n", r[8] - t0,
+            h[1600 + i * 4] - r[8], h[1600 + i * 4 + 1] - r[8], h[1600 + i * 4 + 2] - r[8], h[1600 + i * 4 + 3] - r[8]);
     fprintf(stderr, "  seq %2d step %2d | W ok %7lld | t0: A ok %7lld commit %7lld | t1: A ok %7lld commit %7lld | epi0 ready %7lld done %7lld..%7lld | epi1 ready %7lld done %7lld..%7lld\n",
             i, i % c.n_steps, r[0] - t0, r[1] - t0, r[3] - t0, r[2] - t0, r[4] - t0, rd[0] - t0, lo[0] - t0, hi[0] - t0,
             rd[1] - t0, lo[1] - t0, hi[1] - t0);
@@ -975,9 +977,26 @@ int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float*
     prof_begin(mode == NEFES_MODE_FULL ? "chain_fwd_fine" : (mode == NEFES_MODE_STATIC ? "chain_fwd_coarse" : "chain_fwd_sigma"), st,
                (double)M * (2.0 * (save_ch + in_ch) + 4.0 * c.C), (double)M * 2.0 * macs);
   }
+  c.dbg = chain_dbg_buf();
+  { const char* e = getenv("NEFES_CHAIN_X"); c.xflags = e ? atoi(e) : 0; }
   chain_fwd_ts_kernel<<<grid, kChainThreads, kTsSmem, st>>>(c);
   prof_end(st);
   NEFES_CHECK_LAUNCH("chain_fwd_ts");
+  if (c.dbg) {
+    static int dumps = 0;
+    if (dumps++ < 2) {
+      cudaStreamSynchronize(st);
+      static long long h[2048];
+      cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      const long long t0 = h[0];
+      fprintf(stderr, "[chain_ts dbg] n_steps=%d\n", c.n_steps);
+      for (int i = 0; i < 32 && i < 2 * c.n_steps; ++i) {
+        const long long* r = h + i * 16;
+        fprintf(stderr, "  seq %2d step %2d | mma0 %7lld..%7lld mma1 %7lld..%7lld | epi ready %7lld ld0 +%lld st0 +%lld ld1 +%lld st1 +%lld done +%lld\n", i,
+                i % c.n_steps, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0, r[4] - t0, r[5] - r[4], r[6] - r[4], r[7] - r[4], r[8] - r[4], r[9] - r[4]);
+      }
+    }
+  }
   return NEFES_OK;
 }
 
