@@ -505,13 +505,20 @@ __global__ void encode_images_kernel(const float* __restrict__ pts, const float*
   if (dimg != nullptr) pe_row<kDirFreqs, 4>(dirs + (ok ? m / S : 0) * 3, ok, dimg + tile * (32 * 256) + row * 16, 1.f);
 }
 
-// tile-major raw blocks [T][C][128] <-> row-major [M][C]   (public row-major API of the field query)
+// tile-major raw blocks [T][C][128] -> row-major [M][C]   (public row-major API of the field query).
+// One CTA per tile: coalesced read channel by channel into a row-major shared-memory copy of the tile (pitch C is odd or
+// 4 mod 32 -> conflict-free enough), then the tile's rows, contiguous in the output, leave fully coalesced.
 __global__ void tiles_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t M, int C) {
+  extern __shared__ float t_rows[];                                    // [128][C]
   const int64_t tile = blockIdx.x;
   const int64_t n_valid = min((int64_t)kTile, M - tile * kTile);
   const float* s = src + tile * C * kTile;
   float* d = dst + tile * kTile * C;
-  for (int i = threadIdx.x; i < (int)n_valid * C; i += blockDim.x) d[i] = s[(i % C) * kTile + i / C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nw)
+    for (int r = lane; r < kTile; r += 32) t_rows[r * C + c] = s[(int64_t)c * kTile + r];
+  __syncthreads();
+  for (int i = threadIdx.x; i < (int)n_valid * C; i += blockDim.x) d[i] = t_rows[i];
 }
 
 // d_raw (fp32) -> gradient images of the head pre-activations.  Element (row r of tile t, column c) of raw / d_raw sits
@@ -1433,7 +1440,12 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   if (fwd_ts) TRY(launch_chain_fwd_ts(w, A, mode, M, raw_t, st));
   else TRY(launch_chain_fwd(w, A, mode, M, raw_t, st));
   if (!direct) {
-    tiles_to_rows_kernel<<<T, 256, 0, st>>>(raw_t, raw, M, C);
+    static bool t2r_attr = false;
+    if (!t2r_attr) {
+      NEFES_CUDA(cudaFuncSetAttribute(tiles_to_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTile * 137 * 4));
+      t2r_attr = true;
+    }
+    tiles_to_rows_kernel<<<T, 512, kTile * C * 4, st>>>(raw_t, raw, M, C);
     NEFES_CHECK_LAUNCH("tiles_to_rows");
   }
   return NEFES_OK;

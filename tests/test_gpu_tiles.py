@@ -149,3 +149,29 @@ def test_graph_replayed_refinement_matches_eager_loop():
             assert abs(float(a) - float(b)) < 2e-5, (float(a), float(b))
         assert float((pe[:, :3] - pg[:, :3]).abs().max()) < 2e-2
         assert float((pe[:, 3] - pg[:, 3]).abs().max()) < 6e-2
+
+
+def test_large_ragged_render_is_chunk_invariant():
+    """C5-style inference render: 40 000 rays (not a multiple of the 32 768-ray chunk nor of the tile), test_time, no
+    gradients; the result must not depend on how batchify_rays cuts it."""
+    import nefes_b200 as nb
+    c, f = _nets()
+    H, W, focal = 60, 106, 93.0
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n = 40000 + 37
+    ro = torch.randn(n, 3, device="cuda", generator=g) * 0.1
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda", generator=g), dim=-1)
+
+    class Args:
+        nerfh_nff, use_fine_only, NeRFW, transient_at_test, netchunk = True, False, True, True, 1 << 21
+    q = lambda i, v, ts, fn, typ, ot, test_time, store_rgb: nb.run_network_NeRFH_NFF(
+        i, v, ts, fn, typ=typ, output_transient=ot, netchunk=Args.netchunk, test_time=test_time, store_rgb=store_rgb)
+    kw = dict(rays=(ro, rd), img_idx=torch.zeros(1, 10), near=0., far=10., ndc=False, use_viewdirs=True, network_query_fn=q,
+              N_samples=64, N_importance=64, network_fn=c, network_fine=f, perturb=0., raw_noise_std=0., test_time=True,
+              args=Args())
+    with torch.no_grad():
+        a = nb.render(H, W, focal, chunk=32768, **kw)
+        b = nb.render(H, W, focal, chunk=8192 + 64, **kw)
+    assert a[0].shape == (n, 3) and a[3]["feat_map"].shape == (n, 128)
+    assert torch.isfinite(a[0]).all() and torch.isfinite(a[3]["feat_map"]).all()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3]["feat_map"], b[3]["feat_map"]) and torch.equal(a[1], b[1])
