@@ -348,6 +348,8 @@ class _Composite(Function):
             g = dict(zip(("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig"), grads))
         g = {k: L.f32c(v) for k, v in g.items() if v is not None}
         gs = L.CompGrad(*[L.ptr(g.get(k)) for k in ("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig")])
+        if not ctx.needs_input_grad[0]:              # raw is a constant here (frozen field, no gradient to the rays)
+            return None, None, None, None, None, None, None
         if compact:
             # the field backward picks the compact cotangent up by raw's address; what autograd carries is a placeholder
             # of the right shape that is never read (a 0-dim tensor expanded, no memory, no kernel)
