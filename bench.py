@@ -146,8 +146,7 @@ def run_engine(a):
 
     class Args:
         nerfh_nff, use_fine_only, NeRFW, transient_at_test, netchunk = True, False, True, True, 1 << 21
-    q = lambda i, v, ts, fn, typ, ot, test_time, store_rgb: nb.run_network_NeRFH_NFF(
-        i, v, ts, fn, typ=typ, output_transient=ot, netchunk=Args.netchunk, test_time=test_time, store_rgb=store_rgb)
+    q = nb.StandardQuery(Args.netchunk)          # create_nerf's query function: render_rays is one engine call
     kw = dict(network_query_fn=q, N_importance=64, N_samples=64, network_fn=coarse, network_fine=fine,
               use_viewdirs=True, white_bkgd=False, args=Args(), ndc=False, lindisp=False, near=NEAR, far=FAR,
               perturb=1., raw_noise_std=0., test_time=False, retraw=True)

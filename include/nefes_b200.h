@@ -242,6 +242,56 @@ int nefes_composite_bwd_compact(const float* raw_tiles, const float* z_vals, con
                                 int mode, const nefes_comp_grad_t* g_host, float* compact, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The whole path as one call: render_rays    script/models/rendering.py:68-180
+ * (stratified depths -> coarse field -> compositing -> sample_pdf + merge -> fine field -> compositing), forward and
+ * backward.  Intermediates -- sample points, raw (tile-major on the bf16 path), saved activations, compact cotangents --
+ * live in two caller-provided workspaces sized by nefes_render_rays_workspace: `keep` must survive from the forward to
+ * the backward call, `scratch` is per call.  Both 256-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int n_samples;                   /* N_samples: coarse depths per ray                                   */
+  int n_importance;                /* N_importance: > 0 runs the fine pass on n_samples + n_importance   */
+  int prec;                        /* NEFES_PREC_*                                                        */
+  int test_time;                   /* coarse pass sigma-only, no rgb0/feat0 (rendering.py:122-127)        */
+  int output_transient;            /* args.NeRFW: fine pass in NEFES_MODE_FULL / transient compositing    */
+  int transient_at_test;           /* args.transient_at_test                                              */
+  int net_coarse, net_fine;        /* NEFES_NET_* of network_fn / network_fine                            */
+  float beta_min;                  /* network_fine.beta_min                                               */
+} nefes_render_cfg_t;
+typedef struct {
+  const float* rays;               /* ray_batch [N, ld_rays]: o 0:3, d 3:6, near 6, far 7, viewdirs 8:11  */
+  int ld_rays;                     /* >= 11                                                               */
+  const float* params_coarse;      /* flat parameter buffers (nefes_param_layout)                         */
+  const float* params_fine;        /* NULL when n_importance == 0                                         */
+  const float* t_vals;             /* [n_samples] = torch.linspace(0,1,n_samples), host-made (see K2)     */
+  const float* t_rand;             /* [N, n_samples] or NULL (perturb == 0)                               */
+  const float* u;                  /* [N, n_importance], or [n_importance] with u_per_ray == 0 (det)      */
+  int u_per_ray;
+  const float* noise_coarse;       /* [N, n_samples] randn * raw_noise_std or NULL                        */
+  const float* noise_fine;         /* [N, n_samples + n_importance] or NULL (static fine compositing only) */
+} nefes_render_in_t;
+typedef struct {
+  nefes_comp_out_t coarse;         /* rgb0, feat0, disp0, acc0, weights [N,S], depth, beta (test_time: acc, weights only) */
+  nefes_comp_out_t fine;           /* rgb_map, feat_map, disp_map, acc_map, weights, depth, beta, transient_sigmas        */
+  float* z_coarse;                 /* [N, n_samples]                                                      */
+  float* z_fine;                   /* [N, n_samples + n_importance] sorted union                          */
+  float* z_samples;                /* [N, n_importance] (may be NULL)                                     */
+  int32_t* inds;                   /* [N, n_importance] searchsorted indices (may be NULL)                */
+  float* z_std;                    /* [N] population std of z_samples (may be NULL; needs z_samples)      */
+} nefes_render_out_t;
+int nefes_render_rays_workspace(const nefes_render_cfg_t* cfg_host, int64_t N, int64_t* keep_bytes_host,
+                                int64_t* scratch_fwd_bytes_host, int64_t* scratch_bwd_bytes_host);
+int nefes_render_rays_fwd(const nefes_render_cfg_t* cfg_host, const nefes_render_in_t* in_host, int64_t N,
+                          const nefes_render_out_t* out_host, void* keep, void* scratch, void* stream);
+/* g_coarse / g_fine: cotangents of the two composited output sets (NULL or all-NULL = none).  d_params_* are
+ * ACCUMULATED into (caller zero-fills) or NULL (frozen field); d_rays [N, ld_rays] is overwritten (columns 0:6 and 8:11,
+ * zeros elsewhere) or NULL.  `in` / `out` are the forward call's (same buffers, still holding its results). */
+int nefes_render_rays_bwd(const nefes_render_cfg_t* cfg_host, const nefes_render_in_t* in_host, int64_t N,
+                          const nefes_render_out_t* out_host, const nefes_comp_grad_t* g_coarse_host,
+                          const nefes_comp_grad_t* g_fine_host, const void* keep, void* scratch, float* d_params_coarse,
+                          float* d_params_fine, float* d_rays, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Caller-side helpers on the "next" rows of SURVEY 8f that the training step needs resident.
  * Fused Adam on the flat buffers (torch.optim.Adam, betas (0.9, 0.999), eps 1e-8, no weight
  * decay: nerfh_nff.py:682); grad is scaled by grad_scale first (1/world_size after all-reduce).

@@ -37,6 +37,21 @@ class CompGrad(C.Structure):
     _fields_ = [(n, vp) for n in ("rgb", "feat", "disp", "acc", "weights", "depth", "beta", "tsig")]
 
 
+class RenderCfg(C.Structure):
+    _fields_ = [(n, i32) for n in ("n_samples", "n_importance", "prec", "test_time", "output_transient",
+                                   "transient_at_test", "net_coarse", "net_fine")] + [("beta_min", f32)]
+
+
+class RenderIn(C.Structure):
+    _fields_ = [("rays", vp), ("ld_rays", i32), ("params_coarse", vp), ("params_fine", vp), ("t_vals", vp), ("t_rand", vp),
+                ("u", vp), ("u_per_ray", i32), ("noise_coarse", vp), ("noise_fine", vp)]
+
+
+class RenderOut(C.Structure):
+    _fields_ = [("coarse", CompOut), ("fine", CompOut), ("z_coarse", vp), ("z_fine", vp), ("z_samples", vp), ("inds", vp),
+                ("z_std", vp)]
+
+
 class HashLevel(C.Structure):
     _fields_ = [("scale", f32), ("res", C.c_uint32), ("size", C.c_uint32), ("offset", C.c_uint32), ("dense", C.c_uint32)]
 
@@ -80,6 +95,10 @@ _SIGS = {
     "nefes_adam_step_dev": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, vp]),
     "nefes_nerfw_loss_fwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp]),
     "nefes_nerfw_loss_bwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, vp]),
+    "nefes_render_rays_workspace": (i32, [C.POINTER(RenderCfg), i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+    "nefes_render_rays_fwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), vp, vp, vp]),
+    "nefes_render_rays_bwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), C.POINTER(CompGrad),
+                                    C.POINTER(CompGrad), vp, vp, vp, vp, vp, vp]),
     "nefes_prof_enable": (i32, [i32]),
     "nefes_prof_report": (i32, [C.c_char_p, i32]),
     "nefes_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]),

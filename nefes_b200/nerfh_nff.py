@@ -78,6 +78,21 @@ def run_network_NeRFH_NFF(inputs, viewdirs, ts, fn, embed_fn=None, embeddirs_fn=
     return torch.cat(outs, 0)
 
 
+class StandardQuery:
+    """The `network_query_fn` closure create_nerf builds (nerfh_nff.py:667-675) as an object: same call, and render_rays can
+    recognise it (`nefes_standard`) and hand the whole path to nefes_render_rays_fwd/_bwd as ONE engine call whenever the
+    rays fit one netchunk.  A hand-written query function keeps the staged path."""
+    nefes_standard = True
+
+    def __init__(self, netchunk=1024 * 64, embed_fn=None, embeddirs_fn=None):
+        self.netchunk, self.embed_fn, self.embeddirs_fn = int(netchunk), embed_fn, embeddirs_fn
+
+    def __call__(self, inputs, viewdirs, ts, network_fn, typ, output_transient, test_time, store_rgb):
+        return run_network_NeRFH_NFF(inputs, viewdirs, ts, network_fn, embed_fn=self.embed_fn, embeddirs_fn=self.embeddirs_fn,
+                                     typ=typ, output_transient=output_transient, netchunk=self.netchunk,
+                                     test_time=test_time, store_rgb=store_rgb)
+
+
 # ------------------------------------------------------------------------------------------------
 class Embedder:
     """nerfh_nff.py:234-270: [x, sin(2^k x), cos(2^k x)]_k with log-sampled bands."""
@@ -326,10 +341,7 @@ def create_nerf(args, device=None):
                                in_channels_t=getattr(args, "in_channels_t", 16)).to(device)
         grad_vars += list(model_fine.parameters())
 
-    network_query_fn = lambda inputs, viewdirs, ts, network_fn, typ, output_transient, test_time, store_rgb: \
-        run_network_NeRFH_NFF(inputs, viewdirs, ts, network_fn, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn,
-                              typ=typ, output_transient=output_transient, netchunk=args.netchunk,
-                              test_time=test_time, store_rgb=store_rgb)
+    network_query_fn = StandardQuery(args.netchunk, embed_fn, embeddirs_fn)
     if getattr(args, "no_grad_update", False):
         grad_vars, optimizer = None, None
     else:

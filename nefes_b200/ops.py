@@ -374,6 +374,93 @@ def composite(raw, z, noise, mode, beta_min=0.1):
 
 
 # ------------------------------------------------------------------------------------------------
+# the whole path as one engine call (nefes_render_rays_fwd / _bwd)
+# ------------------------------------------------------------------------------------------------
+class _RenderRays(Function):
+    """ray_batch [N, >=11], flat_coarse, flat_fine (+ explicit random draws) -> the composited outputs of both passes.
+    One autograd node for rendering.py:68-180: sample points, raw, saved activations and compact cotangents never leave
+    the engine's two workspaces."""
+
+    @staticmethod
+    def forward(ctx, rays, flat_c, flat_f, t_rand, u, noise_c, noise_f, cfg):
+        ctx.set_materialize_grads(False)
+        L.need_cuda(rays, flat_c, flat_f, t_rand, u, noise_c, noise_f)
+        rays_c = L.f32c(rays)
+        N, ld = rays_c.shape
+        dev = rays_c.device
+        S, ni = cfg["n_samples"], cfg["n_importance"]
+        Sf = S + ni
+        c = L.RenderCfg(S, ni, cfg["prec"], int(cfg["test_time"]), int(cfg["output_transient"]), int(cfg["transient_at_test"]),
+                        cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]))
+        kb, sfb, sbb = C.c_int64(), C.c_int64(), C.c_int64()
+        L.check(L.lib().nefes_render_rays_workspace(C.byref(c), N, C.byref(kb), C.byref(sfb), C.byref(sbb)),
+                "nefes_render_rays_workspace")
+        keep, scratch = _buf(kb.value, dev), _buf(sfb.value, dev)
+        t_rand, u, noise_c, noise_f = L.f32c(t_rand), L.f32c(u), L.f32c(noise_c), L.f32c(noise_f)
+        per_ray = 1
+        if u is None:
+            u, per_ray = linspace01(ni, dev), 0
+        fc, ff = flat_c.detach(), flat_f.detach()
+        if not (fc.is_contiguous() and ff.is_contiguous() and fc.dtype == ff.dtype == torch.float32):
+            raise RuntimeError("nefes_b200: flat parameter buffers must be contiguous fp32")
+        inp = L.RenderIn(L.ptr(rays_c), ld, L.ptr(fc), L.ptr(ff), L.ptr(linspace01(S, dev)), L.ptr(t_rand), L.ptr(u), per_ray,
+                         L.ptr(noise_c), L.ptr(noise_f))
+        e = lambda *shape: torch.empty(*shape, device=dev)
+        sigma_only = bool(cfg["test_time"])
+        transient = bool(cfg["output_transient"])
+        acc0, w0 = e(N), e(N, S)
+        rgb0 = feat0 = disp0 = depth0 = beta0 = None
+        if not sigma_only:
+            rgb0, feat0, disp0, depth0, beta0 = e(N, 3), e(N, 128), e(N), e(N), e(N)
+        rgb, feat, disp, acc, w, depth, beta = e(N, 3), e(N, 128), e(N), e(N), e(N, Sf), e(N), e(N)
+        tsig = e(N, Sf) if transient else None
+        z_c, z_f, z_s, z_std = e(N, S), e(N, Sf), e(N, ni), e(N)
+        inds = torch.empty(N, ni, dtype=torch.int32, device=dev)
+        out = L.RenderOut(L.CompOut(L.ptr(rgb0), L.ptr(feat0), L.ptr(disp0), L.ptr(acc0), L.ptr(w0), L.ptr(depth0), L.ptr(beta0), None),
+                          L.CompOut(L.ptr(rgb), L.ptr(feat), L.ptr(disp), L.ptr(acc), L.ptr(w), L.ptr(depth), L.ptr(beta), L.ptr(tsig)),
+                          L.ptr(z_c), L.ptr(z_f), L.ptr(z_s), L.ptr(inds), L.ptr(z_std))
+        with torch.cuda.device(dev), _Timed("render_fwd"):
+            L.check(L.lib().nefes_render_rays_fwd(C.byref(c), C.byref(inp), N, C.byref(out), L.ptr(keep), L.ptr(scratch),
+                                                  L.stream_of(rays_c)), "nefes_render_rays_fwd")
+        if any(ctx.needs_input_grad[:3]):
+            ctx.save_for_backward(rays_c, fc, ff, t_rand, u, noise_c, noise_f, z_c, z_f, keep)
+            ctx.meta = (dict(cfg), per_ray, sbb.value, tuple(rays.shape))
+        ctx.mark_non_differentiable(z_c, z_f, z_s, inds, z_std)
+        return (rgb, feat, disp, acc, w, depth, beta, tsig, rgb0, feat0, disp0, acc0, w0, depth0, z_std, z_c, z_f, z_s, inds)
+
+    @staticmethod
+    def backward(ctx, *g):
+        rays_c, fc, ff, t_rand, u, noise_c, noise_f, z_c, z_f, keep = ctx.saved_tensors
+        cfg, per_ray, sbb, rshape = ctx.meta
+        N, ld = rays_c.shape
+        dev = rays_c.device
+        S, ni = cfg["n_samples"], cfg["n_importance"]
+        c = L.RenderCfg(S, ni, cfg["prec"], int(cfg["test_time"]), int(cfg["output_transient"]), int(cfg["transient_at_test"]),
+                        cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]))
+        inp = L.RenderIn(L.ptr(rays_c), ld, L.ptr(fc), L.ptr(ff), L.ptr(linspace01(S, dev)), L.ptr(t_rand), L.ptr(u), per_ray,
+                         L.ptr(noise_c), L.ptr(noise_f))
+        nul = L.CompOut(*([None] * 8))
+        out = L.RenderOut(nul, nul, L.ptr(z_c), L.ptr(z_f), None, None, None)
+        gf = [L.f32c(t) for t in g[0:8]]
+        gc = [L.f32c(t) for t in g[8:14]] + [None, None]
+        g_fine, g_coarse = L.CompGrad(*[L.ptr(t) for t in gf]), L.CompGrad(*[L.ptr(t) for t in gc])
+        need_r, need_c, need_f = ctx.needs_input_grad[:3]
+        d_rays = torch.empty_like(rays_c) if need_r else None
+        d_c = torch.zeros_like(fc) if need_c else None
+        d_f = torch.zeros_like(ff) if need_f else None
+        scratch = _buf(sbb, dev)
+        with torch.cuda.device(dev), _Timed("render_bwd"):
+            L.check(L.lib().nefes_render_rays_bwd(C.byref(c), C.byref(inp), N, C.byref(out), C.byref(g_coarse), C.byref(g_fine),
+                                                  L.ptr(keep), L.ptr(scratch), L.ptr(d_c), L.ptr(d_f), L.ptr(d_rays),
+                                                  L.stream_of(rays_c)), "nefes_render_rays_bwd")
+        return (d_rays.reshape(rshape) if d_rays is not None else None, d_c, d_f, None, None, None, None, None)
+
+
+def render_rays_fused(rays, flat_c, flat_f, cfg, t_rand=None, u=None, noise_c=None, noise_f=None):
+    return _RenderRays.apply(rays, flat_c, flat_f, t_rand, u, noise_c, noise_f, cfg)
+
+
+# ------------------------------------------------------------------------------------------------
 # fused Adam on flat buffers
 # ------------------------------------------------------------------------------------------------
 @torch.no_grad()

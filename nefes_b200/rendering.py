@@ -7,11 +7,13 @@ Extra keyword arguments (all optional, default = reference behaviour):
                        absent they are drawn on the device with torch's generator.
     return_aux       : also return z_vals / z_samples / inds in the result dict.
 """
+import os
+
 import torch
 
 from . import _lib as L
 from . import ops
-from .nerfh_nff import raw2outputs_NeRFH_NFF
+from .nerfh_nff import _PREC, NeRFH_NFF, raw2outputs_NeRFH_NFF
 from .ray_utils import get_rays
 
 
@@ -33,6 +35,64 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False, u=None):
     return out.reshape(*lead, N_samples)
 
 
+# NEFES_FUSED_RENDER=0 keeps render_rays on the staged path (one autograd node per stage) even where the one-call path applies
+FUSED_RENDER = os.environ.get("NEFES_FUSED_RENDER", "1") != "0"
+
+
+def _fused_applies(ray_batch, network_fn, network_query_fn, N_samples, N_importance, network_fine, args):
+    """The whole-path engine call covers the reference's own configuration: the standard query function, both fields on
+    the engine with one arithmetic, a fine pass, view directions present, all rays inside one netchunk."""
+    return (FUSED_RENDER and N_importance > 0 and getattr(network_query_fn, "nefes_standard", False)
+            and isinstance(network_fn, NeRFH_NFF) and isinstance(network_fine, NeRFH_NFF)
+            and network_fn.precision == network_fine.precision and not args.use_fine_only
+            and ray_batch.shape[1] >= 11 and N_samples + N_importance <= 256
+            and ray_batch.shape[0] * (N_samples + N_importance) <= network_query_fn.netchunk)
+
+
+def _render_rays_fused(ray_batch, network_fn, N_samples, perturb, N_importance, network_fine, raw_noise_std, pytest,
+                       test_time, args, t_rand, u, noise, return_aux):
+    N_rays, dev = ray_batch.shape[0], ray_batch.device
+    output_transient = bool(args.NeRFW)
+    if output_transient and network_fine.net_id != L.NET_FINE:
+        raise RuntimeError("nefes_b200: transient output requested from a field without transient heads")
+    if perturb > 0. and t_rand is None:
+        t_rand = torch.rand(N_rays, N_samples, device=dev)                        # rendering.py:110
+    if noise is None and raw_noise_std > 0. and not test_time:
+        noise = torch.randn(N_rays, N_samples, device=dev) * raw_noise_std        # nerfh_nff.py:67
+    det = (perturb == 0.)
+    if not det and u is None:
+        u = torch.rand(N_rays, N_importance, device=dev)                          # rendering.py:36
+    if pytest:
+        import numpy as np
+        np.random.seed(0)
+        u = None if det else torch.Tensor(np.random.rand(N_rays, N_importance)).to(dev)
+    noise_f = None
+    if raw_noise_std > 0. and not output_transient:
+        noise_f = torch.randn(N_rays, N_samples + N_importance, device=dev) * raw_noise_std
+    cfg = dict(n_samples=int(N_samples), n_importance=int(N_importance), prec=_PREC[network_fn.precision],
+               test_time=bool(test_time), output_transient=output_transient, transient_at_test=bool(args.transient_at_test),
+               net_coarse=network_fn.net_id, net_fine=network_fine.net_id, beta_min=network_fine.beta_min)
+    (rgb, feat, disp, acc, w, depth, beta, tsig, rgb0, feat0, disp0, acc0, w0, depth0, z_std, z_c, z_f, z_s, inds) = \
+        ops.render_rays_fused(ray_batch, network_fn.flat, network_fine.flat, cfg, t_rand=t_rand if perturb > 0. else None,
+                              u=None if det else u, noise_c=noise, noise_f=noise_f)
+    ret = {'rgb_map': rgb, 'disp_map': disp, 'acc_map': acc}
+    if args.nerfh_nff:
+        ret['feat_map'] = feat
+    if not test_time:
+        ret['rgb0'], ret['disp0'], ret['acc0'] = rgb0, disp0, acc0
+        ret['z_std'] = z_std
+        if args.NeRFW:
+            ret['transient_sigmas'] = tsig
+            ret['beta'] = beta
+        if args.nerfh_nff and feat0 is not None:
+            ret['feat0'] = feat0
+    if return_aux:
+        aux = dict(z_coarse=z_c, z_samples=z_s, inds=inds, z_fine=z_f, weights_coarse=w0, depth_map=depth, weights_fine=w)
+        for k, v in aux.items():
+            ret['aux_' + k] = v
+    return ret
+
+
 def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
                 i_epoch=-1, embedding_a=None, embedding_t=None, test_time=False, args=None, volume=None,
@@ -45,6 +105,11 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     ray_batch = ray_batch if ray_batch.dtype == torch.float32 else ray_batch.float()
     if not ray_batch.is_contiguous():
         ray_batch = ray_batch.contiguous()
+    if white_bkgd:
+        raise RuntimeError("nefes_b200: white_bkgd=True is not supported (no reference config uses it)")
+    if _fused_applies(ray_batch, network_fn, network_query_fn, N_samples, N_importance, network_fine, args):
+        return _render_rays_fused(ray_batch, network_fn, N_samples, perturb, N_importance, network_fine, raw_noise_std, pytest,
+                                  test_time, args, t_rand, u, noise, return_aux)
     N_rays, width = ray_batch.shape
     rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     viewdirs = ray_batch[:, 8:11] if width > 8 else None

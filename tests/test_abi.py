@@ -74,3 +74,22 @@ def test_cpu_tensors_are_rejected():
     import nefes_b200 as nb
     with pytest.raises(RuntimeError, match="CUDA"):
         nb.get_rays(4, 4, 10.0, torch.eye(4))
+
+
+def test_render_rays_workspace_is_host_arithmetic():
+    """nefes_render_rays_workspace sizes the two workspaces of the one-call path on the host; bad configs are refused."""
+    import ctypes as C
+    from nefes_b200 import _lib as L
+    cfg = L.RenderCfg(64, 64, L.PREC_BF16, 0, 1, 1, L.NET_COARSE, L.NET_FINE, 0.1)
+    k, a, b = C.c_int64(), C.c_int64(), C.c_int64()
+    assert L.lib().nefes_render_rays_workspace(C.byref(cfg), 6144, C.byref(k), C.byref(a), C.byref(b)) == 0
+    # keep >= sample points + both tile-major raw blocks
+    assert k.value >= 6144 * (64 + 128) * 12 + 6144 * 64 * 132 * 4 + 6144 * 128 * 137 * 4
+    assert a.value > 0 and b.value > 0 and k.value % 256 == 0
+    k2 = C.c_int64()
+    assert L.lib().nefes_render_rays_workspace(C.byref(cfg), 12288, C.byref(k2), C.byref(a), C.byref(b)) == 0
+    assert k2.value > k.value
+    bad = L.RenderCfg(64, 300, L.PREC_BF16, 0, 1, 1, L.NET_COARSE, L.NET_FINE, 0.1)
+    assert L.lib().nefes_render_rays_workspace(C.byref(bad), 16, C.byref(k), C.byref(a), C.byref(b)) == 1
+    assert b"sample counts" in L.lib().nefes_last_error()
+    assert L.lib().nefes_render_rays_fwd(C.byref(cfg), None, 16, None, None, None, None) == 1

@@ -58,11 +58,15 @@ class Args:
     netchunk = 1 << 21
 
 
-def render_kwargs(nb, models, test_time):
+def render_kwargs(nb, models, test_time, fused=False):
+    """fused=False: a hand-written query closure, as the reference builds it -> the staged path (one engine call per
+    stage); fused=True: nb.StandardQuery -> render_rays is ONE engine call (nefes_render_rays_fwd/_bwd)."""
     c, f = models
     q = lambda inputs, viewdirs, ts, fn, typ, output_transient, test_time, store_rgb: \
         nb.run_network_NeRFH_NFF(inputs, viewdirs, ts, fn, typ=typ, output_transient=output_transient,
                                  netchunk=Args.netchunk, test_time=test_time, store_rgb=store_rgb)
+    if fused:
+        q = nb.StandardQuery(Args.netchunk)
     return dict(network_query_fn=q, N_importance=64, N_samples=64, network_fn=c, network_fine=f,
                 use_viewdirs=True, white_bkgd=False, args=Args(), ndc=False, lindisp=False, near=NEAR, far=FAR,
                 perturb=0. if test_time else 1., raw_noise_std=0., test_time=test_time)
@@ -276,7 +280,8 @@ def test_mlp_backward_vs_oracle(nb, weights, models):
             assert rel_err(views[key], ref_g.grad) < 2e-4, key
 
 
-def test_render_train_golden(nb, golden, models):
+@pytest.mark.parametrize("fused", [False, True])
+def test_render_train_golden(nb, golden, models, fused):
     """End-to-end render() in train mode on the reference's RNG draws: outputs, sample indices, loss and
     weight gradients against the unmodified reference (fixture g5)."""
     g = golden("g5_render.npz")
@@ -285,7 +290,7 @@ def test_render_train_golden(nb, golden, models):
     rays = (g["rays_o"].to(DEV), g["rays_d"].to(DEV))
     rgb, disp, acc, ex = nb.render(H, W, FOCAL, chunk=32768, rays=rays, img_idx=torch.zeros(1, 10),
                                    t_rand=g["train/t_rand"].to(DEV), u=g["train/u"].to(DEV), return_aux=True,
-                                   retraw=True, **render_kwargs(nb, models, False))
+                                   retraw=True, **render_kwargs(nb, models, False, fused))
     out = dict(rgb_map=rgb, disp_map=disp, acc_map=acc, **ex)
     assert torch.equal(out["aux_z_coarse"].cpu(), g["train/z_coarse"])
     mism = (out["aux_inds"].cpu() != g["train/inds"]).float().mean()
@@ -306,7 +311,8 @@ def test_render_train_golden(nb, golden, models):
             assert rel_err(vc[key[len("train/grad_coarse/"):]], ref) < 2e-3, key
 
 
-def test_render_refinement_pose_gradient_golden(nb, golden, models):
+@pytest.mark.parametrize("fused", [False, True])
+def test_render_refinement_pose_gradient_golden(nb, golden, models, fused):
     """test_time=True full-image render from c2w, cosine feature loss, gradient to the 3x4 pose."""
     g = golden("g5_render.npz")
     c, f = models
@@ -315,7 +321,7 @@ def test_render_refinement_pose_gradient_golden(nb, golden, models):
     try:
         c2w = g["test/c2w"].to(DEV).requires_grad_(True)
         rgb, disp, acc, ex = nb.render(H, W, FOCAL, chunk=32768, c2w=c2w, img_idx=torch.zeros(1, 10), return_aux=True,
-                                       **render_kwargs(nb, models, True))
+                                       **render_kwargs(nb, models, True, fused))
         sub = g["test/sub"].to(DEV)
         assert set(k for k in ex if not k.startswith("aux_")) == {"feat_map"}
         assert rel_err(ex["feat_map"][sub], g["test/feat_map"]) < 1e-3
@@ -330,7 +336,8 @@ def test_render_refinement_pose_gradient_golden(nb, golden, models):
             p.requires_grad_(True)
 
 
-def test_render_vs_oracle_1024_rays_and_properties(nb, weights, models):
+@pytest.mark.parametrize("fused", [False, True])
+def test_render_vs_oracle_1024_rays_and_properties(nb, weights, models, fused):
     """Seeded batch larger than the fixtures, checked against the oracle run on the host, plus
     size-independent properties."""
     wc, wf = weights
@@ -345,7 +352,7 @@ def test_render_vs_oracle_1024_rays_and_properties(nb, weights, models):
         ref = O.render(H, W, FOCAL, wc, wf, rays=rays, near=NEAR, far=FAR, test_time=False, t_rand=t_rand, u=u)
         rgb, disp, acc, ex = nb.render(H, W, FOCAL, rays=(rays[0].to(DEV), rays[1].to(DEV)),
                                        img_idx=torch.zeros(1, 10), t_rand=t_rand.to(DEV), u=u.to(DEV),
-                                       return_aux=True, **render_kwargs(nb, models, False))
+                                       return_aux=True, **render_kwargs(nb, models, False, fused))
     for k, v in dict(rgb_map=rgb, acc_map=acc, feat_map=ex["feat_map"], rgb0=ex["rgb0"], feat0=ex["feat0"],
                      beta=ex["beta"]).items():
         assert rel_err(v, ref[k]) < 1e-3, k

@@ -175,3 +175,52 @@ def test_large_ragged_render_is_chunk_invariant():
     assert a[0].shape == (n, 3) and a[3]["feat_map"].shape == (n, 128)
     assert torch.isfinite(a[0]).all() and torch.isfinite(a[3]["feat_map"]).all()
     assert torch.equal(a[0], b[0]) and torch.equal(a[3]["feat_map"], b[3]["feat_map"]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("precision,test_time", [("bf16", False), ("bf16", True), ("fp32", False)])
+def test_one_call_render_rays_matches_staged_path(precision, test_time):
+    """nefes_render_rays_fwd/_bwd (render_rays as ONE engine call, reached through nb.StandardQuery) against the staged
+    path (a hand-written query closure: one engine call per stage) on the same draws: the same kernels run on the same
+    bits, so outputs are identical; gradients differ only by the order of fp32 atomics / reductions."""
+    import nefes_b200 as nb
+    c, f = _nets()
+    c.precision = f.precision = precision
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n = 333                                                   # ragged: last tile partly filled
+    t_rand, u = torch.rand(n, 64, device="cuda", generator=g), torch.rand(n, 64, device="cuda", generator=g)
+    ro0 = torch.randn(n, 3, device="cuda", generator=g) * 0.1
+    rd0 = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda", generator=g), dim=-1) * 1.3
+
+    class Args:
+        nerfh_nff, use_fine_only, NeRFW, transient_at_test, netchunk = True, False, True, True, 1 << 21
+
+    def run(q):
+        c.zero_grad(); f.zero_grad()
+        ro, rd = ro0.clone().requires_grad_(True), rd0.clone().requires_grad_(True)
+        rgb, disp, acc, ex = nb.render(60, 80, 65.688, rays=(ro, rd), img_idx=torch.zeros(1, 10), near=0., far=4., ndc=False,
+                                       use_viewdirs=True, network_query_fn=q, N_samples=64, N_importance=64, network_fn=c,
+                                       network_fine=f, perturb=0. if test_time else 1., raw_noise_std=0., test_time=test_time,
+                                       args=Args(), t_rand=t_rand, u=u, return_aux=True)
+        loss = rgb.sum() + (ex["feat_map"] ** 2).sum() + disp.mean() + acc.sum()
+        if not test_time:
+            loss = loss + ex["rgb0"].sum() + ex["beta"].sum() + ex["feat0"].abs().sum() + 0.1 * ex["transient_sigmas"].mean()
+        loss.backward()
+        out = dict(rgb=rgb, disp=disp, acc=acc, **ex)
+        grads = dict(ro=ro.grad, rd=rd.grad)
+        if not test_time:
+            grads.update(c=c.flat.grad.clone(), f=f.flat.grad.clone())
+        return {k: v.detach() for k, v in out.items()}, grads
+
+    staged = run(lambda i, v, ts, fn, typ, ot, test_time, store_rgb: nb.run_network_NeRFH_NFF(
+        i, v, ts, fn, typ=typ, output_transient=ot, netchunk=Args.netchunk, test_time=test_time, store_rgb=store_rgb))
+    fused = run(nb.StandardQuery(Args.netchunk))
+    assert set(staged[0]) == set(fused[0])
+    for k, v in staged[0].items():
+        if k == "z_std":
+            assert float((v - fused[0][k]).abs().max()) < 1e-6
+        else:
+            assert torch.equal(v, fused[0][k]), k
+    for k, v in staged[1].items():
+        assert float((v - fused[1][k]).abs().max()) <= 2e-3 * float(v.abs().max()) + 1e-7, k
+    if test_time:                                           # frozen-field refinement: no parameter gradient is produced
+        assert c.flat.grad is None or float(c.flat.grad.abs().max()) == 0.0
