@@ -292,6 +292,31 @@ int nefes_render_rays_bwd(const nefes_render_cfg_t* cfg_host, const nefes_render
                           float* d_params_fine, float* d_rays, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Refinement iteration glue: the pose chain in front of get_rays, the feature-metric loss behind the
+ * render and the optimiser step, so that one iteration of DFM_pose_refine.py:380-440 is engine launches only.
+ *   pose6 = [r(3), t(3)]: c2w = [Exp(r) @ R0 | t + t0] with init_c2w = [R0 | t0] [3,4]
+ *                         (script/models/poses.py:25-50 with lietorch=False; utils/lie_group_helper.py:60-81)
+ *   nefes_pose_rays_fwd  writes c2w_out [3,4] (may be NULL) and the packed ray_batch [H*W, ld >= 11] render() builds
+ *                        (rendering.py:197-243: o, d, near, far, d/|d|, zeros) with get_rays' arithmetic (ray_utils.py:5-16)
+ *   nefes_pose_rays_bwd  cotangent of ray_batch -> d_c2w [3,4], ACCUMULATED (caller zero-fills once)
+ *   nefes_cosine_loss_*  loss = 1 - mean_c cosine_similarity(feat[:, c], target[c, :]) (DFM_pose_refine.py:236-255,
+ *                        per_pixel=False); feat [N,C] row-major, target [C,N]; stats [3,C] ACCUMULATED by _fwd (caller
+ *                        zero-fills once); _bwd writes loss (1 float, may be NULL), loss_hist[(int)*step] when both are
+ *                        given, and d_feat [N,C] (may be NULL)
+ *   nefes_pose_adam_step d_c2w -> (d_r, d_t) through the exponential, torch.optim.Adam on the two groups (lr_r, lr_t);
+ *                        state13 = exp_avg[6], exp_avg_sq[6], step; clears d_c2w and zero[0:n_zero] (the loss statistics)
+ * ------------------------------------------------------------------------------------------ */
+int nefes_pose_rays_fwd(const float* pose6, const float* init_c2w, int H, int W, float focal, float near, float far,
+                        float* c2w_out, float* ray_batch, int ld, void* stream);
+int nefes_pose_rays_bwd(const float* d_ray_batch, const float* ray_batch, int ld, int H, int W, float focal, float* d_c2w,
+                        void* stream);
+int nefes_cosine_loss_fwd(const float* feat, const float* target, int N, int C, float* stats, void* stream);
+int nefes_cosine_loss_bwd(const float* feat, const float* target, const float* stats, int N, int C, float* loss,
+                          float* loss_hist, const float* step, int hist_cap, float* d_feat, void* stream);
+int nefes_pose_adam_step(float* pose6, const float* init_c2w, float* d_c2w, float* zero, int n_zero, float* state13,
+                         float lr_r, float lr_t, float beta1, float beta2, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Caller-side helpers on the "next" rows of SURVEY 8f that the training step needs resident.
  * Fused Adam on the flat buffers (torch.optim.Adam, betas (0.9, 0.999), eps 1e-8, no weight
  * decay: nerfh_nff.py:682); grad is scaled by grad_scale first (1/world_size after all-reduce).

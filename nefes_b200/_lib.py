@@ -99,6 +99,11 @@ _SIGS = {
     "nefes_render_rays_fwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), vp, vp, vp]),
     "nefes_render_rays_bwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), C.POINTER(CompGrad),
                                     C.POINTER(CompGrad), vp, vp, vp, vp, vp, vp]),
+    "nefes_pose_rays_fwd": (i32, [vp, vp, i32, i32, f32, f32, f32, vp, vp, i32, vp]),
+    "nefes_pose_rays_bwd": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
+    "nefes_cosine_loss_fwd": (i32, [vp, vp, i32, i32, vp, vp]),
+    "nefes_cosine_loss_bwd": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]),
+    "nefes_pose_adam_step": (i32, [vp, vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, vp]),
     "nefes_prof_enable": (i32, [i32]),
     "nefes_prof_report": (i32, [C.c_char_p, i32]),
     "nefes_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]),

@@ -1,0 +1,288 @@
+// The refinement iteration's glue around the render, as five small kernels so that one
+// iteration is ~30 engine launches and nothing else:
+//   pose_rays_fwd   (r, t, init_c2w) -> c2w = [Exp(r) R0 | t + t0] -> packed ray_batch rows     poses.py:25-50 (lietorch=False),
+//                                                                       lie_group_helper.py:60-81, ray_utils.py:5-16, rendering.py:197-243
+//   cosine_loss_*   1 - mean_c cos(feat[:, c], target[c, :]) and its gradient                   DFM_pose_refine.py:236-255 (per_pixel=False)
+//   pose_rays_bwd   d ray_batch -> d c2w (view-direction normalisation and camera rays chained)
+//   pose_adam_step  d c2w -> d r, d t through the so(3) exponential; torch.optim.Adam update     DFM_pose_refine.py:380-440
+#include "common.cuh"
+
+namespace nefes {
+
+struct Pose34 { float m[12]; };
+
+// c2w = [Exp(r) @ R0 | t + t0] in fp32, op for op as LearnPose.forward / lie_group_helper.Exp compute it
+__device__ __forceinline__ Pose34 pose_c2w(const float* __restrict__ pose6, const float* __restrict__ init) {
+  const float r0 = pose6[0], r1 = pose6[1], r2 = pose6[2];
+  const float K[9] = {0.f, -r2, r1, r2, 0.f, -r0, -r1, r0, 0.f};
+  const float n = sqrtf(r0 * r0 + r1 * r1 + r2 * r2) + 1e-15f;
+  const float a = sinf(n) / n, b = (1.f - cosf(n)) / (n * n);
+  float R[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float kk = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) kk += K[i * 3 + k] * K[k * 3 + j];
+      R[i * 3 + j] = (i == j ? 1.f : 0.f) + a * K[i * 3 + j] + b * kk;
+    }
+  Pose34 P;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s += R[i * 3 + k] * init[k * 4 + j];
+      P.m[i * 4 + j] = s;
+    }
+    P.m[i * 4 + 3] = pose6[3 + i] + init[i * 4 + 3];
+  }
+  return P;
+}
+
+__global__ void pose_rays_fwd_kernel(const float* __restrict__ pose6, const float* __restrict__ init, int H, int W, float focal,
+                                     float near, float far, float* __restrict__ c2w_out, float* __restrict__ rays, int ld) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const Pose34 P = pose_c2w(pose6, init);
+  if (p == 0 && c2w_out != nullptr)
+#pragma unroll
+    for (int q = 0; q < 12; ++q) c2w_out[q] = P.m[q];
+  const int j = p / W, i = p % W;
+  // ray_utils.py:5-16, same operation order as get_rays_fwd_kernel
+  const float cx = __fdiv_rn(__fsub_rn((float)i, (float)W * .5f), focal);
+  const float cy = -__fdiv_rn(__fsub_rn((float)j, (float)H * .5f), focal);
+  float d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    d[c] = __fadd_rn(__fadd_rn(__fmul_rn(cx, P.m[c * 4 + 0]), __fmul_rn(cy, P.m[c * 4 + 1])), __fmul_rn(-1.f, P.m[c * 4 + 2]));
+  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+  float* r = rays + (int64_t)p * ld;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    r[c] = P.m[c * 4 + 3];
+    r[3 + c] = d[c];
+    r[8 + c] = __fdiv_rn(d[c], nrm);                 // rendering.py:222: viewdirs / norm
+  }
+  r[6] = near;
+  r[7] = far;
+  for (int c = 11; c < ld; ++c) r[c] = 0.f;          // img_idx histogram: accepted and ignored by the field (nerfh_nff.py:168)
+}
+
+// d_c2w[c][k<3] += sum_p d_d[p][c] cam[p][k], d_c2w[c][3] += sum_p d_o[p][c], where d_d includes the cotangent of the
+// normalised view direction: v = d/|d|  ->  d_d += (g_v - v (v . g_v)) / |d|
+__global__ void pose_rays_bwd_kernel(const float* __restrict__ d_rays, const float* __restrict__ rays, int ld, int H, int W,
+                                     float focal, float* __restrict__ d_c2w) {
+  float acc[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) acc[q] = 0.f;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < H * W; p += gridDim.x * blockDim.x) {
+    const float* g = d_rays + (int64_t)p * ld;
+    const float* r = rays + (int64_t)p * ld;
+    const int j = p / W, i = p % W;
+    const float cam[3] = {((float)i - (float)W * .5f) / focal, -((float)j - (float)H * .5f) / focal, -1.f};
+    const float nrm = sqrtf(r[3] * r[3] + r[4] * r[4] + r[5] * r[5]);
+    const float vg = r[8] * g[8] + r[9] * g[9] + r[10] * g[10];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float gd = g[3 + c] + (g[8 + c] - r[8 + c] * vg) / nrm;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc[c * 4 + k] += gd * cam[k];
+      acc[c * 4 + 3] += g[c];
+    }
+  }
+  __shared__ float red[12][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const float v = warp_sum(acc[q]);
+    if (lane == 0) red[q][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+    atomicAdd(&d_c2w[threadIdx.x], s);
+  }
+}
+
+// per-channel sums over the pixels: stats[0][c] = sum_n a b, stats[1][c] = sum_n a^2, stats[2][c] = sum_n b^2 with
+// a = feat[n][c] (row-major [N,C]) and b = target[c][n] ([C,N]).  Block = C threads (thread = channel) x 32 pixels; the
+// target tile goes through shared memory so that both tensors are read along their contiguous axis.
+constexpr int kLossPix = 32;
+__global__ void cosine_stats_kernel(const float* __restrict__ feat, const float* __restrict__ target, int N, int C,
+                                    float* __restrict__ stats) {
+  extern __shared__ float tile[];                    // [C][kLossPix + 1]
+  const int n0 = blockIdx.x * kLossPix, c = threadIdx.x;
+  for (int e = threadIdx.x; e < C * kLossPix; e += blockDim.x) {
+    const int cc = e / kLossPix, nn = e % kLossPix;
+    tile[cc * (kLossPix + 1) + nn] = n0 + nn < N ? target[(int64_t)cc * N + n0 + nn] : 0.f;
+  }
+  __syncthreads();
+  float ab = 0.f, aa = 0.f, bb = 0.f;
+  for (int nn = 0; nn < kLossPix && n0 + nn < N; ++nn) {
+    const float a = feat[(int64_t)(n0 + nn) * C + c], b = tile[c * (kLossPix + 1) + nn];
+    ab += a * b; aa += a * a; bb += b * b;
+  }
+  atomicAdd(&stats[c], ab);
+  atomicAdd(&stats[C + c], aa);
+  atomicAdd(&stats[2 * C + c], bb);
+}
+
+// loss = 1 - mean_c cos_c, cos_c = ab / (max(|a|, eps) max(|b|, eps))  (F.cosine_similarity, eps = 1e-6);
+// d_feat[n][c] = -(1/C) (b / (|a| |b|) - cos_c a / |a|^2).  Block 0 also writes the loss, to loss[0] and, when a
+// history is kept, to loss_hist[(int)*step] (the device-side iteration counter of pose_adam_step).
+__global__ void cosine_grad_kernel(const float* __restrict__ feat, const float* __restrict__ target, const float* __restrict__ stats,
+                                   int N, int C, float* __restrict__ loss, float* __restrict__ loss_hist, const float* __restrict__ step,
+                                   int hist_cap, float* __restrict__ d_feat) {
+  extern __shared__ float tile[];                    // [C][kLossPix + 1] + [C] cos
+  float* s_cos = tile + C * (kLossPix + 1);
+  const int n0 = blockIdx.x * kLossPix, c = threadIdx.x;
+  const float eps = 1e-6f;
+  const float na = fmaxf(sqrtf(stats[C + c]), eps), nb = fmaxf(sqrtf(stats[2 * C + c]), eps);
+  const float cosc = stats[c] / (na * nb);
+  s_cos[c] = cosc;
+  for (int e = threadIdx.x; e < C * kLossPix; e += blockDim.x) {
+    const int cc = e / kLossPix, nn = e % kLossPix;
+    tile[cc * (kLossPix + 1) + nn] = n0 + nn < N ? target[(int64_t)cc * N + n0 + nn] : 0.f;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < C; ++k) s += s_cos[k];
+    const float l = 1.f - s / (float)C;
+    if (loss != nullptr) loss[0] = l;
+    if (loss_hist != nullptr && step != nullptr) {
+      const int it = (int)step[0];
+      if (it >= 0 && it < hist_cap) loss_hist[it] = l;
+    }
+  }
+  if (d_feat == nullptr) return;
+  const float k1 = -1.f / ((float)C * na * nb), k2 = cosc / ((float)C * na * na);
+  for (int nn = 0; nn < kLossPix && n0 + nn < N; ++nn) {
+    const int64_t o = (int64_t)(n0 + nn) * C + c;
+    d_feat[o] = k1 * tile[c * (kLossPix + 1) + nn] + k2 * feat[o];
+  }
+}
+
+// One thread: d_c2w [3,4] -> (d_r, d_t) through c2w = [Exp(r) R0 | t + t0], then torch.optim.Adam on the two parameter
+// groups.  The chain is evaluated in fp64 (a handful of flops; the fp32 autograd chain it replaces is noisier, not
+// different).  state: m[6], v[6], step.  Afterwards d_c2w and `zero` (the loss statistics) are cleared for the next
+// iteration, so an iteration needs no memset.
+__global__ void pose_adam_kernel(float* __restrict__ pose6, const float* __restrict__ init, float* __restrict__ d_c2w,
+                                 float* __restrict__ zero, int n_zero, float* __restrict__ state, float lr_r, float lr_t,
+                                 float beta1, float beta2, float eps) {
+  if (threadIdx.x == 0) {
+    const double r[3] = {pose6[0], pose6[1], pose6[2]};
+    const double nn = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    const double n = nn + 1e-15;
+    const double a = sin(n) / n, b = (1.0 - cos(n)) / (n * n);
+    const double da = (n * cos(n) - sin(n)) / (n * n), db = (n * sin(n) - 2.0 * (1.0 - cos(n))) / (n * n * n);
+    const double K[9] = {0.0, -r[2], r[1], r[2], 0.0, -r[0], -r[1], r[0], 0.0};
+    double KK[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < 3; ++k) s += K[i * 3 + k] * K[k * 3 + j];
+        KK[i * 3 + j] = s;
+      }
+    // dL/dExp = dL/dR_total @ R0^T
+    double GE[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < 3; ++k) s += (double)d_c2w[i * 4 + k] * (double)init[j * 4 + k];
+        GE[i * 3 + j] = s;
+      }
+    double g[6];
+    for (int k = 0; k < 3; ++k) {
+      double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // skew(e_k)
+      if (k == 0) { E[5] = -1.0; E[7] = 1.0; }
+      if (k == 1) { E[2] = 1.0; E[6] = -1.0; }
+      if (k == 2) { E[1] = -1.0; E[3] = 1.0; }
+      const double dn = nn > 0.0 ? r[k] / nn : 0.0;  // torch: the norm's subgradient at 0 is 0
+      double s = 0.0;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double ek = 0.0;                            // (E K + K E)_ij
+          for (int q = 0; q < 3; ++q) ek += E[i * 3 + q] * K[q * 3 + j] + K[i * 3 + q] * E[q * 3 + j];
+          const double dR = da * dn * K[i * 3 + j] + a * E[i * 3 + j] + db * dn * KK[i * 3 + j] + b * ek;
+          s += GE[i * 3 + j] * dR;
+        }
+      g[k] = s;
+      g[3 + k] = (double)d_c2w[k * 4 + 3];
+    }
+    const float step = state[12] + 1.f;
+    state[12] = step;
+    const float bc1 = 1.f - powf(beta1, step), bc2s = sqrtf(1.f - powf(beta2, step));
+    for (int k = 0; k < 6; ++k) {
+      const float gk = (float)g[k], lr = k < 3 ? lr_r : lr_t;
+      const float m = state[k] + (gk - state[k]) * (1.f - beta1);           // exp_avg.lerp_(grad, 1 - beta1)
+      const float v = state[6 + k] * beta2 + (1.f - beta2) * gk * gk;
+      state[k] = m;
+      state[6 + k] = v;
+      pose6[k] -= (lr / bc1) * (m / (sqrtf(v) / bc2s + eps));
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 12; e += blockDim.x) d_c2w[e] = 0.f;
+  for (int e = threadIdx.x; e < n_zero; e += blockDim.x) zero[e] = 0.f;
+}
+
+}  // namespace nefes
+
+extern "C" {
+
+int nefes_pose_rays_fwd(const float* pose6, const float* init_c2w, int H, int W, float focal, float near, float far,
+                        float* c2w_out, float* ray_batch, int ld, void* stream) {
+  NEFES_REQUIRE(pose6 && init_c2w && ray_batch, NEFES_EINVAL, "nefes_pose_rays_fwd: null pointer");
+  NEFES_REQUIRE(H > 0 && W > 0 && focal > 0.f && ld >= 11, NEFES_EINVAL, "nefes_pose_rays_fwd: bad shape H=%d W=%d ld=%d", H, W, ld);
+  nefes::pose_rays_fwd_kernel<<<(unsigned)nefes::ceil_div((int64_t)H * W, 128), 128, 0, (cudaStream_t)stream>>>(
+      pose6, init_c2w, H, W, focal, near, far, c2w_out, ray_batch, ld);
+  NEFES_CHECK_LAUNCH("pose_rays_fwd");
+  return NEFES_OK;
+}
+
+int nefes_pose_rays_bwd(const float* d_ray_batch, const float* ray_batch, int ld, int H, int W, float focal, float* d_c2w,
+                        void* stream) {
+  NEFES_REQUIRE(d_ray_batch && ray_batch && d_c2w, NEFES_EINVAL, "nefes_pose_rays_bwd: null pointer");
+  NEFES_REQUIRE(H > 0 && W > 0 && focal > 0.f && ld >= 11, NEFES_EINVAL, "nefes_pose_rays_bwd: bad shape");
+  const int blocks = (int)nefes::ceil_div((int64_t)H * W, 256 * 2);
+  nefes::pose_rays_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_ray_batch, ray_batch, ld, H, W, focal, d_c2w);
+  NEFES_CHECK_LAUNCH("pose_rays_bwd");
+  return NEFES_OK;
+}
+
+int nefes_cosine_loss_fwd(const float* feat, const float* target, int N, int C, float* stats, void* stream) {
+  NEFES_REQUIRE(feat && target && stats, NEFES_EINVAL, "nefes_cosine_loss_fwd: null pointer");
+  NEFES_REQUIRE(N > 0 && C > 0 && C <= 1024 && C % 32 == 0, NEFES_EINVAL, "nefes_cosine_loss_fwd: bad shape N=%d C=%d", N, C);
+  const size_t smem = sizeof(float) * C * (nefes::kLossPix + 1);
+  nefes::cosine_stats_kernel<<<(unsigned)nefes::ceil_div(N, nefes::kLossPix), C, smem, (cudaStream_t)stream>>>(feat, target, N, C, stats);
+  NEFES_CHECK_LAUNCH("cosine_stats");
+  return NEFES_OK;
+}
+
+int nefes_cosine_loss_bwd(const float* feat, const float* target, const float* stats, int N, int C, float* loss,
+                          float* loss_hist, const float* step, int hist_cap, float* d_feat, void* stream) {
+  NEFES_REQUIRE(feat && target && stats, NEFES_EINVAL, "nefes_cosine_loss_bwd: null pointer");
+  NEFES_REQUIRE(N > 0 && C > 0 && C <= 1024 && C % 32 == 0, NEFES_EINVAL, "nefes_cosine_loss_bwd: bad shape N=%d C=%d", N, C);
+  const size_t smem = sizeof(float) * (C * (nefes::kLossPix + 1) + C);
+  nefes::cosine_grad_kernel<<<(unsigned)nefes::ceil_div(N, nefes::kLossPix), C, smem, (cudaStream_t)stream>>>(
+      feat, target, stats, N, C, loss, loss_hist, step, hist_cap, d_feat);
+  NEFES_CHECK_LAUNCH("cosine_grad");
+  return NEFES_OK;
+}
+
+int nefes_pose_adam_step(float* pose6, const float* init_c2w, float* d_c2w, float* zero, int n_zero, float* state13,
+                         float lr_r, float lr_t, float beta1, float beta2, float eps, void* stream) {
+  NEFES_REQUIRE(pose6 && init_c2w && d_c2w && state13, NEFES_EINVAL, "nefes_pose_adam_step: null pointer");
+  NEFES_REQUIRE(n_zero >= 0 && (zero != nullptr || n_zero == 0), NEFES_EINVAL, "nefes_pose_adam_step: bad zero range");
+  nefes::pose_adam_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(pose6, init_c2w, d_c2w, zero, n_zero, state13, lr_r, lr_t, beta1,
+                                                               beta2, eps);
+  NEFES_CHECK_LAUNCH("pose_adam");
+  return NEFES_OK;
+}
+
+}  // extern "C"

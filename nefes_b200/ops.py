@@ -460,6 +460,60 @@ def render_rays_fused(rays, flat_c, flat_f, cfg, t_rand=None, u=None, noise_c=No
     return _RenderRays.apply(rays, flat_c, flat_f, t_rand, u, noise_c, noise_f, cfg)
 
 
+class RenderCall:
+    """nefes_render_rays_fwd / _bwd on buffers allocated ONCE (no autograd): the form a captured refinement iteration
+    replays.  `forward()` renders the rays in `self.rays`; `backward(g_feat=..., g_rgb=...)` turns cotangents of the fine
+    composited outputs into `self.d_rays` (frozen fields: no parameter gradients)."""
+
+    def __init__(self, n_rays, ld, cfg, flat_c, flat_f, device):
+        dev = torch.device(device)
+        S, ni = cfg["n_samples"], cfg["n_importance"]
+        Sf = S + ni
+        self.N, self.ld, self.dev = n_rays, ld, dev
+        self.cfg = L.RenderCfg(S, ni, cfg["prec"], int(cfg["test_time"]), int(cfg["output_transient"]),
+                               int(cfg["transient_at_test"]), cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]))
+        kb, sfb, sbb = C.c_int64(), C.c_int64(), C.c_int64()
+        L.check(L.lib().nefes_render_rays_workspace(C.byref(self.cfg), n_rays, C.byref(kb), C.byref(sfb), C.byref(sbb)),
+                "nefes_render_rays_workspace")
+        self.keep, self.scratch = _buf(kb.value, dev), _buf(max(sfb.value, sbb.value), dev)
+        e = lambda *shape: torch.empty(*shape, device=dev)
+        self.rays, self.d_rays = torch.zeros(n_rays, ld, device=dev), torch.zeros(n_rays, ld, device=dev)
+        self.flat_c, self.flat_f = flat_c.detach(), flat_f.detach()
+        self.t_vals, self.u = linspace01(S, dev), linspace01(ni, dev)
+        sigma_only, transient = bool(cfg["test_time"]), bool(cfg["output_transient"])
+        self.acc0, self.w0 = e(n_rays), e(n_rays, S)
+        self.rgb0 = self.feat0 = self.disp0 = self.depth0 = self.beta0 = None
+        if not sigma_only:
+            self.rgb0, self.feat0, self.disp0, self.depth0, self.beta0 = e(n_rays, 3), e(n_rays, 128), e(n_rays), e(n_rays), e(n_rays)
+        self.rgb, self.feat, self.disp, self.acc = e(n_rays, 3), e(n_rays, 128), e(n_rays), e(n_rays)
+        self.w, self.depth, self.beta = e(n_rays, Sf), e(n_rays), e(n_rays)
+        self.tsig = e(n_rays, Sf) if transient else None
+        self.z_c, self.z_f = e(n_rays, S), e(n_rays, Sf)
+        p = L.ptr
+        self.inp = L.RenderIn(p(self.rays), ld, p(self.flat_c), p(self.flat_f), p(self.t_vals), None, p(self.u), 0, None, None)
+        self.out = L.RenderOut(L.CompOut(p(self.rgb0), p(self.feat0), p(self.disp0), p(self.acc0), p(self.w0), p(self.depth0),
+                                         p(self.beta0), None),
+                               L.CompOut(p(self.rgb), p(self.feat), p(self.disp), p(self.acc), p(self.w), p(self.depth),
+                                         p(self.beta), p(self.tsig)),
+                               p(self.z_c), p(self.z_f), None, None, None)
+
+    def forward(self):
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().nefes_render_rays_fwd(C.byref(self.cfg), C.byref(self.inp), self.N, C.byref(self.out),
+                                                  L.ptr(self.keep), L.ptr(self.scratch), L.stream_of(self.rays)),
+                    "nefes_render_rays_fwd")
+
+    def backward(self, g_feat=None, g_rgb=None):
+        g_fine = L.CompGrad(L.ptr(g_rgb), L.ptr(g_feat), None, None, None, None, None, None)
+        g_coarse = L.CompGrad(*([None] * 8))
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().nefes_render_rays_bwd(C.byref(self.cfg), C.byref(self.inp), self.N, C.byref(self.out),
+                                                  C.byref(g_coarse), C.byref(g_fine), L.ptr(self.keep), L.ptr(self.scratch),
+                                                  None, None, L.ptr(self.d_rays), L.stream_of(self.rays)),
+                    "nefes_render_rays_bwd")
+        return self.d_rays
+
+
 # ------------------------------------------------------------------------------------------------
 # fused Adam on flat buffers
 # ------------------------------------------------------------------------------------------------

@@ -11,8 +11,9 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import parallel
-from .rendering import render
+from . import _lib as L
+from . import ops, parallel
+from .rendering import _fused_applies, render
 
 
 def vec2skew(v):
@@ -123,22 +124,121 @@ class PoseRefiner:
             return self.pose(0)[:3, :4].clone(), losses
 
 
+class EnginePoseRefiner:
+    """The whole refinement iteration as engine launches (~30 kernels, no torch op): pose chain + camera rays + packing
+    (nefes_pose_rays_fwd), render_rays forward (nefes_render_rays_fwd), cosine feature loss and its gradient
+    (nefes_cosine_loss_*), render_rays backward to the rays, rays -> pose cotangent (nefes_pose_rays_bwd), so(3) chain +
+    Adam (nefes_pose_adam_step).  Captured once into a CUDA graph and replayed; the loss of iteration k lands in
+    `loss_hist[k]` on the device, so a query is n_iters graph launches and nothing else.  Applies to the reference's own
+    refinement configuration (standard query function, frozen fields, test_time render, per_pixel=False loss)."""
+    HIST = 1024
+
+    def __init__(self, H, W, focal, kw, lr_r, lr_t, device, n_ch):
+        c, f, args = kw["network_fn"], kw["network_fine"], kw["args"]
+        dev = torch.device(device)
+        self.H, self.W, self.focal, self.near, self.far = int(H), int(W), float(focal), float(kw["near"]), float(kw["far"])
+        self.lr_r, self.lr_t, self.N, self.C, self.dev = float(lr_r), float(lr_t), int(H) * int(W), int(n_ch), dev
+        from .nerfh_nff import _PREC
+        cfg = dict(n_samples=int(kw["N_samples"]), n_importance=int(kw["N_importance"]), prec=_PREC[c.precision], test_time=True,
+                   output_transient=bool(args.NeRFW), transient_at_test=bool(args.transient_at_test), net_coarse=c.net_id,
+                   net_fine=f.net_id, beta_min=f.beta_min)
+        self.call = ops.RenderCall(self.N, 21, cfg, c.flat, f.flat, dev)
+        z = lambda *shape: torch.zeros(*shape, device=dev)
+        self.pose6, self.init, self.c2w, self.d_c2w = z(6), z(3, 4), z(3, 4), z(12)
+        self.state, self.stats = z(13), z(3, self.C)
+        self.target, self.g_feat = z(self.C, self.N), z(self.N, self.C)
+        self.loss, self.loss_hist = z(1), z(self.HIST)
+        self.graph = None
+
+    def _iter(self):
+        lib, p, st = L.lib(), L.ptr, L.stream_of(self.pose6)
+        with torch.cuda.device(self.dev):
+            L.check(lib.nefes_pose_rays_fwd(p(self.pose6), p(self.init), self.H, self.W, self.focal, self.near, self.far,
+                                            p(self.c2w), p(self.call.rays), 21, st), "nefes_pose_rays_fwd")
+            self.call.forward()
+            L.check(lib.nefes_cosine_loss_fwd(p(self.call.feat), p(self.target), self.N, self.C, p(self.stats), st),
+                    "nefes_cosine_loss_fwd")
+            L.check(lib.nefes_cosine_loss_bwd(p(self.call.feat), p(self.target), p(self.stats), self.N, self.C, p(self.loss),
+                                              p(self.loss_hist), p(self.state[12:]), self.HIST, p(self.g_feat), st),
+                    "nefes_cosine_loss_bwd")
+            d_rays = self.call.backward(g_feat=self.g_feat)
+            L.check(lib.nefes_pose_rays_bwd(p(d_rays), p(self.call.rays), 21, self.H, self.W, self.focal, p(self.d_c2w), st),
+                    "nefes_pose_rays_bwd")
+            L.check(lib.nefes_pose_adam_step(p(self.pose6), p(self.init), p(self.d_c2w), p(self.stats), 3 * self.C,
+                                             p(self.state), self.lr_r, self.lr_t, 0.9, 0.999, 1e-8, st), "nefes_pose_adam_step")
+
+    @torch.no_grad()
+    def refine(self, init_c2w, feat_target, n_iters, use_graph=True):
+        if n_iters > self.HIST:
+            raise RuntimeError(f"nefes_b200: at most {self.HIST} refinement iterations per query")
+        self.init.copy_(init_c2w[:3, :4])
+        self.target.copy_(feat_target)
+        for t in (self.pose6, self.state, self.d_c2w, self.stats):
+            t.zero_()
+        done = 0
+        if use_graph and self.graph is None:
+            for _ in range(min(2, n_iters)):         # warm every kernel with real steps, then capture one iteration
+                self._iter()
+                done += 1
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._iter()
+            self.graph = g
+        for _ in range(n_iters - done):
+            if use_graph:
+                self.graph.replay()
+            else:
+                self._iter()
+        L.check(L.lib().nefes_pose_rays_fwd(L.ptr(self.pose6), L.ptr(self.init), self.H, self.W, self.focal, self.near, self.far,
+                                            L.ptr(self.c2w), L.ptr(self.call.rays), 21, L.stream_of(self.pose6)),
+                "nefes_pose_rays_fwd")               # c2w of the final parameters
+        return self.c2w.clone(), list(self.loss_hist[:n_iters].clone())
+
+
+def _engine_refiner_applies(feat_target, H, W, kw, hist):
+    c, f, args = kw.get("network_fn"), kw.get("network_fine"), kw.get("args")
+    if feat_target.dim() != 2 or feat_target.shape[1] != H * W or feat_target.shape[0] % 32 or feat_target.shape[0] > 1024:
+        return False
+    if not kw.get("test_time") or kw.get("perturb") or kw.get("raw_noise_std") or kw.get("white_bkgd") or kw.get("lindisp"):
+        return False
+    if not kw.get("use_viewdirs") or kw.get("ndc", True) or not getattr(args, "nerfh_nff", False):
+        return False
+    if c is None or f is None or c.flat.requires_grad or f.flat.requires_grad:
+        return False
+    probe = torch.empty(H * W, 21, device="meta")
+    return _fused_applies(probe, c, kw.get("network_query_fn"), kw.get("N_samples"), kw.get("N_importance", 0), f, args)
+
+
 _REFINERS = {}
 
 
 def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=50, lr_r=0.0087, lr_t=0.01,
-                hist=None, chunk=32768, graph=None):
+                hist=None, chunk=32768, graph=None, engine=None):
     """One query: `n_iters` Adam steps on the se(3)-style delta (DFM_pose_refine.py:380-440).
     feat_target [C, H*W].  Returns (refined c2w [3,4], list of losses).
     graph (default: on for n_iters >= 10 on CUDA): run the iterations as replays of a captured CUDA graph (PoseRefiner),
-    cached per (camera, networks, learning rates) so that every further query pays no capture either."""
+    cached per (camera, networks, learning rates) so that every further query pays no capture either.
+    engine (default: on where it applies): the iteration is EnginePoseRefiner's ~30 engine launches (no torch op); False
+    keeps the torch pose chain / loss / optimiser around the engine render; True raises where it does not apply."""
     dev = feat_target.device
     use_graph = ((n_iters >= 10) if graph is None else bool(graph)) and dev.type == "cuda"
+    key = (H, W, float(focal), chunk, float(lr_r), float(lr_t), str(dev), tuple(feat_target.shape),
+           id(render_kwargs_test.get("network_fn")), id(render_kwargs_test.get("network_fine")),
+           getattr(render_kwargs_test.get("network_fn"), "precision", None),
+           getattr(render_kwargs_test.get("network_fine"), "precision", None),
+           float(render_kwargs_test.get("near", 0.)), float(render_kwargs_test.get("far", 1.)))
+    if (engine is None or engine) and dev.type == "cuda" and H * W <= chunk and \
+            _engine_refiner_applies(feat_target, H, W, render_kwargs_test, hist):
+        ref = _REFINERS.get(("engine",) + key)
+        if ref is None:
+            ref = _REFINERS[("engine",) + key] = EnginePoseRefiner(H, W, focal, render_kwargs_test, lr_r, lr_t, dev,
+                                                                   feat_target.shape[0])
+        return ref.refine(init_c2w.to(dev), feat_target, n_iters, use_graph=use_graph)
+    if engine:
+        raise RuntimeError("nefes_b200: the engine-resident refinement iteration does not cover this configuration "
+                           "(needs StandardQuery, frozen fields, test_time render, feat_target [C, H*W])")
     if use_graph:
-        key = (H, W, float(focal), chunk, float(lr_r), float(lr_t), str(dev), tuple(feat_target.shape),
-               id(render_kwargs_test.get("network_fn")), id(render_kwargs_test.get("network_fine")),
-               getattr(render_kwargs_test.get("network_fn"), "precision", None),
-               getattr(render_kwargs_test.get("network_fine"), "precision", None))
         ref = _REFINERS.get(key)
         if ref is None:
             ref = _REFINERS[key] = PoseRefiner(H, W, focal, render_kwargs_test, lr_r, lr_t, chunk, dev, tuple(feat_target.shape))

@@ -224,3 +224,95 @@ def test_one_call_render_rays_matches_staged_path(precision, test_time):
         assert float((v - fused[1][k]).abs().max()) <= 2e-3 * float(v.abs().max()) + 1e-7, k
     if test_time:                                           # frozen-field refinement: no parameter gradient is produced
         assert c.flat.grad is None or float(c.flat.grad.abs().max()) == 0.0
+
+
+def test_refinement_glue_kernels_match_torch():
+    """nefes_pose_rays_fwd/_bwd, nefes_cosine_loss_fwd/_bwd and nefes_pose_adam_step against the torch chain they
+    replace: LearnPose (so(3) exponential) -> get_rays -> render()'s packing; F.cosine_similarity loss; autograd to
+    (r, t); torch.optim.Adam with two parameter groups -- three consecutive steps from a non-zero rotation."""
+    import nefes_b200 as nb
+    from nefes_b200 import _lib as L, refine
+    lib, p = L.lib(), L.ptr
+    dev = torch.device("cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    H, W, focal, C_ = 12, 20, 21.5, 64
+    N = H * W
+    g = torch.Generator(device="cuda").manual_seed(21)
+    init = torch.linalg.qr(torch.randn(3, 3, device=dev, generator=g))[0]
+    init = torch.cat([init, torch.randn(3, 1, device=dev, generator=g)], 1).contiguous()
+    target = torch.randn(C_, N, device=dev, generator=g)
+    mix = torch.randn(21, C_, device=dev, generator=g)            # a differentiable stand-in for the render: feat = rays @ mix
+    pose_t = refine.LearnPose(1, True, True, init[None]).to(dev)
+    with torch.no_grad():
+        pose_t.r.copy_(torch.tensor([[0.03, -0.02, 0.05]]))
+        pose_t.t.copy_(torch.tensor([[0.1, 0.0, -0.2]]))
+    opt = torch.optim.Adam([{"params": [pose_t.r], "lr": 0.0087}, {"params": [pose_t.t], "lr": 0.01}])
+    pose6 = torch.cat([pose_t.r.detach().reshape(-1), pose_t.t.detach().reshape(-1)]).contiguous()
+    rays, c2w, d_c2w = torch.empty(N, 21, device=dev), torch.empty(3, 4, device=dev), torch.zeros(12, device=dev)
+    stats, state, loss, hist = torch.zeros(3, C_, device=dev), torch.zeros(13, device=dev), torch.zeros(1, device=dev), torch.zeros(8, device=dev)
+    d_feat = torch.empty(N, C_, device=dev)
+    for it in range(3):
+        # torch chain
+        m = pose_t(0)
+        ro, rd = nb.get_rays(H, W, focal, m[:3, :4])
+        rd_f, ro_f = rd.reshape(-1, 3), ro.reshape(-1, 3)
+        vd = rd_f / torch.norm(rd_f, dim=-1, keepdim=True)
+        rb = torch.cat([ro_f, rd_f, torch.full((N, 1), 0.5, device=dev), torch.full((N, 1), 4.0, device=dev), vd,
+                        torch.zeros(N, 10, device=dev)], 1)
+        feat_t = rb @ mix
+        loss_t = refine.feature_loss(feat_t.t(), target)
+        opt.zero_grad()
+        loss_t.backward()
+        # engine chain
+        L.check(lib.nefes_pose_rays_fwd(p(pose6), p(init), H, W, focal, 0.5, 4.0, p(c2w), p(rays), 21, st), "fwd")
+        assert float((c2w - m[:3, :4]).abs().max()) < 2e-6
+        assert float((rays - rb).abs().max()) < 1e-5
+        feat = (rays @ mix).contiguous()
+        L.check(lib.nefes_cosine_loss_fwd(p(feat), p(target), N, C_, p(stats), st), "loss fwd")
+        L.check(lib.nefes_cosine_loss_bwd(p(feat), p(target), p(stats), N, C_, p(loss), p(hist), p(state[12:]), 8, p(d_feat), st), "loss bwd")
+        assert abs(float(loss) - float(loss_t)) < 1e-6 and abs(float(hist[it]) - float(loss_t)) < 1e-6
+        d_rays = (d_feat @ mix.t()).contiguous()
+        L.check(lib.nefes_pose_rays_bwd(p(d_rays), p(rays), 21, H, W, focal, p(d_c2w), st), "bwd")
+        opt.step()
+        L.check(lib.nefes_pose_adam_step(p(pose6), p(init), p(d_c2w), p(stats), 3 * C_, p(state), 0.0087, 0.01, 0.9, 0.999, 1e-8, st), "adam")
+        assert float(d_c2w.abs().max()) == 0.0 and float(stats.abs().max()) == 0.0 and float(state[12]) == it + 1
+        ref6 = torch.cat([pose_t.r.detach().reshape(-1), pose_t.t.detach().reshape(-1)])
+        # Adam's first steps are lr * sign(g): any error in the gradient chain shows up at full step size
+        assert float((pose6 - ref6).abs().max()) < 2e-5, (it, pose6, ref6)
+
+
+def test_engine_refinement_iteration_matches_torch_loop():
+    """EnginePoseRefiner (the iteration as ~30 engine launches, replayed from a CUDA graph) against the loop with the torch
+    pose chain / loss / optimiser around the engine render: same loss trajectory, same refined pose up to the loop's own
+    run-to-run spread (see test_graph_replayed_refinement_matches_eager_loop), for two consecutive queries."""
+    import numpy as np, os
+    import nefes_b200 as nb
+    from nefes_b200 import refine
+    c, f = _nets()
+    c.precision = f.precision = "fp32"
+    for p in (c.flat, f.flat):
+        p.requires_grad_(False)
+    H, W, focal = 60, 80, 65.688
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "poses_stairs.npz"))
+
+    class Args:
+        nerfh_nff, use_fine_only, NeRFW, transient_at_test, netchunk = True, False, True, True, 1 << 21
+    kw = dict(network_query_fn=nb.StandardQuery(Args.netchunk), N_importance=64, N_samples=64, network_fn=c, network_fine=f,
+              use_viewdirs=True, white_bkgd=False, args=Args(), ndc=False, lindisp=False, near=0., far=4., perturb=0.,
+              raw_noise_std=0., test_time=True)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    for qi in range(2):
+        init = torch.tensor(g["dfnet_init"][qi].reshape(3, 4), dtype=torch.float32, device="cuda")
+        target = torch.randn(128, H * W, device="cuda", generator=gen)
+        pe, le = refine.refine_pose(init, target, H, W, focal, kw, n_iters=12, graph=False, engine=False)
+        pg, lg = refine.refine_pose(init, target, H, W, focal, kw, n_iters=12, graph=True, engine=True)
+        assert len(le) == len(lg) == 12
+        for a, b in zip(le, lg):
+            assert abs(float(a) - float(b)) < 2e-5, (float(a), float(b))
+        assert float((pe[:, :3] - pg[:, :3]).abs().max()) < 2e-2
+        assert float((pe[:, 3] - pg[:, 3]).abs().max()) < 6e-2
+    # bf16 fields go the same way (trajectories drift with operand roundings; the first losses must still agree)
+    c.precision = f.precision = "bf16"
+    pe, le = refine.refine_pose(init, target, H, W, focal, kw, n_iters=4, graph=False, engine=False)
+    pg, lg = refine.refine_pose(init, target, H, W, focal, kw, n_iters=4, graph=False, engine=True)
+    assert abs(float(le[0]) - float(lg[0])) < 1e-5
