@@ -3,6 +3,7 @@
 // caller's stream with every intermediate -- sample points, raw in tile-major layout, saved activations, compact
 // cotangents -- living in two caller-provided workspaces, so nothing but the per-ray results crosses the boundary.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nefes {
 
@@ -75,7 +76,11 @@ __global__ void ray_points_bwd_kernel(const float* __restrict__ dpc, const float
   }
 }
 
-static inline int64_t al(int64_t x) { return round_up(x, 256); }
+// sub-buffer alignment inside the workspaces (NEFES_WS_ALIGN overrides, for placement experiments)
+static inline int64_t al(int64_t x) {
+  static const int64_t a = [] { const char* e = getenv("NEFES_WS_ALIGN"); const int64_t v = e ? atoll(e) : 0; return v >= 256 ? v : 256; }();
+  return round_up(x, a);
+}
 
 // Where everything lives.  `keep` survives from the forward to the backward call; `scratch` is per call.
 struct RenderPlan {
