@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
               mbar_wait(&bar_ld[g][st.wait_load2], ld_ph[st.wait_load2]);
               ld_ph[st.wait_load2] ^= 1u;
             }
+            if (dbg && cnt < 32) A.dbg[cnt * 48 + 40 + g] = clock64();     // barriers passed, before the tcgen05 fence
             tc_fence_after();
             if (dbg && cnt < 32) A.dbg[cnt * 48 + 1 + g] = clock64();
             const uint64_t da0 = smem_desc(smem_u32(smem + g * kReg + st.a_off), kChunkBytes, 128);
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const ChainArgs
             if (dbg && cnt < 32) A.dbg[cnt * 48 + 3 + g] = clock64();
           }
           mma_commit(&bar_wempty[slot]);       // the slot is free once BOTH tiles' MMAs retired (count 2)
+          if (dbg && cnt < 32) A.dbg[cnt * 48 + 5 + g] = clock64();
         }
       }
     }

@@ -826,6 +826,8 @@ void chain_dbg_dump(const char* what, const ChainArgs& c, cudaStream_t st) {
     }
     fprintf(stderr, "  [epi warp 0: ready %lld | tmem loaded +%lld | computed+stored +%lld | fenced +%lld | group barrier +%lld]\n", r[8] - t0,
             h[1600 + i * 4] - r[8], h[1600 + i * 4 + 1] - r[8], h[1600 + i * 4 + 2] - r[8], h[1600 + i * 4 + 3] - r[8]);
+    fprintf(stderr, "  [issuer 0: waits passed %lld fence +%lld acc commit +%lld wempty commit +%lld | issuer 1: waits passed %lld fence +%lld acc commit +%lld wempty commit +%lld]\n",
+            r[40] - t0, r[1] - r[40], r[3] - r[40], r[5] - r[40], r[41] - t0, r[2] - r[41], r[4] - r[41], r[6] - r[41]);
     fprintf(stderr, "  seq %2d step %2d | W ok %7lld | t0: A ok %7lld commit %7lld | t1: A ok %7lld commit %7lld | epi0 ready %7lld done %7lld..%7lld | epi1 ready %7lld done %7lld..%7lld\n",
             i, i % c.n_steps, r[0] - t0, r[1] - t0, r[3] - t0, r[2] - t0, r[4] - t0, rd[0] - t0, lo[0] - t0, hi[0] - t0,
             rd[1] - t0, lo[1] - t0, hi[1] - t0);
