@@ -175,6 +175,7 @@ int nefes_render_rays_fwd(const nefes_render_cfg_t* cfg, const nefes_render_in_t
   const char* who = "nefes_render_rays_fwd";
   RenderPlan P;
   if (int e = make_plan(who, cfg, N, &P)) return e;
+  if (N == 0) return NEFES_OK;                       // an empty ray batch: nothing to launch, nothing to check
   NEFES_REQUIRE(in && out && keep && scratch, NEFES_EINVAL, "%s: null pointer", who);
   NEFES_REQUIRE(in->rays && in->ld_rays >= 11 && in->params_coarse && in->t_vals, NEFES_EINVAL,
                 "%s: rays [N, ld >= 11], coarse parameters and t_vals are required", who);
@@ -183,7 +184,6 @@ int nefes_render_rays_fwd(const nefes_render_cfg_t* cfg, const nefes_render_in_t
   NEFES_REQUIRE(!P.fine || (out->z_fine && out->fine.acc && out->fine.weights), NEFES_EINVAL, "%s: fine outputs missing", who);
   NEFES_REQUIRE(((uintptr_t)keep & 255) == 0 && ((uintptr_t)scratch & 255) == 0, NEFES_EALIGN,
                 "%s: workspaces must be 256-byte aligned", who);
-  if (N == 0) return NEFES_OK;
   cudaStream_t st = (cudaStream_t)stream;
   char* K = (char*)keep;
   float* pts_c = (float*)(K + P.pts_c);
@@ -226,12 +226,12 @@ int nefes_render_rays_bwd(const nefes_render_cfg_t* cfg, const nefes_render_in_t
   const char* who = "nefes_render_rays_bwd";
   RenderPlan P;
   if (int e = make_plan(who, cfg, N, &P)) return e;
+  if (N == 0) return NEFES_OK;
   NEFES_REQUIRE(in && out && keep && scratch, NEFES_EINVAL, "%s: null pointer", who);
   NEFES_REQUIRE(in->rays && in->params_coarse && out->z_coarse && (!P.fine || (in->params_fine && out->z_fine)), NEFES_EINVAL,
                 "%s: the forward call's inputs and depths are required", who);
   NEFES_REQUIRE(((uintptr_t)keep & 255) == 0 && ((uintptr_t)scratch & 255) == 0, NEFES_EALIGN,
                 "%s: workspaces must be 256-byte aligned", who);
-  if (N == 0) return NEFES_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const char* K = (const char*)keep;
   char* W = (char*)scratch;

@@ -316,3 +316,38 @@ def test_engine_refinement_iteration_matches_torch_loop():
     pe, le = refine.refine_pose(init, target, H, W, focal, kw, n_iters=4, graph=False, engine=False)
     pg, lg = refine.refine_pose(init, target, H, W, focal, kw, n_iters=4, graph=False, engine=True)
     assert abs(float(le[0]) - float(lg[0])) < 1e-5
+
+
+def test_one_call_render_edge_cases():
+    """Empty ray batch; ray chunks (`chunk` < N: batchify_rays cuts the batch, every chunk is one engine call) against the
+    single call; a netchunk smaller than the batch sends render_rays down the staged route with the same numbers."""
+    import nefes_b200 as nb
+    c, f = _nets()
+    g = torch.Generator(device="cuda").manual_seed(13)
+    n = 700
+    ro = torch.randn(n, 3, device="cuda", generator=g) * 0.1
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda", generator=g), dim=-1)
+    t_rand, u = torch.rand(n, 64, device="cuda", generator=g), torch.rand(n, 64, device="cuda", generator=g)
+
+    class Args:
+        nerfh_nff, use_fine_only, NeRFW, transient_at_test = True, False, True, True
+
+    def run(rays, chunk, netchunk, tr, uu):
+        kw = dict(rays=rays, img_idx=torch.zeros(1, 10), near=0., far=4., ndc=False, use_viewdirs=True,
+                  network_query_fn=nb.StandardQuery(netchunk), N_samples=64, N_importance=64, network_fn=c, network_fine=f,
+                  perturb=1., raw_noise_std=0., test_time=False, args=Args(), t_rand=tr, u=uu)
+        with torch.no_grad():
+            rgb, disp, acc, ex = nb.render(60, 80, 65.688, chunk=chunk, **kw)
+        return rgb, disp, acc, ex
+
+    one = run((ro, rd), 32768, 1 << 21, t_rand, u)
+    cut = run((ro, rd), 256, 1 << 21, t_rand, u)                 # 3 ray chunks, each one engine call
+    staged = run((ro, rd), 32768, 128 * 64, t_rand, u)           # netchunk < batch: staged route, 128-ray field queries
+    for other in (cut, staged):
+        for a, b in zip(one[:3], other[:3]):
+            assert torch.equal(a, b)
+        for k in ("feat_map", "rgb0", "beta", "transient_sigmas"):
+            assert torch.equal(one[3][k], other[3][k]), k
+        assert float((one[3]["z_std"] - other[3]["z_std"]).abs().max()) < 1e-6
+    empty = run((ro[:0], rd[:0]), 32768, 1 << 21, t_rand[:0], u[:0])
+    assert empty[0].shape == (0, 3) and empty[3]["feat_map"].shape == (0, 128) and empty[3]["transient_sigmas"].shape == (0, 128)
