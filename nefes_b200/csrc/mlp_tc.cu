@@ -62,6 +62,10 @@ struct TileGemmArgs {
   uint4* mask_out; const uint4* mask_in; int mask_shift;      // mask_shift: first mask bit of D column 0 (multiple of 16)
   // fp32 output: D columns [d_col0, d_col0 + raw_ncol) -> raw[row*raw_ld + raw_col0 + i]
   float* raw; int raw_ld, raw_col0, d_col0, raw_ncol, raw_act;
+  // EPI_RAWBULK reductions of the staged fp32 rows instead of storing them (input gradients of the refinement path):
+  //   pe_x != null: the rows are cotangents of the frequency encoding of pe_x [M,3] -> raw = d_x [M,3]
+  //   ray_S > 0   : rows summed over each ray's ray_S consecutive points -> raw [n_rays, raw_ld]
+  const float* pe_x; int pe_L; int ray_S; int64_t n_rays;
   // shared-memory carve-up (bytes from the dynamic base), computed on the host
   uint32_t off_a, a_stage_stride, off_out, out_bytes, off_raw, raw_pitch, off_bias;
 };
@@ -264,10 +268,51 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tile_gemm_kernel(const TileGe
       }
       if (raw_staged) {
         epi_barrier();
-        for (int rr = warp - kEpiWarp0; rr < kTile; rr += kEpiWarps) {
-          const int64_t gr = (int64_t)tile * kTile + rr;
-          if (gr < g.M)
-            for (int c = lane; c < g.raw_ncol; c += 32) g.raw[gr * g.raw_ld + g.raw_col0 + c] = sRaw[rr * g.raw_pitch + c];
+        if (g.pe_x != nullptr) {
+          // rows = d(encoding) of one point each: chain through [x, sin(2^l x), cos(2^l x)] (nerfh_nff.py:241-270), one
+          // (point, coordinate) per thread; x and d_x are [M,3], so consecutive threads touch consecutive floats
+          for (int i = et; i < kTile * 3; i += kEpiThreads) {
+            const int rr = i / 3, c = i - 3 * rr;
+            const int64_t gr = (int64_t)tile * kTile + rr;
+            if (gr < g.M) {
+              const float v = g.pe_x[gr * 3 + c];
+              const float* gi = sRaw + rr * g.raw_pitch + c;
+              float acc = gi[0], f = 1.f;
+              for (int l = 0; l < g.pe_L; ++l, f *= 2.f) {
+                float sn, co;
+                sincosf(v * f, &sn, &co);
+                acc += f * (gi[3 + 6 * l] * co - gi[6 + 6 * l] * sn);
+              }
+              g.raw[gr * 3 + c] = acc;
+            }
+          }
+        } else if (g.ray_S > 0) {
+          // per-ray sums over the ray's ray_S consecutive rows (a multiple of 16 dividing 128): 16-row partial sums by
+          // (column, part) threads, then one thread per (ray, column)
+          float* sPart = sRaw + kTile * g.raw_pitch;                   // [8][32]
+          const int c = et & 31, part = et >> 5;
+          if (c < g.raw_ncol) {
+            float a = 0.f;
+#pragma unroll 4
+            for (int r2 = 0; r2 < 16; ++r2) a += sRaw[(part * 16 + r2) * g.raw_pitch + c];
+            sPart[part * 32 + c] = a;
+          }
+          epi_barrier();
+          const int rays_per_tile = kTile / g.ray_S, parts_per_ray = g.ray_S >> 4;
+          if (part < rays_per_tile && c < g.raw_ncol) {
+            const int64_t ray = (int64_t)tile * rays_per_tile + part;
+            if (ray < g.n_rays) {
+              float a = 0.f;
+              for (int q2 = 0; q2 < parts_per_ray; ++q2) a += sPart[(part * parts_per_ray + q2) * 32 + c];
+              g.raw[ray * g.raw_ld + g.raw_col0 + c] = a;
+            }
+          }
+        } else {
+          for (int rr = warp - kEpiWarp0; rr < kTile; rr += kEpiWarps) {
+            const int64_t gr = (int64_t)tile * kTile + rr;
+            if (gr < g.M)
+              for (int c = lane; c < g.raw_ncol; c += 32) g.raw[gr * g.raw_ld + g.raw_col0 + c] = sRaw[rr * g.raw_pitch + c];
+          }
         }
         epi_barrier();
       }
@@ -711,6 +756,7 @@ struct GemmDesc {
   uint8_t* out_img = nullptr; int64_t out_tile_stride = 0; int out_ch = 0; int relu = 0;
   uint4* mask_out = nullptr; const uint4* mask_in = nullptr; int mask_shift = 0;
   float* raw = nullptr; int raw_ld = 0, raw_col0 = 0, d_col0 = 0, raw_ncol = 0, raw_act = 0;
+  const float* pe_x = nullptr; int pe_L = 0; int ray_S = 0; int64_t n_rays = 0;     // see TileGemmArgs
 };
 
 int launch_tile_gemm(const GemmDesc& d, int n_tiles, int64_t M, cudaStream_t st, const char* what) {
@@ -721,6 +767,10 @@ int launch_tile_gemm(const GemmDesc& d, int n_tiles, int64_t M, cudaStream_t st,
   g.out_img = d.out_img; g.out_tile_stride = d.out_tile_stride; g.out_ch = d.out_img ? d.out_ch : 0; g.relu = d.relu;
   g.mask_out = d.mask_out; g.mask_in = d.mask_in; g.mask_shift = d.mask_shift;
   g.raw = d.raw; g.raw_ld = d.raw_ld; g.raw_col0 = d.raw_col0; g.d_col0 = d.d_col0; g.raw_ncol = d.raw_ncol; g.raw_act = d.raw_act;
+  g.pe_x = d.pe_x; g.pe_L = d.pe_L; g.ray_S = d.ray_S; g.n_rays = d.n_rays;
+  NEFES_REQUIRE(!d.pe_x || (d.raw_ncol >= 3 + 6 * d.pe_L && d.raw_ncol > 8 && !d.ray_S), NEFES_EINVAL, "%s: bad encoding-backward epilogue", what);
+  NEFES_REQUIRE(!d.ray_S || (d.ray_S % 16 == 0 && kTile % d.ray_S == 0 && d.raw_ncol > 8 && d.raw_ncol <= 32), NEFES_EINVAL,
+                "%s: bad per-ray reduction epilogue (S=%d)", what, d.ray_S);
   uint32_t src_bytes = 0;
   for (int q = 0; q < d.n_src; ++q) src_bytes += d.a[q].bytes;
   NEFES_REQUIRE(src_bytes == (uint32_t)d.K * 256u, NEFES_EINVAL, "%s: A sources (%u B) do not add up to K=%d", what, src_bytes, d.K);
@@ -730,7 +780,7 @@ int launch_tile_gemm(const GemmDesc& d, int n_tiles, int64_t M, cudaStream_t st,
   g.out_bytes = (uint32_t)g.out_ch * 256u;
   const uint32_t out_total = 2 * r1k(g.out_bytes);
   g.raw_pitch = (uint32_t)(d.raw_ncol | 1);
-  const uint32_t raw_total = (d.raw && d.raw_ncol > 8) ? r1k(kTile * g.raw_pitch * 4u) : 0u;   // EPI_RAWBULK staging
+  const uint32_t raw_total = (d.raw && d.raw_ncol > 8) ? r1k(kTile * g.raw_pitch * 4u + (d.ray_S ? 1024u : 0u)) : 0u;   // EPI_RAWBULK staging
   const uint32_t bias_total = 1024;
   const uint32_t fixed = r1k(w_bytes) + out_total + raw_total + bias_total;
   NEFES_REQUIRE(fixed + 2 * a_stage <= kSmemBudget, NEFES_EINVAL, "%s: shared memory budget exceeded", what);
@@ -1494,18 +1544,25 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
     ASrc g1 = src_of(b.G[0]);
     d.a[0] = src_of(b.G[4]); d.a[1] = g1; d.n_src = 2;
     d.K = 256; d.N = 64; d.w_img = A.W(PL_DX); d.w_rows = 64;
-    d.raw = b.dX; d.raw_ld = 64; d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = 64; d.raw_act = RAW_ACT_NONE;
-    TRY(launch_tile_gemm(d, T, Mp, st, "dgrad xyz PE"));
-    TRY(nefes_encode_pe_bwd(pts, b.dX, 64, M, kXyzFreqs, d_pts, st));
+    // ... and the encoding's own backward on the staged rows, so the [M,64] fp32 cotangent never goes to HBM
+    d.raw = d_pts; d.raw_ld = 3; d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = 64; d.raw_act = RAW_ACT_NONE;
+    d.pe_x = pts; d.pe_L = kXyzFreqs;
+    TRY(launch_tile_gemm(d, T, M, st, "dgrad xyz PE"));
   }
   if (d_dirs != nullptr && mode != NEFES_MODE_SIGMA) {   // d dirPE = GDT W_DT[:, 128:155], summed over each ray's samples
     GemmDesc d;
     const int pl = (mode == NEFES_MODE_FULL) ? PL_DT : PL_DIR;
     d.a[0] = src_of(b.GDT); d.K = w.DT.ch; d.N = 32; d.w_img = A.WT(pl); d.w_rows = packed_dims(pl).K; d.w_row0 = 128;
-    d.raw = b.dDIR; d.raw_ld = 32; d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = 32; d.raw_act = RAW_ACT_NONE;
-    TRY(launch_tile_gemm(d, T, Mp, st, "dgrad dir PE"));
-    ray_reduce_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(b.dDIR, 32, 32, S, N, b.dDIRray);
-    NEFES_CHECK_LAUNCH("ray_reduce");
+    d.raw_col0 = 0; d.d_col0 = 0; d.raw_ncol = 32; d.raw_act = RAW_ACT_NONE;
+    if (S % 16 == 0 && kTile % S == 0) {   // the per-ray sum happens on the staged rows: [M,32] fp32 never goes to HBM
+      d.raw = b.dDIRray; d.raw_ld = 32; d.ray_S = S; d.n_rays = N;
+      TRY(launch_tile_gemm(d, T, Mp, st, "dgrad dir PE"));
+    } else {
+      d.raw = b.dDIR; d.raw_ld = 32;
+      TRY(launch_tile_gemm(d, T, Mp, st, "dgrad dir PE"));
+      ray_reduce_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(b.dDIR, 32, 32, S, N, b.dDIRray);
+      NEFES_CHECK_LAUNCH("ray_reduce");
+    }
     TRY(nefes_encode_pe_bwd(dirs, b.dDIRray, 32, N, kDirFreqs, d_dirs, st));
   }
 
