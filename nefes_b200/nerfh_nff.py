@@ -145,6 +145,36 @@ class FusionNet(nn.Module):
         return x[:, 3:] + y if self.fusion_residule else y
 
 
+class ExposureMLP(nn.Module):
+    """The exposure network of the coarse model (nerfh_nff.py:511-522): tiny-cuda-nn `FullyFusedMLP`, 10 -> 32 -> 32 -> 32
+    -> 12, ReLU, no biases, restated in plain torch -- a caller-side module after the render path.
+    tiny-cuda-nn is an un-vendored dependency with no pinned version (reference README.md:24) and no reference test holds
+    a vector for it: PARITY UNPINNED.  Restated from its published algorithm: one flat `params` buffer holding the weight
+    matrices [out, in] row-major in layer order, input width padded to a multiple of 16 (10 -> 16), output width padded
+    to 16 (12 -> 16), Xavier-uniform init; the arithmetic here is fp32 (tiny-cuda-nn: fp16 operands, fp32 accumulate)."""
+    SHAPES = ((32, 16), (32, 32), (32, 32), (16, 32))
+
+    def __init__(self, n_in=10, n_out=12):
+        super().__init__()
+        self.n_in, self.n_out = n_in, n_out
+        parts = []
+        for o, i in self.SHAPES:
+            bound = (6.0 / (o + i)) ** 0.5
+            parts.append((torch.rand(o * i) * 2 - 1) * bound)
+        self.params = nn.Parameter(torch.cat(parts))
+
+    def forward(self, x):
+        h = torch.nn.functional.pad(x.to(self.params.dtype), (0, self.SHAPES[0][1] - self.n_in))
+        off = 0
+        for li, (o, i) in enumerate(self.SHAPES):
+            w = self.params[off:off + o * i].view(o, i)
+            off += o * i
+            h = h @ w.t()
+            if li + 1 < len(self.SHAPES):
+                h = torch.relu(h)
+        return h[:, :self.n_out]
+
+
 class NeRFH_NFF(nn.Module):
     """The NeFeS field (nerfh_nff.py:421-626): xyz PE(63) -> 8x128 ReLU trunk with a skip at layer
     4 -> softplus sigma, 128 'final' -> [final | dir PE(27)] -> 64 -> 131 (rgb 3 + feature 128),
@@ -208,6 +238,7 @@ class NeRFH_NFF(nn.Module):
         self._rows = rows
         if typ == "coarse":
             self.fusion_net = FusionNet(self.W_features, fusion_residule, no_BN)
+            self.exposure_embedding = ExposureMLP()              # APPLY_HISTOGRAM = True (nerfh_nff.py:20, :511)
         self.sigmoid = nn.Sigmoid()
 
     # ---- reference-keyed views -------------------------------------------------------------
@@ -248,9 +279,6 @@ class NeRFH_NFF(nn.Module):
         child = tuple(prefix + c + "." for c, _ in self.named_children())
         for k in state_dict:
             if k.startswith(prefix) and k not in own and not k.startswith(child):
-                # reference-only tensors with no counterpart on this path (tcnn exposure MLP)
-                if k == prefix + "exposure_embedding.params":
-                    continue
                 unexpected_keys.append(k)
 
     # ---- kernels ---------------------------------------------------------------------------
@@ -280,8 +308,16 @@ class NeRFH_NFF(nn.Module):
         return render_rgb, render_feature, self.fusion_net(fusion_input)
 
     def affine_color_transform(self, args, rgb, hist, batch_size):
-        raise RuntimeError("nefes_b200: affine_color_transform needs the tiny-cuda-nn exposure MLP, which is outside "
-                           "the render hot path (SURVEY.md 8f-2) and not built in this round")
+        """nerfh_nff.py:605-626: rgb [B*N,3], hist [B,10] -> sigmoid(K_b rgb + bias_b), (K_b, bias_b) from the exposure MLP
+        of image b's histogram (cast to integers first, as the reference does)."""
+        if not (getattr(args, "encode_hist", False) and self.typ == "coarse"):
+            raise RuntimeError("nefes_b200: affine_color_transform needs args.encode_hist and the coarse model")
+        self.a_embedded = self.exposure_embedding(hist.long()).float()
+        kernel = self.a_embedded[:, :9].reshape(-1, 3, 3)
+        bias = self.a_embedded[:, 9:].reshape(-1, 3, 1)
+        rgb = rgb.reshape(batch_size, -1, 3)
+        rgb = torch.bmm(kernel, rgb.transpose(1, 2)) + bias
+        return self.sigmoid(rgb.transpose(1, 2).reshape(-1, 3))
 
 
 # ------------------------------------------------------------------------------------------------

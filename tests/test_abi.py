@@ -65,8 +65,41 @@ def test_model_state_dict_round_trip(weights):
     sdc = c.state_dict()
     assert all(torch.equal(sdc[k], wc[k]) for k in wc)
     assert any(k.startswith("fusion_net.net.") for k in sdc)
-    missing = c.load_state_dict({**wc, "exposure_embedding.params": torch.zeros(3)}, strict=False)
+    # the coarse model also carries the reference's caller-side modules under the reference's keys
+    assert sdc["exposure_embedding.params"].shape == (3072,)         # tcnn FullyFusedMLP 10(->16)x32, 32x32 x2, 32x12(->16)
+    missing = c.load_state_dict({**wc, "exposure_embedding.params": torch.zeros(3072)}, strict=False)
     assert all(k.startswith("fusion_net") for k in missing.missing_keys) and not missing.unexpected_keys
+    assert float(c.exposure_embedding.params.abs().max()) == 0.0
+
+
+def test_affine_color_transform_matches_its_definition():
+    """nerfh_nff.py:605-626 restated on the torch exposure MLP (tiny-cuda-nn FullyFusedMLP: parity unpinned)."""
+    import nefes_b200 as nb
+    c = nb.NeRFH_NFF("coarse", W=128)
+
+    class Args:
+        encode_hist = True
+    g = torch.Generator().manual_seed(4)
+    B, n = 3, 7
+    rgb = torch.rand(B * n, 3, generator=g, requires_grad=True)
+    hist = torch.randint(0, 4, (B, 10), generator=g).float()
+    out = c.affine_color_transform(Args(), rgb, hist, B)
+    assert out.shape == (B * n, 3) and bool(((out >= 0) & (out <= 1)).all())
+    e = c.exposure_embedding
+    h = torch.nn.functional.pad(hist, (0, 6))
+    off = 0
+    for li, (o, i) in enumerate(e.SHAPES):
+        h = h @ e.params[off:off + o * i].view(o, i).t()
+        off += o * i
+        h = torch.relu(h) if li < 3 else h
+    ref = torch.stack([torch.sigmoid(h[b, :9].view(3, 3) @ rgb[b * n + k] + h[b, 9:12]) for b in range(B) for k in range(n)])
+    assert float((out - ref).abs().max()) < 1e-6
+    out.sum().backward()
+    assert rgb.grad is not None and e.params.grad is not None and float(e.params.grad.abs().sum()) > 0
+    f = nb.NeRFH_NFF("fine", W=128, encode_appearance=True, encode_transient=True)
+    import pytest
+    with pytest.raises(RuntimeError, match="coarse"):
+        f.affine_color_transform(Args(), rgb, hist, B)
 
 
 def test_cpu_tensors_are_rejected():
