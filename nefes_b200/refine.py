@@ -125,7 +125,7 @@ class PoseRefiner:
 
 
 class EnginePoseRefiner:
-    """The whole refinement iteration as engine launches (~30 kernels, no torch op): pose chain + camera rays + packing
+    """The whole refinement iteration as engine launches (24 kernels, no torch op): pose chain + camera rays + packing
     (nefes_pose_rays_fwd), render_rays forward (nefes_render_rays_fwd), cosine feature loss and its gradient
     (nefes_cosine_loss_*), render_rays backward to the rays, rays -> pose cotangent (nefes_pose_rays_bwd), so(3) chain +
     Adam (nefes_pose_adam_step).  Captured once into a CUDA graph and replayed; the loss of iteration k lands in
@@ -219,7 +219,7 @@ def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=
     feat_target [C, H*W].  Returns (refined c2w [3,4], list of losses).
     graph (default: on for n_iters >= 10 on CUDA): run the iterations as replays of a captured CUDA graph (PoseRefiner),
     cached per (camera, networks, learning rates) so that every further query pays no capture either.
-    engine (default: on where it applies): the iteration is EnginePoseRefiner's ~30 engine launches (no torch op); False
+    engine (default: on where it applies): the iteration is EnginePoseRefiner's 24 engine launches (no torch op); False
     keeps the torch pose chain / loss / optimiser around the engine render; True raises where it does not apply."""
     dev = feat_target.device
     use_graph = ((n_iters >= 10) if graph is None else bool(graph)) and dev.type == "cuda"
