@@ -4,7 +4,7 @@
  * The reference (ActiveVisionLab/NeFeS) has no FFI: its render path is Python callables
  * wired through a `render_kwargs` dict.  Each entry point below names the
  * reference callable (file:line under /root/reference/) whose arithmetic it replaces.  The Python
- * host side (nefes_b200/*.py) keeps the reference's call surface and reaches these symbols
+ * host side (the nefes_b200 Python package) keeps the reference's call surface and reaches these symbols
  * through ctypes; no torch types cross this boundary -- plain device pointers, sizes and a
  * cudaStream_t (passed as void*).
  *

@@ -69,7 +69,7 @@ def test_model_state_dict_round_trip(weights):
     assert sdc["exposure_embedding.params"].shape == (3072,)         # tcnn FullyFusedMLP 10(->16)x32, 32x32 x2, 32x12(->16)
     missing = c.load_state_dict({**wc, "exposure_embedding.params": torch.zeros(3072)}, strict=False)
     assert all(k.startswith("fusion_net") for k in missing.missing_keys) and not missing.unexpected_keys
-    assert float(c.exposure_embedding.params.abs().max()) == 0.0
+    assert float(c.exposure_embedding.params.detach().abs().max()) == 0.0
 
 
 def test_affine_color_transform_matches_its_definition():
@@ -126,3 +126,19 @@ def test_render_rays_workspace_is_host_arithmetic():
     assert L.lib().nefes_render_rays_workspace(C.byref(bad), 16, C.byref(k), C.byref(a), C.byref(b)) == 1
     assert b"sample counts" in L.lib().nefes_last_error()
     assert L.lib().nefes_render_rays_fwd(C.byref(cfg), None, 16, None, None, None, None) == 1
+
+
+def test_header_is_plain_c_and_matches_the_ctypes_table():
+    """include/nefes_b200.h must compile as C99 (the boundary is a C ABI: no C++ or torch types) and declare exactly the
+    entry points the ctypes table binds."""
+    import os, re, shutil, subprocess
+    from nefes_b200 import _lib as L
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "nefes_b200.h")
+    gcc = shutil.which("gcc")
+    if gcc:
+        r = subprocess.run([gcc, "-x", "c", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(hdr).read()
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(nefes_[a-z0-9_]+)\(", text, flags=re.M))
+    assert declared == set(L.exported_symbols()), (declared ^ set(L.exported_symbols()))
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", text, flags=re.S)          # no torch types in any signature
