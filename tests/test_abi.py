@@ -142,3 +142,31 @@ def test_header_is_plain_c_and_matches_the_ctypes_table():
     declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(nefes_[a-z0-9_]+)\(", text, flags=re.M))
     assert declared == set(L.exported_symbols()), (declared ^ set(L.exported_symbols()))
     assert "torch" not in re.sub(r"/\*.*?\*/", "", text, flags=re.S)          # no torch types in any signature
+
+
+def test_random_pixel_and_patch_selection():
+    """batching.select_random_pixels / select_random_patches (run_nefes.py:51-65, :86-95): distinct, in range, inside
+    the valid set; patches are whole crop x crop blocks inside the image."""
+    import pytest
+    import nefes_b200 as nb
+    g = torch.Generator().manual_seed(2)
+    H, W, B, n = 12, 20, 3, 50
+    sel = nb.select_random_pixels(B, H, W, n, generator=g)
+    assert sel.shape == (B, n) and int(sel.min()) >= 0 and int(sel.max()) < H * W
+    assert all(len(set(row.tolist())) == n for row in sel)
+    valid = [torch.arange(0, H * W, 2), torch.arange(100, 160), torch.arange(H * W)]
+    sel = nb.select_random_pixels(B, H, W, n, valid_inds=valid, generator=g)
+    for b in range(B):
+        assert set(sel[b].tolist()) <= set(valid[b].tolist()) and len(set(sel[b].tolist())) == n
+    with pytest.raises(RuntimeError, match="valid pixels"):
+        nb.select_random_pixels(B, H, W, 61, valid_inds=valid, generator=g)
+    full = nb.select_random_pixels(1, H, W, H * W, generator=g)                      # all pixels = a permutation
+    assert sorted(full[0].tolist()) == list(range(H * W))
+    pat = nb.select_random_patches(40, 60, num_crops=5, crop_size=8, generator=g)
+    assert pat.shape == (5 * 64,)
+    for k in range(5):
+        blk = pat[k * 64:(k + 1) * 64].reshape(8, 8)
+        r, c = blk // 60, blk % 60
+        assert bool((r[:, 0] == r[:, -1]).all()) and bool((c[0] == c[-1]).all())
+        assert bool((r[1:, 0] - r[:-1, 0] == 1).all()) and bool((c[0, 1:] - c[0, :-1] == 1).all())
+        assert int(r.max()) < 40 and int(c.max()) < 60

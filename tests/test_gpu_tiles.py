@@ -351,3 +351,29 @@ def test_one_call_render_edge_cases():
         assert float((one[3]["z_std"] - other[3]["z_std"]).abs().max()) < 1e-6
     empty = run((ro[:0], rd[:0]), 32768, 1 << 21, t_rand[:0], u[:0])
     assert empty[0].shape == (0, 3) and empty[3]["feat_map"].shape == (0, 128) and empty[3]["transient_sigmas"].shape == (0, 128)
+
+
+def test_gather_ray_batch_matches_the_reference_loops():
+    """batching.gather_ray_batch against run_nefes.py:66-74 written as the reference writes it (per-image fancy
+    indexing + cat), for per-image selections and for the shared patch selection."""
+    import nefes_b200 as nb
+    g = torch.Generator(device="cuda").manual_seed(17)
+    B, H, W, n = 3, 12, 20, 40
+    pose = torch.cat([torch.linalg.qr(torch.randn(B, 3, 3, device="cuda", generator=g))[0],
+                      torch.randn(B, 3, 1, device="cuda", generator=g)], -1)
+    target = torch.rand(B, H, W, 3, device="cuda", generator=g)
+    ftarget = torch.randn(B, H, W, 16, device="cuda", generator=g)
+    hist = torch.rand(B, 10, device="cuda", generator=g)
+    ro, rd = nb.get_rays_batch(H, W, 21.5, pose)
+    for sel in (nb.select_random_pixels(B, H, W, n, device="cuda", generator=g),
+                nb.select_random_patches(H, W, num_crops=2, crop_size=4, device="cuda", generator=g)):
+        rays, ts, tf, he = nb.gather_ray_batch(H, W, 21.5, pose, sel, target, ftarget, hist)
+        selb = sel if sel.dim() == 2 else sel[None].expand(B, -1)
+        rows, cols = selb // W, selb % W
+        ref_o = torch.cat([ro[k, rows[k], cols[k]] for k in range(B)])
+        ref_d = torch.cat([rd[k, rows[k], cols[k]] for k in range(B)])
+        ref_t = torch.cat([target[k, rows[k], cols[k]] for k in range(B)])
+        ref_f = torch.cat([ftarget[k, rows[k], cols[k]] for k in range(B)])
+        ref_h = torch.cat([hist[k].expand(selb.shape[1], 10) for k in range(B)])
+        assert torch.equal(rays[0], ref_o) and torch.equal(rays[1], ref_d)
+        assert torch.equal(ts, ref_t) and torch.equal(tf, ref_f) and torch.equal(he, ref_h)
