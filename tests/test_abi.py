@@ -170,3 +170,28 @@ def test_random_pixel_and_patch_selection():
         assert bool((r[:, 0] == r[:, -1]).all()) and bool((c[0] == c[-1]).all())
         assert bool((r[1:, 0] - r[:-1, 0] == 1).all()) and bool((c[0, 1:] - c[0, :-1] == 1).all())
         assert int(r.max()) < 40 and int(c.max()) < 60
+
+
+def _build_c_example(tmp_path):
+    import os, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    cuda = "/usr/local/cuda"
+    if not gcc or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        return None
+    exe = os.path.join(str(tmp_path), "render_c_abi")
+    libdir = os.path.join(root, "nefes_b200", "lib")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(root, "examples", "render_c_abi.c"), "-L", libdir, "-lnefes_b200",
+                        "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_c_host_links_against_the_library(tmp_path):
+    """examples/render_c_abi.c -- a C99 host with no Python and no torch -- compiles against include/nefes_b200.h and
+    links against libnefes_b200.so (running it needs a GPU: tests/test_gpu_tiles.py)."""
+    import pytest
+    if _build_c_example(tmp_path) is None:
+        pytest.skip("gcc or the CUDA runtime headers are not available")

@@ -377,3 +377,16 @@ def test_gather_ray_batch_matches_the_reference_loops():
         ref_h = torch.cat([hist[k].expand(selb.shape[1], 10) for k in range(B)])
         assert torch.equal(rays[0], ref_o) and torch.equal(rays[1], ref_d)
         assert torch.equal(ts, ref_t) and torch.equal(tf, ref_f) and torch.equal(he, ref_h)
+
+
+def test_plain_c_host_renders_through_the_c_abi(tmp_path):
+    """The C99 example host (no Python, no torch in the process) runs render_rays forward + backward through
+    libnefes_b200.so and gets finite outputs and non-zero weight gradients for both fields."""
+    import subprocess
+    from test_abi import _build_c_example
+    exe = _build_c_example(tmp_path)
+    if exe is None:
+        pytest.skip("gcc or the CUDA runtime headers are not available")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ok") and "|d params fine|" in r.stdout
