@@ -856,6 +856,17 @@ long long* chain_dbg_buf() {
   if (on && d == nullptr) { cudaMalloc(&d, 2048 * sizeof(long long)); }
   return on ? d : nullptr;
 }
+// Timing experiments of the chain kernels (NEFES_CHAIN_X bit mask: drop the saved copies, the weight traffic, the raw
+// stores ...).  They change RESULTS, so the mask is honoured only together with NEFES_UNSAFE_EXPERIMENTS=1.
+int chain_xflags() {
+  static const int flags = [] {
+    const char* u = getenv("NEFES_UNSAFE_EXPERIMENTS");
+    const char* e = getenv("NEFES_CHAIN_X");
+    return (u && u[0] == '1' && e) ? atoi(e) : 0;
+  }();
+  return flags;
+}
+
 void chain_dbg_dump(const char* what, const ChainArgs& c, cudaStream_t st) {
   if (c.dbg == nullptr) return;
   static int dumps = 0;
@@ -962,7 +973,7 @@ int launch_chain_fwd(const Ws& w, const Arena& A, int mode, int64_t M, float* ra
   c.M = M; c.n_tiles = T;
   c.raw = raw_t; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
   c.dbg = chain_dbg_buf();
-  { const char* e = getenv("NEFES_CHAIN_X"); c.xflags = e ? atoi(e) : 0; }
+  c.xflags = chain_xflags();
   static bool attr_done = false;
   if (!attr_done) {
     NEFES_CUDA(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdChainSmem));
@@ -1037,7 +1048,7 @@ int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float*
                (double)M * (2.0 * (save_ch + in_ch) + 4.0 * c.C), (double)M * 2.0 * macs);
   }
   c.dbg = chain_dbg_buf();
-  { const char* e = getenv("NEFES_CHAIN_X"); c.xflags = e ? atoi(e) : 0; }
+  c.xflags = chain_xflags();
   chain_fwd_ts_kernel<<<grid, kChainThreads, kTsSmem, st>>>(c);
   prof_end(st);
   NEFES_CHECK_LAUNCH("chain_fwd_ts");
@@ -1113,7 +1124,7 @@ int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_
   c.n_steps = n;
   c.M = M; c.n_tiles = T;
   c.dbg = chain_dbg_buf();
-  { const char* e = getenv("NEFES_CHAIN_X"); c.xflags = e ? atoi(e) : 0; }
+  c.xflags = chain_xflags();
   for (int l = 0; l < kChainLoads; ++l)
     if (c.load[l].bytes == 0) c.load[l].issue_step = -1;
   static bool attr_done = false;
