@@ -111,7 +111,9 @@ class PoseRefiner:
                 with torch.cuda.graph(g):
                     self.static_loss = self._iter()
                 self.graph = g
-            except Exception:                        # capture is an optimisation; the eager loop is the definition
+            except Exception as e:                   # capture is an optimisation; the eager loop is the definition
+                import warnings
+                warnings.warn(f"nefes_b200: CUDA-graph capture of the refinement iteration failed ({e}); running eagerly")
                 self.graph = False
                 torch.cuda.synchronize()
         for _ in range(n_iters - done):
