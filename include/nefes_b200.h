@@ -200,6 +200,16 @@ int nefes_mlp_bwd(const float* params, int net, int mode, int prec, const float*
                   const void* saved, void* scratch, float* d_params, float* d_pts, float* d_dirs,
                   void* stream);
 
+/* The two halves of nefes_mlp_bwd on their own: data gradient only (frozen field: pose refinement; d_pts / d_dirs as
+ * above, at least one non-NULL) and weight gradient only (d_params ACCUMULATED).  Same saved / scratch workspaces.
+ * Weights are re-packed into the tensor path's bf16 operand images inside every forward call (the images live in
+ * `saved`, which backward reads), so there is no separate repack call for a caller to forget after an optimiser step. */
+int nefes_mlp_dgrad(const float* params, int net, int mode, int prec, const float* pts, const float* dirs, int64_t N, int S,
+                    const float* raw, const float* d_raw, const void* saved, void* scratch, float* d_pts, float* d_dirs,
+                    void* stream);
+int nefes_mlp_wgrad(const float* params, int net, int mode, int prec, const float* pts, const float* dirs, int64_t N, int S,
+                    const float* raw, const float* d_raw, const void* saved, void* scratch, float* d_params, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K6  raw2outputs_NeRFH_NFF                 script/models/nerfh_nff.py:25-166
  * ------------------------------------------------------------------------------------------ */

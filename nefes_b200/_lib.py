@@ -99,6 +99,8 @@ _SIGS = {
     "nefes_render_rays_fwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), vp, vp, vp]),
     "nefes_render_rays_bwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), C.POINTER(CompGrad),
                                     C.POINTER(CompGrad), vp, vp, vp, vp, vp, vp]),
+    "nefes_mlp_dgrad": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "nefes_mlp_wgrad": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
     "nefes_pose_rays_fwd": (i32, [vp, vp, i32, i32, f32, f32, f32, vp, vp, i32, vp]),
     "nefes_pose_rays_bwd": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
     "nefes_cosine_loss_fwd": (i32, [vp, vp, i32, i32, vp, vp]),

@@ -126,6 +126,21 @@ int nefes_mlp_bwd_tiles(const float* params, int net, int mode, int prec, const 
                      d_raw_tiles, saved, scratch, d_params, d_pts, d_dirs, stream);
 }
 
+// the two halves of nefes_mlp_bwd under the names of SURVEY 8b's export list
+int nefes_mlp_dgrad(const float* params, int net, int mode, int prec, const float* pts, const float* dirs, int64_t N, int S,
+                    const float* raw, const float* d_raw, const void* saved, void* scratch, float* d_pts, float* d_dirs,
+                    void* stream) {
+  NEFES_REQUIRE(d_pts != nullptr || d_dirs != nullptr, NEFES_EINVAL, "nefes_mlp_dgrad: no output requested");
+  return mlp_bwd_any("nefes_mlp_dgrad", NEFES_RAW_ROWS, params, net, mode, prec, pts, dirs, N, S, raw, d_raw, saved, scratch,
+                     nullptr, d_pts, d_dirs, stream);
+}
+int nefes_mlp_wgrad(const float* params, int net, int mode, int prec, const float* pts, const float* dirs, int64_t N, int S,
+                    const float* raw, const float* d_raw, const void* saved, void* scratch, float* d_params, void* stream) {
+  NEFES_REQUIRE(d_params != nullptr, NEFES_EINVAL, "nefes_mlp_wgrad: null d_params");
+  return mlp_bwd_any("nefes_mlp_wgrad", NEFES_RAW_ROWS, params, net, mode, prec, pts, dirs, N, S, raw, d_raw, saved, scratch,
+                     d_params, nullptr, nullptr, stream);
+}
+
 int nefes_mlp_bwd_compact(const float* params, int net, int mode, int prec, const float* pts, const float* dirs,
                           int64_t N, int S, const float* raw_tiles, const float* compact, const float* g_rgb,
                           const float* g_feat, const void* saved, void* scratch, float* d_params, float* d_pts,

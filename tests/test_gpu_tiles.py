@@ -390,3 +390,38 @@ def test_plain_c_host_renders_through_the_c_abi(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().endswith("ok") and "|d params fine|" in r.stdout
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mlp_dgrad_and_wgrad_halves_match_the_combined_backward(precision):
+    """nefes_mlp_dgrad + nefes_mlp_wgrad (SURVEY 8b's export names) against nefes_mlp_bwd on the same saved state."""
+    import ctypes as C
+    from nefes_b200 import _lib as L
+    from nefes_b200 import ops
+    c, f = _nets()
+    lib, p = L.lib(), L.ptr
+    prec = L.PREC_BF16 if precision == "bf16" else L.PREC_FP32
+    g = torch.Generator(device="cuda").manual_seed(31)
+    N, S, mode, net = 70, 64, L.MODE_FULL, L.NET_FINE
+    pts = torch.rand(N, S, 3, device="cuda", generator=g) * 2 - 1
+    dirs = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda", generator=g), dim=-1)
+    flat = f.flat.detach()
+    sv, sf, sb = L.mlp_workspace(net, mode, prec, N * S, N)
+    saved, scr_f, scr_b = ops._buf(sv, "cuda"), ops._buf(sf, "cuda"), ops._buf(sb, "cuda")
+    raw = torch.empty(N, S, 137, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.nefes_mlp_fwd(p(flat), net, mode, prec, p(pts), p(dirs), N, S, p(raw), p(saved), p(scr_f), st), "fwd")
+    d_raw = torch.randn(N, S, 137, device="cuda", generator=g)
+    dP, dp, dd = torch.zeros_like(flat), torch.empty_like(pts), torch.empty_like(dirs)
+    L.check(lib.nefes_mlp_bwd(p(flat), net, mode, prec, p(pts), p(dirs), N, S, p(raw), p(d_raw), p(saved), p(scr_b), p(dP), p(dp),
+                              p(dd), st), "bwd")
+    dp2, dd2, dP2 = torch.empty_like(pts), torch.empty_like(dirs), torch.zeros_like(flat)
+    L.check(lib.nefes_mlp_dgrad(p(flat), net, mode, prec, p(pts), p(dirs), N, S, p(raw), p(d_raw), p(saved), p(scr_b), p(dp2), p(dd2),
+                                st), "dgrad")
+    L.check(lib.nefes_mlp_wgrad(p(flat), net, mode, prec, p(pts), p(dirs), N, S, p(raw), p(d_raw), p(saved), p(scr_b), p(dP2), st),
+            "wgrad")
+    tol = 1e-5 if precision == "fp32" else 2e-2        # bf16: the combined call takes the fused wgrad launches (other rounding points)
+    for a, b in ((dp, dp2), (dd, dd2), (dP, dP2)):
+        assert float((a - b).abs().max()) <= tol * float(a.abs().max()) + 1e-8
+    assert lib.nefes_mlp_dgrad(p(flat), net, mode, prec, p(pts), p(dirs), N, S, p(raw), p(d_raw), p(saved), p(scr_b), None, None, st) == 1
+    assert lib.nefes_mlp_wgrad(p(flat), net, mode, prec, p(pts), p(dirs), N, S, p(raw), p(d_raw), p(saved), p(scr_b), None, st) == 1
