@@ -267,6 +267,7 @@ typedef struct {
   int transient_at_test;           /* args.transient_at_test                                              */
   int net_coarse, net_fine;        /* NEFES_NET_* of network_fn / network_fine                            */
   float beta_min;                  /* network_fine.beta_min                                               */
+  int forward_only;                /* 1: no backward call will follow (inference): activations are not saved */
 } nefes_render_cfg_t;
 typedef struct {
   const float* rays;               /* ray_batch [N, ld_rays]: o 0:3, d 3:6, near 6, far 7, viewdirs 8:11  */

@@ -39,7 +39,7 @@ class CompGrad(C.Structure):
 
 class RenderCfg(C.Structure):
     _fields_ = [(n, i32) for n in ("n_samples", "n_importance", "prec", "test_time", "output_transient",
-                                   "transient_at_test", "net_coarse", "net_fine")] + [("beta_min", f32)]
+                                   "transient_at_test", "net_coarse", "net_fine")] + [("beta_min", f32), ("forward_only", i32)]
 
 
 class RenderIn(C.Structure):

@@ -20,6 +20,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static thread_local bool t_forward_only = false;
+void set_forward_only(bool on) { t_forward_only = on; }
+bool forward_only() { return t_forward_only; }
 
 namespace {
 struct ProfRec { const char* tag; cudaEvent_t e0, e1; double bytes, flops; };

@@ -15,6 +15,16 @@ void count_launch(int n = 1);
 void prof_begin(const char* tag, cudaStream_t st, double alg_bytes, double alg_flops);
 void prof_end(cudaStream_t st);
 
+// Forward-only field queries (a render under no_grad, the sigma-only coarse pass of a test-time render): while set on the
+// calling thread, the bf16 forward chain does not write the saved activation copies (nobody will run the backward).
+void set_forward_only(bool on);
+bool forward_only();
+struct ForwardOnlyScope {
+  bool prev;
+  explicit ForwardOnlyScope(bool on) : prev(forward_only()) { set_forward_only(on); }
+  ~ForwardOnlyScope() { set_forward_only(prev); }
+};
+
 #define NEFES_REQUIRE(cond, code, ...)                 \
   do {                                                 \
     if (!(cond)) {                                     \

@@ -927,7 +927,8 @@ int launch_chain_fwd(const Ws& w, const Arena& A, int mode, int64_t M, float* ra
       s.wait_load = (int8_t)(part == 0 ? wait_load : wait_load_b);
       s.bias = last ? A.bias(pl) : nullptr; s.bias_off = (uint16_t)boff;
       set_weights(s, A.W(pl) + (int64_t)(k0 / 8) * pd.N * 16, (k1 - k0) / 8, pd.N, 0, pd.N);
-      s.gdst = (save && last) ? save->p : nullptr; s.g_tile_stride = (save && last) ? (uint32_t)save->tile_stride() : 0u;
+      const bool keep = save && last && !forward_only();     // no saved copies when nobody will run the backward
+      s.gdst = keep ? save->p : nullptr; s.g_tile_stride = keep ? (uint32_t)save->tile_stride() : 0u;
     }
   };
   auto load = [&](int idx, const Img& img, uint32_t dst_off, int issue_step) {
@@ -983,7 +984,7 @@ int launch_chain_fwd(const Ws& w, const Arena& A, int mode, int64_t M, float* ra
   const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
   {
     // algorithmic HBM bytes per point: encodings in, every saved activation image out (bf16), raw out (fp32); flops: 2 x MACs
-    const double save_ch = (mode == NEFES_MODE_SIGMA) ? 8 * 128 : (mode == NEFES_MODE_STATIC ? 8 * 128 + 128 + 64 : 8 * 128 + 128 + 128 + 64 + 64);
+    const double save_ch = forward_only() ? 0 : ((mode == NEFES_MODE_SIGMA) ? 8 * 128 : (mode == NEFES_MODE_STATIC ? 8 * 128 + 128 + 64 : 8 * 128 + 128 + 128 + 64 + 64));
     const double in_ch = (mode == NEFES_MODE_SIGMA) ? 64 : 96;
     const double macs = (mode == NEFES_MODE_SIGMA) ? 130944 : (mode == NEFES_MODE_STATIC ? 165632 : 184064);
     prof_begin(mode == NEFES_MODE_FULL ? "chain_fwd_fine" : (mode == NEFES_MODE_STATIC ? "chain_fwd_coarse" : "chain_fwd_sigma"), st,

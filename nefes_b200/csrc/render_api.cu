@@ -196,8 +196,12 @@ int nefes_render_rays_fwd(const nefes_render_cfg_t* cfg, const nefes_render_in_t
                                   out->z_coarse, stream)) return e;
   ray_points_kernel<<<grid, 256, 0, st>>>(in->rays, in->ld_rays, out->z_coarse, (int)N, P.Sc, pts_c, dirs, nullptr, 0, nullptr);
   NEFES_CHECK_LAUNCH("ray_points");
-  if (int e = (P.tiled_c ? nefes_mlp_fwd_tiles : nefes_mlp_fwd)(in->params_coarse, cfg->net_coarse, P.mode_c, cfg->prec, pts_c,
-                                                                dirs, N, P.Sc, raw_c, K + P.saved_c, scratch, stream)) return e;
+  {
+    // nothing flows back into the sigma-only coarse pass of a test-time render (the importance samples are detached)
+    ForwardOnlyScope fo(cfg->forward_only != 0 || P.mode_c == NEFES_MODE_SIGMA);
+    if (int e = (P.tiled_c ? nefes_mlp_fwd_tiles : nefes_mlp_fwd)(in->params_coarse, cfg->net_coarse, P.mode_c, cfg->prec, pts_c,
+                                                                  dirs, N, P.Sc, raw_c, K + P.saved_c, scratch, stream)) return e;
+  }
   if (int e = (P.tiled_c ? nefes_composite_fwd_tiles : nefes_composite_fwd)(raw_c, out->z_coarse, in->noise_coarse, (int)N, P.Sc,
                                                                             P.comp_c, cfg->beta_min, &out->coarse, stream)) return e;
   if (!P.fine) return NEFES_OK;
@@ -212,8 +216,11 @@ int nefes_render_rays_fwd(const nefes_render_cfg_t* cfg, const nefes_render_in_t
                                           cfg->n_importance, out->z_std);
   NEFES_CHECK_LAUNCH("ray_points");
   const int net_f = cfg->net_fine;
-  if (int e = (P.tiled_f ? nefes_mlp_fwd_tiles : nefes_mlp_fwd)(in->params_fine, net_f, P.mode_f, cfg->prec, pts_f, dirs, N, P.Sf,
-                                                                raw_f, K + P.saved_f, scratch, stream)) return e;
+  {
+    ForwardOnlyScope fo(cfg->forward_only != 0);
+    if (int e = (P.tiled_f ? nefes_mlp_fwd_tiles : nefes_mlp_fwd)(in->params_fine, net_f, P.mode_f, cfg->prec, pts_f, dirs, N, P.Sf,
+                                                                  raw_f, K + P.saved_f, scratch, stream)) return e;
+  }
   return (P.tiled_f ? nefes_composite_fwd_tiles : nefes_composite_fwd)(raw_f, out->z_fine, in->noise_fine, (int)N, P.Sf, P.comp_f,
                                                                        cfg->beta_min, &out->fine, stream);
 }
@@ -227,6 +234,9 @@ int nefes_render_rays_bwd(const nefes_render_cfg_t* cfg, const nefes_render_in_t
   RenderPlan P;
   if (int e = make_plan(who, cfg, N, &P)) return e;
   if (N == 0) return NEFES_OK;
+  NEFES_REQUIRE(!cfg->forward_only, NEFES_EINVAL, "%s: the forward call ran with forward_only = 1 and kept no activations", who);
+  NEFES_REQUIRE(P.mode_c != NEFES_MODE_SIGMA || !any_grad(g_coarse), NEFES_EUNSUPPORTED,
+                "%s: the sigma-only coarse pass of a test-time render keeps no activations (no gradient path: rendering.py:136)", who);
   NEFES_REQUIRE(in && out && keep && scratch, NEFES_EINVAL, "%s: null pointer", who);
   NEFES_REQUIRE(in->rays && in->params_coarse && out->z_coarse && (!P.fine || (in->params_fine && out->z_fine)), NEFES_EINVAL,
                 "%s: the forward call's inputs and depths are required", who);

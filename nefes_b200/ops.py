@@ -390,8 +390,9 @@ class _RenderRays(Function):
         dev = rays_c.device
         S, ni = cfg["n_samples"], cfg["n_importance"]
         Sf = S + ni
+        need_bwd = any(ctx.needs_input_grad[:3])
         c = L.RenderCfg(S, ni, cfg["prec"], int(cfg["test_time"]), int(cfg["output_transient"]), int(cfg["transient_at_test"]),
-                        cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]))
+                        cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]), 0 if need_bwd else 1)
         kb, sfb, sbb = C.c_int64(), C.c_int64(), C.c_int64()
         L.check(L.lib().nefes_render_rays_workspace(C.byref(c), N, C.byref(kb), C.byref(sfb), C.byref(sbb)),
                 "nefes_render_rays_workspace")
@@ -422,7 +423,7 @@ class _RenderRays(Function):
         with torch.cuda.device(dev), _Timed("render_fwd"):
             L.check(L.lib().nefes_render_rays_fwd(C.byref(c), C.byref(inp), N, C.byref(out), L.ptr(keep), L.ptr(scratch),
                                                   L.stream_of(rays_c)), "nefes_render_rays_fwd")
-        if any(ctx.needs_input_grad[:3]):
+        if need_bwd:
             ctx.save_for_backward(rays_c, fc, ff, t_rand, u, noise_c, noise_f, z_c, z_f, keep)
             ctx.meta = (dict(cfg), per_ray, sbb.value, tuple(rays.shape))
         ctx.mark_non_differentiable(z_c, z_f, z_s, inds, z_std)
@@ -436,7 +437,7 @@ class _RenderRays(Function):
         dev = rays_c.device
         S, ni = cfg["n_samples"], cfg["n_importance"]
         c = L.RenderCfg(S, ni, cfg["prec"], int(cfg["test_time"]), int(cfg["output_transient"]), int(cfg["transient_at_test"]),
-                        cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]))
+                        cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]), 0)
         inp = L.RenderIn(L.ptr(rays_c), ld, L.ptr(fc), L.ptr(ff), L.ptr(linspace01(S, dev)), L.ptr(t_rand), L.ptr(u), per_ray,
                          L.ptr(noise_c), L.ptr(noise_f))
         nul = L.CompOut(*([None] * 8))
@@ -471,7 +472,7 @@ class RenderCall:
         Sf = S + ni
         self.N, self.ld, self.dev = n_rays, ld, dev
         self.cfg = L.RenderCfg(S, ni, cfg["prec"], int(cfg["test_time"]), int(cfg["output_transient"]),
-                               int(cfg["transient_at_test"]), cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]))
+                               int(cfg["transient_at_test"]), cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]), 0)
         kb, sfb, sbb = C.c_int64(), C.c_int64(), C.c_int64()
         L.check(L.lib().nefes_render_rays_workspace(C.byref(self.cfg), n_rays, C.byref(kb), C.byref(sfb), C.byref(sbb)),
                 "nefes_render_rays_workspace")

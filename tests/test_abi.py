@@ -113,7 +113,7 @@ def test_render_rays_workspace_is_host_arithmetic():
     """nefes_render_rays_workspace sizes the two workspaces of the one-call path on the host; bad configs are refused."""
     import ctypes as C
     from nefes_b200 import _lib as L
-    cfg = L.RenderCfg(64, 64, L.PREC_BF16, 0, 1, 1, L.NET_COARSE, L.NET_FINE, 0.1)
+    cfg = L.RenderCfg(64, 64, L.PREC_BF16, 0, 1, 1, L.NET_COARSE, L.NET_FINE, 0.1, 0)
     k, a, b = C.c_int64(), C.c_int64(), C.c_int64()
     assert L.lib().nefes_render_rays_workspace(C.byref(cfg), 6144, C.byref(k), C.byref(a), C.byref(b)) == 0
     # keep >= sample points + both tile-major raw blocks
@@ -122,7 +122,7 @@ def test_render_rays_workspace_is_host_arithmetic():
     k2 = C.c_int64()
     assert L.lib().nefes_render_rays_workspace(C.byref(cfg), 12288, C.byref(k2), C.byref(a), C.byref(b)) == 0
     assert k2.value > k.value
-    bad = L.RenderCfg(64, 300, L.PREC_BF16, 0, 1, 1, L.NET_COARSE, L.NET_FINE, 0.1)
+    bad = L.RenderCfg(64, 300, L.PREC_BF16, 0, 1, 1, L.NET_COARSE, L.NET_FINE, 0.1, 0)
     assert L.lib().nefes_render_rays_workspace(C.byref(bad), 16, C.byref(k), C.byref(a), C.byref(b)) == 1
     assert b"sample counts" in L.lib().nefes_last_error()
     assert L.lib().nefes_render_rays_fwd(C.byref(cfg), None, 16, None, None, None, None) == 1
