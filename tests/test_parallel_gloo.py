@@ -38,6 +38,23 @@ def _worker(rank, world, port, q):
         local = torch.stack([torch.full((12,), float(i)) for i in ids])
         full = P.gather_rows(local, ids, 7)
         assert torch.equal(full[:, 0], torch.arange(7.))
+        # refine_queries: every rank refines only its strided share of the queries, all ranks end with all poses
+        from nefes_b200 import refine as R
+        seen = []
+
+        def stub(init_c2w, feat_target, H, W, focal, kw, **opts):
+            seen.append(int(feat_target[0, 0]))
+            return init_c2w * 2.0 + float(feat_target[0, 0]), []
+        real, R.refine_pose = R.refine_pose, stub
+        try:
+            n_q = 5
+            inits = torch.arange(n_q * 12, dtype=torch.float32).reshape(n_q, 3, 4)
+            targets = torch.arange(n_q, dtype=torch.float32).reshape(n_q, 1, 1).expand(n_q, 4, 6)
+            out = R.refine_queries(inits, targets, 2, 3, 1.0, {})
+        finally:
+            R.refine_pose = real
+        assert seen == list(range(rank, n_q, world))
+        assert torch.equal(out, inits * 2.0 + torch.arange(n_q, dtype=torch.float32).reshape(n_q, 1, 1))
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
