@@ -1010,7 +1010,8 @@ int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float*
     s.bias = A.bias(pl); s.bias_off = (uint16_t)bias_floats;
     bias_floats += (pd.N + 3) & ~3;
     set_weights(s, A.W(pl), pd.K / 8, pd.N, 0, pd.N);
-    s.gdst = save ? save->p : nullptr; s.g_tile_stride = save ? (uint32_t)save->tile_stride() : 0u;
+    const bool keep = save && !forward_only();       // no saved copies when nobody will run the backward
+    s.gdst = keep ? save->p : nullptr; s.g_tile_stride = keep ? (uint32_t)save->tile_stride() : 0u;
   };
   add(PL_T0, kTsX, CK_HIDDEN, kTsH, 128, &w.H[0]);
   for (int l = 1; l < 8; ++l) add(PL_T0 + l, l == 4 ? kTsX : kTsH, CK_HIDDEN, kTsH, 128, &w.H[l]);
@@ -1042,7 +1043,7 @@ int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float*
   const int n_pairs = (T + 1) / 2;
   const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
   {
-    const double save_ch = (mode == NEFES_MODE_SIGMA) ? 8 * 128 : (mode == NEFES_MODE_STATIC ? 8 * 128 + 128 + 64 : 8 * 128 + 128 + 128 + 64 + 64);
+    const double save_ch = forward_only() ? 0 : ((mode == NEFES_MODE_SIGMA) ? 8 * 128 : (mode == NEFES_MODE_STATIC ? 8 * 128 + 128 + 64 : 8 * 128 + 128 + 128 + 64 + 64));
     const double in_ch = (mode == NEFES_MODE_SIGMA) ? 64 : 96;
     const double macs = (mode == NEFES_MODE_SIGMA) ? 130944 : (mode == NEFES_MODE_STATIC ? 165632 : 184064);
     prof_begin(mode == NEFES_MODE_FULL ? "chain_fwd_fine" : (mode == NEFES_MODE_STATIC ? "chain_fwd_coarse" : "chain_fwd_sigma"), st,
@@ -1060,11 +1061,18 @@ int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float*
       static long long h[2048];
       cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost);
       const long long t0 = h[0];
-      fprintf(stderr, "[chain_ts dbg] n_steps=%d\n", c.n_steps);
+      fprintf(stderr, "[chain_ts dbg] n_steps=%d  (cycles since tile 0's first issue)\n", c.n_steps);
       for (int i = 0; i < 32 && i < 2 * c.n_steps; ++i) {
-        const long long* r = h + i * 16;
-        fprintf(stderr, "  seq %2d step %2d | mma0 %7lld..%7lld mma1 %7lld..%7lld | epi ready %7lld ld0 +%lld st0 +%lld ld1 +%lld st1 +%lld done +%lld\n", i,
-                i % c.n_steps, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0, r[4] - t0, r[5] - r[4], r[6] - r[4], r[7] - r[4], r[8] - r[4], r[9] - r[4]);
+        const long long* r = h + i * 48;
+        long long rd[2] = {0, 0}, lo[2] = {1ll << 62, 1ll << 62}, hi[2] = {0, 0};
+        for (int w2 = 0; w2 < 16; ++w2) {
+          rd[w2 >> 3] = r[8 + w2] > rd[w2 >> 3] ? r[8 + w2] : rd[w2 >> 3];
+          lo[w2 >> 3] = r[24 + w2] < lo[w2 >> 3] ? r[24 + w2] : lo[w2 >> 3];
+          hi[w2 >> 3] = r[24 + w2] > hi[w2 >> 3] ? r[24 + w2] : hi[w2 >> 3];
+        }
+        fprintf(stderr, "  seq %2d step %2d | t0: W %7lld A %7lld issued %7lld  epi ready %7lld done %7lld..%7lld | t1: W %7lld A %7lld issued %7lld  epi ready %7lld done %7lld..%7lld\n",
+                i, i % c.n_steps, r[40] - t0, r[0] - t0, r[1] - t0, rd[0] - t0, lo[0] - t0, hi[0] - t0,
+                r[41] - t0, r[2] - t0, r[3] - t0, rd[1] - t0, lo[1] - t0, hi[1] - t0);
       }
     }
   }
@@ -1500,7 +1508,11 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   float* raw_t = direct ? raw : reinterpret_cast<float*>(scratch);
   // NEFES_FWD_TS=1: activations in tensor memory (mlp_chain_ts.cuh).  Measured equal to the shared-memory-operand chain
   // within 2 % at the bench shape (both sit on the same HBM write stream), so the older, longer-validated one is the default.
-  static const bool fwd_ts = getenv("NEFES_FWD_TS") != nullptr;
+  // forward-only calls (no saved copies) run with the activations in tensor memory (mlp_chain_ts.cuh: 0.52 ms against 0.55
+  // for the fine query at 6144 rays); with saves the shared-memory-operand chain is the faster one (0.66 against 0.79 ms).
+  // NEFES_FWD_TS=1 / NEFES_FWD_SS=1 force one or the other.
+  static const bool force_ts = getenv("NEFES_FWD_TS") != nullptr, force_ss = getenv("NEFES_FWD_SS") != nullptr;
+  const bool fwd_ts = force_ts || (!force_ss && forward_only());
   if (fwd_ts) TRY(launch_chain_fwd_ts(w, A, mode, M, raw_t, st));
   else TRY(launch_chain_fwd(w, A, mode, M, raw_t, st));
   if (!direct) {

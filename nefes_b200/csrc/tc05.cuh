@@ -19,6 +19,28 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---- warp-uniform issue -------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / cp.async.bulk take their operands from UNIFORM registers.  Issued from a divergent
+// `if (lane == 0)` branch with operands in ordinary registers, ptxas wraps every one of them in a "waterfall" loop
+// (ELECT, R2UR.BROADCAST x n, the instruction, BRA.U.ANY) that costs the issuing thread 50-100 cycles per instruction:
+// measured on B200 (tools/tc_issue.cu) a stream of N=128 MMAs with A in TMEM retires at 79 cycles/MMA from a lane-0
+// branch and at 64.7 (the tensor-pipe floor) from a converged warp.  So role warps stay CONVERGED: all 32 lanes run the
+// loops and the waits, operands are laundered through uni() (a shuffle from lane 0, which ptxas treats as uniform), and
+// only the issuing instruction itself is predicated on one elected lane.
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ int uni(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint64_t uni(uint64_t v) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, 0), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), 0);
+  return ((uint64_t)hi << 32) | lo;
+}
+template <class T> __device__ __forceinline__ const T* uni(const T* p) { return reinterpret_cast<const T*>(uni((uint64_t)(uintptr_t)p)); }
+template <class T> __device__ __forceinline__ T* uni(T* p) { return reinterpret_cast<T*>(uni((uint64_t)(uintptr_t)p)); }
+__device__ __forceinline__ bool elect_one() {      // one lane of a fully converged warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -164,7 +164,9 @@ class ExposureMLP(nn.Module):
         self.params = nn.Parameter(torch.cat(parts))
 
     def forward(self, x):
-        h = torch.nn.functional.pad(x.to(self.params.dtype), (0, self.SHAPES[0][1] - self.n_in))
+        # tiny-cuda-nn wraps the MLP in an Identity encoding aligned to 16 inputs whose padded dimensions are ONES (so the
+        # first layer's weight columns 10..15 act as a learned bias), not zeros
+        h = torch.nn.functional.pad(x.to(self.params.dtype), (0, self.SHAPES[0][1] - self.n_in), value=1.0)
         off = 0
         for li, (o, i) in enumerate(self.SHAPES):
             w = self.params[off:off + o * i].view(o, i)
@@ -328,6 +330,23 @@ class FlatAdam(torch.optim.Optimizer):
 
     def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def set_lr(self, lr, group=None):
+        """Write a new learning rate into param_groups AND the device scalar the kernel reads.  A step replayed from a
+        CUDA graph never passes through step() on the host, so the reference's per-step decay (run_nefes.py:266-270)
+        must come through here (outside capture) when the step is graph-replayed."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("nefes_b200.FlatAdam: change the learning rate outside graph capture")
+        for gi, grp in enumerate(self.param_groups):
+            if group is not None and gi != group:
+                continue
+            grp["lr"] = float(lr)
+            for p in grp["params"]:
+                st = self.state.get(p)
+                if st:
+                    st["dev"][1] = float(lr)
+                    st["lr_host"] = float(lr)
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):

@@ -235,7 +235,7 @@ class _FieldQuery(Function):
     (tiled=True: the tile-major block tensor [T,C,128] of TiledRaw)."""
 
     @staticmethod
-    def forward(ctx, pts, dirs, flat, net, mode, prec, tiled):
+    def forward(ctx, pts, dirs, flat, net, mode, prec, tiled, grad_on=True):
         L.need_cuda(pts, dirs, flat)
         pts_c = L.f32c(pts)
         N, S = pts_c.shape[0], pts_c.shape[1]
@@ -245,7 +245,9 @@ class _FieldQuery(Function):
             raise RuntimeError("nefes_b200: flat parameter buffer must be contiguous fp32")
         Cc = L.RAW_CH[mode]
         dev = pts_c.device
-        need_bwd = any(ctx.needs_input_grad[:3])
+        # needs_input_grad reports requires_grad of the inputs even under torch.no_grad(); grad_on is
+        # torch.is_grad_enabled() sampled by the caller (inside forward() it is always False)
+        need_bwd = bool(grad_on) and any(ctx.needs_input_grad[:3])
         sv, sf, _ = L.mlp_workspace(net, mode, prec, N * S, N)
         saved = _buf(sv, dev)
         scratch = _buf(sf, dev)
@@ -266,6 +268,10 @@ class _FieldQuery(Function):
         dev = pts_c.device
         compact = _COMPACT.pop(raw.data_ptr(), None) if tiled else None
         if compact is None:
+            if tiled and d_raw is not None and d_raw.numel() > 1 and all(s_ == 0 for s_ in d_raw.stride()):
+                raise RuntimeError("nefes_b200: the compact cotangent of a private tile-major raw is gone (the placeholder "
+                                   "d_raw reached the field backward); was the graph backpropagated twice or ops._COMPACT cleared "
+                                   "mid-backward?")
             d_raw = L.f32c(d_raw)
         need_p, need_d, need_w = ctx.needs_input_grad[:3]
         d_pts = torch.empty_like(pts_c) if need_p else None
@@ -286,15 +292,16 @@ class _FieldQuery(Function):
                            L.ptr(raw), L.ptr(d_raw), L.ptr(saved), L.ptr(scratch), L.ptr(d_flat),
                            L.ptr(d_pts), L.ptr(d_dirs), L.stream_of(pts_c)), "nefes_mlp_bwd")
         return (d_pts.reshape(pshape) if d_pts is not None else None,
-                d_dirs.reshape(dshape) if d_dirs is not None else None, d_flat, None, None, None, None)
+                d_dirs.reshape(dshape) if d_dirs is not None else None, d_flat, None, None, None, None, None)
 
 
 def field_query(pts, dirs, flat, net, mode, prec=L.PREC_FP32):
     """-> raw [N,S,C]; inside a `tiled_raw()` block (render_rays) a TiledRaw where the engine supports it."""
+    grad_on = torch.is_grad_enabled()
     if want_tiled(prec, mode, pts.shape[1]):
-        t = _FieldQuery.apply(pts, dirs, flat, int(net), int(mode), int(prec), True)
+        t = _FieldQuery.apply(pts, dirs, flat, int(net), int(mode), int(prec), True, grad_on)
         return TiledRaw(t, pts.shape[0], pts.shape[1], L.RAW_CH[mode])
-    return _FieldQuery.apply(pts, dirs, flat, int(net), int(mode), int(prec), False)
+    return _FieldQuery.apply(pts, dirs, flat, int(net), int(mode), int(prec), False, grad_on)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -357,6 +364,8 @@ class _Composite(Function):
             with torch.cuda.device(raw_c.device):
                 L.check(L.lib().nefes_composite_bwd_compact(L.ptr(raw_c), L.ptr(z_c), L.ptr(noise_c), N, S, mode, C.byref(gs),
                                                             L.ptr(cg), L.stream_of(raw_c)), "nefes_composite_bwd_compact")
+            while len(_COMPACT) >= 4096:             # leftovers of aborted backward passes: drop the oldest
+                _COMPACT.pop(next(iter(_COMPACT)))
             _COMPACT[raw_c.data_ptr()] = (cg, g.get("rgb"), g.get("feat"))
             return cg.new_zeros(()).expand(rshape), None, None, None, None, None, None
         d_raw = torch.empty_like(raw_c)
@@ -390,7 +399,7 @@ class _RenderRays(Function):
         dev = rays_c.device
         S, ni = cfg["n_samples"], cfg["n_importance"]
         Sf = S + ni
-        need_bwd = any(ctx.needs_input_grad[:3])
+        need_bwd = bool(cfg.get("grad_on", True)) and any(ctx.needs_input_grad[:3])
         c = L.RenderCfg(S, ni, cfg["prec"], int(cfg["test_time"]), int(cfg["output_transient"]), int(cfg["transient_at_test"]),
                         cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]), 0 if need_bwd else 1)
         kb, sfb, sbb = C.c_int64(), C.c_int64(), C.c_int64()
@@ -458,6 +467,7 @@ class _RenderRays(Function):
 
 
 def render_rays_fused(rays, flat_c, flat_f, cfg, t_rand=None, u=None, noise_c=None, noise_f=None):
+    cfg = dict(cfg, grad_on=torch.is_grad_enabled())     # no_grad renders are forward-only: no saved activations
     return _RenderRays.apply(rays, flat_c, flat_f, t_rand, u, noise_c, noise_f, cfg)
 
 

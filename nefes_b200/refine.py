@@ -213,6 +213,12 @@ def _engine_refiner_applies(feat_target, H, W, kw, hist):
 
 
 _REFINERS = {}
+_MAX_REFINERS = 8
+
+
+def clear_refiner_cache():
+    """Drop every cached refiner (captured graphs + workspaces)."""
+    _REFINERS.clear()
 
 
 def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=50, lr_r=0.0087, lr_t=0.01,
@@ -225,11 +231,20 @@ def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=
     keeps the torch pose chain / loss / optimiser around the engine render; True raises where it does not apply."""
     dev = feat_target.device
     use_graph = ((n_iters >= 10) if graph is None else bool(graph)) and dev.type == "cuda"
+    kw_ = render_kwargs_test
+    nets = (kw_.get("network_fn"), kw_.get("network_fine"))
+    a_ = kw_.get("args")
+    # everything a cached refiner bakes in: camera, rates, sample counts, flags, and the STORAGE of the frozen weights
+    # (a refiner holds raw pointers to flat.detach(): model.to() / a reloaded Parameter must miss the cache)
     key = (H, W, float(focal), chunk, float(lr_r), float(lr_t), str(dev), tuple(feat_target.shape),
-           id(render_kwargs_test.get("network_fn")), id(render_kwargs_test.get("network_fine")),
-           getattr(render_kwargs_test.get("network_fn"), "precision", None),
-           getattr(render_kwargs_test.get("network_fine"), "precision", None),
-           float(render_kwargs_test.get("near", 0.)), float(render_kwargs_test.get("far", 1.)))
+           tuple(id(n) for n in nets), tuple(getattr(n, "precision", None) for n in nets),
+           tuple(n.flat.data_ptr() if hasattr(n, "flat") else None for n in nets),
+           kw_.get("N_samples"), kw_.get("N_importance"), getattr(kw_.get("network_query_fn"), "netchunk", None),
+           bool(getattr(a_, "NeRFW", False)), bool(getattr(a_, "transient_at_test", False)),
+           bool(getattr(a_, "nerfh_nff", False)), bool(getattr(a_, "use_fine_only", False)),
+           float(kw_.get("near", 0.)), float(kw_.get("far", 1.)))
+    while len(_REFINERS) >= _MAX_REFINERS:           # bounded: a refiner pins its GPU workspaces
+        _REFINERS.pop(next(iter(_REFINERS)))
     if (engine is None or engine) and dev.type == "cuda" and H * W <= chunk and \
             _engine_refiner_applies(feat_target, H, W, render_kwargs_test, hist):
         ref = _REFINERS.get(("engine",) + key)

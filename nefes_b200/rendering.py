@@ -101,7 +101,6 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     if lindisp:
         raise RuntimeError("nefes_b200: lindisp sampling is not built (no reference config uses it)")
     L.need_cuda(ray_batch)
-    ops._COMPACT.clear()      # compact cotangents live only inside one backward pass; drop leftovers of an aborted one
     ray_batch = ray_batch if ray_batch.dtype == torch.float32 else ray_batch.float()
     if not ray_batch.is_contiguous():
         ray_batch = ray_batch.contiguous()
