@@ -86,7 +86,9 @@ def test_affine_color_transform_matches_its_definition():
     out = c.affine_color_transform(Args(), rgb, hist, B)
     assert out.shape == (B * n, 3) and bool(((out >= 0) & (out <= 1)).all())
     e = c.exposure_embedding
-    h = torch.nn.functional.pad(hist, (0, 6))
+    # tiny-cuda-nn pads the 10 inputs to 16 with ONES (Identity encoding): weight columns 10..15 act as a learned bias
+    h = torch.nn.functional.pad(hist, (0, 6), value=1.0)
+    assert float(e.params[:32 * 16].view(32, 16)[:, 10:].abs().max()) > 0
     off = 0
     for li, (o, i) in enumerate(e.SHAPES):
         h = h @ e.params[off:off + o * i].view(o, i).t()
