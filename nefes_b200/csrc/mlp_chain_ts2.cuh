@@ -1,0 +1,417 @@
+// Forward layer chain, round 2: activations in TENSOR MEMORY, every layer split into N-blocks with their own accumulator
+// columns and their own hand-over, activations double-buffered -- so that inside ONE tile the epilogue of block 0 runs
+// while the tensor pipe computes block 1, and the next layer's first K-steps issue while block 1 is still in its epilogue.
+//
+// Why (measured, tools/tc_issue.cu + NEFES_CHAIN_DBG stamps): a 128-wide layer of one tile is 8 MMAs =
+// 520 cycles of tensor pipe, but the serial chain  issue -> retire (+330) -> tcgen05.ld / bias / pack / tcgen05.st (~1000)
+// -> hand-over (+170)  is ~2000 cycles, and two tiles per SM (all that fits TMEM) cannot hide it: they drift into
+// lock-step and the pipe idles 70-80 % of the time.  Splitting the layer shortens the chain itself.
+//
+//   TMEM of tile g (256 columns from g*256):  ACC [0,128)  |  HA [128,192)  |  HB [192,256)
+//     ACC  fp32 accumulators, one column range per N-block (the 144-wide colour head spills into HA[0,16), dead by then)
+//     HA / HB  the bf16 activation image of a layer (64 columns = 128 channels as pairs): a layer reads one and writes the
+//              other, so its block-0 epilogue may store while its block-1 MMAs still read
+//   the xyz / direction encodings stay in SHARED memory (bulk-copied by the producer) and enter as SS-mode K-steps
+//   (4 of the 12 K-steps of the skip layer, 2 of 10 of the direction layer).
+//
+//   warp 0       producer: weight ring (bulk copies), the encodings of the next tile pair
+//   warp 1 / 18  MMA issuer of tile 0 / 1: CONVERGED warp, uniform operands, one elected lane issues (tc05.cuh uni())
+//   warps 2-9 / 10-17  epilogue of tile 0 / 1: warp = TMEM lane quarter x 32-column half of a 64-column block
+//
+// Synchronisation is by "latest completion" of per-tile mbarriers: acc_ready[g][b] (issuer -> epilogue, block b of the
+// current step retired) and k_ready[g][b] (epilogue -> issuer: block b's operand columns written AND its accumulator
+// columns drained).  Both sides count completions per barrier from the same step table, and a wait always names the LATEST
+// completion so far (parity (n-1)&1), which can never be more than one phase behind.
+//
+// The saved copy of a layer leaves through a per-tile 32 KB staging image in shared memory and ONE bulk store (TMA
+// engine), issued behind the hand-over: per-thread st.global of the same bytes stalls the epilogue warps at issue once
+// HBM is the limit, and an mbarrier.arrive (release) behind global stores waits for them to drain.
+// Included by mlp_tc.cu.   script/models/nerfh_nff.py:525-576.
+#pragma once
+
+namespace nefes {
+
+enum { BK_HID_RELU = 0,   // bias + ReLU -> bf16 pairs -> out_col (+ staging image)
+       BK_HID = 1,        // bias        -> bf16 pairs -> out_col (+ staging image)       (xyz_encoding_final)
+       BK_RAW = 2,        // bias -> fp32 raw channels [raw_c0, raw_c0 + raw_n)            (rgb + feature head)
+       BK_SIGMA = 3,      // column 0: bias, softplus -> raw[raw_c0]
+       BK_HEADS = 4 };    // columns 0..4: sigmoid x3, softplus x2 -> raw[raw_c0 .. +5)
+enum { GS_TMEM = 0, GS_X = 1, GS_D = 2 };
+enum { W_K0 = 1, W_K1 = 2, W_K2 = 4, W_X = 8, W_D = 16 };
+
+struct Ts2Block {
+  uint16_t n0, nw;          // rows [n0, n0 + nw) of the weight image; MMA N = nw (multiple of 16)
+  uint16_t acc_col;         // accumulator column of the block
+  uint16_t out_col;         // HID: TMEM column receiving the bf16 pairs of channels [n0, n0 + nw)
+  uint16_t raw_c0, raw_n;   // RAW / SIGMA / HEADS: first raw channel, number of raw channels from this block
+  uint8_t kind, wait;       // wait: W_K* completions required before the block's first MMA (beyond the K-group waits)
+  uint8_t save;             // HID: 1 = write the staging image, 2 = ... and it is the last block of the step: bulk store
+  uint8_t pad;
+};
+struct Ts2Group {           // a run of 16-wide K-steps with one operand source
+  uint8_t src, wait;        // GS_*, W_* completion required before its first MMA
+  uint16_t col;             // GS_TMEM: first TMEM column (8 per K-step); GS_X / GS_D: byte offset inside the encoding image
+  uint16_t ksteps, k0;      // number of K-steps, first K-step index inside the weight image
+};
+struct Ts2Step {
+  Ts2Block blk[3];
+  Ts2Group grp[3];
+  uint8_t n_blk, n_grp;
+  uint16_t bias_off;        // offset of the step's biases in the shared bias table (floats), indexed by weight row
+  uint32_t w_bytes, w_rows; // weight image [K/8][w_rows][8] bf16
+  const uint8_t* w_img;
+  const float* bias;        // [w_rows]
+  uint8_t* gdst;            // saved image (or null)
+  uint32_t g_tile_stride, save_bytes;
+};
+// The MMA issuer's program, compiled on the host: one 8-byte entry per tcgen05.mma, so that between an operand becoming
+// ready and the MMA the device does a shared-memory load, three shifts and the descriptor OR -- no table walk.
+//   w0: [0,16)  A operand: TMEM column (from the tile's base) or byte offset >> 4 inside the encoding image
+//       [16,32) B operand: byte offset >> 4 inside the ring slot
+//   w1: [0,9) accumulator column  [9,11) GS_* source  [11] accumulate  [12,17) W_* completions to wait for first
+//       [17] commit acc_ready[block] afterwards  [18,20) block  [20] ... and the stagger barrier
+constexpr int kTs2MaxMma = 26;
+struct Ts2Prog {
+  uint32_t idesc[3];          // per block
+  uint32_t lbo_field;         // (lbo >> 4) << 16: the LBO field of the B descriptor's low word
+  uint32_t n_mma;
+  uint32_t k1_implies_k0;     // the previous step had >= 2 blocks: its K1 completion implies its K0 completion
+  uint32_t pad[2];
+  uint32_t mma[kTs2MaxMma][2];
+};
+constexpr int kTs2MaxSteps = 14;
+struct Ts2Args {
+  Ts2Step step[kTs2MaxSteps];
+  const Ts2Prog* prog;        // [n_steps] in global memory (workspace arena), copied to shared memory at kernel start
+  int n_steps;
+  int64_t M; int n_tiles;
+  float* raw; int C;
+  const uint8_t* x_img; const uint8_t* d_img;     // encodings (bf16 images) written by encode_images_kernel
+  int x_issue, d_issue;       // producer step at which the NEXT pair's encodings are requested (>= last reader + ring depth)
+  int n_slots; uint32_t off_ring;   // depth and position of the weight ring (see ts2_off_ring)
+  long long* dbg;
+  int xflags;                 // timing experiments (NEFES_CHAIN_X): 1 no saves, 4 no raw stores
+};
+
+// Shared memory: [ bias table | xyz encodings x2 | direction encodings x2 | staging images x2 (only when the launch saves) |
+// weight ring ].  A weight image takes ~2400 cycles from L2 under load (measured), more than a step, and a slot is only
+// released when BOTH tiles have retired the step -- so the ring is as deep as the space allows: 3 slots without the staging
+// images (forward-only launches), 2 with them.
+constexpr int kTs2MaxSlots = 3;
+constexpr uint32_t kTs2WSlot = 49152;
+constexpr uint32_t kTs2X = 16384, kTs2D = 8192, kTs2Stage = 32768;
+constexpr uint32_t kTs2OffBias = 0;
+constexpr uint32_t kTs2OffProg = 6656;                               // >= kChainBiasBytes
+constexpr uint32_t kTs2ProgBytes = kTs2MaxSteps * sizeof(Ts2Prog);
+constexpr uint32_t kTs2OffX = 10240;                                 // >= kTs2OffProg + kTs2ProgBytes, 512-byte aligned
+static_assert(kTs2OffProg + kTs2ProgBytes <= kTs2OffX, "issue program overlaps the encodings");
+constexpr uint32_t kTs2OffD = kTs2OffX + 2 * kTs2X;
+constexpr uint32_t kTs2OffStage = kTs2OffD + 2 * kTs2D;
+static_assert(kTs2OffProg >= kChainBiasBytes, "bias table overlaps the issue program");
+inline uint32_t ts2_off_ring(bool saves) { return kTs2OffStage + (saves ? 2 * kTs2Stage : 0u); }
+inline int ts2_slots(bool saves) { return saves ? 2 : 3; }
+inline uint32_t ts2_smem(bool saves) { return ts2_off_ring(saves) + ts2_slots(saves) * kTs2WSlot; }
+constexpr uint32_t kTs2Acc = 0, kTs2HA = 128, kTs2HB = 192;
+
+__global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const __grid_constant__ Ts2Args A) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar_wfull[kTs2MaxSlots], bar_wempty[kTs2MaxSlots], bar_acc[2][3], bar_k[2][3], bar_x[2], bar_d[2], bar_stag;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sW = smem + A.off_ring;
+  float* sBias = reinterpret_cast<float*>(smem + kTs2OffBias);
+  const int n_slots = A.n_slots;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTs2MaxSlots; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 2); }
+    for (int g = 0; g < 2; ++g) {
+      for (int b = 0; b < 3; ++b) { mbar_init(&bar_acc[g][b], 1); mbar_init(&bar_k[g][b], kChainEpiWarps * 32); }
+      mbar_init(&bar_x[g], 1); mbar_init(&bar_d[g], 1);
+    }
+    mbar_init(&bar_stag, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_slot);
+  for (int s = 0; s < A.n_steps; ++s)
+    if (A.step[s].bias != nullptr)
+      for (int i = threadIdx.x; i < (int)A.step[s].w_rows; i += kChainThreads) sBias[A.step[s].bias_off + i] = A.step[s].bias[i];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(A.prog);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + kTs2OffProg);
+    for (int i = threadIdx.x; i < (int)(A.n_steps * sizeof(Ts2Prog) / 4); i += kChainThreads) dst[i] = src[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int n_pairs = (A.n_tiles + 1) >> 1;
+  const int n_steps = A.n_steps;
+
+  if (warp == 0) {
+    // ------------------------------- producer (converged warp, one elected lane issues) --------------------------------
+    const bool leader = elect_one();
+    const bool has_d = A.d_img != nullptr;
+    auto load_enc = [&](int pair, bool x, bool d) {
+      if (!leader) return;
+      for (int g = 0; g < 2; ++g) {
+        const int tile = pair * 2 + g;
+        if (tile >= A.n_tiles) break;
+        if (x) {
+          mbar_arrive_expect_tx(&bar_x[g], kTs2X);
+          bulk_g2s(smem + kTs2OffX + g * kTs2X, A.x_img + (int64_t)tile * kTs2X, kTs2X, &bar_x[g]);
+        }
+        if (d && has_d) {
+          mbar_arrive_expect_tx(&bar_d[g], kTs2D);
+          bulk_g2s(smem + kTs2OffD + g * kTs2D, A.d_img + (int64_t)tile * kTs2D, kTs2D, &bar_d[g]);
+        }
+      }
+    };
+    if ((int)blockIdx.x < n_pairs) load_enc(blockIdx.x, true, true);
+    uint32_t cnt = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int next = pair + (int)gridDim.x;
+      for (int s = 0; s < n_steps; ++s, ++cnt) {
+        const int slot = cnt % n_slots;
+        mbar_wait(&bar_wempty[slot], ((cnt / n_slots) & 1) ^ 1);
+        const uint32_t bytes = A.step[s].w_bytes;
+        const uint8_t* src = A.step[s].w_img;
+        if (leader && (A.xflags & 16) && cnt >= 2u * n_steps) {    // timing experiment: no weight traffic after two pairs
+          mbar_arrive(&bar_wfull[slot]);
+        } else if (leader) {
+          mbar_arrive_expect_tx(&bar_wfull[slot], bytes);
+          // every SM streams the SAME image at about the same time: pieces of 4 KB, each SM starting at a different one,
+          // so that the requests of the 148 SMs do not queue up on the same L2 lines (NEFES_CHAIN_X & 64: two 16 KB pieces)
+          if (A.xflags & 64) {
+            for (uint32_t off = 0; off < bytes; off += 16384u)
+              bulk_g2s(sW + slot * kTs2WSlot + off, src + off, min(16384u, bytes - off), &bar_wfull[slot]);
+          } else {
+            const uint32_t np = (bytes + 4095u) >> 12; // the last piece may be short
+            uint32_t i = (blockIdx.x * 5u) % np;
+            for (uint32_t n = 0; n < np; ++n) {
+              const uint32_t off = i << 12;
+              bulk_g2s(sW + slot * kTs2WSlot + off, src + off, min(4096u, bytes - off), &bar_wfull[slot]);
+              i = (i + 1 == np) ? 0u : i + 1;
+            }
+          }
+        }
+        // The wait above proves that the MMAs of step s - n_slots of BOTH tiles retired (and, the pipe being in order, all
+        // earlier ones): an encoding image whose last reader is that step may be overwritten.  A request that falls behind
+        // the last step of the pair is made at the start of the next pair, for that pair itself.
+        if (s == A.x_issue && next < n_pairs) load_enc(next, true, false);
+        if (s == A.d_issue && next < n_pairs) load_enc(next, false, true);
+        if (pair != (int)blockIdx.x) {
+          if (s + n_steps == A.x_issue) load_enc(pair, true, false);
+          if (s + n_steps == A.d_issue) load_enc(pair, false, true);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1 || warp == 2 + 2 * kChainEpiWarps) {
+    // ------------------------------- MMA issuer of tile g -----------------------------------------------------------------
+    // Measured on the first versions of this kernel (NEFES_CHAIN_DBG stamps): walking the step table on the device cost the
+    // issuer ~1300 cycles of preparation + ~650 of barrier waits + ~1500 of issue per step for 16 MMAs that take 530 on the
+    // pipe -- the issuer WAS the critical path.  Now the host compiles the step into a list of MMAs (Ts2Prog) that sits in
+    // shared memory; completed barriers are not waited for twice (K1 complete implies K0 complete: same threads, in order).
+    const int g = uni(warp == 1 ? 0 : 1);
+    const uint32_t tm = uni(tmem) + g * 256;
+    const bool leader = elect_one();
+    const bool dbg = A.dbg != nullptr && blockIdx.x == 0;
+    const uint32_t xs16 = smem_u32(smem + kTs2OffX + g * kTs2X) >> 4, ds16 = smem_u32(smem + kTs2OffD + g * kTs2D) >> 4;
+    const Ts2Prog* progs = reinterpret_cast<const Ts2Prog*>(smem + kTs2OffProg);
+    uint32_t cnt = 0, nk0 = 0u, nk1 = 0u, nk2 = 0u, n_tile = 0;
+    auto wait_latest = [&](uint64_t* bar, uint32_t n) { if (n > 0) mbar_wait(bar, (n - 1) & 1); };
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const bool valid = pair * 2 + g < A.n_tiles;
+      if (valid) ++n_tile;
+      for (int s = 0; s < n_steps; ++s, ++cnt) {
+        const Ts2Prog& P = progs[s];
+        const int slot = cnt % n_slots;
+        const uint32_t wb16 = smem_u32(sW + slot * kTs2WSlot) >> 4;
+        const uint32_t lbo_field = P.lbo_field, n_mma = P.n_mma;
+        const uint32_t id0 = P.idesc[0], id1 = P.idesc[1], id2 = P.idesc[2];
+        if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 4 + g] = clock64();        // step header read
+        if (valid) {
+          if (g == 1 && cnt == 0) mbar_wait(&bar_stag, 0);      // first pair: start half a step behind tile 0
+          // already complete?  then neither K0 nor K1 of the previous step needs a wait (a wait costs 100-200 cycles even
+          // when it passes at once)
+          uint32_t sat = 0u;
+          if (P.k1_implies_k0 && nk1 > 0 && mbar_try_wait(&bar_k[g][1], (nk1 - 1) & 1)) sat = W_K0 | W_K1;
+          const uint32_t nk0_in = nk0, nk1_in = nk1;   // completions of the PREVIOUS steps (K0/K1 waits of the K-groups refer to them)
+          bool w_ok = false;
+          for (uint32_t i = 0; i < n_mma; ++i) {
+            const uint32_t w0 = P.mma[i][0], w1 = P.mma[i][1];
+            const uint32_t wm = (w1 >> 12) & 31u;
+            if (wm) {
+              // K0 / K1 name the latest completion BEFORE this step, except in a block that waits for an earlier block of
+              // its own step (the sigma block of the final layer): there the counter has moved on and `sat` does not apply
+              if (wm & W_K0) { if (nk0 != nk0_in) wait_latest(&bar_k[g][0], nk0); else if (!(sat & W_K0)) wait_latest(&bar_k[g][0], nk0); }
+              if (wm & W_K1) { if (nk1 != nk1_in) wait_latest(&bar_k[g][1], nk1); else if (!(sat & W_K1)) wait_latest(&bar_k[g][1], nk1); }
+              if (wm & W_K2) wait_latest(&bar_k[g][2], nk2);
+              if (wm & W_X) wait_latest(&bar_x[g], n_tile);
+              if (wm & W_D) wait_latest(&bar_d[g], n_tile);
+              if (dbg && leader && cnt < 32 && i == 0) A.dbg[cnt * 48 + 46 + g] = clock64();   // first operands ready
+            }
+            if (!w_ok) {
+              mbar_wait(&bar_wfull[slot], (cnt / n_slots) & 1);
+              w_ok = true;
+              if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 40 + g] = clock64();
+            }
+            if (wm || i == 0) tc_fence_after();
+            if (dbg && leader && cnt < 32 && i == 0) A.dbg[cnt * 48 + g * 2] = clock64();
+            const uint32_t blk = (w1 >> 18) & 3u;
+            if (leader) {
+              const uint32_t src = (w1 >> 9) & 3u, accum = (w1 >> 11) & 1u;
+              const uint32_t d = tm + (w1 & 511u);
+              const uint32_t idesc = blk == 0 ? id0 : (blk == 1 ? id1 : id2);
+              const uint64_t db = ((uint64_t)0x4008u << 32) | (((wb16 + (w0 >> 16)) & 0x3FFFu) | lbo_field);
+              if (src == GS_TMEM) {
+                mma_ts(d, tm + (w0 & 0xFFFFu), db, idesc, accum);
+              } else {
+                const uint32_t a16 = (src == GS_X ? xs16 : ds16) + (w0 & 0xFFFFu);
+                const uint64_t da = ((uint64_t)0x4008u << 32) | ((a16 & 0x3FFFu) | ((kChunkBytes >> 4) << 16));
+                mma_ss(d, da, db, idesc, accum);
+              }
+              if (w1 & (1u << 17)) mma_commit(&bar_acc[g][blk]);
+              if ((w1 & (1u << 20)) && g == 0 && cnt == 0) mma_commit(&bar_stag);
+            }
+            if (w1 & (1u << 17)) { if (blk == 0) ++nk0; else if (blk == 1) ++nk1; else ++nk2; }
+          }
+          if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + g * 2 + 1] = clock64();
+        } else {
+          mbar_wait(&bar_wfull[slot], (cnt / n_slots) & 1);
+        }
+        if (leader) mma_commit(&bar_wempty[slot]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps -------------------------------------------------------------------------
+    const int ew = warp - 2;
+    const int g = ew >> 3;
+    const int jj = (ew >> 2) & 1;                     // which 32 columns of a 64-column block
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int gt = (ew & 7) * 32 + lane;              // 0..255 inside the tile's group
+    const uint32_t tbase = tmem + g * 256 + ((uint32_t)(q * 32) << 16);
+    uint8_t* stage = smem + kTs2OffStage + g * kTs2Stage;
+    uint32_t na[3] = {0u, 0u, 0u}, ecnt = 0;
+    bool store_pending = false;
+    const bool dbg = A.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int tile = pair * 2 + g;
+      if (tile >= A.n_tiles) break;
+      const bool ok = (int64_t)tile * kTile + row < A.M;
+      float* rawt = A.raw + (int64_t)tile * A.C * kTile + row;
+      for (int s = 0; s < n_steps; ++s, ++ecnt) {
+        const int n_blk = A.step[s].n_blk;
+        const float* bias = sBias + A.step[s].bias_off;
+        uint8_t* gdst = (A.xflags & 1) ? nullptr : A.step[s].gdst;
+        const uint32_t g_stride = A.step[s].g_tile_stride, save_bytes = A.step[s].save_bytes;
+        for (int b = 0; b < n_blk; ++b) {
+          // the block's fields as locals: later asm statements clobber "memory" and would force re-loads
+          const int kind = A.step[s].blk[b].kind, n0 = A.step[s].blk[b].n0, nw = A.step[s].blk[b].nw;
+          const uint32_t acc = tbase + A.step[s].blk[b].acc_col, out_col = A.step[s].blk[b].out_col;
+          const int raw_c0 = A.step[s].blk[b].raw_c0, raw_n = A.step[s].blk[b].raw_n, save = A.step[s].blk[b].save;
+          ++na[b];
+          mbar_wait(&bar_acc[g][b], (na[b] - 1) & 1);
+          tc_fence_after();
+          if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 8 + ew] = clock64();
+          if (dbg && ecnt < 32 && b == 1 && (ew & 7) == 0) A.dbg[ecnt * 48 + 42 + g] = clock64();
+          if (kind == BK_HID_RELU || kind == BK_HID) {
+            // 64-column block (or a 32-column one: nw == 32 is not used; nw == 64 always here): this warp's 32 columns
+            const int c = jj * 32;
+            float4 bv[8];
+            uint32_t v[32], w[16];
+            lds_bias32(bias + n0 + c, bv);
+            tmem_ld32(acc + c, v);
+            tmem_ld_wait();
+            if (kind == BK_HID_RELU) pack32<true>(v, bv, w); else pack32<false>(v, bv, w);
+            tmem_st16(tbase + out_col + (c >> 1), w);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bar_k[g][b]);
+            if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
+            if (dbg && ecnt < 32 && b == 1 && (ew & 7) == 0) A.dbg[ecnt * 48 + 44 + g] = clock64();
+            if (gdst != nullptr && save) {
+              if (store_pending) {                     // the previous bulk store must have read the staging image
+                if (gt == 0) bulk_wait_read<0>();
+                group_barrier(g);
+                store_pending = false;
+              }
+              uint8_t* srow = stage + ((n0 + c) >> 3) * kChunkBytes + row * 16;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(srow + j * kChunkBytes) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+              if (save == 2) {
+                fence_async_smem();
+                group_barrier(g);
+                if (gt == 0) {
+                  bulk_s2g(gdst + (int64_t)tile * g_stride, stage, save_bytes);
+                  bulk_commit();
+                }
+                store_pending = true;
+              }
+            }
+          } else if (kind == BK_RAW) {
+            // raw channels [raw_c0, raw_c0 + raw_n) from accumulator columns [0, raw_n): warp jj takes columns [32 jj, 32 jj + 32),
+            // the jj == 0 warps also the tail beyond 64 (the three channels 128..130 of the colour head)
+            const int c = jj * 32;
+            uint32_t v[32], t4[4] = {0u, 0u, 0u, 0u};
+            tmem_ld32(acc + c, v);
+            if (jj == 0 && raw_n > 64)
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(t4[0]), "=r"(t4[1]), "=r"(t4[2]), "=r"(t4[3]) : "r"(acc + 64) : "memory");
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bar_k[g][b]);
+            if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
+            if (ok && !(A.xflags & 4)) {
+              const float* bp = bias + n0 + c;
+              float* rp = rawt + (raw_c0 + c) * kTile;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bp + 4 * j);
+                stg32f(rp + (4 * j + 0) * kTile, __uint_as_float(v[4 * j + 0]) + b4.x);
+                stg32f(rp + (4 * j + 1) * kTile, __uint_as_float(v[4 * j + 1]) + b4.y);
+                stg32f(rp + (4 * j + 2) * kTile, __uint_as_float(v[4 * j + 2]) + b4.z);
+                stg32f(rp + (4 * j + 3) * kTile, __uint_as_float(v[4 * j + 3]) + b4.w);
+              }
+              if (jj == 0 && raw_n > 64) {
+                for (int e = 0; e < raw_n - 64 && e < 4; ++e)
+                  stg32f(rawt + (raw_c0 + 64 + e) * kTile, __uint_as_float(t4[e]) + bias[n0 + 64 + e]);
+              }
+            }
+          } else {                                     // BK_SIGMA / BK_HEADS: a few activated columns
+            uint32_t v[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (jj == 0) {
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                           : "r"(acc) : "memory");
+              tmem_ld_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_k[g][b]);
+            if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
+            if (jj == 0 && ok) {
+              if (kind == BK_SIGMA) {
+                stg32f(rawt + raw_c0 * kTile, softplus_f(__uint_as_float(v[0]) + bias[n0]));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 5; ++e) {
+                  const float x = __uint_as_float(v[e]) + bias[n0 + e];
+                  stg32f(rawt + (raw_c0 + e) * kTile, e < 3 ? sigmoid_f(x) : softplus_f(x));
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (gt == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace nefes

@@ -661,6 +661,7 @@ __global__ void ray_reduce_kernel(const float* __restrict__ src, int ld, int nco
 }  // namespace nefes
 #include "mlp_chain.cuh"
 #include "mlp_chain_ts.cuh"
+#include "mlp_chain_ts2.cuh"
 #include "mlp_trunk_bwd.cuh"
 #include "mlp_fused_bwd.cuh"
 extern "C" int nefes_encode_pe_bwd(const float*, const float*, int, int64_t, int, float*, void*);
@@ -997,6 +998,30 @@ int launch_chain_fwd(const Ws& w, const Arena& A, int mode, int64_t M, float* ra
   return NEFES_OK;
 }
 
+// clock stamps of CTA 0 of the TMEM-operand chains (NEFES_CHAIN_DBG=1): stride 48 per sequence number
+void chain_ts_dbg_dump(long long* dbg, int n_steps, cudaStream_t st) {
+  if (dbg == nullptr) return;
+  static int dumps = 0;
+  if (dumps++ >= 2) return;
+  cudaStreamSynchronize(st);
+  static long long h[2048];
+  cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+  const long long t0 = h[0];
+  fprintf(stderr, "[chain_ts dbg] n_steps=%d  (cycles since tile 0's first issue)\n", n_steps);
+  for (int i = 0; i < 32 && i < 2 * n_steps; ++i) {
+    const long long* r = h + i * 48;
+    long long rd[2] = {0, 0}, lo[2] = {1ll << 62, 1ll << 62}, hi[2] = {0, 0};
+    for (int w2 = 0; w2 < 16; ++w2) {
+      rd[w2 >> 3] = r[8 + w2] > rd[w2 >> 3] ? r[8 + w2] : rd[w2 >> 3];
+      lo[w2 >> 3] = r[24 + w2] < lo[w2 >> 3] ? r[24 + w2] : lo[w2 >> 3];
+      hi[w2 >> 3] = r[24 + w2] > hi[w2 >> 3] ? r[24 + w2] : hi[w2 >> 3];
+    }
+    fprintf(stderr, "  seq %2d step %2d | prep %7lld %7lld | t0: K %7lld W %7lld A %7lld issued %7lld  epi0 ready %7lld done %7lld..%7lld epi1 %7lld..%7lld | t1: K %7lld W %7lld A %7lld issued %7lld  epi0 ready %7lld done %7lld..%7lld epi1 %7lld..%7lld\n",
+            i, i % n_steps, r[4] - t0, r[5] - t0, r[46] - t0, r[40] - t0, r[0] - t0, r[1] - t0, rd[0] - t0, lo[0] - t0, hi[0] - t0, r[42] - t0, r[44] - t0,
+            r[47] - t0, r[41] - t0, r[2] - t0, r[3] - t0, rd[1] - t0, lo[1] - t0, hi[1] - t0, r[43] - t0, r[45] - t0);
+  }
+}
+
 // The same forward chain with the activations in tensor memory (mlp_chain_ts.cuh): step operands are TMEM columns.
 int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float* raw_t, cudaStream_t st) {
   const int T = (int)ceil_div(M, kTile);
@@ -1054,28 +1079,195 @@ int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float*
   chain_fwd_ts_kernel<<<grid, kChainThreads, kTsSmem, st>>>(c);
   prof_end(st);
   NEFES_CHECK_LAUNCH("chain_fwd_ts");
-  if (c.dbg) {
-    static int dumps = 0;
-    if (dumps++ < 2) {
-      cudaStreamSynchronize(st);
-      static long long h[2048];
-      cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-      const long long t0 = h[0];
-      fprintf(stderr, "[chain_ts dbg] n_steps=%d  (cycles since tile 0's first issue)\n", c.n_steps);
-      for (int i = 0; i < 32 && i < 2 * c.n_steps; ++i) {
-        const long long* r = h + i * 48;
-        long long rd[2] = {0, 0}, lo[2] = {1ll << 62, 1ll << 62}, hi[2] = {0, 0};
-        for (int w2 = 0; w2 < 16; ++w2) {
-          rd[w2 >> 3] = r[8 + w2] > rd[w2 >> 3] ? r[8 + w2] : rd[w2 >> 3];
-          lo[w2 >> 3] = r[24 + w2] < lo[w2 >> 3] ? r[24 + w2] : lo[w2 >> 3];
-          hi[w2 >> 3] = r[24 + w2] > hi[w2 >> 3] ? r[24 + w2] : hi[w2 >> 3];
-        }
-        fprintf(stderr, "  seq %2d step %2d | t0: W %7lld A %7lld issued %7lld  epi ready %7lld done %7lld..%7lld | t1: W %7lld A %7lld issued %7lld  epi ready %7lld done %7lld..%7lld\n",
-                i, i % c.n_steps, r[40] - t0, r[0] - t0, r[1] - t0, rd[0] - t0, lo[0] - t0, hi[0] - t0,
-                r[41] - t0, r[2] - t0, r[3] - t0, rd[1] - t0, lo[1] - t0, hi[1] - t0);
+  chain_ts_dbg_dump(c.dbg, c.n_steps, st);
+  return NEFES_OK;
+}
+
+// Round-2 forward chain (mlp_chain_ts2.cuh): N-split layers, double-buffered activations in tensor memory.
+int launch_chain_fwd_ts2(const Ws& w, const Arena& A, int mode, int64_t M, float* raw_t, cudaStream_t st) {
+  const int T = (int)ceil_div(M, kTile);
+  Ts2Args c = {};
+  int n = 0, bias_floats = 0;
+  const bool keep_all = !forward_only();
+  auto begin = [&](int pl, const Img* save) -> Ts2Step& {
+    Ts2Step& s = c.step[n++];
+    const PackedDims pd = packed_dims(pl);
+    s.w_img = A.W(pl); s.w_rows = (uint32_t)pd.N; s.w_bytes = (uint32_t)pd.K * pd.N * 2u;
+    s.bias = A.bias(pl); s.bias_off = (uint16_t)bias_floats;
+    bias_floats += (pd.N + 3) & ~3;
+    const bool keep = save && keep_all;
+    s.gdst = keep ? save->p : nullptr; s.g_tile_stride = keep ? (uint32_t)save->tile_stride() : 0u;
+    s.save_bytes = keep ? (uint32_t)save->ch * 256u : 0u;
+    return s;
+  };
+  auto grp = [&](Ts2Step& s, int src, int wait, int col, int ksteps, int k0) {
+    Ts2Group& g = s.grp[s.n_grp++];
+    g.src = (uint8_t)src; g.wait = (uint8_t)wait; g.col = (uint16_t)col; g.ksteps = (uint16_t)ksteps; g.k0 = (uint16_t)k0;
+  };
+  auto blk = [&](Ts2Step& s, int kind, int n0, int nw, int acc_col, int wait, int out_col, int save, int raw_c0 = 0, int raw_n = 0) {
+    Ts2Block& b = s.blk[s.n_blk++];
+    b.kind = (uint8_t)kind; b.n0 = (uint16_t)n0; b.nw = (uint16_t)nw; b.acc_col = (uint16_t)acc_col; b.wait = (uint8_t)wait;
+    b.out_col = (uint16_t)out_col; b.save = (uint8_t)save; b.raw_c0 = (uint16_t)raw_c0; b.raw_n = (uint16_t)raw_n;
+  };
+  // a 128-wide hidden layer: two 64-column blocks, reading H buffer `in` (both halves), writing buffer `out`
+  auto hidden128 = [&](Ts2Step& s, int kind, uint32_t out, int wait0, int wait1) {
+    blk(s, kind, 0, 64, kTs2Acc, wait0, out, 1);
+    blk(s, kind, 64, 64, kTs2Acc + 64, wait1, out + 32, 2);
+  };
+  auto h_groups = [&](Ts2Step& s, uint32_t in, int k0) {
+    grp(s, GS_TMEM, W_K0, in, 4, k0);
+    grp(s, GS_TMEM, W_K1, in + 32, 4, k0 + 4);
+  };
+  uint32_t hin = kTs2HB, hout = kTs2HA;               // layer l reads `hin`, writes `hout`; swapped after every 128-wide layer
+  {                                                    // T0: xyz encoding (shared memory) -> HA.  A new tile: both accumulator halves
+    Ts2Step& s = begin(PL_T0, &w.H[0]);                // must have been drained by the previous tile's last users
+    grp(s, GS_X, W_X, 0, 4, 0);
+    hidden128(s, BK_HID_RELU, hout, W_K0, W_K1);
+  }
+  for (int l = 1; l < 8; ++l) {
+    uint32_t t = hin; hin = hout; hout = t;
+    Ts2Step& s = begin(PL_T0 + l, &w.H[l]);
+    if (l == 4) { grp(s, GS_X, W_X, 0, 4, 0); h_groups(s, hin, 4); }        // skip layer: [xyzPE | h4]
+    else h_groups(s, hin, 0);
+    hidden128(s, BK_HID_RELU, hout, 0, 0);
+  }
+  { uint32_t t = hin; hin = hout; hout = t; }          // hin = h8
+  int x_last = 4, d_last = -1;
+  if (mode == NEFES_MODE_SIGMA) {
+    Ts2Step& s = begin(PL_SIG, nullptr);
+    h_groups(s, hin, 0);
+    blk(s, BK_SIGMA, 0, 16, kTs2Acc, 0, 0, 0, 0, 1);
+  } else {
+    {                                                  // final (128, no activation) -> hout; sigma (row 128) as a third block once
+      Ts2Step& s = begin(PL_FS, &w.FIN);               // block 0's accumulator columns are drained (W_K0 then names THIS step's)
+      h_groups(s, hin, 0);
+      hidden128(s, BK_HID, hout, 0, 0);
+      blk(s, BK_SIGMA, 128, 16, kTs2Acc, W_K0, 0, 0, 131, 1);
+    }
+    { uint32_t t = hin; hin = hout; hout = t; }        // hin = final, hout = the buffer that held h8
+    if (mode == NEFES_MODE_FULL) {
+      {                                                // [final | dirPE] -> [dir hidden | t1]
+        Ts2Step& s = begin(PL_DT, &w.DT);
+        h_groups(s, hin, 0);
+        grp(s, GS_D, W_D, 0, 2, 8);
+        blk(s, BK_HID_RELU, 0, 64, kTs2Acc, W_K2, hout, 1);
+        blk(s, BK_HID_RELU, 64, 64, kTs2Acc + 64, 0, hout + 32, 2);
+        d_last = n - 1;
+      }
+      {                                                // t1 (hout[32,64)) -> t2, parked in hin[32,64) (final is dead)
+        Ts2Step& s = begin(PL_TE1, &w.T2);
+        grp(s, GS_TMEM, W_K1, hout + 32, 4, 0);
+        blk(s, BK_HID_RELU, 0, 64, kTs2Acc, W_K0, hin + 32, 2);
+      }
+      {                                                // dir hidden (hout[0,32)) -> 131 raw channels; columns 128..143 spill into HA[0,16)
+        Ts2Step& s = begin(PL_RGB, nullptr);
+        NEFES_REQUIRE(hin == kTs2HA, NEFES_EINVAL, "chain_fwd_ts2: the colour head's spill columns must be the dead buffer");
+        grp(s, GS_TMEM, W_K0, hout, 4, 0);
+        blk(s, BK_RAW, 0, 64, kTs2Acc, 0, 0, 0, 0, 64);
+        blk(s, BK_RAW, 64, 80, kTs2Acc + 64, W_K1, 0, 0, 64, 67);
+      }
+      {                                                // t2 -> t3 over the dir hidden
+        Ts2Step& s = begin(PL_TE2, &w.T3);
+        grp(s, GS_TMEM, W_K0, hin + 32, 4, 0);
+        blk(s, BK_HID_RELU, 0, 64, kTs2Acc, 0, hout, 2);
+      }
+      {
+        Ts2Step& s = begin(PL_TH, nullptr);
+        grp(s, GS_TMEM, W_K0, hout, 4, 0);
+        blk(s, BK_HEADS, 0, 16, kTs2Acc, 0, 0, 0, 132, 5);
+      }
+    } else {
+      {
+        Ts2Step& s = begin(PL_DIR, &w.DT);
+        h_groups(s, hin, 0);
+        grp(s, GS_D, W_D, 0, 2, 8);
+        blk(s, BK_HID_RELU, 0, 64, kTs2Acc, W_K2, hout, 2);
+        d_last = n - 1;
+      }
+      {
+        Ts2Step& s = begin(PL_RGB, nullptr);
+        NEFES_REQUIRE(hin == kTs2HA, NEFES_EINVAL, "chain_fwd_ts2: the colour head's spill columns must be the dead buffer");
+        grp(s, GS_TMEM, W_K0, hout, 4, 0);
+        blk(s, BK_RAW, 0, 64, kTs2Acc, 0, 0, 0, 0, 64);
+        blk(s, BK_RAW, 64, 80, kTs2Acc + 64, W_K1, 0, 0, 64, 67);
       }
     }
   }
+  NEFES_REQUIRE(n <= kTs2MaxSteps && bias_floats * 4 <= (int)kChainBiasBytes, NEFES_EINVAL, "chain_fwd_ts2: step table overflow");
+  for (int i = 0; i < n; ++i)
+    NEFES_REQUIRE(c.step[i].w_bytes <= kTs2WSlot, NEFES_EINVAL, "chain_fwd_ts2: weight image of step %d exceeds the ring slot", i);
+  // compile the issuer's program (Ts2Prog): one entry per MMA.  It depends on the geometry of the step table only, which is
+  // the same for every call of a (mode, saves) combination: built and uploaded once per combination.
+  static Ts2Prog* d_prog[3][2] = {};
+  const int pmode = mode == NEFES_MODE_FULL ? 0 : (mode == NEFES_MODE_STATIC ? 1 : 2);
+  if (d_prog[pmode][keep_all ? 1 : 0] == nullptr) {
+    static Ts2Prog h_prog[kTs2MaxSteps];
+    for (int i = 0; i < n; ++i) {
+      const Ts2Step& s = c.step[i];
+      Ts2Prog& P = h_prog[i];
+      P = Ts2Prog{};
+      const uint32_t lbo = s.w_rows * 16u;
+      NEFES_REQUIRE((lbo >> 4) < 0x4000u, NEFES_EINVAL, "chain_fwd_ts2: LBO overflow");
+      P.lbo_field = (lbo >> 4) << 16;
+      P.k1_implies_k0 = (i > 0 && c.step[i - 1].n_blk >= 2) ? 1u : 0u;
+      uint32_t m = 0;
+      for (int b = 0; b < s.n_blk; ++b) {
+        const Ts2Block& bk = s.blk[b];
+        P.idesc[b] = idesc_bf16(128, bk.nw, 0, 0);
+        bool first = true;
+        for (int j = 0; j < s.n_grp; ++j) {
+          const Ts2Group& gr = s.grp[j];
+          for (int k = 0; k < gr.ksteps; ++k, ++m) {
+            NEFES_REQUIRE(m < (uint32_t)kTs2MaxMma, NEFES_EINVAL, "chain_fwd_ts2: more than %d MMAs in step %d", kTs2MaxMma, i);
+            const uint32_t a = gr.src == GS_TMEM ? (uint32_t)(gr.col + k * 8) : (uint32_t)((gr.col + k * 2 * kChunkBytes) >> 4);
+            const uint32_t boff = ((gr.k0 + k) * 2u * lbo + bk.n0 * 16u) >> 4;
+            uint32_t wait = 0;
+            if (k == 0 && b == 0) wait |= gr.wait;               // operands: waited for once, by the first block that reads them
+            if (first) wait |= bk.wait;                          // accumulator columns drained / own-step dependency
+            NEFES_REQUIRE(a < 65536u && boff < 65536u, NEFES_EINVAL, "chain_fwd_ts2: operand offset overflow");
+            P.mma[m][0] = a | (boff << 16);
+            P.mma[m][1] = bk.acc_col | ((uint32_t)gr.src << 9) | ((first ? 0u : 1u) << 11) | (wait << 12) | ((uint32_t)b << 18);
+            first = false;
+          }
+        }
+        P.mma[m - 1][1] |= 1u << 17;                             // last MMA of the block: commit
+        if (i == 0 && b == 0) P.mma[m - 1][1] |= 1u << 20;
+      }
+      P.n_mma = m;
+    }
+    Ts2Prog* dp = nullptr;
+    NEFES_CUDA(cudaMalloc(&dp, sizeof(h_prog)));
+    NEFES_CUDA(cudaMemcpy(dp, h_prog, sizeof(h_prog), cudaMemcpyHostToDevice));
+    d_prog[pmode][keep_all ? 1 : 0] = dp;
+  }
+  c.prog = d_prog[pmode][keep_all ? 1 : 0];
+  c.n_steps = n; c.M = M; c.n_tiles = T;
+  c.raw = raw_t; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
+  c.x_img = w.X.p; c.d_img = (mode == NEFES_MODE_SIGMA) ? nullptr : w.DIRPE.p;
+  const bool saves = keep_all && !(chain_xflags() & 1);
+  c.n_slots = ts2_slots(saves); c.off_ring = ts2_off_ring(saves);
+  c.x_issue = x_last + c.n_slots; c.d_issue = d_last < 0 ? -1 : d_last + c.n_slots;
+  NEFES_REQUIRE(c.x_issue < 2 * n && c.d_issue < 2 * n, NEFES_EINVAL, "chain_fwd_ts2: encoding request falls two pairs ahead");
+  static bool attr_done = false;
+  if (!attr_done) {
+    NEFES_CUDA(cudaFuncSetAttribute(chain_fwd_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts2_smem(true) > (int)ts2_smem(false) ? (int)ts2_smem(true) : (int)ts2_smem(false)));
+    attr_done = true;
+  }
+  const int n_pairs = (T + 1) / 2;
+  const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
+  {
+    const double save_ch = !keep_all ? 0 : ((mode == NEFES_MODE_SIGMA) ? 8 * 128 : (mode == NEFES_MODE_STATIC ? 8 * 128 + 128 + 64 : 8 * 128 + 128 + 128 + 64 + 64));
+    const double in_ch = (mode == NEFES_MODE_SIGMA) ? 64 : 96;
+    const double macs = (mode == NEFES_MODE_SIGMA) ? 130944 : (mode == NEFES_MODE_STATIC ? 165632 : 184064);
+    prof_begin(mode == NEFES_MODE_FULL ? "chain_fwd_fine" : (mode == NEFES_MODE_STATIC ? "chain_fwd_coarse" : "chain_fwd_sigma"), st,
+               (double)M * (2.0 * (save_ch + in_ch) + 4.0 * c.C), (double)M * 2.0 * macs);
+  }
+  c.dbg = chain_dbg_buf();
+  c.xflags = chain_xflags();
+  chain_fwd_ts2_kernel<<<grid, kChainThreads, ts2_smem(saves), st>>>(c);
+  prof_end(st);
+  NEFES_CHECK_LAUNCH("chain_fwd_ts2");
+  chain_ts_dbg_dump(c.dbg, c.n_steps, st);
   return NEFES_OK;
 }
 
@@ -1512,8 +1704,10 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   // for the fine query at 6144 rays); with saves the shared-memory-operand chain is the faster one (0.66 against 0.79 ms).
   // NEFES_FWD_TS=1 / NEFES_FWD_SS=1 force one or the other.
   static const bool force_ts = getenv("NEFES_FWD_TS") != nullptr, force_ss = getenv("NEFES_FWD_SS") != nullptr;
+  static const bool force_ts2 = getenv("NEFES_FWD_TS2") != nullptr;
   const bool fwd_ts = force_ts || (!force_ss && forward_only());
-  if (fwd_ts) TRY(launch_chain_fwd_ts(w, A, mode, M, raw_t, st));
+  if (force_ts2) TRY(launch_chain_fwd_ts2(w, A, mode, M, raw_t, st));
+  else if (fwd_ts) TRY(launch_chain_fwd_ts(w, A, mode, M, raw_t, st));
   else TRY(launch_chain_fwd(w, A, mode, M, raw_t, st));
   if (!direct) {
     static bool t2r_attr = false;

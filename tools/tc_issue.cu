@@ -32,13 +32,8 @@ __device__ __forceinline__ void mma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 template <bool UNI>
-__global__ void __launch_bounds__(128) k(int mode, int N, int n_acc, int issuers, int fresh, int reps, long long* out) {
+__global__ void __launch_bounds__(640) k(int mode, int N, int n_acc, int issuers, int fresh, int reps, long long* out, int side, int nside, int lbo_rows, volatile int* stop) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar[2];
   __shared__ uint32_t slot;
@@ -64,7 +59,7 @@ __global__ void __launch_bounds__(128) k(int mode, int N, int n_acc, int issuers
         db[s] = smem_desc(b0 + s * 2 * N * 16, N * 16, 128);
       } else {
         da[s] = smem_desc(a0 + s * 4096, 2048, 128);
-        db[s] = smem_desc(b0 + s * 2 * N * 16, N * 16, 128);
+        db[s] = smem_desc(b0 + s * 2 * lbo_rows * 16, lbo_rows * 16, 128);
       }
     }
     const uint32_t idesc = mode == 3 ? idesc_tf32(128, N) : idesc_bf16(128, N, 0, 0);
@@ -91,14 +86,36 @@ __global__ void __launch_bounds__(128) k(int mode, int N, int n_acc, int issuers
     if (leader) {
       out[warp * 2] = t2 - t0;
       out[warp * 2 + 1] = t1 - t0;     // issue time only
+      atomicAdd((int*)stop, 1);
     }
+  }
+  if (warp >= 4 && warp < 4 + nside && side > 0) {
+    // epilogue-like side traffic on TMEM columns 256..447 of this warp's lane quarter until the issuers are done
+    const uint32_t taddr = tmem + 256 + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc = 0; int it = 0;
+    while (*stop < issuers) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (it & 3) * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc += v[i];
+      if (side == 2) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = v[i] + v[i + 16];
+        tmem_st16(taddr + 128 + (it & 3) * 16, w);
+        tmem_st_wait();
+      }
+      ++it;
+    }
+    if (lane == 0) out[8 + (warp - 4)] = it + (acc == 12345u);
   }
   tc_fence_before(); __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 int main() {
-  long long* d; cudaMalloc(&d, 64);
+  long long* d; cudaMalloc(&d, 256); int* stopf; cudaMalloc(&stopf, 4);
   cudaFuncSetAttribute(k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const char* names[4] = {"SS interleaved bf16", "SS swizzle128 bf16 ", "TS (A in TMEM) bf16", "SS interleaved tf32"};
@@ -111,9 +128,10 @@ int main() {
           for (int fresh : {0, 1}) {
             if (issuers * n_acc * N > 448) continue;
             if (fresh && n_acc > 1) continue;
-            cudaMemset(d, 0, 64);
-            if (uni) k<true><<<1, 128, 196608>>>(mode, N, n_acc, issuers, fresh, reps, d);
-            else k<false><<<1, 128, 196608>>>(mode, N, n_acc, issuers, fresh, reps, d);
+            cudaMemset(d, 0, 256);
+            cudaMemset(stopf, 0, 4);
+            if (uni) k<true><<<1, 640, 196608>>>(mode, N, n_acc, issuers, fresh, reps, d, 0, 0, N, stopf);
+            else k<false><<<1, 640, 196608>>>(mode, N, n_acc, issuers, fresh, reps, d, 0, 0, N, stopf);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s (mode %d N %d)\n", cudaGetErrorString(e), mode, N); return 1; }
             long long h[8]; cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
@@ -123,6 +141,24 @@ int main() {
             printf("%s %s N=%3d issuers=%d acc/issuer=%d %s: %6.1f cycles per MMA slot (all issuers: %6.1f per MMA), issue-only %6.1f, floor %5.1f\n",
                    uni ? "uniform-issue" : "lane0-branch ", names[mode], N, issuers, n_acc, fresh ? "overwrite " : "accumulate", (double)tot / (reps * 8),
                    (double)tot / (reps * 8 * issuers), (double)h[1] / (reps * 8), floor_c);
+          }
+  // contention: uniform-issue TS MMAs against epilogue-like TMEM traffic (what the N-split chain runs concurrently)
+  for (int N : {64, 128})
+    for (int issuers : {1, 2})
+      for (int lbo_rows : {N, 128})
+        for (int side : {0, 1, 2})
+          for (int nside : {8, 16}) {
+            if (lbo_rows < N || (side == 0 && nside == 16)) continue;
+            cudaMemset(d, 0, 256); cudaMemset(stopf, 0, 4);
+            k<true><<<1, 640, 196608>>>(2, N, 2, issuers, 0, 256, d, side, nside, lbo_rows, stopf);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+            long long h[32]; cudaMemcpy(h, d, 256, cudaMemcpyDeviceToHost);
+            const long long tot = h[0] > h[2] ? h[0] : h[2];
+            long long its = 0; for (int w = 0; w < nside; ++w) its += h[8 + w];
+            printf("contention: TS N=%3d (B image %3d rows) issuers=%d + %2d warps of %s: %6.1f cycles per MMA (all issuers), side traffic %.1f B/cycle TMEM read\n",
+                   N, lbo_rows, issuers, side ? nside : 0, side == 0 ? "nothing      " : side == 1 ? "tcgen05.ld   " : "tcgen05.ld+st", (double)tot / (256 * 8 * issuers),
+                   (double)its * 4096 / tot);
           }
   return 0;
 }
