@@ -64,25 +64,29 @@ struct Ts2Step {
   uint8_t* gdst;            // saved image (or null)
   uint32_t g_tile_stride, save_bytes;
 };
-// The MMA issuer's program, compiled on the host: one 8-byte entry per tcgen05.mma, so that between an operand becoming
-// ready and the MMA the device does a shared-memory load, three shifts and the descriptor OR -- no table walk.
-//   w0: [0,16)  A operand: TMEM column (from the tile's base) or byte offset >> 4 inside the encoding image
-//       [16,32) B operand: byte offset >> 4 inside the ring slot
-//   w1: [0,9) accumulator column  [9,11) GS_* source  [11] accumulate  [12,17) W_* completions to wait for first
-//       [17] commit acc_ready[block] afterwards  [18,20) block  [20] ... and the stagger barrier
-constexpr int kTs2MaxMma = 26;
-struct Ts2Prog {
-  uint32_t idesc[3];          // per block
-  uint32_t lbo_field;         // (lbo >> 4) << 16: the LBO field of the B descriptor's low word
-  uint32_t n_mma;
-  uint32_t k1_implies_k0;     // the previous step had >= 2 blocks: its K1 completion implies its K0 completion
-  uint32_t pad[2];
-  uint32_t mma[kTs2MaxMma][2];
+// What the MMA issuer needs of a step, precomputed on the host and kept in SHARED memory (nine 16-byte loads per step):
+// walking the step table in parameter space cost the issuer ~1300 cycles per step (indexed constant loads, descriptor
+// arithmetic), on the critical path of every layer.
+struct Ts2Issue {
+  uint32_t idesc[3];        // per block: instruction descriptor (M = 128, N = nw)
+  uint32_t lbo_field;       // (lbo >> 4) << 16: the LBO field of the B descriptor's low word
+  uint32_t d_col[3];        // per block: accumulator column
+  uint32_t dbk;             // (2 * lbo) >> 4: B descriptor advance per K-step
+  uint32_t a[3];            // per group: TMEM column, or byte offset inside the encoding image
+  uint32_t n_blk;
+  uint32_t ks[3];           // per group: K-steps (0: group absent)
+  uint32_t gwait;           // W_* completions the K-groups need (waited for once, ahead of block 0)
+  uint32_t src[3];          // per group: GS_*
+  uint32_t k1_implies_k0;   // the previous step had >= 2 blocks: its K1 completion implies its K0 completion
+  uint32_t bwait[3];        // per block: W_* completions required before the block's first MMA
+  uint32_t pad0;
+  uint32_t b16[3][4];       // [block][group]: (group.k0 * 2 * lbo + block.n0 * 16) >> 4, B operand offset inside the ring slot
 };
+static_assert(sizeof(Ts2Issue) % 16 == 0, "Ts2Issue is read with 16-byte loads");
 constexpr int kTs2MaxSteps = 14;
 struct Ts2Args {
   Ts2Step step[kTs2MaxSteps];
-  const Ts2Prog* prog;        // [n_steps] in global memory (workspace arena), copied to shared memory at kernel start
+  const Ts2Issue* iss;        // [n_steps] in global memory, copied to shared memory at kernel start
   int n_steps;
   int64_t M; int n_tiles;
   float* raw; int C;
@@ -102,7 +106,7 @@ constexpr uint32_t kTs2WSlot = 49152;
 constexpr uint32_t kTs2X = 16384, kTs2D = 8192, kTs2Stage = 32768;
 constexpr uint32_t kTs2OffBias = 0;
 constexpr uint32_t kTs2OffProg = 6656;                               // >= kChainBiasBytes
-constexpr uint32_t kTs2ProgBytes = kTs2MaxSteps * sizeof(Ts2Prog);
+constexpr uint32_t kTs2ProgBytes = kTs2MaxSteps * sizeof(Ts2Issue);
 constexpr uint32_t kTs2OffX = 10240;                                 // >= kTs2OffProg + kTs2ProgBytes, 512-byte aligned
 static_assert(kTs2OffProg + kTs2ProgBytes <= kTs2OffX, "issue program overlaps the encodings");
 constexpr uint32_t kTs2OffD = kTs2OffX + 2 * kTs2X;
@@ -136,9 +140,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
     if (A.step[s].bias != nullptr)
       for (int i = threadIdx.x; i < (int)A.step[s].w_rows; i += kChainThreads) sBias[A.step[s].bias_off + i] = A.step[s].bias[i];
   {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(A.prog);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(A.iss);
     uint32_t* dst = reinterpret_cast<uint32_t*>(smem + kTs2OffProg);
-    for (int i = threadIdx.x; i < (int)(A.n_steps * sizeof(Ts2Prog) / 4); i += kChainThreads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(A.n_steps * sizeof(Ts2Issue) / 4); i += kChainThreads) dst[i] = src[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -208,77 +212,92 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
     }
   } else if (warp == 1 || warp == 2 + 2 * kChainEpiWarps) {
     // ------------------------------- MMA issuer of tile g -----------------------------------------------------------------
-    // Measured on the first versions of this kernel (NEFES_CHAIN_DBG stamps): walking the step table on the device cost the
-    // issuer ~1300 cycles of preparation + ~650 of barrier waits + ~1500 of issue per step for 16 MMAs that take 530 on the
-    // pipe -- the issuer WAS the critical path.  Now the host compiles the step into a list of MMAs (Ts2Prog) that sits in
-    // shared memory; completed barriers are not waited for twice (K1 complete implies K0 complete: same threads, in order).
+    // Measured (NEFES_CHAIN_DBG stamps): the issuer IS the critical path of this kernel -- every cycle it spends between a
+    // hand-over and the first MMA is added to the layer.  So: the step's operands are prepared from Ts2Issue BEFORE the
+    // waits, a completed K1 skips the K0 wait (a wait costs 100-200 cycles even when it passes at once), and the K-loops run
+    // inside the elected-lane region, where ptxas keeps counters and operands in uniform registers (an MMA list interpreted
+    // entry by entry from shared memory issued one MMA per 540 cycles).
     const int g = uni(warp == 1 ? 0 : 1);
     const uint32_t tm = uni(tmem) + g * 256;
     const bool leader = elect_one();
     const bool dbg = A.dbg != nullptr && blockIdx.x == 0;
-    const uint32_t xs16 = smem_u32(smem + kTs2OffX + g * kTs2X) >> 4, ds16 = smem_u32(smem + kTs2OffD + g * kTs2D) >> 4;
-    const Ts2Prog* progs = reinterpret_cast<const Ts2Prog*>(smem + kTs2OffProg);
+    const uint32_t xs = smem_u32(smem + kTs2OffX + g * kTs2X), ds = smem_u32(smem + kTs2OffD + g * kTs2D);
+    const Ts2Issue* iss = reinterpret_cast<const Ts2Issue*>(smem + kTs2OffProg);
     uint32_t cnt = 0, nk0 = 0u, nk1 = 0u, nk2 = 0u, n_tile = 0;
     auto wait_latest = [&](uint64_t* bar, uint32_t n) { if (n > 0) mbar_wait(bar, (n - 1) & 1); };
+    auto wait_mask = [&](uint32_t m) {
+      if (m & W_K0) wait_latest(&bar_k[g][0], nk0);
+      if (m & W_K1) wait_latest(&bar_k[g][1], nk1);
+      if (m & W_K2) wait_latest(&bar_k[g][2], nk2);
+      if (m & W_X) wait_latest(&bar_x[g], n_tile);
+      if (m & W_D) wait_latest(&bar_d[g], n_tile);
+    };
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const bool valid = pair * 2 + g < A.n_tiles;
       if (valid) ++n_tile;
       for (int s = 0; s < n_steps; ++s, ++cnt) {
-        const Ts2Prog& P = progs[s];
         const int slot = cnt % n_slots;
+        // ---- operands of every MMA of the step, before any wait ----
+        const uint4* I4 = reinterpret_cast<const uint4*>(iss + s);
+        const uint4 q0 = I4[0], q1 = I4[1], q2 = I4[2], q3 = I4[3], q4 = I4[4], q5 = I4[5], q6 = I4[6], q7 = I4[7], q8 = I4[8];
+        const uint32_t idesc[3] = {q0.x, q0.y, q0.z}, lbo_field = q0.w;
+        const uint32_t dcol[3] = {tm + q1.x, tm + q1.y, tm + q1.z}, dbk = q1.w;
+        const uint32_t a_in[3] = {q2.x, q2.y, q2.z}, n_blk = q2.w;
+        const uint32_t ks[3] = {q3.x, q3.y, q3.z}, gwait = q3.w;
+        const uint32_t src[3] = {q4.x, q4.y, q4.z}, k1k0 = q4.w;
+        const uint32_t bwait[3] = {q5.x, q5.y, q5.z};
+        const uint32_t b16[3][3] = {{q6.x, q6.y, q6.z}, {q7.x, q7.y, q7.z}, {q8.x, q8.y, q8.z}};
         const uint32_t wb16 = smem_u32(sW + slot * kTs2WSlot) >> 4;
-        const uint32_t lbo_field = P.lbo_field, n_mma = P.n_mma;
-        const uint32_t id0 = P.idesc[0], id1 = P.idesc[1], id2 = P.idesc[2];
-        if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 4 + g] = clock64();        // step header read
+        uint32_t a_op[3], blo[3][3];
+        uint64_t a_desc[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          a_op[j] = tm + a_in[j];
+          a_desc[j] = smem_desc((src[j] == GS_X ? xs : ds) + a_in[j], kChunkBytes, 128);
+#pragma unroll
+          for (int b = 0; b < 3; ++b) blo[b][j] = ((wb16 + b16[b][j]) & 0x3FFFu) | lbo_field;
+        }
+        if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 4 + g] = clock64();        // operands prepared
+        // operands first (they usually arrive first), the weights last
         if (valid) {
           if (g == 1 && cnt == 0) mbar_wait(&bar_stag, 0);      // first pair: start half a step behind tile 0
-          // already complete?  then neither K0 nor K1 of the previous step needs a wait (a wait costs 100-200 cycles even
-          // when it passes at once)
-          uint32_t sat = 0u;
-          if (P.k1_implies_k0 && nk1 > 0 && mbar_try_wait(&bar_k[g][1], (nk1 - 1) & 1)) sat = W_K0 | W_K1;
-          const uint32_t nk0_in = nk0, nk1_in = nk1;   // completions of the PREVIOUS steps (K0/K1 waits of the K-groups refer to them)
-          bool w_ok = false;
-          for (uint32_t i = 0; i < n_mma; ++i) {
-            const uint32_t w0 = P.mma[i][0], w1 = P.mma[i][1];
-            const uint32_t wm = (w1 >> 12) & 31u;
-            if (wm) {
-              // K0 / K1 name the latest completion BEFORE this step, except in a block that waits for an earlier block of
-              // its own step (the sigma block of the final layer): there the counter has moved on and `sat` does not apply
-              if (wm & W_K0) { if (nk0 != nk0_in) wait_latest(&bar_k[g][0], nk0); else if (!(sat & W_K0)) wait_latest(&bar_k[g][0], nk0); }
-              if (wm & W_K1) { if (nk1 != nk1_in) wait_latest(&bar_k[g][1], nk1); else if (!(sat & W_K1)) wait_latest(&bar_k[g][1], nk1); }
-              if (wm & W_K2) wait_latest(&bar_k[g][2], nk2);
-              if (wm & W_X) wait_latest(&bar_x[g], n_tile);
-              if (wm & W_D) wait_latest(&bar_d[g], n_tile);
-              if (dbg && leader && cnt < 32 && i == 0) A.dbg[cnt * 48 + 46 + g] = clock64();   // first operands ready
-            }
-            if (!w_ok) {
-              mbar_wait(&bar_wfull[slot], (cnt / n_slots) & 1);
-              w_ok = true;
-              if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 40 + g] = clock64();
-            }
-            if (wm || i == 0) tc_fence_after();
-            if (dbg && leader && cnt < 32 && i == 0) A.dbg[cnt * 48 + g * 2] = clock64();
-            const uint32_t blk = (w1 >> 18) & 3u;
-            if (leader) {
-              const uint32_t src = (w1 >> 9) & 3u, accum = (w1 >> 11) & 1u;
-              const uint32_t d = tm + (w1 & 511u);
-              const uint32_t idesc = blk == 0 ? id0 : (blk == 1 ? id1 : id2);
-              const uint64_t db = ((uint64_t)0x4008u << 32) | (((wb16 + (w0 >> 16)) & 0x3FFFu) | lbo_field);
-              if (src == GS_TMEM) {
-                mma_ts(d, tm + (w0 & 0xFFFFu), db, idesc, accum);
-              } else {
-                const uint32_t a16 = (src == GS_X ? xs16 : ds16) + (w0 & 0xFFFFu);
-                const uint64_t da = ((uint64_t)0x4008u << 32) | ((a16 & 0x3FFFu) | ((kChunkBytes >> 4) << 16));
-                mma_ss(d, da, db, idesc, accum);
+          uint32_t need = gwait | bwait[0];
+          if (k1k0 && (need & W_K0) && nk1 > 0 && mbar_try_wait(&bar_k[g][1], (nk1 - 1) & 1)) need &= ~(W_K0 | W_K1);
+          wait_mask(need);
+          if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 46 + g] = clock64();     // operands ready
+        }
+        mbar_wait(&bar_wfull[slot], (cnt / n_slots) & 1);
+        if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 40 + g] = clock64();
+        if (valid) {
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            if (b < (int)n_blk) {
+              if (b > 0) wait_mask(bwait[b]);
+              tc_fence_after();
+              if (dbg && leader && cnt < 32 && b == 0) A.dbg[cnt * 48 + g * 2] = clock64();
+              if (leader) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                  const uint64_t db0 = ((uint64_t)0x4008u << 32) | blo[b][j];     // SBO = 128 B, descriptor version 1
+                  const uint64_t dbk64 = (uint64_t)dbk;
+                  const int nks = (int)ks[j];
+                  const uint32_t d = dcol[b], id = idesc[b];
+                  if (src[j] == GS_TMEM) {
+                    const uint32_t a0 = a_op[j];
+                    for (int k = 0; k < nks; ++k) mma_ts(d, a0 + k * 8, db0 + (uint64_t)k * dbk64, id, (j > 0 || k > 0) ? 1u : 0u);
+                  } else {
+                    const uint64_t da0 = a_desc[j];
+                    for (int k = 0; k < nks; ++k)
+                      mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)k * dbk64, id, (j > 0 || k > 0) ? 1u : 0u);
+                  }
+                }
+                mma_commit(&bar_acc[g][b]);
+                if (g == 0 && cnt == 0 && b == 0) mma_commit(&bar_stag);
               }
-              if (w1 & (1u << 17)) mma_commit(&bar_acc[g][blk]);
-              if ((w1 & (1u << 20)) && g == 0 && cnt == 0) mma_commit(&bar_stag);
+              if (b == 0) ++nk0; else if (b == 1) ++nk1; else ++nk2;    // the epilogue completes bar_k[g][b] once for this block
             }
-            if (w1 & (1u << 17)) { if (blk == 0) ++nk0; else if (blk == 1) ++nk1; else ++nk2; }
           }
           if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + g * 2 + 1] = clock64();
-        } else {
-          mbar_wait(&bar_wfull[slot], (cnt / n_slots) & 1);
         }
         if (leader) mma_commit(&bar_wempty[slot]);
         __syncwarp();

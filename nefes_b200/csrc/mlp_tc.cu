@@ -1196,51 +1196,34 @@ int launch_chain_fwd_ts2(const Ws& w, const Arena& A, int mode, int64_t M, float
   NEFES_REQUIRE(n <= kTs2MaxSteps && bias_floats * 4 <= (int)kChainBiasBytes, NEFES_EINVAL, "chain_fwd_ts2: step table overflow");
   for (int i = 0; i < n; ++i)
     NEFES_REQUIRE(c.step[i].w_bytes <= kTs2WSlot, NEFES_EINVAL, "chain_fwd_ts2: weight image of step %d exceeds the ring slot", i);
-  // compile the issuer's program (Ts2Prog): one entry per MMA.  It depends on the geometry of the step table only, which is
-  // the same for every call of a (mode, saves) combination: built and uploaded once per combination.
-  static Ts2Prog* d_prog[3][2] = {};
+  // the issuer's view of the table (Ts2Issue).  It depends on the geometry of the step table only, which is the same for
+  // every call of a (mode, saves) combination: built and uploaded once per combination.
+  static Ts2Issue* d_iss[3][2] = {};
   const int pmode = mode == NEFES_MODE_FULL ? 0 : (mode == NEFES_MODE_STATIC ? 1 : 2);
-  if (d_prog[pmode][keep_all ? 1 : 0] == nullptr) {
-    static Ts2Prog h_prog[kTs2MaxSteps];
+  if (d_iss[pmode][keep_all ? 1 : 0] == nullptr) {
+    static Ts2Issue h_iss[kTs2MaxSteps];
     for (int i = 0; i < n; ++i) {
       const Ts2Step& s = c.step[i];
-      Ts2Prog& P = h_prog[i];
-      P = Ts2Prog{};
+      Ts2Issue& I = h_iss[i];
+      I = Ts2Issue{};
       const uint32_t lbo = s.w_rows * 16u;
       NEFES_REQUIRE((lbo >> 4) < 0x4000u, NEFES_EINVAL, "chain_fwd_ts2: LBO overflow");
-      P.lbo_field = (lbo >> 4) << 16;
-      P.k1_implies_k0 = (i > 0 && c.step[i - 1].n_blk >= 2) ? 1u : 0u;
-      uint32_t m = 0;
-      for (int b = 0; b < s.n_blk; ++b) {
-        const Ts2Block& bk = s.blk[b];
-        P.idesc[b] = idesc_bf16(128, bk.nw, 0, 0);
-        bool first = true;
-        for (int j = 0; j < s.n_grp; ++j) {
-          const Ts2Group& gr = s.grp[j];
-          for (int k = 0; k < gr.ksteps; ++k, ++m) {
-            NEFES_REQUIRE(m < (uint32_t)kTs2MaxMma, NEFES_EINVAL, "chain_fwd_ts2: more than %d MMAs in step %d", kTs2MaxMma, i);
-            const uint32_t a = gr.src == GS_TMEM ? (uint32_t)(gr.col + k * 8) : (uint32_t)((gr.col + k * 2 * kChunkBytes) >> 4);
-            const uint32_t boff = ((gr.k0 + k) * 2u * lbo + bk.n0 * 16u) >> 4;
-            uint32_t wait = 0;
-            if (k == 0 && b == 0) wait |= gr.wait;               // operands: waited for once, by the first block that reads them
-            if (first) wait |= bk.wait;                          // accumulator columns drained / own-step dependency
-            NEFES_REQUIRE(a < 65536u && boff < 65536u, NEFES_EINVAL, "chain_fwd_ts2: operand offset overflow");
-            P.mma[m][0] = a | (boff << 16);
-            P.mma[m][1] = bk.acc_col | ((uint32_t)gr.src << 9) | ((first ? 0u : 1u) << 11) | (wait << 12) | ((uint32_t)b << 18);
-            first = false;
-          }
-        }
-        P.mma[m - 1][1] |= 1u << 17;                             // last MMA of the block: commit
-        if (i == 0 && b == 0) P.mma[m - 1][1] |= 1u << 20;
+      I.n_blk = s.n_blk; I.lbo_field = (lbo >> 4) << 16; I.dbk = (2u * lbo) >> 4;
+      I.k1_implies_k0 = (i > 0 && c.step[i - 1].n_blk >= 2) ? 1u : 0u;
+      for (int j = 0; j < s.n_grp; ++j) {
+        I.a[j] = s.grp[j].col; I.ks[j] = s.grp[j].ksteps; I.src[j] = s.grp[j].src; I.gwait |= s.grp[j].wait;
       }
-      P.n_mma = m;
+      for (int b = 0; b < s.n_blk; ++b) {
+        I.idesc[b] = idesc_bf16(128, s.blk[b].nw, 0, 0); I.d_col[b] = s.blk[b].acc_col; I.bwait[b] = s.blk[b].wait;
+        for (int j = 0; j < s.n_grp; ++j) I.b16[b][j] = (s.grp[j].k0 * 2u * lbo + s.blk[b].n0 * 16u) >> 4;
+      }
     }
-    Ts2Prog* dp = nullptr;
-    NEFES_CUDA(cudaMalloc(&dp, sizeof(h_prog)));
-    NEFES_CUDA(cudaMemcpy(dp, h_prog, sizeof(h_prog), cudaMemcpyHostToDevice));
-    d_prog[pmode][keep_all ? 1 : 0] = dp;
+    Ts2Issue* dp = nullptr;
+    NEFES_CUDA(cudaMalloc(&dp, sizeof(h_iss)));
+    NEFES_CUDA(cudaMemcpy(dp, h_iss, sizeof(h_iss), cudaMemcpyHostToDevice));
+    d_iss[pmode][keep_all ? 1 : 0] = dp;
   }
-  c.prog = d_prog[pmode][keep_all ? 1 : 0];
+  c.iss = d_iss[pmode][keep_all ? 1 : 0];
   c.n_steps = n; c.M = M; c.n_tiles = T;
   c.raw = raw_t; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
   c.x_img = w.X.p; c.d_img = (mode == NEFES_MODE_SIGMA) ? nullptr : w.DIRPE.p;

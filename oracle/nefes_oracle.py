@@ -307,23 +307,28 @@ def composite(raw, z, noise=None, output_transient=False, beta_min=0.1, test_tim
 # --------------------------------------------------------------------------------------
 def march_rays(ray_batch, P_coarse, P_fine, n_coarse=64, n_fine=64, test_time=False,
                t_rand=None, noise=None, u=None, transient=True, transient_at_test=True,
-               beta_min=0.1, return_aux=False):
+               beta_min=0.1, return_aux=False, emulate_bf16=False):
     """script/models/rendering.py:68-180 with args.nerfh_nff=True, use_fine_only=False,
     NeRFW=`transient`.  Train mode needs t_rand [N,n_coarse] and u [N,n_fine];
-    test mode (perturb=0) uses neither."""
+    test mode (perturb=0) uses neither.
+    emulate_bf16 (not in the reference): both fields run with the rounding points of the engine's tensor-core path
+    (weights and every matmul operand rounded to bf16, fp32 accumulation; see field_forward's `q`)."""
+    q = None
+    if emulate_bf16:
+        P_coarse, P_fine, q = bf16_weights(P_coarse), bf16_weights(P_fine), bf16_round
     o, d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     view = ray_batch[:, 8:11]
     near, far = ray_batch[:, 6:7], ray_batch[:, 7:8]
     z_c = coarse_depths(near, far, n_coarse, None if test_time else t_rand, ray_batch.dtype)
     pts = o[:, None, :] + d[:, None, :] * z_c[..., None]
-    raw_c = query_field(P_coarse, pts, view, "coarse", False, test_time)
+    raw_c = query_field(P_coarse, pts, view, "coarse", False, test_time, q=q)
     c0 = composite(raw_c, z_c, noise=noise, test_time=test_time, typ="coarse")
     mids = .5 * (z_c[..., 1:] + z_c[..., :-1])
     z_s, inds, cdf = importance_depths(mids, c0.weights[..., 1:-1], n_fine, None if test_time else u)
     z_s = z_s.detach()
     z_f, _ = torch.sort(torch.cat([z_c, z_s], -1), -1)
     pts_f = o[:, None, :] + d[:, None, :] * z_f[..., None]
-    raw_f = query_field(P_fine, pts_f, view, "fine", transient, test_time)
+    raw_f = query_field(P_fine, pts_f, view, "fine", transient, test_time, q=q)
     c1 = composite(raw_f, z_f, output_transient=transient, beta_min=beta_min, test_time=test_time,
                    typ="fine", transient_at_test=transient_at_test)
     ret = {"rgb_map": c1.rgb, "disp_map": c1.disp, "acc_map": c1.acc, "feat_map": c1.feat}
