@@ -1,7 +1,7 @@
 # Builds libnefes_b200.so (the C-ABI engine) for sm_100a.  `python -c "import __graft_entry__ as g; g.build()"` calls this.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $(EXTRA)
 SRC := $(wildcard nefes_b200/csrc/*.cu)
 OBJ := $(patsubst nefes_b200/csrc/%.cu,build/%.o,$(SRC))
 LIB := nefes_b200/lib/libnefes_b200.so

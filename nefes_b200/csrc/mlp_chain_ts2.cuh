@@ -64,29 +64,30 @@ struct Ts2Step {
   uint8_t* gdst;            // saved image (or null)
   uint32_t g_tile_stride, save_bytes;
 };
-// What the MMA issuer needs of a step, precomputed on the host and kept in SHARED memory (nine 16-byte loads per step):
-// walking the step table in parameter space cost the issuer ~1300 cycles per step (indexed constant loads, descriptor
-// arithmetic), on the critical path of every layer.
-struct Ts2Issue {
-  uint32_t idesc[3];        // per block: instruction descriptor (M = 128, N = nw)
-  uint32_t lbo_field;       // (lbo >> 4) << 16: the LBO field of the B descriptor's low word
-  uint32_t d_col[3];        // per block: accumulator column
-  uint32_t dbk;             // (2 * lbo) >> 4: B descriptor advance per K-step
-  uint32_t a[3];            // per group: TMEM column, or byte offset inside the encoding image
-  uint32_t n_blk;
-  uint32_t ks[3];           // per group: K-steps (0: group absent)
-  uint32_t gwait;           // W_* completions the K-groups need (waited for once, ahead of block 0)
-  uint32_t src[3];          // per group: GS_*
-  uint32_t k1_implies_k0;   // the previous step had >= 2 blocks: its K1 completion implies its K0 completion
-  uint32_t bwait[3];        // per block: W_* completions required before the block's first MMA
-  uint32_t pad0;
-  uint32_t b16[3][4];       // [block][group]: (group.k0 * 2 * lbo + block.n0 * 16) >> 4, B operand offset inside the ring slot
+// The MMA issuer's program: one record per RUN of K-steps (one operand source, one accumulator), built on the host and
+// kept in SHARED memory.  The issuer is ONE small loop over these records.  Measured (NEFES_CHAIN_DBG stamps, round 2): a
+// straight-line issuer specialised per (block, group, source) -- every MMA site executed once per step -- spent 64-76
+// cycles per N=64 MMA and ~340 cycles between two blocks although the pipe was idle: each step walked ~50 cold
+// instruction-cache lines (the SM's 19 warps run four different roles through a 56 KB kernel; L0 is ~6 KB).  The same
+// MMAs issue at the 32-cycle floor from a loop that stays resident (tools/tc_issue.cu).
+enum { RF_SRC = 3,            // GS_*
+       RF_FRESH = 4,          // first run of a block: its first MMA overwrites the accumulator
+       RF_FIRST = 8,          // first run of a step: turn-taking wait, weights wait
+       RF_END = 16,           // last run of a step: release the weight slot
+       RF_HID = 128,          // a whole 128-wide hidden layer (two 64-column blocks, both commits): nks = 0 H only, 1 X only, 2 X then H
+       RF_COMMIT_SHIFT = 5,   // bits 5-6: 1 + block index whose accumulator barrier is committed behind this run (0: none)
+       RF_WAIT_SHIFT = 8 };   // bits 8-15: W_* completions required before the run's first MMA
+struct Ts2Run {
+  uint32_t d_col, idesc, a, nks;        // accumulator column, instruction descriptor, TMEM column / encoding byte offset, K-steps
+  uint32_t b16, lbo_field, dbk, flags;  // B offset in the ring slot (>>4), LBO field of the B descriptor, B advance per K-step (>>4)
 };
-static_assert(sizeof(Ts2Issue) % 16 == 0, "Ts2Issue is read with 16-byte loads");
+static_assert(sizeof(Ts2Run) == 32, "Ts2Run is read with two 16-byte loads");
+constexpr int kTs2MaxRuns = 56;
 constexpr int kTs2MaxSteps = 14;
 struct Ts2Args {
   Ts2Step step[kTs2MaxSteps];
-  const Ts2Issue* iss;        // [n_steps] in global memory, copied to shared memory at kernel start
+  const Ts2Run* runs;         // [n_runs] in global memory, copied to shared memory at kernel start
+  int n_runs;
   int n_steps;
   int64_t M; int n_tiles;
   float* raw; int C;
@@ -95,6 +96,7 @@ struct Ts2Args {
   int n_slots; uint32_t off_ring;   // depth and position of the weight ring (see ts2_off_ring)
   long long* dbg;
   int xflags;                 // timing experiments (NEFES_CHAIN_X): 1 no saves, 4 no raw stores
+  int save_mode;              // 0: staging image + one bulk store per step; 1: st.global.v4 from the epilogue registers
 };
 
 // Shared memory: [ bias table | xyz encodings x2 | direction encodings x2 | staging images x2 (only when the launch saves) |
@@ -106,7 +108,7 @@ constexpr uint32_t kTs2WSlot = 49152;
 constexpr uint32_t kTs2X = 16384, kTs2D = 8192, kTs2Stage = 32768;
 constexpr uint32_t kTs2OffBias = 0;
 constexpr uint32_t kTs2OffProg = 6656;                               // >= kChainBiasBytes
-constexpr uint32_t kTs2ProgBytes = kTs2MaxSteps * sizeof(Ts2Issue);
+constexpr uint32_t kTs2ProgBytes = kTs2MaxRuns * sizeof(Ts2Run);
 constexpr uint32_t kTs2OffX = 10240;                                 // >= kTs2OffProg + kTs2ProgBytes, 512-byte aligned
 static_assert(kTs2OffProg + kTs2ProgBytes <= kTs2OffX, "issue program overlaps the encodings");
 constexpr uint32_t kTs2OffD = kTs2OffX + 2 * kTs2X;
@@ -116,10 +118,35 @@ inline uint32_t ts2_off_ring(bool saves) { return kTs2OffStage + (saves ? 2 * kT
 inline int ts2_slots(bool saves) { return saves ? 2 : 3; }
 inline uint32_t ts2_smem(bool saves) { return ts2_off_ring(saves) + ts2_slots(saves) * kTs2WSlot; }
 constexpr uint32_t kTs2Acc = 0, kTs2HA = 128, kTs2HB = 192;
+constexpr uint32_t kTs2AccCol = 0;
+
+// Straight-line issue of a 128-wide hidden layer of one tile: block b (b = 0, 1) accumulates weight rows [64 b, 64 b + 64)
+// into accumulator columns [64 b, 64 b + 64) over VAR = 0: the 8 K-steps of the activation columns `hin`; VAR = 1: the 4
+// K-steps of the xyz encoding in shared memory (first layer); VAR = 2: both (skip layer, encoding first).  Weight images
+// have 128 rows: a K-step advances the B descriptor by 2 * 2048 B, block 1 starts 64 rows = 1024 B in.  ~4 instructions per
+// MMA; one commit per block.
+template <int VAR>
+__device__ __forceinline__ void ts2_issue_hidden(uint32_t tm, uint32_t hin, uint32_t blo, uint32_t xs, uint32_t idesc,
+                                                 uint64_t* acc0, uint64_t* acc1) {
+  constexpr int KX = (VAR != 0) ? 4 : 0, KH = (VAR != 1) ? 8 : 0;
+  const uint64_t hi = (uint64_t)0x4008u << 32;                 // SBO = 128 B, descriptor version 1
+  const uint64_t xd = smem_desc(xs, kChunkBytes, 128);
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const uint32_t d = tm + kTs2AccCol + 64u * b;
+#pragma unroll
+    for (int k = 0; k < KX; ++k)
+      mma_ss(d, xd + (uint64_t)(k * (2 * kChunkBytes >> 4)), hi | (uint64_t)(blo + 64u * b + 256u * k), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < KH; ++k)
+      mma_ts(d, tm + hin + 8u * k, hi | (uint64_t)(blo + 64u * b + 256u * (k + KX)), idesc, (k + KX) > 0 ? 1u : 0u);
+    mma_commit(b == 0 ? acc0 : acc1);
+  }
+}
 
 __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const __grid_constant__ Ts2Args A) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_wfull[kTs2MaxSlots], bar_wempty[kTs2MaxSlots], bar_acc[2][3], bar_k[2][3], bar_x[2], bar_d[2], bar_stag;
+  __shared__ uint64_t bar_wfull[kTs2MaxSlots], bar_wempty[kTs2MaxSlots], bar_acc[2][3], bar_k[2][3], bar_x[2], bar_d[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* sW = smem + A.off_ring;
@@ -129,10 +156,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTs2MaxSlots; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 2); }
     for (int g = 0; g < 2; ++g) {
-      for (int b = 0; b < 3; ++b) { mbar_init(&bar_acc[g][b], 1); mbar_init(&bar_k[g][b], kChainEpiWarps * 32); }
+      for (int b = 0; b < 3; ++b) { mbar_init(&bar_acc[g][b], 1); mbar_init(&bar_k[g][b], kChainEpiWarps); }
       mbar_init(&bar_x[g], 1); mbar_init(&bar_d[g], 1);
     }
-    mbar_init(&bar_stag, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_slot);
@@ -140,9 +166,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
     if (A.step[s].bias != nullptr)
       for (int i = threadIdx.x; i < (int)A.step[s].w_rows; i += kChainThreads) sBias[A.step[s].bias_off + i] = A.step[s].bias[i];
   {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(A.iss);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(A.runs);
     uint32_t* dst = reinterpret_cast<uint32_t*>(smem + kTs2OffProg);
-    for (int i = threadIdx.x; i < (int)(A.n_steps * sizeof(Ts2Issue) / 4); i += kChainThreads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(A.n_runs * sizeof(Ts2Run) / 4); i += kChainThreads) dst[i] = src[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -212,94 +238,94 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
     }
   } else if (warp == 1 || warp == 2 + 2 * kChainEpiWarps) {
     // ------------------------------- MMA issuer of tile g -----------------------------------------------------------------
-    // Measured (NEFES_CHAIN_DBG stamps): the issuer IS the critical path of this kernel -- every cycle it spends between a
-    // hand-over and the first MMA is added to the layer.  So: the step's operands are prepared from Ts2Issue BEFORE the
-    // waits, a completed K1 skips the K0 wait (a wait costs 100-200 cycles even when it passes at once), and the K-loops run
-    // inside the elected-lane region, where ptxas keeps counters and operands in uniform registers (an MMA list interpreted
-    // entry by entry from shared memory issued one MMA per 540 cycles).
+    // The issuer is a single warp executing a serial instruction stream at ~4 cycles per instruction (measured, ncu warp
+    // sampling: 70 % of its samples are fixed-latency / branch stalls inside its own code, not barrier waits).  A 128-wide
+    // layer is 512 cycles of tensor pipe, so the issuer may spend ~100 instructions on it: the hidden layers (most of the
+    // MMAs) go through a straight-line template with compile-time operand offsets (ts2_issue_hidden), everything else
+    // through one lean loop over run records.
     const int g = uni(warp == 1 ? 0 : 1);
     const uint32_t tm = uni(tmem) + g * 256;
     const bool leader = elect_one();
+#ifdef NEFES_TS2_STAMPS
     const bool dbg = A.dbg != nullptr && blockIdx.x == 0;
+#endif
     const uint32_t xs = smem_u32(smem + kTs2OffX + g * kTs2X), ds = smem_u32(smem + kTs2OffD + g * kTs2D);
-    const Ts2Issue* iss = reinterpret_cast<const Ts2Issue*>(smem + kTs2OffProg);
+    const uint4* runs = reinterpret_cast<const uint4*>(smem + kTs2OffProg);
+    const int n_runs = A.n_runs;
+    const uint32_t w0 = smem_u32(sW) >> 4;
     uint32_t cnt = 0, nk0 = 0u, nk1 = 0u, nk2 = 0u, n_tile = 0;
+    uint32_t slot = 0, wphase = 0, wslot16 = w0;
     auto wait_latest = [&](uint64_t* bar, uint32_t n) { if (n > 0) mbar_wait(bar, (n - 1) & 1); };
-    auto wait_mask = [&](uint32_t m) {
-      if (m & W_K0) wait_latest(&bar_k[g][0], nk0);
-      if (m & W_K1) wait_latest(&bar_k[g][1], nk1);
-      if (m & W_K2) wait_latest(&bar_k[g][2], nk2);
-      if (m & W_X) wait_latest(&bar_x[g], n_tile);
-      if (m & W_D) wait_latest(&bar_d[g], n_tile);
-    };
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const bool valid = pair * 2 + g < A.n_tiles;
       if (valid) ++n_tile;
-      for (int s = 0; s < n_steps; ++s, ++cnt) {
-        const int slot = cnt % n_slots;
-        // ---- operands of every MMA of the step, before any wait ----
-        const uint4* I4 = reinterpret_cast<const uint4*>(iss + s);
-        const uint4 q0 = I4[0], q1 = I4[1], q2 = I4[2], q3 = I4[3], q4 = I4[4], q5 = I4[5], q6 = I4[6], q7 = I4[7], q8 = I4[8];
-        const uint32_t idesc[3] = {q0.x, q0.y, q0.z}, lbo_field = q0.w;
-        const uint32_t dcol[3] = {tm + q1.x, tm + q1.y, tm + q1.z}, dbk = q1.w;
-        const uint32_t a_in[3] = {q2.x, q2.y, q2.z}, n_blk = q2.w;
-        const uint32_t ks[3] = {q3.x, q3.y, q3.z}, gwait = q3.w;
-        const uint32_t src[3] = {q4.x, q4.y, q4.z}, k1k0 = q4.w;
-        const uint32_t bwait[3] = {q5.x, q5.y, q5.z};
-        const uint32_t b16[3][3] = {{q6.x, q6.y, q6.z}, {q7.x, q7.y, q7.z}, {q8.x, q8.y, q8.z}};
-        const uint32_t wb16 = smem_u32(sW + slot * kTs2WSlot) >> 4;
-        uint32_t a_op[3], blo[3][3];
-        uint64_t a_desc[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          a_op[j] = tm + a_in[j];
-          a_desc[j] = smem_desc((src[j] == GS_X ? xs : ds) + a_in[j], kChunkBytes, 128);
-#pragma unroll
-          for (int b = 0; b < 3; ++b) blo[b][j] = ((wb16 + b16[b][j]) & 0x3FFFu) | lbo_field;
+      for (int r = 0; r < n_runs; ++r) {
+        const uint4 q0 = runs[2 * r], q1 = runs[2 * r + 1];
+        const uint32_t flags = q1.w;
+        const uint32_t m = (flags >> RF_WAIT_SHIFT) & 0xffu;
+        if (valid && m != 0u) {
+          if (m & W_K0) wait_latest(&bar_k[g][0], nk0);
+          if (m & W_K1) wait_latest(&bar_k[g][1], nk1);
+          if (m & W_K2) wait_latest(&bar_k[g][2], nk2);
+          if (m & W_X) wait_latest(&bar_x[g], n_tile);
+          if (m & W_D) wait_latest(&bar_d[g], n_tile);
         }
-        if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 4 + g] = clock64();        // operands prepared
-        // operands first (they usually arrive first), the weights last
-        if (valid) {
-          if (g == 1 && cnt == 0) mbar_wait(&bar_stag, 0);      // first pair: start half a step behind tile 0
-          uint32_t need = gwait | bwait[0];
-          if (k1k0 && (need & W_K0) && nk1 > 0 && mbar_try_wait(&bar_k[g][1], (nk1 - 1) & 1)) need &= ~(W_K0 | W_K1);
-          wait_mask(need);
-          if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 46 + g] = clock64();     // operands ready
+        if (flags & RF_FIRST) {
+#ifdef NEFES_TS2_STAMPS
+          if (dbg && leader && valid && cnt < 32) A.dbg[cnt * 48 + 46 + g] = clock64();     // operands ready
+#endif
+          mbar_wait(&bar_wfull[slot], wphase);
         }
-        mbar_wait(&bar_wfull[slot], (cnt / n_slots) & 1);
-        if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + 40 + g] = clock64();
         if (valid) {
-#pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            if (b < (int)n_blk) {
-              if (b > 0) wait_mask(bwait[b]);
-              tc_fence_after();
-              if (dbg && leader && cnt < 32 && b == 0) A.dbg[cnt * 48 + g * 2] = clock64();
-              if (leader) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                  const uint64_t db0 = ((uint64_t)0x4008u << 32) | blo[b][j];     // SBO = 128 B, descriptor version 1
-                  const uint64_t dbk64 = (uint64_t)dbk;
-                  const int nks = (int)ks[j];
-                  const uint32_t d = dcol[b], id = idesc[b];
-                  if (src[j] == GS_TMEM) {
-                    const uint32_t a0 = a_op[j];
-                    for (int k = 0; k < nks; ++k) mma_ts(d, a0 + k * 8, db0 + (uint64_t)k * dbk64, id, (j > 0 || k > 0) ? 1u : 0u);
-                  } else {
-                    const uint64_t da0 = a_desc[j];
-                    for (int k = 0; k < nks; ++k)
-                      mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)k * dbk64, id, (j > 0 || k > 0) ? 1u : 0u);
-                  }
-                }
-                mma_commit(&bar_acc[g][b]);
-                if (g == 0 && cnt == 0 && b == 0) mma_commit(&bar_stag);
-              }
-              if (b == 0) ++nk0; else if (b == 1) ++nk1; else ++nk2;    // the epilogue completes bar_k[g][b] once for this block
+          tc_fence_after();
+#ifdef NEFES_TS2_STAMPS
+          if (dbg && leader && cnt < 32 && (flags & RF_FIRST)) A.dbg[cnt * 48 + g * 2] = clock64();
+#endif
+          if (flags & RF_HID) {
+            if (leader) {
+              const uint32_t blo = (wslot16 + q1.x) | q1.y;
+              if (q0.w == 0u) ts2_issue_hidden<0>(tm, q0.z, blo, xs, q0.y, &bar_acc[g][0], &bar_acc[g][1]);
+              else if (q0.w == 1u) ts2_issue_hidden<1>(tm, q0.z, blo, xs, q0.y, &bar_acc[g][0], &bar_acc[g][1]);
+              else ts2_issue_hidden<2>(tm, q0.z, blo, xs, q0.y, &bar_acc[g][0], &bar_acc[g][1]);
             }
+            ++nk0; ++nk1;
+          } else {
+            const uint32_t commit = (flags >> RF_COMMIT_SHIFT) & 3u;
+            if (leader) {
+              const uint32_t d = tm + q0.x, id = q0.y;
+              const uint64_t db0 = ((uint64_t)0x4008u << 32) | (uint64_t)((wslot16 + q1.x) | q1.y);
+              const uint64_t dbk = (uint64_t)q1.z;
+              const int nks = (int)q0.w;                  // always even
+              const uint32_t keep = (flags & RF_FRESH) ? 0u : 1u;
+              if ((flags & RF_SRC) == GS_TMEM) {
+                const uint32_t a0 = tm + q0.z;
+#pragma unroll 1
+                for (int k = 0; k < nks; k += 2) {
+                  mma_ts(d, a0 + k * 8, db0 + (uint64_t)k * dbk, id, k > 0 ? 1u : keep);
+                  mma_ts(d, a0 + k * 8 + 8, db0 + (uint64_t)(k + 1) * dbk, id, 1u);
+                }
+              } else {
+                const uint64_t da0 = smem_desc(((flags & RF_SRC) == GS_X ? xs : ds) + q0.z, kChunkBytes, 128);
+#pragma unroll 1
+                for (int k = 0; k < nks; k += 2) {
+                  mma_ss(d, da0 + (uint64_t)(k * (2 * kChunkBytes >> 4)), db0 + (uint64_t)k * dbk, id, k > 0 ? 1u : keep);
+                  mma_ss(d, da0 + (uint64_t)((k + 1) * (2 * kChunkBytes >> 4)), db0 + (uint64_t)(k + 1) * dbk, id, 1u);
+                }
+              }
+              if (commit) mma_commit(&bar_acc[g][commit - 1]);
+            }
+            if (commit == 1u) ++nk0; else if (commit == 2u) ++nk1; else if (commit == 3u) ++nk2;   // the epilogue completes bar_k[g][b] once per block
           }
-          if (dbg && leader && cnt < 32) A.dbg[cnt * 48 + g * 2 + 1] = clock64();
         }
-        if (leader) mma_commit(&bar_wempty[slot]);
+        if (flags & RF_END) {
+#ifdef NEFES_TS2_STAMPS
+          if (dbg && leader && valid && cnt < 32) A.dbg[cnt * 48 + g * 2 + 1] = clock64();
+#endif
+          if (leader) mma_commit(&bar_wempty[slot]);
+          ++cnt;
+          wslot16 += kTs2WSlot >> 4;
+          if (++slot == (uint32_t)n_slots) { slot = 0; wphase ^= 1u; wslot16 = w0; }
+        }
         __syncwarp();
       }
     }
@@ -314,6 +340,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
     const uint32_t tbase = tmem + g * 256 + ((uint32_t)(q * 32) << 16);
     uint8_t* stage = smem + kTs2OffStage + g * kTs2Stage;
     uint32_t na[3] = {0u, 0u, 0u}, ecnt = 0;
+    // ONE arrival per warp: 256 per-thread arrivals on one barrier word serialise in the SM's barrier unit (32 cycles per
+    // warp instruction) and the issuer's own waits queue behind them.  Every lane has fenced its tensor-memory accesses
+    // (tcgen05.fence::before_thread_sync) before the warp meets.
+    auto warp_arrive = [&](uint64_t* bar) { __syncwarp(); if (lane == 0) mbar_arrive(bar); };
     bool store_pending = false;
     const bool dbg = A.dbg != nullptr && blockIdx.x == 0 && lane == 0;
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -348,27 +378,37 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
             tmem_st16(tbase + out_col + (c >> 1), w);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bar_k[g][b]);
+            warp_arrive(&bar_k[g][b]);
             if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
             if (dbg && ecnt < 32 && b == 1 && (ew & 7) == 0) A.dbg[ecnt * 48 + 44 + g] = clock64();
             if (gdst != nullptr && save) {
-              if (store_pending) {                     // the previous bulk store must have read the staging image
-                if (gt == 0) bulk_wait_read<0>();
-                group_barrier(g);
-                store_pending = false;
-              }
-              uint8_t* srow = stage + ((n0 + c) >> 3) * kChunkBytes + row * 16;
+              // Three mechanisms measured within 4 % of each other (round 2: one 32 KB bulk store per step 0.599 ms, st.global.v4
+              // from the registers 0.607, four 512-byte bulk stores per warp and block 0.624; without saved copies 0.476): the
+              // launch then writes 4.7 TB/s and it is the memory system, not the mechanism, that holds it.
+              if (A.save_mode == 1) {
+                // straight from the registers: a warp writes 512 contiguous bytes per 8-channel chunk (rows 32 q .. 32 q + 31)
+                uint8_t* grow = gdst + (int64_t)tile * g_stride + ((n0 + c) >> 3) * kChunkBytes + row * 16;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(srow + j * kChunkBytes) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-              if (save == 2) {
-                fence_async_smem();
-                group_barrier(g);
-                if (gt == 0) {
-                  bulk_s2g(gdst + (int64_t)tile * g_stride, stage, save_bytes);
-                  bulk_commit();
+                for (int j = 0; j < 4; ++j) stg128(grow + j * kChunkBytes, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+              } else {
+                if (store_pending) {                     // the previous bulk store must have read the staging image
+                  if (gt == 0) bulk_wait_read<0>();
+                  group_barrier(g);
+                  store_pending = false;
                 }
-                store_pending = true;
+                uint8_t* srow = stage + ((n0 + c) >> 3) * kChunkBytes + row * 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(srow + j * kChunkBytes) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                if (save == 2) {
+                  fence_async_smem();
+                  group_barrier(g);
+                  if (gt == 0) {
+                    bulk_s2g(gdst + (int64_t)tile * g_stride, stage, save_bytes);
+                    bulk_commit();
+                  }
+                  store_pending = true;
+                }
               }
             }
           } else if (kind == BK_RAW) {
@@ -382,7 +422,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
                            : "=r"(t4[0]), "=r"(t4[1]), "=r"(t4[2]), "=r"(t4[3]) : "r"(acc + 64) : "memory");
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&bar_k[g][b]);
+            warp_arrive(&bar_k[g][b]);
             if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
             if (ok && !(A.xflags & 4)) {
               const float* bp = bias + n0 + c;
@@ -409,7 +449,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
               tmem_ld_wait();
             }
             tc_fence_before();
-            mbar_arrive(&bar_k[g][b]);
+            warp_arrive(&bar_k[g][b]);
             if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
             if (jj == 0 && ok) {
               if (kind == BK_SIGMA) {

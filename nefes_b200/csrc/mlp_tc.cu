@@ -1006,6 +1006,7 @@ void chain_ts_dbg_dump(long long* dbg, int n_steps, cudaStream_t st) {
   cudaStreamSynchronize(st);
   static long long h[2048];
   cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaMemset(dbg, 0, sizeof(h));
   const long long t0 = h[0];
   fprintf(stderr, "[chain_ts dbg] n_steps=%d  (cycles since tile 0's first issue)\n", n_steps);
   for (int i = 0; i < 32 && i < 2 * n_steps; ++i) {
@@ -1019,6 +1020,14 @@ void chain_ts_dbg_dump(long long* dbg, int n_steps, cudaStream_t st) {
     fprintf(stderr, "  seq %2d step %2d | prep %7lld %7lld | t0: K %7lld W %7lld A %7lld issued %7lld  epi0 ready %7lld done %7lld..%7lld epi1 %7lld..%7lld | t1: K %7lld W %7lld A %7lld issued %7lld  epi0 ready %7lld done %7lld..%7lld epi1 %7lld..%7lld\n",
             i, i % n_steps, r[4] - t0, r[5] - t0, r[46] - t0, r[40] - t0, r[0] - t0, r[1] - t0, rd[0] - t0, lo[0] - t0, hi[0] - t0, r[42] - t0, r[44] - t0,
             r[47] - t0, r[41] - t0, r[2] - t0, r[3] - t0, rd[1] - t0, lo[1] - t0, hi[1] - t0, r[43] - t0, r[45] - t0);
+    if (i < 8)
+      for (int g = 0; g < 2; ++g)
+        for (int rr = 0; rr < 4; ++rr) {
+          const long long* q = h + 1600 + ((i * 4 + rr) * 2 + g) * 7;
+          if (q[0] == 0) continue;
+          fprintf(stderr, "      issuer t%d run %d: top %lld | record +%lld | waits +%lld | weights +%lld | fence +%lld | MMAs issued +%lld | commit +%lld\n",
+                  g, rr, q[0] - t0, q[1] - q[0], q[2] - q[0], q[3] - q[0], q[4] - q[0], q[5] - q[0], q[6] - q[0]);
+        }
   }
 }
 
@@ -1196,34 +1205,75 @@ int launch_chain_fwd_ts2(const Ws& w, const Arena& A, int mode, int64_t M, float
   NEFES_REQUIRE(n <= kTs2MaxSteps && bias_floats * 4 <= (int)kChainBiasBytes, NEFES_EINVAL, "chain_fwd_ts2: step table overflow");
   for (int i = 0; i < n; ++i)
     NEFES_REQUIRE(c.step[i].w_bytes <= kTs2WSlot, NEFES_EINVAL, "chain_fwd_ts2: weight image of step %d exceeds the ring slot", i);
-  // the issuer's view of the table (Ts2Issue).  It depends on the geometry of the step table only, which is the same for
+  // the issuer's program (Ts2Run records).  It depends on the geometry of the step table only, which is the same for
   // every call of a (mode, saves) combination: built and uploaded once per combination.
-  static Ts2Issue* d_iss[3][2] = {};
+  static Ts2Run* d_runs[3][2] = {};
+  static int n_runs_of[3][2] = {};
   const int pmode = mode == NEFES_MODE_FULL ? 0 : (mode == NEFES_MODE_STATIC ? 1 : 2);
-  if (d_iss[pmode][keep_all ? 1 : 0] == nullptr) {
-    static Ts2Issue h_iss[kTs2MaxSteps];
+  if (d_runs[pmode][keep_all ? 1 : 0] == nullptr) {
+    static Ts2Run h_runs[kTs2MaxRuns];
+    int nr = 0;
     for (int i = 0; i < n; ++i) {
       const Ts2Step& s = c.step[i];
-      Ts2Issue& I = h_iss[i];
-      I = Ts2Issue{};
       const uint32_t lbo = s.w_rows * 16u;
       NEFES_REQUIRE((lbo >> 4) < 0x4000u, NEFES_EINVAL, "chain_fwd_ts2: LBO overflow");
-      I.n_blk = s.n_blk; I.lbo_field = (lbo >> 4) << 16; I.dbk = (2u * lbo) >> 4;
-      I.k1_implies_k0 = (i > 0 && c.step[i - 1].n_blk >= 2) ? 1u : 0u;
-      for (int j = 0; j < s.n_grp; ++j) {
-        I.a[j] = s.grp[j].col; I.ks[j] = s.grp[j].ksteps; I.src[j] = s.grp[j].src; I.gwait |= s.grp[j].wait;
+      const int first = nr;
+      // a 128-wide hidden layer (two 64-column HID blocks on accumulator columns 0 / 64 over the xyz encoding and / or the
+      // 8 K-steps of one activation buffer) is ONE record for the issuer's straight-line template; further blocks of the
+      // step (the sigma column of the final layer) follow as ordinary runs
+      int b_first = 0;
+      {
+        const bool two = s.n_blk >= 2 && (s.blk[0].kind == BK_HID_RELU || s.blk[0].kind == BK_HID) && s.blk[1].kind == s.blk[0].kind &&
+                         s.blk[0].nw == 64 && s.blk[1].nw == 64 && s.blk[0].n0 == 0 && s.blk[1].n0 == 64 &&
+                         s.blk[0].acc_col == kTs2Acc && s.blk[1].acc_col == kTs2Acc + 64 && s.w_rows == 128;
+        int var = -1; uint32_t hin = 0, wait = 0;
+        if (two) {
+          const Ts2Group* G = s.grp;
+          auto is_h = [&](int j0) { return G[j0].src == GS_TMEM && G[j0 + 1].src == GS_TMEM && G[j0].ksteps == 4 && G[j0 + 1].ksteps == 4 &&
+                                           G[j0 + 1].col == G[j0].col + 32 && G[j0 + 1].k0 == G[j0].k0 + 4; };
+          if (s.n_grp == 2 && is_h(0) && G[0].k0 == 0) { var = 0; hin = G[0].col; }
+          else if (s.n_grp == 1 && G[0].src == GS_X && G[0].ksteps == 4 && G[0].k0 == 0 && G[0].col == 0) { var = 1; }
+          else if (s.n_grp == 3 && G[0].src == GS_X && G[0].ksteps == 4 && G[0].k0 == 0 && G[0].col == 0 && is_h(1) && G[1].k0 == 4) { var = 2; hin = G[1].col; }
+          for (int j = 0; j < s.n_grp; ++j) wait |= G[j].wait;
+          wait |= s.blk[0].wait | s.blk[1].wait;
+        }
+        if (var >= 0) {
+          NEFES_REQUIRE(nr < kTs2MaxRuns, NEFES_EINVAL, "chain_fwd_ts2: run table overflow");
+          Ts2Run& R = h_runs[nr++];
+          R = Ts2Run{};
+          R.d_col = kTs2Acc; R.idesc = idesc_bf16(128, 64, 0, 0); R.a = hin; R.nks = (uint32_t)var;
+          R.b16 = 0; R.lbo_field = (lbo >> 4) << 16; R.dbk = (2u * lbo) >> 4;
+          R.flags = (uint32_t)RF_HID | (wait << RF_WAIT_SHIFT);
+          b_first = 2;
+        }
       }
-      for (int b = 0; b < s.n_blk; ++b) {
-        I.idesc[b] = idesc_bf16(128, s.blk[b].nw, 0, 0); I.d_col[b] = s.blk[b].acc_col; I.bwait[b] = s.blk[b].wait;
-        for (int j = 0; j < s.n_grp; ++j) I.b16[b][j] = (s.grp[j].k0 * 2u * lbo + s.blk[b].n0 * 16u) >> 4;
-      }
+      for (int b = b_first; b < s.n_blk; ++b)
+        for (int j = 0; j < s.n_grp; ++j) {
+          NEFES_REQUIRE(nr < kTs2MaxRuns, NEFES_EINVAL, "chain_fwd_ts2: run table overflow");
+          Ts2Run& R = h_runs[nr++];
+          R = Ts2Run{};
+          R.d_col = s.blk[b].acc_col; R.idesc = idesc_bf16(128, s.blk[b].nw, 0, 0);
+          R.a = s.grp[j].col; R.nks = s.grp[j].ksteps;
+          R.b16 = (s.grp[j].k0 * 2u * lbo + s.blk[b].n0 * 16u) >> 4;
+          R.lbo_field = (lbo >> 4) << 16; R.dbk = (2u * lbo) >> 4;
+          // a K-group's operands are waited for where block 0 first reads them (later blocks read the same columns); a
+          // block's own wait (its accumulator columns drained) sits on its first run
+          uint32_t wait = (b == 0 ? s.grp[j].wait : 0u) | (j == 0 ? s.blk[b].wait : 0u);
+          uint32_t flags = (uint32_t)s.grp[j].src | (j == 0 ? (uint32_t)RF_FRESH : 0u) | (wait << RF_WAIT_SHIFT);
+          if (j == s.n_grp - 1) flags |= (uint32_t)(b + 1) << RF_COMMIT_SHIFT;
+          R.flags = flags;
+        }
+      h_runs[first].flags |= RF_FIRST;
+      h_runs[nr - 1].flags |= RF_END;
     }
-    Ts2Issue* dp = nullptr;
-    NEFES_CUDA(cudaMalloc(&dp, sizeof(h_iss)));
-    NEFES_CUDA(cudaMemcpy(dp, h_iss, sizeof(h_iss), cudaMemcpyHostToDevice));
-    d_iss[pmode][keep_all ? 1 : 0] = dp;
+    Ts2Run* dp = nullptr;
+    NEFES_CUDA(cudaMalloc(&dp, sizeof(h_runs)));
+    NEFES_CUDA(cudaMemcpy(dp, h_runs, sizeof(h_runs), cudaMemcpyHostToDevice));
+    d_runs[pmode][keep_all ? 1 : 0] = dp;
+    n_runs_of[pmode][keep_all ? 1 : 0] = nr;
   }
-  c.iss = d_iss[pmode][keep_all ? 1 : 0];
+  c.runs = d_runs[pmode][keep_all ? 1 : 0];
+  c.n_runs = n_runs_of[pmode][keep_all ? 1 : 0];
   c.n_steps = n; c.M = M; c.n_tiles = T;
   c.raw = raw_t; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
   c.x_img = w.X.p; c.d_img = (mode == NEFES_MODE_SIGMA) ? nullptr : w.DIRPE.p;
@@ -1247,6 +1297,8 @@ int launch_chain_fwd_ts2(const Ws& w, const Arena& A, int mode, int64_t M, float
   }
   c.dbg = chain_dbg_buf();
   c.xflags = chain_xflags();
+  static const int save_mode = [] { const char* e = getenv("NEFES_TS2_STG"); return e ? atoi(e) : 0; }();
+  c.save_mode = save_mode;
   chain_fwd_ts2_kernel<<<grid, kChainThreads, ts2_smem(saves), st>>>(c);
   prof_end(st);
   NEFES_CHECK_LAUNCH("chain_fwd_ts2");
@@ -1681,17 +1733,14 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   NEFES_CHECK_LAUNCH("encode_images");
   const bool direct = (layout == NEFES_RAW_TILES) || C == 1;      // C == 1: the two layouts coincide
   float* raw_t = direct ? raw : reinterpret_cast<float*>(scratch);
-  // NEFES_FWD_TS=1: activations in tensor memory (mlp_chain_ts.cuh).  Measured equal to the shared-memory-operand chain
-  // within 2 % at the bench shape (both sit on the same HBM write stream), so the older, longer-validated one is the default.
-  // forward-only calls (no saved copies) run with the activations in tensor memory (mlp_chain_ts.cuh: 0.52 ms against 0.55
-  // for the fine query at 6144 rays); with saves the shared-memory-operand chain is the faster one (0.66 against 0.79 ms).
-  // NEFES_FWD_TS=1 / NEFES_FWD_SS=1 force one or the other.
+  // Three forward chains.  Default since round 2: mlp_chain_ts2.cuh (activations in tensor memory, N-split layers, straight-
+  // line issuer) -- fine query at 6144 rays 0.599 ms with saved copies / 0.476 without, against 0.65 / 0.55 for the shared-
+  // memory-operand chain (mlp_chain.cuh, NEFES_FWD_SS=1) and 0.79 / 0.52 for the first tensor-memory chain (mlp_chain_ts.cuh,
+  // NEFES_FWD_TS=1).  All three are parity-tested against the same oracle.
   static const bool force_ts = getenv("NEFES_FWD_TS") != nullptr, force_ss = getenv("NEFES_FWD_SS") != nullptr;
-  static const bool force_ts2 = getenv("NEFES_FWD_TS2") != nullptr;
-  const bool fwd_ts = force_ts || (!force_ss && forward_only());
-  if (force_ts2) TRY(launch_chain_fwd_ts2(w, A, mode, M, raw_t, st));
-  else if (fwd_ts) TRY(launch_chain_fwd_ts(w, A, mode, M, raw_t, st));
-  else TRY(launch_chain_fwd(w, A, mode, M, raw_t, st));
+  if (force_ss) TRY(launch_chain_fwd(w, A, mode, M, raw_t, st));
+  else if (force_ts) TRY(launch_chain_fwd_ts(w, A, mode, M, raw_t, st));
+  else TRY(launch_chain_fwd_ts2(w, A, mode, M, raw_t, st));
   if (!direct) {
     static bool t2r_attr = false;
     if (!t2r_attr) {
