@@ -10,11 +10,17 @@ fine field with transient heads, compositing] -> NeRF-W colour loss -> backward 
 random init; data is synthetic.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--precision fp32|bf16]
+                    [--workload train|c3|refine|sweep] [--scaling weak|strong]
 
 One JSON line on stdout (rank 0).  `value` times K steps with inputs resident in HBM; `e2e` times the
 same steps through the public API with the step's host inputs copied from pinned memory and the loss
-read back every step.  `--impl reference` times the CPU oracle port of the reference path on the
-host cores (the reference itself is Python and cannot travel to the GPU box).
+read back every step.  `--impl reference` times the UNMODIFIED reference (staged under oracle/_ref by
+oracle/build_ref.py; the oracle port when that copy is absent) on the host cores, same workload.
+
+Workloads: train = C2 (the default and the headline); c3 = the stage-2 step (C2 + the 128-channel
+feature L1 term, so the feature cotangent path runs); refine = C4 (50 pose-gradient iterations per query, queries sharded
+over ranks, final gather; metric refine iters/s); sweep = C5-shaped inference render of 2^12..2^20 rays (ray ranges sharded).
+--scaling strong keeps the GLOBAL batch at 6144 rays (6144 / N per GPU) for train / c3.
 """
 import argparse
 import json
@@ -36,9 +42,17 @@ RAYS = N_IMAGES * N_RAND
 # algorithmic MLP work per ray, SURVEY.md 8d: fwd 68.32 MFLOP, fwd+bwd 204.96 MFLOP (train mode)
 MLP_FLOP_PER_RAY_FWD_BWD = 204.96e6
 METRIC = "NeFeS rays/sec (fwd+bwd, 64+64 samples)"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at the bench shape, from the `ncu --set full` captures
-# summarised in profiles/ (fine net, 6144 rays x 128 samples); per-launch like roofline.achieved
-NCU_TRAFFIC = {"chain_fwd_fine": 2.738e9}
+MLP_FLOP_FINE_FWD_PER_POINT = 2 * 184064       # MACs per point of the fine field
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch per kernel tag at the bench shape, from this round's
+    `ncu --set full` capture (tools/ncu_traffic.py writes profiles/r2_ncu_traffic.json next to the .txt summary)."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def nerfw_loss(ret, target, lambda_u=0.01):
@@ -104,26 +118,35 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-def host_batches(n_steps, seed, pinned=True):
+def host_batches(n_steps, seed, pinned=True, n_rand=N_RAND, feat=False):
     """Per-step host inputs, as the reference's DataLoader + np.random.choice produce them
-    (run_nefes.py:47-71): poses [4,3,4], pixel indices [4,1536], target rgb [6144,3], hist [4,10]."""
+    (run_nefes.py:47-71): poses [4,3,4], pixel indices [4,n_rand], target rgb [4*n_rand,3], hist [4,10]
+    (+ target features [4*n_rand,128] for the stage-2 step)."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
     poses = torch.tensor(g["train_gt"][:N_IMAGES].reshape(N_IMAGES, 3, 4), dtype=torch.float32)
     rng = np.random.RandomState(seed)
     pin = (lambda t: t.pin_memory()) if (pinned and torch.cuda.is_available()) else (lambda t: t)
     out = []
     for _ in range(n_steps):
-        idx = np.stack([rng.choice(H * W, N_RAND, replace=False) for _ in range(N_IMAGES)])
-        out.append(dict(pose=pin(poses.clone()), idx=pin(torch.from_numpy(idx).long()),
-                        target=pin(torch.from_numpy(rng.rand(RAYS, 3).astype(np.float32))),
-                        hist=pin(torch.zeros(N_IMAGES, 10))))
+        idx = np.stack([rng.choice(H * W, n_rand, replace=False) for _ in range(N_IMAGES)])
+        b = dict(pose=pin(poses.clone()), idx=pin(torch.from_numpy(idx).long()),
+                 target=pin(torch.from_numpy(rng.rand(N_IMAGES * n_rand, 3).astype(np.float32))),
+                 hist=pin(torch.zeros(N_IMAGES, 10)))
+        if feat:
+            b["target_f"] = pin(torch.from_numpy(rng.randn(N_IMAGES * n_rand, 128).astype(np.float32)))
+        out.append(b)
     return out
 
 
-def run_engine(a):
+class Args:
+    nerfh_nff, use_fine_only, NeRFW, transient_at_test, netchunk = True, False, True, True, 1 << 21
+
+
+def engine_setup(a):
+    """Process group, device, the two fields and the render kwargs create_nerf builds."""
     import torch.distributed as dist
     import nefes_b200 as nb
-    from nefes_b200 import _lib, ops, parallel
+    from nefes_b200 import _lib
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -138,41 +161,12 @@ def run_engine(a):
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
     _lib.lib()
-
     coarse = nb.NeRFH_NFF("coarse", W=128, precision=a.precision).to(dev)
     fine = nb.NeRFH_NFF("fine", W=128, encode_appearance=True, encode_transient=True, precision=a.precision).to(dev)
-    params = [coarse.flat, fine.flat]          # stage 1 trains the two fields (FusionNet joins at stage 3)
-    opt = nb.FlatAdam(params, lr=5e-4)
-
-    class Args:
-        nerfh_nff, use_fine_only, NeRFW, transient_at_test, netchunk = True, False, True, True, 1 << 21
     q = nb.StandardQuery(Args.netchunk)          # create_nerf's query function: render_rays is one engine call
     kw = dict(network_query_fn=q, N_importance=64, N_samples=64, network_fn=coarse, network_fine=fine,
               use_viewdirs=True, white_bkgd=False, args=Args(), ndc=False, lindisp=False, near=NEAR, far=FAR,
               perturb=1., raw_noise_std=0., test_time=False, retraw=True)
-
-    loss_fn = nb.NerfWLoss(coef=1, lambda_u=0.01)                                # losses.py:96-132 on two kernels
-
-    def step(b):
-        """b: dict of DEVICE tensors.  One optimiser step, returns the loss tensor."""
-        ro, rd = nb.get_rays_batch(H, W, FOCAL, b["pose"])                      # [4,60,80,3]
-        ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, b["idx"][..., None].expand(-1, -1, 3)).reshape(-1, 3)
-        rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, b["idx"][..., None].expand(-1, -1, 3)).reshape(-1, 3)
-        hist = b["hist"][:, None, :].expand(-1, N_RAND, -1).reshape(-1, 10)
-        rgb, disp, acc, ex = nb.render(H, W, FOCAL, chunk=32768, rays=(ro, rd), img_idx=hist, **kw)
-        loss = loss_fn({"rgb_coarse": ex["rgb0"], "rgb_fine": rgb, "beta": ex["beta"],
-                        "transient_sigmas": ex["transient_sigmas"]}, b["target"])
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if world > 1:
-            parallel.allreduce_grads(params)
-        opt.step(grad_scale=1.0 / world)
-        return loss
-
-    n_total = a.warmup + a.steps
-    host = host_batches(n_total, seed=1000 + rank)
-    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -185,6 +179,64 @@ def run_engine(a):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
+
+    return dict(nb=nb, dist=dist, rank=rank, world=world, local=local, dev=dev, coarse=coarse, fine=fine, kw=kw,
+                barrier=barrier, max_over_ranks=max_over_ranks)
+
+
+def finish(c, out):
+    if c["rank"] == 0:
+        print(json.dumps(out), flush=True)
+    if c["world"] > 1:
+        # a process group whose collectives were captured into a CUDA graph does not always tear down cleanly
+        # (observed: destroy_process_group / interpreter exit hanging after the result was printed): drain the device,
+        # meet once more, and leave without running the teardown
+        torch.cuda.synchronize()
+        c["dist"].barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def run_train(a, c):
+    """Workloads train (C2) and c3 (stage 2): the optimiser step of run_nefes.py:113-270 through the public API."""
+    from nefes_b200 import _lib, ops, parallel
+    nb, dev, world, rank, coarse, fine, kw = c["nb"], c["dev"], c["world"], c["rank"], c["coarse"], c["fine"], c["kw"]
+    barrier, max_over_ranks = c["barrier"], c["max_over_ranks"]
+    stage2 = a.workload == "c3"
+    n_rand = N_RAND // world if a.scaling == "strong" else N_RAND
+    rays = N_IMAGES * n_rand
+    params = [coarse.flat, fine.flat]          # stages 1-2 train the two fields (FusionNet joins at stage 3)
+    opt = nb.FlatAdam(params, lr=5e-4)
+    loss_fn = nb.NerfWLoss(coef=1, lambda_u=0.01)                                # losses.py:96-132 on two kernels
+    loss_fn2 = nb.ColorFeatureFusionNerfWLoss(coef=1, L1_loss=True)              # run_nefes.py:360
+
+    def step(b):
+        """b: dict of DEVICE tensors.  One optimiser step, returns the loss tensor."""
+        ro, rd = nb.get_rays_batch(H, W, FOCAL, b["pose"])                      # [4,60,80,3]
+        ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, b["idx"][..., None].expand(-1, -1, 3)).reshape(-1, 3)
+        rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, b["idx"][..., None].expand(-1, -1, 3)).reshape(-1, 3)
+        hist = b["hist"][:, None, :].expand(-1, n_rand, -1).reshape(-1, 10)
+        rgb, disp, acc, ex = nb.render(H, W, FOCAL, chunk=32768, rays=(ro, rd), img_idx=hist, **kw)
+        res = {"rgb_coarse": ex["rgb0"], "rgb_fine": rgb, "beta": ex["beta"], "transient_sigmas": ex["transient_sigmas"]}
+        if stage2:                                                               # run_nefes.py:244-248
+            res["feat_fine"] = ex["feat_map"]
+            l_rgb, l_f = loss_fn2(res, {"rgb": b["target"], "feat": b["target_f"]}, switch_on=False, color_only_switch=False)
+            loss = l_rgb + 0.04 * l_f
+        else:
+            loss = loss_fn(res, b["target"])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_grads(params)
+        opt.step(grad_scale=1.0 / world)
+        return loss
+
+    n_total = a.warmup + a.steps
+    host = host_batches(n_total, seed=1000 + rank, n_rand=n_rand, feat=stage2)
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    torch.cuda.synchronize()
 
     # ---- warm-up (eager), then the step is captured ONCE into a CUDA graph: ~100 launches, most of them small, replay
     #      without per-launch CPU cost.  Inputs enter through static device buffers; Adam's step count / lr live on the
@@ -236,7 +288,7 @@ def run_engine(a):
     run_step(resident[0])
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with ClockSampler(c["local"]) as clk:
         ev0.record()
         for b in resident[a.warmup:]:
             run_step(b)
@@ -244,7 +296,7 @@ def run_engine(a):
         barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = launches_per_step * a.steps
-    value = world * RAYS * a.steps / (ms / 1e3)
+    value = world * rays * a.steps / (ms / 1e3)
 
     # ---- end to end: host inputs from pinned memory, loss read back, every step ----------------
     losses = []
@@ -259,11 +311,11 @@ def run_engine(a):
     ev1.record()
     barrier()
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
-    e2e_value = world * RAYS * a.steps / (ms_e2e / 1e3)
+    e2e_value = world * rays * a.steps / (ms_e2e / 1e3)
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
     tf_peak, hbm_peak, which = measured_peaks()
-    achieved = MLP_FLOP_PER_RAY_FWD_BWD * RAYS / (mlp_ms / 1e3) / 1e12
+    achieved = MLP_FLOP_PER_RAY_FWD_BWD * rays / (mlp_ms / 1e3) / 1e12
     # per-kernel table: achieved = algorithmic bytes (flops) of the launches / their measured duration
     table = {}
     for tag, k in kern.items():
@@ -274,27 +326,35 @@ def run_engine(a):
                       "hbm_frac": k["alg_bytes"] / k["ms"] / 1e6 / hbm_peak, "tensor_frac": k["alg_flops"] / k["ms"] / 1e9 / tf_peak}
     # dominant kernel = the single launch that takes longest (a tag that launches 8 small kernels does not outrank it)
     top = max(table, key=lambda t: table[t]["ms_per_step"] / table[t]["launches_per_step"]) if table else None
+    roof = None
+    if top:
+        t = table[top]
+        per_launch = t["ms_per_step"] / t["launches_per_step"]
+        # K5 (the field MLP) is TENSOR-bound -- algorithmic FLOP of the launch (2 x MACs/point x points) over
+        # its measured duration against the sustained bf16 peak is the headline; the same launch against the HBM peak
+        # (algorithmic bytes INCLUDING the saved activation copies this design writes) is the second figure.
+        roof = {"bound": "tensor", "kernel": top, "achieved": t["TFLOP_per_s"], "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": t["tensor_frac"], "traffic": ncu_traffic().get(top), "peak_source": which,
+                "ms_per_launch": per_launch, "ms_per_step_in_kernel": t["ms_per_step"],
+                "share_of_step": t["ms_per_step"] / (ms / a.steps),
+                "hbm": {"bound": "hbm", "achieved": t["GB_per_s"], "peak": hbm_peak, "unit": "GB/s", "frac": t["hbm_frac"],
+                        "note": "algorithmic bytes include the bf16 activation copies saved for backward (design choice, DESIGN.md 4)"}}
+    wl = ("C2 stage-1 colour-only NeRF-W training step" if not stage2 else
+          "C3 stage-2 training step (C2 + 0.04 x L1 of the rendered 128-channel feature map against target features)")
     out = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
-        "config": {"workload": "C2 stage-1 colour-only NeRF-W training step, 7-Scenes-stairs camera 640x480 -> 60x80, "
-                               "4 images x 1536 rays = 6144 rays/GPU/step, 64 coarse + 64 fine samples, Adam",
-                   "rays_per_gpu_per_step": RAYS, "global_rays_per_step": RAYS * world, "parallelism": f"dp{world} (rays sharded, 1 gradient all-reduce)",
+        "config": {"workload": f"{wl}, 7-Scenes-stairs camera 640x480 -> 60x80, 4 images x {n_rand} rays = {rays} rays/GPU/step, "
+                               "64 coarse + 64 fine samples, Adam",
+                   "rays_per_gpu_per_step": rays, "global_rays_per_step": rays * world, "parallelism": f"dp{world} (rays sharded, 1 gradient all-reduce)",
                    "mlp_precision": a.precision, "cuda_graph": graph is not None,
                    "l2": "no explicit flush: each step streams >20 GB of activation / gradient tiles through HBM (>> 126 MB L2); "
                          "only the 1.4 MB of weights is legitimately L2-resident"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches,
-        # dominant kernel of the step (largest share of device time).  Every MLP kernel of this design streams saved
-        # activation / gradient images through HBM and is bounded by it, hence bound = hbm;
-        # `traffic` is dram read+write of one launch from the committed ncu capture (profiles/), null if not captured.
-        "roofline": ({"bound": "hbm", "kernel": top, "achieved": table[top]["GB_per_s"], "peak": hbm_peak, "unit": "GB/s",
-                      "frac": table[top]["hbm_frac"], "traffic": NCU_TRAFFIC.get(top), "peak_source": which,
-                      "ms_per_launch": table[top]["ms_per_step"] / table[top]["launches_per_step"],
-                      "ms_per_step_in_kernel": table[top]["ms_per_step"],
-                      "share_of_step": table[top]["ms_per_step"] / (ms / a.steps)} if top else None),
+        "roofline": roof,
         "kernels": table,
         "mlp_tensor": {"what": "field MLP (K5) forward+backward, all launches of one step, against the tensor roofline",
                        "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
@@ -302,23 +362,169 @@ def run_engine(a):
         "clocks": clk.summary(),
         "final_loss": losses[-1] if losses else None,
     }
-    if world == 1 and not a.no_extras:
+    graph = None
+    # BASELINE's second metric at every N: refinement iterations/s (queries sharded over ranks, no collective)
+    if not a.no_extras and not stage2:
+        out["refine_iters_per_s"] = refine_rate(a, c, n_queries=1)["iters_per_s"]
+    if world == 1 and not a.no_extras and not stage2:
         out["extras"] = side_measurements(a, nb, step, coarse, fine, resident, kw, dev)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(sample_rays=a.cpu_rays, reps=a.cpu_reps)
-    if rank == 0:
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        # a process group whose collectives were captured into a CUDA graph does not always tear down cleanly
-        # (observed: destroy_process_group / interpreter exit hanging after the result was printed): release the graph,
-        # drain the device, meet once more, and leave without running the teardown
-        graph = None
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        out["cpu_baseline"] = cpu_baseline(a)
+    finish(c, out)
+
+
+def refine_rate(a, c, n_queries, n_iters=50, e2e=False):
+    """C4: every rank refines `n_queries` queries of `n_iters` iterations (bf16 fields, engine-resident iteration replayed
+    from a CUDA graph); whole-job iterations/s = world x queries x iters / max-over-ranks device time."""
+    from nefes_b200 import refine
+    dev, world, rank, coarse, fine = c["dev"], c["world"], c["rank"], c["coarse"], c["fine"]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
+    kwt = dict(c["kw"])
+    kwt.update(perturb=0., test_time=True)
+    kwt.pop("retraw", None)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rng = np.random.RandomState(77 + rank)
+    n_all = g["dfnet_init"].shape[0]
+    ids = [(rank + i * world) % n_all for i in range(n_queries + 1)]          # rank r: queries r, r+W, ... (8e)
+    host_q = [(torch.tensor(g["dfnet_init"][i].reshape(3, 4), dtype=torch.float32).pin_memory(),
+               torch.from_numpy(rng.randn(128, H * W).astype(np.float32)).pin_memory()) for i in ids]
+    for p in (coarse.flat, fine.flat):
+        p.requires_grad_(False)
+    try:
+        init, tgt = host_q[0][0].to(dev), host_q[0][1].to(dev)
+        refine.refine_pose(init, tgt, H, W, FOCAL, kwt, n_iters=10)             # warm-up query: captures the iteration graph
+        dev_q = [(i_.to(dev), t_.to(dev)) for i_, t_ in host_q[1:]]
+        c["barrier"]()
+        ev0.record()
+        poses = []
+        for qi in range(n_queries):
+            if e2e:
+                i_, t_ = host_q[1 + qi][0].to(dev, non_blocking=True), host_q[1 + qi][1].to(dev, non_blocking=True)
+                poses.append(refine.refine_pose(i_, t_, H, W, FOCAL, kwt, n_iters=n_iters)[0].cpu())
+            else:
+                poses.append(refine.refine_pose(dev_q[qi][0], dev_q[qi][1], H, W, FOCAL, kwt, n_iters=n_iters)[0])
+        ev1.record()
+        c["barrier"]()
+        ms = c["max_over_ranks"](ev0.elapsed_time(ev1))
+    finally:
+        for p in (coarse.flat, fine.flat):
+            p.requires_grad_(True)
+    its = world * n_queries * n_iters
+    return {"iters_per_s": its / (ms / 1e3), "ms_per_iter": ms / (n_queries * n_iters), "queries_per_s": world * n_queries / (ms / 1e3),
+            "ms": ms, "h2d_bytes_per_query": 48 + 128 * H * W * 4, "d2h_bytes_per_query": 48}
+
+
+def run_refine(a, c):
+    """Workload refine (C4): a step = one query of 50 pose-gradient iterations per GPU."""
+    from nefes_b200 import _lib
+    world = c["world"]
+    l0 = _lib.lib().nefes_launch_count()
+    with ClockSampler(c["local"]) as clk:
+        r = refine_rate(a, c, n_queries=a.steps)
+    launches = int(_lib.lib().nefes_launch_count() - l0)
+    r2 = refine_rate(a, c, n_queries=a.steps, e2e=True)
+    tf_peak, hbm_peak, which = measured_peaks()
+    flop_iter = 111.0e6 * H * W                       # SURVEY.md 8d: refine fwd 63.88 + bwd 47.12 MFLOP per ray
+    ach = flop_iter / (r["ms_per_iter"] / 1e3) / 1e12
+    out = {"metric": "NeFeS refine iters/sec (50 pose-gradient iterations per query, 60x80 render, 64+64 samples)",
+           "value": r["iters_per_s"], "unit": "iters/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": r["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+           "config": {"workload": "C4 DFNet+NeFeS50 test-time refinement: per query 50 Adam iterations on the 6 pose parameters, each a full "
+                                  "60x80 test_time render (4800 rays, 64+64 samples) + cosine feature loss + backward to the pose; "
+                                  "initial poses = DFNet_stairs_results rows, random-normal target features, frozen random-init fields; "
+                                  "FusionNet / exposure MLP / DFNet excluded (SURVEY.md 8d C4)",
+                      "queries_per_gpu": a.steps, "parallelism": f"dp{world} (queries r, r+N, ...; no collective)", "mlp_precision": a.precision,
+                      "cuda_graph": True, "l2": "each iteration streams ~3 GB of activation / gradient tiles (>> L2)"},
+           "queries_per_s": r["queries_per_s"], "ms_per_iter": r["ms_per_iter"],
+           "e2e": {"value": r2["iters_per_s"], "unit": "iters/s", "h2d_bytes_per_step": r2["h2d_bytes_per_query"],
+                   "d2h_bytes_per_step": r2["d2h_bytes_per_query"], "ms_per_step": r2["ms"] / a.steps},
+           "gpu_launches": launches,
+           "roofline": {"bound": "tensor", "kernel": "refinement iteration (all launches)", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                        "frac": ach / tf_peak, "traffic": None, "peak_source": which},
+           "clocks": clk.summary()}
+    if c["rank"] == 0 and world == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(a)
+    finish(c, out)
+
+
+def run_sweep(a, c):
+    """Workload sweep (C5-shaped): test_time render (no gradients) of 2^12 .. 2^20 rays in the reference's chunks of 32768,
+    contiguous ray ranges per rank (8e), front-end A.  `value` = rays/s at 2^20 rays."""
+    from nefes_b200 import _lib, parallel
+    nb, dev, world, rank = c["nb"], c["dev"], c["world"], c["rank"]
+    kwt = dict(c["kw"])
+    kwt.update(perturb=0., test_time=True, near=0., far=10.)
+    kwt.pop("retraw", None)
+    Hc, Wc, fc = 60, 106, 93.0                        # Cambridge-shaped camera (cambridge_scenes.py:149)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
+    pose = torch.tensor(g["test_gt"][0].reshape(3, 4), dtype=torch.float32, device=dev)
+    ro, rd = nb.get_rays(Hc, Wc, fc, pose)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    hist = torch.zeros(1, 10, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    table, launches = {}, 0
+    sizes = [1 << k for k in range(12, 21)]
+    with torch.no_grad(), ClockSampler(c["local"]) as clk:
+        for n in sizes:
+            lo, hi = parallel.shard_range(n, rank, world)
+            pix = torch.randint(0, Hc * Wc, (hi - lo,), device=dev, generator=gen)
+            rays = (ro[pix].contiguous(), rd[pix].contiguous())
+            reps = max(a.steps if n == sizes[-1] else 3, 1)
+            for _ in range(max(a.warmup if n == sizes[-1] else 1, 1)):
+                nb.render(Hc, Wc, fc, chunk=32768, rays=rays, img_idx=hist, **kwt)
+            c["barrier"]()
+            l0 = _lib.lib().nefes_launch_count()
+            ev0.record()
+            for _ in range(reps):
+                rgb, _, _, ex = nb.render(Hc, Wc, fc, chunk=32768, rays=rays, img_idx=hist, **kwt)
+            ev1.record()
+            c["barrier"]()
+            ms = c["max_over_ranks"](ev0.elapsed_time(ev1)) / reps
+            launches = int(_lib.lib().nefes_launch_count() - l0)
+            table[str(n)] = {"rays_per_s": n / (ms / 1e3), "ms": ms, "rays_per_gpu": hi - lo}
+        # end to end at the largest size: rays from pinned host memory, rgb + feature map read back
+        n = sizes[-1]
+        lo, hi = parallel.shard_range(n, rank, world)
+        h_o, h_d = rays[0].cpu().pin_memory(), rays[1].cpu().pin_memory()
+        c["barrier"]()
+        ev0.record()
+        for _ in range(a.steps):
+            r_ = (h_o.to(dev, non_blocking=True), h_d.to(dev, non_blocking=True))
+            rgb, _, _, ex = nb.render(Hc, Wc, fc, chunk=32768, rays=r_, img_idx=hist, **kwt)
+            out_h = (rgb.cpu(), ex["feat_map"].cpu())
+        ev1.record()
+        c["barrier"]()
+        ms_e2e = c["max_over_ranks"](ev0.elapsed_time(ev1)) / a.steps
+    tf_peak, hbm_peak, which = measured_peaks()
+    top = table[str(n)]
+    ach = 63.88e6 * n / (top["ms"] / 1e3) / 1e12      # SURVEY.md 8d: refine/inference forward 63.88 MFLOP per ray
+    out = {"metric": "NeFeS rays/sec (inference render, 64+64 samples)", "value": top["rays_per_s"], "unit": "rays/s", "n_gpus": world,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": top["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+           "config": {"workload": "C5-shaped ray sweep, front-end A: Cambridge camera 60x106 f=93, near 0 far 10, test_time render without "
+                                  "gradients, 2^12..2^20 rays in chunks of 32768; value at 2^20 rays", "global_rays": n,
+                      "parallelism": f"dp{world} (contiguous ray ranges, no collective)", "mlp_precision": a.precision, "cuda_graph": False,
+                      "l2": "2^20 rays stream 30 GB of raw tiles through HBM (>> L2)"},
+           "sweep": table,
+           "e2e": {"value": n / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": (hi - lo) * 24, "d2h_bytes_per_step": (hi - lo) * 131 * 4,
+                   "ms_per_step": ms_e2e},
+           "gpu_launches": launches * a.steps,
+           "roofline": {"bound": "tensor", "kernel": "inference render (all launches)", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                        "frac": ach / tf_peak, "traffic": None, "peak_source": which},
+           "clocks": clk.summary()}
+    finish(c, out)
+
+
+def run_engine(a):
+    c = engine_setup(a)
+    if a.workload in ("train", "c3"):
+        run_train(a, c)
+    elif a.workload == "refine":
+        run_refine(a, c)
+    else:
+        run_sweep(a, c)
 
 
 def side_measurements(a, nb, step, coarse, fine, resident, kw, dev):
@@ -390,34 +596,151 @@ def side_measurements(a, nb, step, coarse, fine, resident, kw, dev):
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_baseline(sample_rays=1024, reps=3):
-    """The reference path's CPU arithmetic (oracle port, torch CPU fp32, all host threads) on a bounded
-    sample of the same step: sample_rays of the 6144 rays, forward + NeRF-W loss + backward + Adam."""
-    from oracle import nefes_oracle as O
+def reference_arm(workload, n_rays):
+    """-> (step, kind, what): `step()` runs ONE step of `workload` on the host cores and returns the number of work units
+    (rays, or refinement iterations) it processed.  kind "reference": the UNMODIFIED reference modules staged under
+    oracle/_ref (oracle/build_ref.py) -- its render(), its NeRFH_NFF, its losses, torch.optim.Adam as create_nerf builds it;
+    kind "port": the oracle restatement, when no reference tree travels with the repo."""
+    from oracle import ref_loader
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    hb = host_batches(1, seed=7, pinned=False, feat=True)[0]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
+    root = ref_loader.reference_root()
+    if root is not None:
+        R, M, U = ref_loader.import_reference(root)
+        import models.losses as RLoss
+        coarse, fine, base = ref_loader.reference_render_kwargs(M)
+        params = list(coarse.parameters()) + list(fine.parameters())           # nerfh_nff.py:661-680 grad_vars
+        if workload in ("train", "c3"):
+            opt = torch.optim.Adam(params=params, lr=5e-4, betas=(0.9, 0.999))  # nerfh_nff.py:682
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):                      # the class prints its mode on stdout
+                loss_func = RLoss.ColorFeatureFusionNerfWLoss(coef=1, L1_loss=True)
+            ro, rd = U.get_rays_batch(H, W, FOCAL, hb["pose"])
+            idx = hb["idx"][..., None].expand(-1, -1, 3)
+            ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n_rays]
+            rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n_rays]
+            hist = hb["hist"][:, None, :].expand(-1, N_RAND, -1).reshape(-1, 10)[:n_rays]
+
+            def step():
+                rgb, disp, acc, ex = R.render(H, W, FOCAL, chunk=32768, rays=torch.stack([ro, rd], 0), retraw=True, img_idx=hist,
+                                              perturb=1., raw_noise_std=0., test_time=False, near=NEAR, far=FAR, **base)
+                res = {"rgb_fine": rgb, "rgb_coarse": ex["rgb0"], "feat_fine": ex["feat_map"], "beta": ex["beta"],
+                       "transient_sigmas": ex["transient_sigmas"]}                # run_nefes.py:217-231
+                if workload == "c3":
+                    l_rgb, l_f = loss_func(res, {"rgb": hb["target"][:n_rays], "feat": hb["target_f"][:n_rays]}, switch_on=False,
+                                           color_only_switch=False)
+                    loss = l_rgb + 0.04 * l_f
+                else:
+                    loss = loss_func(res, {"rgb": hb["target"][:n_rays]}, switch_on=False, color_only_switch=True)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                return n_rays
+        elif workload == "refine":
+            import models.poses as RPose
+            for p_ in params:
+                p_.requires_grad_(False)
+            init = torch.eye(4)
+            init[:3] = torch.tensor(g["dfnet_init"][0].reshape(3, 4), dtype=torch.float32)
+            pose_net = RPose.LearnPose(1, True, True, init_c2w=init[None].clone(), lietorch=False)
+            opt = torch.optim.Adam([{"params": [pose_net.r], "lr": 0.0087}, {"params": [pose_net.t], "lr": 0.01}])
+            target = torch.randn(128, H * W, generator=torch.Generator().manual_seed(3))
+            hist = torch.zeros(1, 10)
+
+            def step():
+                c2w = pose_net(0)
+                rgb, disp, acc, ex = R.render(H, W, FOCAL, chunk=32768, c2w=c2w[:3, :4], img_idx=hist, perturb=False, raw_noise_std=0.,
+                                              test_time=True, near=NEAR, far=FAR, **base)
+                loss = 1 - torch.nn.functional.cosine_similarity(ex["feat_map"].t(), target, dim=1, eps=1e-6).mean()
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                return 1
+        else:                                                                      # sweep: inference render
+            pose = torch.tensor(g["test_gt"][0].reshape(3, 4), dtype=torch.float32)
+            ro, rd = U.get_rays(60, 106, 93.0, pose)
+            pix = torch.randint(0, 60 * 106, (n_rays,), generator=torch.Generator().manual_seed(5))
+            rays = torch.stack([ro.reshape(-1, 3)[pix], rd.reshape(-1, 3)[pix]], 0)
+            hist = torch.zeros(1, 10)
+
+            def step():
+                with torch.no_grad():
+                    R.render(60, 106, 93.0, chunk=32768, rays=rays, img_idx=hist, perturb=False, raw_noise_std=0., test_time=True,
+                             near=0., far=10., **base)
+                return n_rays
+        return step, "reference", (f"the unmodified reference ({os.path.relpath(root, ROOT) if root.startswith(ROOT) else root}: models/rendering.py render(), "
+                                   "nerfh_nff.py NeRFH_NFF, losses.py, torch.optim.Adam), torch CPU fp32, anomaly mode off")
+    # ---- no reference tree: the oracle restatement --------------------------------------------------------------------------
+    from oracle import nefes_oracle as O
     Pc, Pf = O.clone_params(O.init_field("coarse"), requires_grad=True), O.clone_params(O.init_field("fine"), requires_grad=True)
-    opt = torch.optim.Adam(list(Pc.values()) + list(Pf.values()), lr=5e-4)
-    b = host_batches(1, seed=7, pinned=False)[0]
-    ro, rd = O.camera_rays_batch(H, W, FOCAL, b["pose"])
-    idx = b["idx"][..., None].expand(-1, -1, 3)
-    ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:sample_rays]
-    rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:sample_rays]
-    times = []
-    for i in range(reps + 1):
-        t_rand, u = torch.rand(sample_rays, 64), torch.rand(sample_rays, 64)
+    if workload in ("train", "c3"):
+        opt = torch.optim.Adam(list(Pc.values()) + list(Pf.values()), lr=5e-4)
+        ro, rd = O.camera_rays_batch(H, W, FOCAL, hb["pose"])
+        idx = hb["idx"][..., None].expand(-1, -1, 3)
+        ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n_rays]
+        rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n_rays]
+
+        def step():
+            t_rand, u = torch.rand(n_rays, 64), torch.rand(n_rays, 64)
+            ret = O.render(H, W, FOCAL, Pc, Pf, rays=(ro, rd), near=NEAR, far=FAR, test_time=False, t_rand=t_rand, u=u)
+            loss = nerfw_loss(ret, hb["target"][:n_rays])
+            if workload == "c3":
+                loss = loss + 0.04 * (ret["feat_map"] - hb["target_f"][:n_rays]).abs().mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return n_rays
+    elif workload == "refine":
+        Pc, Pf = O.init_field("coarse"), O.init_field("fine")
+        init = torch.tensor(g["dfnet_init"][0].reshape(3, 4), dtype=torch.float32)
+        r6 = torch.zeros(6, requires_grad=True)
+        opt = torch.optim.Adam([r6], lr=0.01)
+        target = torch.randn(128, H * W, generator=torch.Generator().manual_seed(3))
+
+        def step():
+            Rm = O.so3_exp(r6[:3]) @ init[:, :3]
+            c2w = torch.cat([Rm, (r6[3:] + init[:, 3])[:, None]], 1)
+            ret = O.render(H, W, FOCAL, Pc, Pf, c2w=c2w, near=NEAR, far=FAR, test_time=True)
+            loss = O.cosine_feature_loss(ret["feat_map"].t(), target)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return 1
+    else:
+        Pc, Pf = O.init_field("coarse"), O.init_field("fine")
+        pose = torch.tensor(g["test_gt"][0].reshape(3, 4), dtype=torch.float32)
+        ro, rd = O.camera_rays(60, 106, 93.0, pose)
+        pix = torch.randint(0, 60 * 106, (n_rays,), generator=torch.Generator().manual_seed(5))
+        rays = (ro.reshape(-1, 3)[pix], rd.reshape(-1, 3)[pix])
+
+        def step():
+            with torch.no_grad():
+                O.render(60, 106, 93.0, Pc, Pf, rays=rays, near=0., far=10., test_time=True)
+            return n_rays
+    return step, "port", "oracle port of the reference path (no reference tree on this box), torch CPU fp32, anomaly mode off"
+
+
+WORK_UNIT = {"train": ("rays/s", RAYS), "c3": ("rays/s", RAYS), "refine": ("iters/s", 1), "sweep": ("rays/s", 4096)}
+
+
+def cpu_baseline(a, budget_s=25.0):
+    """The reference's own CPU implementation of the workload on all host cores, on a bounded sample (about 10-30 s of CPU
+    work): full-size steps (6144 rays for train / c3, one 4800-ray refinement iteration, a 4096-ray inference render),
+    1 warm-up + as many timed steps as fit the budget (at least 2)."""
+    unit, n = WORK_UNIT[a.workload]
+    step, kind, what = reference_arm(a.workload, n)
+    step()
+    times, units = [], 0
+    while len(times) < 2 or (sum(times) < budget_s and len(times) < 8):
         t0 = time.perf_counter()
-        ret = O.render(H, W, FOCAL, Pc, Pf, rays=(ro, rd), near=NEAR, far=FAR, test_time=False, t_rand=t_rand, u=u)
-        loss = nerfw_loss(ret, b["target"][:sample_rays])
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
+        units += step()
         times.append(time.perf_counter() - t0)
-    med = float(np.median(times[1:]))
-    return {"value": sample_rays / med, "unit": "rays/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_rays} of the step's 6144 rays, 64+64 samples, fwd+loss+bwd+Adam, median of {reps} after 1 warm-up, "
-                      f"torch {torch.__version__} CPU fp32, autograd anomaly mode off (the stock scripts turn it on)",
-            "seconds_per_sample": med}
+    return {"value": units / sum(times), "unit": unit, "cores": os.cpu_count() or 1, "kind": kind,
+            "sample": f"{len(times)} full-size steps ({n} {'rays' if unit == 'rays/s' else 'iteration(s)'} each) after 1 warm-up; {what}; torch {torch.__version__}",
+            "seconds_per_step": sum(times) / len(times)}
 
 
 def run_reference(a):
@@ -425,45 +748,34 @@ def run_reference(a):
     if rank != 0:
         return
     steps, warm = max(1, a.steps), max(1, a.warmup)
-    from oracle import nefes_oracle as O
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    n = a.cpu_rays
-    Pc, Pf = O.clone_params(O.init_field("coarse"), requires_grad=True), O.clone_params(O.init_field("fine"), requires_grad=True)
-    opt = torch.optim.Adam(list(Pc.values()) + list(Pf.values()), lr=5e-4)
-    hb = host_batches(1, seed=7, pinned=False)[0]
-    ro, rd = O.camera_rays_batch(H, W, FOCAL, hb["pose"])
-    idx = hb["idx"][..., None].expand(-1, -1, 3)
-    ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n]
-    rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n]
-    # keep the whole run within a few minutes: cap the number of timed steps
-    budget_s, t_first = 150.0, None
-    times = []
+    unit, n = WORK_UNIT[a.workload]
+    step, kind, what = reference_arm(a.workload, n)
+    # keep the whole run within a few minutes: cap the time spent in timed steps
+    budget_s, times, units = 150.0, [], 0
     for i in range(warm + steps):
-        t_rand, u = torch.rand(n, 64), torch.rand(n, 64)
         t0 = time.perf_counter()
-        ret = O.render(H, W, FOCAL, Pc, Pf, rays=(ro, rd), near=NEAR, far=FAR, test_time=False, t_rand=t_rand, u=u)
-        loss = nerfw_loss(ret, hb["target"][:n])
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
+        u = step()
         dt = time.perf_counter() - t0
         if i >= warm:
             times.append(dt)
+            units += u
         if sum(times) > budget_s:
             break
-    k = len(times)
-    tot = sum(times)
-    v = n * k / tot
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": a.gpus, "steps": k,
-           "warmup": warm, "ms_per_step": 1e3 * tot / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "C2 stage-1 colour-only NeRF-W training step (same as the engine arm); each step is a bounded "
-                                  f"sample of {n} of the 6144 rays", "rays_per_step_sample": n},
-           "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                            "sample": f"{n} rays/step x {k} steps, oracle port of the reference path (the reference is Python "
-                                      "and absent on the GPU box), torch CPU fp32, all host threads"},
-           "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    k, tot = len(times), sum(times)
+    v = units / tot
+    metric = {"train": METRIC, "c3": METRIC, "refine": "NeFeS refine iters/sec (50 pose-gradient iterations per query, 60x80 render, 64+64 samples)",
+              "sweep": "NeFeS rays/sec (inference render, 64+64 samples)"}[a.workload]
+    wl = {"train": "C2 stage-1 colour-only NeRF-W training step (same as the engine arm), full 6144 rays per step",
+          "c3": "C3 stage-2 training step (same as the engine arm), full 6144 rays per step",
+          "refine": "C4 refinement: one step = ONE pose-gradient iteration (full 60x80 render + cosine loss + backward to the pose + Adam)",
+          "sweep": "C5-shaped inference render, one step = 4096 rays"}[a.workload]
+    out = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": k,
+           "warmup": warm, "ms_per_step": 1e3 * tot / k, "higher_is_better": True, "scaling": a.scaling if a.workload in ("train", "c3") else "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl, "units_per_step": n},
+           "cpu_baseline": {"value": v, "unit": unit, "cores": os.cpu_count() or 1, "kind": kind,
+                            "sample": f"{k} steps x {n} {'rays' if unit == 'rays/s' else 'iteration'}; {what}; all host threads"},
+           "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
@@ -477,8 +789,8 @@ def main():
     p.add_argument("--precision", default=os.environ.get("NEFES_PRECISION", "bf16"), choices=["fp32", "bf16"])
     p.add_argument("--no-extras", action="store_true", help="skip the fp32-path and refinement side measurements")
     p.add_argument("--no-graph", action="store_true", help="time eager steps instead of a captured CUDA graph of the step")
-    p.add_argument("--cpu-rays", type=int, default=1024)
-    p.add_argument("--cpu-reps", type=int, default=3)
+    p.add_argument("--workload", default="train", choices=["train", "c3", "refine", "sweep"])
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     a = p.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "engine" else a.warmup

@@ -353,6 +353,14 @@ int nefes_nerfw_loss_bwd(const float* rgb_coarse, const float* rgb_fine, const f
                          const float* d_loss, int64_t N, int S, float coef, float lambda_u, float* d_rgb_coarse,
                          float* d_rgb_fine, float* d_beta, float* d_transient_sigmas, void* stream);
 
+/* Feature loss of the stage-2/3 training step -- script/models/losses.py:134-173 (ColorFeatureFusionNerfWLoss.f_loss:
+ * nn.L1Loss / nn.MSELoss, reduction 'mean').  loss = mean_f(feat_a - target) [+ mean_f(feat_b - target) when feat_b != NULL],
+ * f = |.| (mode 0) or (.)^2 (mode 1); n_elems = N * 128 (a multiple of 4; pointers 16-byte aligned).  scratch2: 2 floats. */
+int nefes_feat_loss_fwd(const float* feat_a, const float* feat_b, const float* target, int64_t n_elems, int mode, float* scratch2,
+                        float* loss, void* stream);
+int nefes_feat_loss_bwd(const float* feat_a, const float* feat_b, const float* target, const float* d_loss, int64_t n_elems,
+                        int mode, float* d_feat_a, float* d_feat_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,7 @@ kernel call does, and raises if it is missing (there is no CPU fallback)."""
 from .nerfh_nff import (FlatAdam, FusionNet, NeRFH_NFF, create_nerf, get_embedder, img2mse, mse2psnr,  # noqa: F401
                         raw2outputs_NeRFH_NFF, run_network_NeRFH_NFF, StandardQuery, to8b)
 from .batching import gather_ray_batch, select_random_patches, select_random_pixels  # noqa: F401
-from .losses import NerfWLoss  # noqa: F401
+from .losses import NerfWLoss, ColorFeatureFusionNerfWLoss  # noqa: F401
 from .ray_utils import get_rays, get_rays_batch  # noqa: F401
 from .rendering import batchify_rays, render, render_rays, sample_pdf  # noqa: F401
 

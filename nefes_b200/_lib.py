@@ -95,6 +95,8 @@ _SIGS = {
     "nefes_adam_step_dev": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, vp]),
     "nefes_nerfw_loss_fwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp]),
     "nefes_nerfw_loss_bwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, vp]),
+    "nefes_feat_loss_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp, vp]),
+    "nefes_feat_loss_bwd": (i32, [vp, vp, vp, vp, i64, i32, vp, vp, vp]),
     "nefes_render_rays_workspace": (i32, [C.POINTER(RenderCfg), i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "nefes_render_rays_fwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), vp, vp, vp]),
     "nefes_render_rays_bwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), C.POINTER(CompGrad),

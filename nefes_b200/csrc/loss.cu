@@ -77,6 +77,57 @@ __global__ void nerfw_loss_bwd_kernel(const float* __restrict__ rgb0, const floa
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N * S; i += stride) d_tsig[i] = ds;
 }
 
+// Feature loss of the stage-2/3 step (script/models/losses.py:134-173, ColorFeatureFusionNerfWLoss: f_loss = nn.L1Loss /
+// nn.MSELoss, reduction 'mean', of feat_fine [+ feat_coarse] [N,128] against the target feature map), one input per launch
+// side: value = mean |a - t|   (mode 0)   or   mean (a - t)^2   (mode 1); with b != null the second term is added.
+__global__ void feat_loss_fwd_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ t,
+                                     int64_t n4, int mode, float inv_n, float* __restrict__ acc, unsigned int* __restrict__ done,
+                                     float* __restrict__ loss) {
+  float s = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 tv = t[i], av = a[i];
+    const float d0 = av.x - tv.x, d1 = av.y - tv.y, d2 = av.z - tv.z, d3 = av.w - tv.w;
+    s += mode == 0 ? fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3) : d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    if (b != nullptr) {
+      const float4 bv = b[i];
+      const float e0 = bv.x - tv.x, e1 = bv.y - tv.y, e2 = bv.z - tv.z, e3 = bv.w - tv.w;
+      s += mode == 0 ? fabsf(e0) + fabsf(e1) + fabsf(e2) + fabsf(e3) : e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    }
+  }
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
+    atomicAdd(acc, v);
+    __threadfence();
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      __threadfence();
+      *loss = atomicAdd(acc, 0.f) * inv_n;
+    }
+  }
+}
+
+__global__ void feat_loss_bwd_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ t,
+                                     const float* __restrict__ g, int64_t n4, int mode, float inv_n, float4* __restrict__ d_a,
+                                     float4* __restrict__ d_b) {
+  const float gs = g[0] * inv_n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // torch: d|x|/dx = sign(x) with sign(0) = 0; d x^2/dx = 2x
+  auto dv = [&](float x) { return mode == 0 ? (x > 0.f ? gs : (x < 0.f ? -gs : 0.f)) : 2.f * gs * x; };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 tv = t[i], av = a[i];
+    d_a[i] = make_float4(dv(av.x - tv.x), dv(av.y - tv.y), dv(av.z - tv.z), dv(av.w - tv.w));
+    if (b != nullptr) {
+      const float4 bv = b[i];
+      d_b[i] = make_float4(dv(bv.x - tv.x), dv(bv.y - tv.y), dv(bv.z - tv.z), dv(bv.w - tv.w));
+    }
+  }
+}
+
 }  // namespace nefes
 
 extern "C" {
@@ -107,6 +158,37 @@ int nefes_nerfw_loss_bwd(const float* rgb_coarse, const float* rgb_fine, const f
                                                                         lambda_u, d_rgb_coarse, d_rgb_fine, d_beta,
                                                                         d_transient_sigmas);
   NEFES_CHECK_LAUNCH("nerfw_loss_bwd");
+  return NEFES_OK;
+}
+
+int nefes_feat_loss_fwd(const float* feat_a, const float* feat_b, const float* target, int64_t n_elems, int mode, float* scratch2,
+                        float* loss, void* stream) {
+  NEFES_REQUIRE(feat_a && target && scratch2 && loss, NEFES_EINVAL, "nefes_feat_loss_fwd: null pointer");
+  NEFES_REQUIRE(n_elems >= 4 && n_elems % 4 == 0 && (mode == 0 || mode == 1), NEFES_EINVAL,
+                "nefes_feat_loss_fwd: n_elems=%lld must be a positive multiple of 4, mode 0 (L1) or 1 (MSE)", (long long)n_elems);
+  cudaStream_t st = (cudaStream_t)stream;
+  NEFES_CUDA(cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st));
+  const int64_t n4 = n_elems / 4;
+  const int blocks = (int)nefes::ceil_div(n4, 256 * 4) < 592 ? (int)nefes::ceil_div(n4, 256 * 4) : 592;
+  nefes::feat_loss_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(feat_a), reinterpret_cast<const float4*>(feat_b),
+                                                      reinterpret_cast<const float4*>(target), n4, mode, 1.f / (float)n_elems, scratch2,
+                                                      reinterpret_cast<unsigned int*>(scratch2 + 1), loss);
+  NEFES_CHECK_LAUNCH("feat_loss_fwd");
+  return NEFES_OK;
+}
+
+int nefes_feat_loss_bwd(const float* feat_a, const float* feat_b, const float* target, const float* d_loss, int64_t n_elems,
+                        int mode, float* d_feat_a, float* d_feat_b, void* stream) {
+  NEFES_REQUIRE(feat_a && target && d_loss && d_feat_a && (feat_b == nullptr || d_feat_b), NEFES_EINVAL,
+                "nefes_feat_loss_bwd: null pointer");
+  NEFES_REQUIRE(n_elems >= 4 && n_elems % 4 == 0 && (mode == 0 || mode == 1), NEFES_EINVAL,
+                "nefes_feat_loss_bwd: n_elems=%lld must be a positive multiple of 4, mode 0 (L1) or 1 (MSE)", (long long)n_elems);
+  const int64_t n4 = n_elems / 4;
+  const int blocks = (int)nefes::ceil_div(n4, 256 * 4) < 592 ? (int)nefes::ceil_div(n4, 256 * 4) : 592;
+  nefes::feat_loss_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(feat_a), reinterpret_cast<const float4*>(feat_b), reinterpret_cast<const float4*>(target), d_loss,
+      n4, mode, 1.f / (float)n_elems, reinterpret_cast<float4*>(d_feat_a), reinterpret_cast<float4*>(d_feat_b));
+  NEFES_CHECK_LAUNCH("feat_loss_bwd");
   return NEFES_OK;
 }
 

@@ -1,5 +1,6 @@
-"""Mirror of script/models/losses.py:96-132 (NerfWLoss) -- same constructor, same `inputs` / `targets` convention --
-with the transient-head case evaluated by two kernels (forward, backward) instead of ~45 elementwise launches."""
+"""Mirror of script/models/losses.py:96-173 (NerfWLoss, ColorFeatureFusionNerfWLoss) -- same constructors, same `inputs` /
+`targets` conventions -- with the transient-head colour loss and the feature losses evaluated by two kernels each (forward,
+backward) instead of ~45 / ~10 elementwise launches."""
 import torch
 from torch import nn
 from torch.autograd import Function
@@ -52,3 +53,60 @@ class NerfWLoss(nn.Module):
             raise RuntimeError("nefes_b200: NerfWLoss is built for the coarse+fine NeRF-W case (every reference config)")
         return _NerfW.apply(inputs['rgb_coarse'], inputs['rgb_fine'], inputs['beta'], inputs['transient_sigmas'], targets,
                             self.coef, self.lambda_u)
+
+
+class _FeatLoss(Function):
+    """mean |a - t| (+ mean |b - t|) or the squared version: nefes_feat_loss_{fwd,bwd}."""
+
+    @staticmethod
+    def forward(ctx, a, b, target, mode):
+        ts = [t for t in (a, b, target) if t is not None]
+        L.need_cuda(*ts)
+        a_c, t_c = L.f32c(a), L.f32c(target)
+        b_c = None if b is None else L.f32c(b)
+        if a_c.shape != t_c.shape or (b_c is not None and b_c.shape != t_c.shape):
+            raise RuntimeError(f"nefes_b200: feature loss shapes differ: {tuple(a.shape)} / {tuple(target.shape)}")
+        n = a_c.numel()
+        dev = a_c.device
+        scratch, loss = torch.empty(2, device=dev), torch.empty((), device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.lib().nefes_feat_loss_fwd(L.ptr(a_c), L.ptr(b_c) if b_c is not None else None, L.ptr(t_c), n, int(mode),
+                                                L.ptr(scratch), L.ptr(loss), L.stream_of(a_c)), "nefes_feat_loss_fwd")
+        ctx.save_for_backward(*( [a_c, t_c] + ([b_c] if b_c is not None else []) ))
+        ctx.meta = (n, int(mode), tuple(a.shape), b is not None)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        n, mode, shape, has_b = ctx.meta
+        a_c, t_c = ctx.saved_tensors[:2]
+        b_c = ctx.saved_tensors[2] if has_b else None
+        g = L.f32c(g.reshape(1))
+        d_a = torch.empty_like(a_c)
+        d_b = torch.empty_like(b_c) if has_b else None
+        with torch.cuda.device(a_c.device):
+            L.check(L.lib().nefes_feat_loss_bwd(L.ptr(a_c), L.ptr(b_c) if has_b else None, L.ptr(t_c), L.ptr(g), n, mode, L.ptr(d_a),
+                                                L.ptr(d_b) if has_b else None, L.stream_of(a_c)), "nefes_feat_loss_bwd")
+        return d_a.reshape(shape), (d_b.reshape(shape) if has_b else None), None, None
+
+
+class ColorFeatureFusionNerfWLoss(nn.Module):
+    """Drop-in for losses.py:134-173.  forward(inputs, targets, switch_on, color_only_switch):
+    colour-only -> loss; stage 2 (switch_on=False) -> (loss, loss_f); stage 3 -> (loss, loss_f, loss_fusion), where
+    loss_f = f(feat_fine, t) [+ f(feat_coarse, t)] and loss_fusion = f(feat_fusion, t), f = L1 or MSE mean."""
+
+    def __init__(self, coef=1, L1_loss=False, lambda_u=0.01):
+        super().__init__()
+        self.coef = coef
+        self.lambda_u = lambda_u
+        self.loss = NerfWLoss(coef=coef, lambda_u=lambda_u)
+        self.mode = 0 if L1_loss else 1
+
+    def forward(self, inputs, targets, switch_on=True, color_only_switch=False):
+        loss = self.loss(inputs, targets['rgb'])
+        if color_only_switch:
+            return loss
+        loss_f = _FeatLoss.apply(inputs['feat_fine'], inputs.get('feat_coarse'), targets['feat'], self.mode)
+        if switch_on:
+            return loss, loss_f, _FeatLoss.apply(inputs['feat_fusion'], None, targets['feat'], self.mode)
+        return loss, loss_f

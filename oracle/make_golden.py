@@ -21,24 +21,9 @@ sys.path.insert(0, ROOT)
 
 
 def import_reference():
-    """Stub the four third-party modules the reference imports but never runs on this path."""
-    for name in ("imageio", "matplotlib", "matplotlib.pyplot"):
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    tcnn = types.ModuleType("tinycudann")
-
-    class _Placeholder(torch.nn.Module):
-        def __init__(self, *a, **k):
-            super().__init__()
-    tcnn.Network = _Placeholder
-    tcnn.Encoding = _Placeholder
-    sys.modules["tinycudann"] = tcnn
-    sys.path.insert(0, os.path.join(REF, "script"))
-    sys.path.insert(0, REF)
-    import models.rendering as R
-    import models.nerfh_nff as M
-    import models.ray_utils as U
-    return R, M, U
+    """The unmodified reference modules, third-party imports stubbed (oracle/ref_loader.py)."""
+    from oracle import ref_loader
+    return ref_loader.import_reference(REF)
 
 
 def eq(name, a, b):
@@ -290,6 +275,38 @@ def main():
                "test/inds": out_o["_aux"]["inds"][sub].to(torch.int32),
                "test/z_fine": out_o["_aux"]["z_fine"][sub], "test/c2w": c2w})
     np.savez_compressed(os.path.join(OUT, "g5_render.npz"), **npy(g5))
+
+    # ---- G6: stage-2/3 loss, ColorFeatureFusionNerfWLoss (losses.py:134-173), L1 and MSE feature terms -------------
+    import models.losses as RLoss
+    g = torch.Generator().manual_seed(6)
+    n = 96
+    res = {"rgb_fine": torch.rand(n, 3, generator=g), "rgb_coarse": torch.rand(n, 3, generator=g),
+           "beta": torch.rand(n, generator=g) + 0.1, "transient_sigmas": torch.rand(n, 128, generator=g),
+           "feat_fine": torch.randn(n, 128, generator=g), "feat_coarse": torch.randn(n, 128, generator=g),
+           "feat_fusion": torch.randn(n, 128, generator=g)}
+    tg = {"rgb": torch.rand(n, 3, generator=g), "feat": torch.randn(n, 128, generator=g)}
+    tg["feat"][:4] = res["feat_fine"][:4]                     # exact zeros of a - t: sign(0) = 0 in the L1 gradient
+    g6 = {"in/" + k: v for k, v in res.items()}
+    g6.update({"target/" + k: v for k, v in tg.items()})
+    for l1 in (True, False):
+        lf = RLoss.ColorFeatureFusionNerfWLoss(coef=1, L1_loss=l1)
+        for tag, kw_ in (("color", dict(switch_on=False, color_only_switch=True)), ("stage2", dict(switch_on=False, color_only_switch=False)),
+                         ("stage3", dict(switch_on=True, color_only_switch=False))):
+            leaf = {k: v.clone().requires_grad_(True) for k, v in res.items()}
+            out_r = lf(leaf, tg, **kw_)
+            out_o = O.color_feature_fusion_nerfw_loss(res, tg, L1_loss=l1, **kw_)
+            out_r = out_r if isinstance(out_r, tuple) else (out_r,)
+            out_o = out_o if isinstance(out_o, tuple) else (out_o,)
+            assert len(out_r) == len(out_o)
+            for i, (a, b) in enumerate(zip(out_o, out_r)):
+                eq(f"loss[{'l1' if l1 else 'mse'}/{tag}][{i}]", a, b)
+                g6[f"{'l1' if l1 else 'mse'}/{tag}/{i}"] = b
+            w = (1.0, 0.04, 0.02)
+            sum(wi * li for wi, li in zip(w, out_r)).backward()   # the caller's weighting (run_nefes.py:238-251)
+            for k in ("feat_fine", "feat_coarse", "feat_fusion"):
+                if leaf[k].grad is not None:
+                    g6[f"{'l1' if l1 else 'mse'}/{tag}/grad/{k}"] = leaf[k].grad
+    np.savez_compressed(os.path.join(OUT, "g6_loss.npz"), **npy(g6))
 
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"[make_golden] all reference-vs-oracle checks bit-equal; wrote {tot / 1e6:.2f} MB to {OUT}")

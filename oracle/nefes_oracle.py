@@ -390,6 +390,22 @@ def nerfw_loss(ret, target_rgb, lambda_u=0.01):
     return c_l + f_l + b_l + s_l
 
 
+def color_feature_fusion_nerfw_loss(results, targets, switch_on=True, color_only_switch=False, L1_loss=True, lambda_u=0.01):
+    """script/models/losses.py:134-173 (ColorFeatureFusionNerfWLoss, coef=1).  `results` uses the caller's key names
+    (run_nefes.py:217-231): rgb_fine, rgb_coarse, beta, transient_sigmas, feat_fine, [feat_coarse], [feat_fusion]."""
+    loss = nerfw_loss({"rgb0": results["rgb_coarse"], "rgb_map": results["rgb_fine"], "beta": results["beta"],
+                       "transient_sigmas": results["transient_sigmas"]}, targets["rgb"], lambda_u)
+    if color_only_switch:
+        return loss
+    f = (lambda a, b: (a - b).abs().mean()) if L1_loss else (lambda a, b: ((a - b) ** 2).mean())
+    loss_f = f(results["feat_fine"], targets["feat"])
+    if "feat_coarse" in results:
+        loss_f = loss_f + f(results["feat_coarse"], targets["feat"])
+    if switch_on:
+        return loss, loss_f, f(results["feat_fusion"], targets["feat"])
+    return loss, loss_f
+
+
 def cosine_feature_loss(feat_render, feat_target):
     """script/dm/DFM_pose_refine.py:236-255, per_pixel=False, inputs [C, N]."""
     return 1 - F.cosine_similarity(feat_render, feat_target, dim=1, eps=1e-6).mean()

@@ -105,3 +105,17 @@ def test_render_train_and_test_mode(golden, weights):
     l.backward()
     ref = g["test/d_c2w"]
     assert torch.allclose(c2w.grad, ref, rtol=2e-5, atol=1e-7 * float(ref.abs().max()))
+
+
+def test_stage23_loss_golden(golden):
+    """ColorFeatureFusionNerfWLoss (losses.py:134-173): values bit-equal to the reference class in all three call modes."""
+    g = golden("g6_loss.npz")
+    res = {k[3:]: v for k, v in g.items() if k.startswith("in/")}
+    tg = {k[7:]: v for k, v in g.items() if k.startswith("target/")}
+    for l1 in (True, False):
+        for tag, kw in (("color", dict(switch_on=False, color_only_switch=True)), ("stage2", dict(switch_on=False, color_only_switch=False)),
+                        ("stage3", dict(switch_on=True, color_only_switch=False))):
+            out = O.color_feature_fusion_nerfw_loss(res, tg, L1_loss=l1, **kw)
+            out = out if isinstance(out, tuple) else (out,)
+            for i, v in enumerate(out):
+                assert torch.equal(v, g[f"{'l1' if l1 else 'mse'}/{tag}/{i}"]), (l1, tag, i)
