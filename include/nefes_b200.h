@@ -307,6 +307,11 @@ int nefes_render_rays_bwd(const nefes_render_cfg_t* cfg_host, const nefes_render
  * render and the optimiser step, so that one iteration of DFM_pose_refine.py:380-440 is engine launches only.
  *   pose6 = [r(3), t(3)]: c2w = [Exp(r) @ R0 | t + t0] with init_c2w = [R0 | t0] [3,4]
  *                         (script/models/poses.py:25-50 with lietorch=False; utils/lie_group_helper.py:60-81)
+ *   chain6 (HOST pointer to 6 floats, or NULL = {0, 1, 0, 0, 0, 1}) = {se3, pose_scale, move_x, move_y, move_z, pose_scale2}:
+ *                         se3 != 0: the translation goes through the SE(3) exponential, c2w = [Exp(r) R0 | V(r) t + t0]
+ *                         (poses.py:31-32, 44: SE3.exp([t, r]).matrix() -- the lietorch=True branch DFM_pose_refine.py:374 uses;
+ *                         closed form evaluated in fp64); then the translation column x becomes ((x * pose_scale) + move) *
+ *                         pose_scale2 (dm/direct_pose_model.py:210-232, fix_coord_supp) before the rays are generated
  *   nefes_pose_rays_fwd  writes c2w_out [3,4] (may be NULL) and the packed ray_batch [H*W, ld >= 11] render() builds
  *                        (rendering.py:197-243: o, d, near, far, d/|d|, zeros) with get_rays' arithmetic (ray_utils.py:5-16)
  *   nefes_pose_rays_bwd  cotangent of ray_batch -> d_c2w [3,4], ACCUMULATED (caller zero-fills once)
@@ -318,14 +323,14 @@ int nefes_render_rays_bwd(const nefes_render_cfg_t* cfg_host, const nefes_render
  *                        state13 = exp_avg[6], exp_avg_sq[6], step; clears d_c2w and zero[0:n_zero] (the loss statistics)
  * ------------------------------------------------------------------------------------------ */
 int nefes_pose_rays_fwd(const float* pose6, const float* init_c2w, int H, int W, float focal, float near, float far,
-                        float* c2w_out, float* ray_batch, int ld, void* stream);
+                        float* c2w_out, float* ray_batch, int ld, const float* chain6, void* stream);
 int nefes_pose_rays_bwd(const float* d_ray_batch, const float* ray_batch, int ld, int H, int W, float focal, float* d_c2w,
                         void* stream);
 int nefes_cosine_loss_fwd(const float* feat, const float* target, int N, int C, float* stats, void* stream);
 int nefes_cosine_loss_bwd(const float* feat, const float* target, const float* stats, int N, int C, float* loss,
                           float* loss_hist, const float* step, int hist_cap, float* d_feat, void* stream);
 int nefes_pose_adam_step(float* pose6, const float* init_c2w, float* d_c2w, float* zero, int n_zero, float* state13,
-                         float lr_r, float lr_t, float beta1, float beta2, float eps, void* stream);
+                         float lr_r, float lr_t, float beta1, float beta2, float eps, const float* chain6, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Caller-side helpers on the "next" rows of SURVEY 8f that the training step needs resident.
@@ -360,6 +365,46 @@ int nefes_feat_loss_fwd(const float* feat_a, const float* feat_b, const float* t
                         float* loss, void* stream);
 int nefes_feat_loss_bwd(const float* feat_a, const float* feat_b, const float* target, const float* d_loss, int64_t n_elems,
                         int mode, float* d_feat_a, float* d_feat_b, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Post-render appearance + fusion stage, pixel-major tensors ([P, C], P = B*H*W image-major).
+ *   FusionNet  script/models/nerfh_nff.py:356-418, :578-603: rgb [P,3] (normalised inside with the ImageNet mean / std) and
+ *              feat [P,128] -> conv 131->64 (3x3) ReLU -> 64->64 ReLU -> 64->64 ReLU -> 64->128 (5x5) -> BatchNorm2d(128)
+ *              -> out [P,128].  Weights in torch layout [Cout, Cin, kh, kw]; training != 0: batch statistics and the running
+ *              estimates are updated (momentum); training == 0: running statistics; no_bn: the net ends at conv4;
+ *              residual (fusion_residule): out += feat.  workspace: nefes_fusion_workspace(P) bytes, shared by _fwd and _bwd
+ *              (it keeps X0, the three hidden activations and the pre-BN output).  _bwd ACCUMULATES into the non-NULL
+ *              members of `grads` and overwrites d_rgb [P,3] / d_feat [P,128] (either may be NULL).
+ *   affine colour transform  nerfh_nff.py:511-522, :605-626: exposure_params = the exposure network's flat tiny-cuda-nn
+ *              buffer (weights [32x16 | 32x32 | 32x32 | 16x32] row-major, no biases; its 10 inputs are padded to 16 with
+ *              ONES); hist [B,10] (truncated to integers, as hist.long()); rgb [B * n_per_image, 3] image-major;
+ *              out = sigmoid(K_b rgb + b_b).  ab12 [B,12] and hidden96 [B,96] are written by _fwd and read by _bwd, which
+ *              overwrites d_ab12 [B,12] and d_rgb (may be NULL) and ACCUMULATES into d_exposure_params (may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* weight[4];          /* net.0 / net.2 / net.4 / net.6 .weight: [64,131,3,3] [64,64,3,3] [64,64,3,3] [128,64,5,5] */
+  const float* bias[4];            /* ... .bias                                                                             */
+  const float* bn_weight;          /* net.7.weight [128] (NULL when no_bn)                                                   */
+  const float* bn_bias;            /* net.7.bias                                                                             */
+  const float* bn_running_mean;    /* net.7.running_mean (updated in place when training)                                    */
+  const float* bn_running_var;     /* net.7.running_var                                                                      */
+} nefes_fusion_params_t;
+typedef struct {
+  float* weight[4];                /* accumulated into; any member may be NULL                                               */
+  float* bias[4];
+  float* bn_weight;
+  float* bn_bias;
+} nefes_fusion_grads_t;
+int64_t nefes_fusion_workspace(int64_t n_pixels);
+int nefes_fusion_fwd(const nefes_fusion_params_t* params_host, const float* rgb, const float* feat, int B, int H, int W, int training,
+                     int no_bn, int residual, float momentum, float eps, void* workspace, float* out, void* stream);
+int nefes_fusion_bwd(const nefes_fusion_params_t* params_host, const nefes_fusion_grads_t* grads_host, const float* d_out, int B, int H,
+                     int W, int training, int no_bn, int residual, void* workspace, float* d_rgb, float* d_feat, void* stream);
+int nefes_affine_color_fwd(const float* exposure_params, const float* hist, const float* rgb, int B, int64_t n_per_image, float* ab12,
+                           float* hidden96, float* out, void* stream);
+int nefes_affine_color_bwd(const float* exposure_params, const float* hist, const float* rgb, const float* out, const float* d_out,
+                           const float* ab12, const float* hidden96, int B, int64_t n_per_image, float* d_ab12, float* d_rgb,
+                           float* d_exposure_params, void* stream);
 
 #ifdef __cplusplus
 }

@@ -97,17 +97,22 @@ _SIGS = {
     "nefes_nerfw_loss_bwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, vp]),
     "nefes_feat_loss_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp, vp]),
     "nefes_feat_loss_bwd": (i32, [vp, vp, vp, vp, i64, i32, vp, vp, vp]),
+    "nefes_fusion_workspace": (i64, [i64]),
+    "nefes_fusion_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp]),
+    "nefes_fusion_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "nefes_affine_color_fwd": (i32, [vp, vp, vp, i32, i64, vp, vp, vp, vp]),
+    "nefes_affine_color_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp]),
     "nefes_render_rays_workspace": (i32, [C.POINTER(RenderCfg), i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "nefes_render_rays_fwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), vp, vp, vp]),
     "nefes_render_rays_bwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), C.POINTER(CompGrad),
                                     C.POINTER(CompGrad), vp, vp, vp, vp, vp, vp]),
     "nefes_mlp_dgrad": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
     "nefes_mlp_wgrad": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
-    "nefes_pose_rays_fwd": (i32, [vp, vp, i32, i32, f32, f32, f32, vp, vp, i32, vp]),
+    "nefes_pose_rays_fwd": (i32, [vp, vp, i32, i32, f32, f32, f32, vp, vp, i32, vp, vp]),
     "nefes_pose_rays_bwd": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
     "nefes_cosine_loss_fwd": (i32, [vp, vp, i32, i32, vp, vp]),
     "nefes_cosine_loss_bwd": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]),
-    "nefes_pose_adam_step": (i32, [vp, vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, vp]),
+    "nefes_pose_adam_step": (i32, [vp, vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, vp, vp]),
     "nefes_prof_enable": (i32, [i32]),
     "nefes_prof_report": (i32, [C.c_char_p, i32]),
     "nefes_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]),

@@ -10,23 +10,69 @@
 namespace nefes {
 
 struct Pose34 { float m[12]; };
+// What lies between the six learned parameters and the pose the renderer sees:
+//   se3 = 0  c2w = [Exp(r) R0 | t + t0]                 poses.py:25-50 with lietorch=False (lie_group_helper.py:60-81)
+//   se3 = 1  c2w = [Exp(r) R0 | V(r) t + t0]            poses.py:31-32, 44: SE3.exp([t, r]).matrix(), the translation goes through
+//                                                       V(r) = I + (1 - cos n)/n^2 K + (n - sin n)/n^3 K^2   (lietorch=True)
+//   then the translation column becomes ((x * sc) + move) * sc2                 dm/direct_pose_model.py:210-232 (fix_coord_supp)
+struct PoseChain { int se3; float sc, mv[3], sc2; };
 
-// c2w = [Exp(r) @ R0 | t + t0] in fp32, op for op as LearnPose.forward / lie_group_helper.Exp compute it
-__device__ __forceinline__ Pose34 pose_c2w(const float* __restrict__ pose6, const float* __restrict__ init) {
+// sin(n)/n, (1 - cos n)/n^2, (n - sin n)/n^3 and their derivatives in n, fp64, series below 1e-4 (the closed forms cancel)
+struct ExpCoef { double a, b, c, da, db, dc; };
+__device__ __forceinline__ ExpCoef exp_coef(double n) {
+  ExpCoef e;
+  if (n < 1e-4) {
+    const double n2 = n * n;
+    e.a = 1.0 - n2 / 6.0;          e.da = -n / 3.0;
+    e.b = 0.5 - n2 / 24.0;         e.db = -n / 12.0;
+    e.c = 1.0 / 6.0 - n2 / 120.0;  e.dc = -n / 60.0;
+  } else {
+    const double sn = sin(n), cs = cos(n), n2 = n * n;
+    e.a = sn / n;                  e.da = (n * cs - sn) / n2;
+    e.b = (1.0 - cs) / n2;         e.db = (n * sn - 2.0 * (1.0 - cs)) / (n2 * n);
+    e.c = (n - sn) / (n2 * n);     e.dc = ((1.0 - cs) * n - 3.0 * (n - sn)) / (n2 * n2);
+  }
+  return e;
+}
+
+// c2w in fp32, op for op as LearnPose.forward / lie_group_helper.Exp compute it (se3 = 0); the SE(3) exponential (se3 = 1)
+// is evaluated in fp64 and rounded -- lietorch is not vendored by the reference, so that branch follows the closed form
+__device__ __forceinline__ Pose34 pose_c2w(const float* __restrict__ pose6, const float* __restrict__ init, const PoseChain ch) {
   const float r0 = pose6[0], r1 = pose6[1], r2 = pose6[2];
   const float K[9] = {0.f, -r2, r1, r2, 0.f, -r0, -r1, r0, 0.f};
-  const float n = sqrtf(r0 * r0 + r1 * r1 + r2 * r2) + 1e-15f;
-  const float a = sinf(n) / n, b = (1.f - cosf(n)) / (n * n);
-  float R[9];
+  float R[9], tr[3];
+  if (ch.se3) {
+    const double n = sqrt((double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2);
+    const ExpCoef e = exp_coef(n);
+    const double t[3] = {pose6[3], pose6[4], pose6[5]};
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i) {
+      double vt = t[i];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float kk = 0.f;
+      for (int j = 0; j < 3; ++j) {
+        double kk = 0.0;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) kk += K[i * 3 + k] * K[k * 3 + j];
-      R[i * 3 + j] = (i == j ? 1.f : 0.f) + a * K[i * 3 + j] + b * kk;
+        for (int k = 0; k < 3; ++k) kk += (double)K[i * 3 + k] * (double)K[k * 3 + j];
+        R[i * 3 + j] = (float)((i == j ? 1.0 : 0.0) + e.a * K[i * 3 + j] + e.b * kk);
+        vt += (e.b * K[i * 3 + j] + e.c * kk) * t[j];
+      }
+      tr[i] = (float)vt;
     }
+  } else {
+    const float n = sqrtf(r0 * r0 + r1 * r1 + r2 * r2) + 1e-15f;
+    const float a = sinf(n) / n, b = (1.f - cosf(n)) / (n * n);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float kk = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) kk += K[i * 3 + k] * K[k * 3 + j];
+        R[i * 3 + j] = (i == j ? 1.f : 0.f) + a * K[i * 3 + j] + b * kk;
+      }
+      tr[i] = pose6[3 + i];
+    }
+  }
   Pose34 P;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -37,16 +83,17 @@ __device__ __forceinline__ Pose34 pose_c2w(const float* __restrict__ pose6, cons
       for (int k = 0; k < 3; ++k) s += R[i * 3 + k] * init[k * 4 + j];
       P.m[i * 4 + j] = s;
     }
-    P.m[i * 4 + 3] = pose6[3 + i] + init[i * 4 + 3];
+    P.m[i * 4 + 3] = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(tr[i], init[i * 4 + 3]), ch.sc), ch.mv[i]), ch.sc2);
   }
   return P;
 }
 
 __global__ void pose_rays_fwd_kernel(const float* __restrict__ pose6, const float* __restrict__ init, int H, int W, float focal,
-                                     float near, float far, float* __restrict__ c2w_out, float* __restrict__ rays, int ld) {
+                                     float near, float far, float* __restrict__ c2w_out, float* __restrict__ rays, int ld,
+                                     const PoseChain ch) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= H * W) return;
-  const Pose34 P = pose_c2w(pose6, init);
+  const Pose34 P = pose_c2w(pose6, init, ch);
   if (p == 0 && c2w_out != nullptr)
 #pragma unroll
     for (int q = 0; q < 12; ++q) c2w_out[q] = P.m[q];
@@ -173,13 +220,19 @@ __global__ void cosine_grad_kernel(const float* __restrict__ feat, const float* 
 // iteration, so an iteration needs no memset.
 __global__ void pose_adam_kernel(float* __restrict__ pose6, const float* __restrict__ init, float* __restrict__ d_c2w,
                                  float* __restrict__ zero, int n_zero, float* __restrict__ state, float lr_r, float lr_t,
-                                 float beta1, float beta2, float eps) {
+                                 float beta1, float beta2, float eps, const PoseChain ch) {
   if (threadIdx.x == 0) {
     const double r[3] = {pose6[0], pose6[1], pose6[2]};
     const double nn = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-    const double n = nn + 1e-15;
-    const double a = sin(n) / n, b = (1.0 - cos(n)) / (n * n);
-    const double da = (n * cos(n) - sin(n)) / (n * n), db = (n * sin(n) - 2.0 * (1.0 - cos(n))) / (n * n * n);
+    ExpCoef e;
+    if (ch.se3) {
+      e = exp_coef(nn);
+    } else {                                          // the reference's own formula: n = |r| + 1e-15 (lie_group_helper.py:66)
+      const double n = nn + 1e-15;
+      e.a = sin(n) / n; e.b = (1.0 - cos(n)) / (n * n);
+      e.da = (n * cos(n) - sin(n)) / (n * n); e.db = (n * sin(n) - 2.0 * (1.0 - cos(n))) / (n * n * n);
+      e.c = 0.0; e.dc = 0.0;
+    }
     const double K[9] = {0.0, -r[2], r[1], r[2], 0.0, -r[0], -r[1], r[0], 0.0};
     double KK[9];
     for (int i = 0; i < 3; ++i)
@@ -196,6 +249,9 @@ __global__ void pose_adam_kernel(float* __restrict__ pose6, const float* __restr
         for (int k = 0; k < 3; ++k) s += (double)d_c2w[i * 4 + k] * (double)init[j * 4 + k];
         GE[i * 3 + j] = s;
       }
+    // cotangent of the translation BEFORE fix_coord_supp's scale / shift / scale
+    const double gt[3] = {(double)d_c2w[3] * ch.sc * ch.sc2, (double)d_c2w[7] * ch.sc * ch.sc2, (double)d_c2w[11] * ch.sc * ch.sc2};
+    const double t[3] = {pose6[3], pose6[4], pose6[5]};
     double g[6];
     for (int k = 0; k < 3; ++k) {
       double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // skew(e_k)
@@ -203,16 +259,22 @@ __global__ void pose_adam_kernel(float* __restrict__ pose6, const float* __restr
       if (k == 1) { E[2] = 1.0; E[6] = -1.0; }
       if (k == 2) { E[1] = -1.0; E[3] = 1.0; }
       const double dn = nn > 0.0 ? r[k] / nn : 0.0;  // torch: the norm's subgradient at 0 is 0
-      double s = 0.0;
+      double s = 0.0, gv = gt[k];
       for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
           double ek = 0.0;                            // (E K + K E)_ij
           for (int q = 0; q < 3; ++q) ek += E[i * 3 + q] * K[q * 3 + j] + K[i * 3 + q] * E[q * 3 + j];
-          const double dR = da * dn * K[i * 3 + j] + a * E[i * 3 + j] + db * dn * KK[i * 3 + j] + b * ek;
+          const double dR = e.da * dn * K[i * 3 + j] + e.a * E[i * 3 + j] + e.db * dn * KK[i * 3 + j] + e.b * ek;
           s += GE[i * 3 + j] * dR;
+          if (ch.se3) {
+            // translation = V(r) t: d/dr_k through V = I + b K + c K^2, and d/dt_k = column k of V
+            const double dV = e.db * dn * K[i * 3 + j] + e.b * E[i * 3 + j] + e.dc * dn * KK[i * 3 + j] + e.c * ek;
+            s += gt[i] * dV * t[j];
+            if (j == k) gv += gt[i] * (e.b * K[i * 3 + j] + e.c * KK[i * 3 + j]);
+          }
         }
       g[k] = s;
-      g[3 + k] = (double)d_c2w[k * 4 + 3];
+      g[3 + k] = gv;
     }
     const float step = state[12] + 1.f;
     state[12] = step;
@@ -235,12 +297,21 @@ __global__ void pose_adam_kernel(float* __restrict__ pose6, const float* __restr
 
 extern "C" {
 
+// chain6 (HOST pointer, may be NULL = {0, 1, 0, 0, 0, 1}): {se3, pose_scale, move_x, move_y, move_z, pose_scale2}
+static nefes::PoseChain pose_chain(const float* chain6) {
+  nefes::PoseChain ch = {0, 1.f, {0.f, 0.f, 0.f}, 1.f};
+  if (chain6 != nullptr) {
+    ch.se3 = chain6[0] != 0.f ? 1 : 0; ch.sc = chain6[1]; ch.mv[0] = chain6[2]; ch.mv[1] = chain6[3]; ch.mv[2] = chain6[4]; ch.sc2 = chain6[5];
+  }
+  return ch;
+}
+
 int nefes_pose_rays_fwd(const float* pose6, const float* init_c2w, int H, int W, float focal, float near, float far,
-                        float* c2w_out, float* ray_batch, int ld, void* stream) {
+                        float* c2w_out, float* ray_batch, int ld, const float* chain6, void* stream) {
   NEFES_REQUIRE(pose6 && init_c2w && ray_batch, NEFES_EINVAL, "nefes_pose_rays_fwd: null pointer");
   NEFES_REQUIRE(H > 0 && W > 0 && focal > 0.f && ld >= 11, NEFES_EINVAL, "nefes_pose_rays_fwd: bad shape H=%d W=%d ld=%d", H, W, ld);
   nefes::pose_rays_fwd_kernel<<<(unsigned)nefes::ceil_div((int64_t)H * W, 128), 128, 0, (cudaStream_t)stream>>>(
-      pose6, init_c2w, H, W, focal, near, far, c2w_out, ray_batch, ld);
+      pose6, init_c2w, H, W, focal, near, far, c2w_out, ray_batch, ld, pose_chain(chain6));
   NEFES_CHECK_LAUNCH("pose_rays_fwd");
   return NEFES_OK;
 }
@@ -276,11 +347,11 @@ int nefes_cosine_loss_bwd(const float* feat, const float* target, const float* s
 }
 
 int nefes_pose_adam_step(float* pose6, const float* init_c2w, float* d_c2w, float* zero, int n_zero, float* state13,
-                         float lr_r, float lr_t, float beta1, float beta2, float eps, void* stream) {
+                         float lr_r, float lr_t, float beta1, float beta2, float eps, const float* chain6, void* stream) {
   NEFES_REQUIRE(pose6 && init_c2w && d_c2w && state13, NEFES_EINVAL, "nefes_pose_adam_step: null pointer");
   NEFES_REQUIRE(n_zero >= 0 && (zero != nullptr || n_zero == 0), NEFES_EINVAL, "nefes_pose_adam_step: bad zero range");
   nefes::pose_adam_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(pose6, init_c2w, d_c2w, zero, n_zero, state13, lr_r, lr_t, beta1,
-                                                               beta2, eps);
+                                                               beta2, eps, pose_chain(chain6));
   NEFES_CHECK_LAUNCH("pose_adam");
   return NEFES_OK;
 }

@@ -34,9 +34,9 @@ def raw2outputs_NeRFH_NFF(raw, z_vals, raw_noise_std=0, output_transient=False, 
                           test_time=False, typ="coarse", store_rgb=False, transient_at_test=False, noise=None):
     """Drop-in for nerfh_nff.py:25.  Returns (rgb_map, features_map, disp_map, acc_map, weights,
     depth_map, transient_sigmas, beta).  `noise` (extra, optional) supplies randn*raw_noise_std
-    explicitly for RNG parity; otherwise it is drawn on the device when raw_noise_std > 0."""
-    if white_bkgd:
-        raise RuntimeError("nefes_b200: white_bkgd=True is not supported (no reference config uses it)")
+    explicitly for RNG parity; otherwise it is drawn on the device when raw_noise_std > 0.
+    white_bkgd acts where the reference still applies it (:126-127: the transient compositing adds 1 - acc to the static
+    colour); in the other branches the reference has it commented out (:104, :158) and so it has no effect there."""
     if typ == "coarse" and test_time and not store_rgb:                      # :33-35, :83-89
         acc, weights = ops.composite(raw[..., :1], z_vals, None, L.COMP_SIGMA, beta_min)
         return None, None, None, acc, weights, None, None, None
@@ -45,6 +45,8 @@ def raw2outputs_NeRFH_NFF(raw, z_vals, raw_noise_std=0, output_transient=False, 
             raise RuntimeError(f"nefes_b200: transient compositing expects 137 channels, got {raw.shape[-1]}")
         mode = L.COMP_TRANSIENT_STATIC_ONLY if (test_time and not transient_at_test) else L.COMP_TRANSIENT
         rgb, feat, disp, acc, weights, depth, beta, tsig = ops.composite(raw, z_vals, None, mode, beta_min)
+        if white_bkgd and mode == L.COMP_TRANSIENT:
+            rgb = rgb + (1 - acc[..., None])
         return rgb, feat, disp, acc, weights, depth, tsig, beta
     if raw.shape[-1] != 132:
         raise RuntimeError(f"nefes_b200: static compositing expects 132 channels, got {raw.shape[-1]}")
@@ -124,8 +126,9 @@ def get_embedder(multires, i=0, reduce_mode=-1, epochToMaxFreq=-1):
 
 # ------------------------------------------------------------------------------------------------
 class FusionNet(nn.Module):
-    """nerfh_nff.py:356-418 -- caller-side CNN after the render path (SURVEY 8f-2, "next");
-    kept as plain torch so checkpoints load and run_fusion_net works."""
+    """nerfh_nff.py:356-418 -- the CNN right after the render path.  The module owns the parameters under the
+    reference's keys (net.0 ... net.7) so checkpoints load; NeRFH_NFF.run_fusion_net runs it on the engine (fusion.py ->
+    nefes_fusion_fwd/_bwd); this torch forward remains for NCHW callers and as a CPU mirror."""
     mean = [0.485, 0.456, 0.406]
     std = [0.229, 0.224, 0.225]
 
@@ -303,9 +306,15 @@ class NeRFH_NFF(nn.Module):
         return self.query(xyz, dirs, mode)[:, 0]
 
     def run_fusion_net(self, rgb, feature, H, W, B):
-        """nerfh_nff.py:578-603."""
+        """nerfh_nff.py:578-603: rgb [B*H*W,3], feature [B*H*W,128] -> (render_rgb [B,3,H,W], render_feature [B,128,H,W],
+        feature_output [B,128,H,W]).  On CUDA the four convolutions + BatchNorm run as engine launches on the pixel-major
+        tensors the render produced (no NCHW shuffle on the way in); the NCHW results are views."""
         render_rgb = rgb.reshape(B, H, W, 3).permute(0, 3, 1, 2)
         render_feature = feature.reshape(B, H, W, self.W_features).permute(0, 3, 1, 2)
+        if rgb.is_cuda:
+            from . import fusion
+            out = fusion.fusion_net(self.fusion_net, rgb.reshape(-1, 3), feature.reshape(-1, self.W_features), B, H, W)
+            return render_rgb, render_feature, out.reshape(B, H, W, self.W_features).permute(0, 3, 1, 2)
         fusion_input = torch.cat([render_rgb, render_feature], dim=1)
         return render_rgb, render_feature, self.fusion_net(fusion_input)
 
@@ -314,6 +323,10 @@ class NeRFH_NFF(nn.Module):
         of image b's histogram (cast to integers first, as the reference does)."""
         if not (getattr(args, "encode_hist", False) and self.typ == "coarse"):
             raise RuntimeError("nefes_b200: affine_color_transform needs args.encode_hist and the coarse model")
+        if rgb.is_cuda:
+            from . import fusion
+            out, self.a_embedded = fusion.affine_color(self.exposure_embedding.params, rgb, hist, batch_size)
+            return out
         self.a_embedded = self.exposure_embedding(hist.long()).float()
         kernel = self.a_embedded[:, :9].reshape(-1, 3, 3)
         bias = self.a_embedded[:, 9:].reshape(-1, 3, 1)

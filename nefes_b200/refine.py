@@ -30,27 +30,73 @@ def so3_exp(r):
     return eye + (torch.sin(n) / n) * K + ((1 - torch.cos(n)) / n ** 2) * (K @ K)
 
 
+def se3_exp(t, r):
+    """SE3.exp([t, r]).matrix() of poses.py:31-32, 44 (the lietorch=True branch; lietorch itself is an un-vendored CUDA
+    dependency of the reference, so this is the closed form it implements): R = Exp(r), translation = V(r) t with
+    V = I + (1 - cos n)/n^2 K + (n - sin n)/n^3 K^2.  Evaluated in fp64 (series below n = 1e-4, where the closed-form
+    coefficients cancel) and cast back; differentiable in t and r.  Returns (R [3,3], V t [3])."""
+    dt = r.dtype
+    r64, t64 = r.double(), t.double()
+    K = vec2skew(r64)
+    n2 = (r64 * r64).sum()
+    n = torch.sqrt(n2.clamp_min(1e-300))
+    small = n2 < 1e-8
+    ns = torch.where(small, torch.ones_like(n), n)                    # keeps the unused branch finite for autograd
+    a = torch.where(small, 1 - n2 / 6, torch.sin(ns) / ns)
+    b = torch.where(small, 0.5 - n2 / 24, (1 - torch.cos(ns)) / ns ** 2)
+    c = torch.where(small, 1 / 6 - n2 / 120, (ns - torch.sin(ns)) / ns ** 3)
+    eye = torch.eye(3, dtype=torch.float64, device=r.device)
+    KK = K @ K
+    return (eye + a * K + b * KK).to(dt), ((eye + b * K + c * KK) @ t64).to(dt)
+
+
 class LearnPose(nn.Module):
-    """poses.py:6-50 with lietorch=False: c2w = [Exp(r) @ R0 | t + t0] per camera."""
+    """poses.py:6-50: c2w = [Exp(r) @ R0 | t + t0] per camera (lietorch=False, the reference's own pure-torch chain), or
+    [Exp(r) @ R0 | V(r) t + t0] (lietorch=True: SE3.exp([t, r]), what dm/DFM_pose_refine.py:374 constructs)."""
 
     def __init__(self, num_cams, learn_R=True, learn_t=True, init_c2w=None, lietorch=False):
         super().__init__()
-        if lietorch:
-            raise RuntimeError("nefes_b200: the lietorch SE3 path is a third-party CUDA dependency that is not vendored; "
-                               "use lietorch=False (the reference's own pure-torch path)")
         self.num_cams = num_cams
+        self.lietorch = bool(lietorch)
         self.init_c2w = None if init_c2w is None else nn.Parameter(init_c2w.clone(), requires_grad=False)
         self.r = nn.Parameter(torch.zeros(num_cams, 3), requires_grad=learn_R)
         self.t = nn.Parameter(torch.zeros(num_cams, 3), requires_grad=learn_t)
 
     def forward(self, cam_id: int):
-        R = so3_exp(self.r[cam_id])
-        t = self.t[cam_id]
+        if self.lietorch:
+            R, t = se3_exp(self.t[cam_id], self.r[cam_id])
+        else:
+            R, t = so3_exp(self.r[cam_id]), self.t[cam_id]
         if self.init_c2w is not None:
             R = R @ self.init_c2w[cam_id, :3, :3]
             t = t + self.init_c2w[cam_id, :3, 3]
         c2w = torch.eye(4, dtype=R.dtype, device=R.device)
         return torch.cat([torch.cat([R, t[:, None]], 1), c2w[3:]], 0)
+
+
+def fix_coord_supp(args, pose, world_setup_dict, device=None):
+    """dm/direct_pose_model.py:210-232: pose [N,3,4]; the translation column becomes ((x * pose_scale) + move_all_cam_vec) *
+    pose_scale2.  Out of place (the reference writes into its argument; callers use the return value)."""
+    if not torch.is_tensor(pose):
+        pose = torch.as_tensor(pose, dtype=torch.float32, device=device)
+    move = torch.as_tensor(world_setup_dict['move_all_cam_vec'], dtype=pose.dtype, device=pose.device)
+    tr = (pose[:, :3, 3] * world_setup_dict['pose_scale'] + move) * world_setup_dict['pose_scale2']
+    return torch.cat([pose[:, :3, :3], tr[..., None]], -1)
+
+
+def svd_reg(pose):
+    """dm/DFM_pose_refine.py:119-129 (Direct-PN: orthogonalise the rotation block): pose [B,3,4] -> [B,3,4], R <- U V^T."""
+    u, s, v = torch.svd(pose[:, :3, :3])
+    return torch.cat([u @ v.transpose(-2, -1), pose[:, :3, 3:]], -1)
+
+
+def _chain6(lietorch, world_setup_dict):
+    """The engine's pose-chain descriptor {se3, pose_scale, move(3), pose_scale2} (include/nefes_b200.h) as a ctypes array."""
+    import ctypes
+    w = world_setup_dict or {}
+    mv = [float(x) for x in w.get('move_all_cam_vec', (0., 0., 0.))]
+    return (ctypes.c_float * 6)(1.0 if lietorch else 0.0, float(w.get('pose_scale', 1.0)), mv[0], mv[1], mv[2],
+                                float(w.get('pose_scale2', 1.0)))
 
 
 def feature_loss(feature_rgb, feature_target):
@@ -64,10 +110,11 @@ class PoseRefiner:
     A query only rewrites the graph's static inputs (initial pose, target features) and zeroes the pose delta and the
     Adam state; the arithmetic is that of the eager loop (`refine_pose(..., graph=False)`)."""
 
-    def __init__(self, H, W, focal, render_kwargs_test, lr_r, lr_t, chunk, device, feat_shape):
+    def __init__(self, H, W, focal, render_kwargs_test, lr_r, lr_t, chunk, device, feat_shape, lietorch=False, world_setup_dict=None):
         self.args = (H, W, focal, chunk)
         self.kw = render_kwargs_test
-        self.pose = LearnPose(1, True, True, torch.eye(4, device=device)[:3][None]).to(device)
+        self.world = world_setup_dict
+        self.pose = LearnPose(1, True, True, torch.eye(4, device=device)[:3][None], lietorch=lietorch).to(device)
         self.opt = torch.optim.Adam([{"params": [self.pose.r], "lr": lr_r}, {"params": [self.pose.t], "lr": lr_t}], capturable=True)
         self.target = torch.zeros(feat_shape, device=device)
         self.hist = torch.zeros(1, 10, device=device)
@@ -75,8 +122,10 @@ class PoseRefiner:
 
     def _iter(self):
         H, W, focal, chunk = self.args
-        c2w = self.pose(0)
-        rgb, disp, acc, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], img_idx=self.hist, **self.kw)
+        c2w = self.pose(0)[:3, :4]
+        if self.world is not None:
+            c2w = fix_coord_supp(None, c2w[None], self.world)[0]
+        rgb, disp, acc, extras = render(H, W, focal, chunk=chunk, c2w=c2w, img_idx=self.hist, **self.kw)
         loss = feature_loss(extras["feat_map"].t(), self.target)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -123,7 +172,7 @@ class PoseRefiner:
             else:
                 losses.append(self._iter())
         with torch.no_grad():
-            return self.pose(0)[:3, :4].clone(), losses
+            return self.pose(0)[:3, :4].clone(), losses        # the LEARNED pose (before fix_coord_supp), as the reference reports it
 
 
 class EnginePoseRefiner:
@@ -135,8 +184,9 @@ class EnginePoseRefiner:
     refinement configuration (standard query function, frozen fields, test_time render, per_pixel=False loss)."""
     HIST = 1024
 
-    def __init__(self, H, W, focal, kw, lr_r, lr_t, device, n_ch):
+    def __init__(self, H, W, focal, kw, lr_r, lr_t, device, n_ch, lietorch=False, world_setup_dict=None):
         c, f, args = kw["network_fn"], kw["network_fine"], kw["args"]
+        self.chain, self.plain = _chain6(lietorch, world_setup_dict), _chain6(lietorch, None)
         dev = torch.device(device)
         self.H, self.W, self.focal, self.near, self.far = int(H), int(W), float(focal), float(kw["near"]), float(kw["far"])
         self.lr_r, self.lr_t, self.N, self.C, self.dev = float(lr_r), float(lr_t), int(H) * int(W), int(n_ch), dev
@@ -156,7 +206,7 @@ class EnginePoseRefiner:
         lib, p, st = L.lib(), L.ptr, L.stream_of(self.pose6)
         with torch.cuda.device(self.dev):
             L.check(lib.nefes_pose_rays_fwd(p(self.pose6), p(self.init), self.H, self.W, self.focal, self.near, self.far,
-                                            p(self.c2w), p(self.call.rays), 21, st), "nefes_pose_rays_fwd")
+                                            p(self.c2w), p(self.call.rays), 21, self.chain, st), "nefes_pose_rays_fwd")
             self.call.forward()
             L.check(lib.nefes_cosine_loss_fwd(p(self.call.feat), p(self.target), self.N, self.C, p(self.stats), st),
                     "nefes_cosine_loss_fwd")
@@ -167,7 +217,7 @@ class EnginePoseRefiner:
             L.check(lib.nefes_pose_rays_bwd(p(d_rays), p(self.call.rays), 21, self.H, self.W, self.focal, p(self.d_c2w), st),
                     "nefes_pose_rays_bwd")
             L.check(lib.nefes_pose_adam_step(p(self.pose6), p(self.init), p(self.d_c2w), p(self.stats), 3 * self.C,
-                                             p(self.state), self.lr_r, self.lr_t, 0.9, 0.999, 1e-8, st), "nefes_pose_adam_step")
+                                             p(self.state), self.lr_r, self.lr_t, 0.9, 0.999, 1e-8, self.chain, st), "nefes_pose_adam_step")
 
     @torch.no_grad()
     def refine(self, init_c2w, feat_target, n_iters, use_graph=True):
@@ -193,8 +243,8 @@ class EnginePoseRefiner:
             else:
                 self._iter()
         L.check(L.lib().nefes_pose_rays_fwd(L.ptr(self.pose6), L.ptr(self.init), self.H, self.W, self.focal, self.near, self.far,
-                                            L.ptr(self.c2w), L.ptr(self.call.rays), 21, L.stream_of(self.pose6)),
-                "nefes_pose_rays_fwd")               # c2w of the final parameters
+                                            L.ptr(self.c2w), L.ptr(self.call.rays), 21, self.plain, L.stream_of(self.pose6)),
+                "nefes_pose_rays_fwd")               # learned c2w of the final parameters (before fix_coord_supp)
         return self.c2w.clone(), list(self.loss_hist[:n_iters].clone())
 
 
@@ -222,13 +272,16 @@ def clear_refiner_cache():
 
 
 def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=50, lr_r=0.0087, lr_t=0.01,
-                hist=None, chunk=32768, graph=None, engine=None):
+                hist=None, chunk=32768, graph=None, engine=None, lietorch=False, world_setup_dict=None):
     """One query: `n_iters` Adam steps on the se(3)-style delta (DFM_pose_refine.py:380-440).
     feat_target [C, H*W].  Returns (refined c2w [3,4], list of losses).
     graph (default: on for n_iters >= 10 on CUDA): run the iterations as replays of a captured CUDA graph (PoseRefiner),
     cached per (camera, networks, learning rates) so that every further query pays no capture either.
     engine (default: on where it applies): the iteration is EnginePoseRefiner's 24 engine launches (no torch op); False
-    keeps the torch pose chain / loss / optimiser around the engine render; True raises where it does not apply."""
+    keeps the torch pose chain / loss / optimiser around the engine render; True raises where it does not apply.
+    lietorch: the pose delta goes through SE3.exp([t, r]) (poses.py:31-32, what DFM_pose_refine.py:374 constructs) instead of
+    the reference's pure-torch [Exp(r) | t].  world_setup_dict: fix_coord_supp's pose_scale / move_all_cam_vec / pose_scale2
+    (direct_pose_model.py:210-232) between the learned pose and the renderer; the returned pose is the learned one."""
     dev = feat_target.device
     use_graph = ((n_iters >= 10) if graph is None else bool(graph)) and dev.type == "cuda"
     kw_ = render_kwargs_test
@@ -242,7 +295,7 @@ def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=
            kw_.get("N_samples"), kw_.get("N_importance"), getattr(kw_.get("network_query_fn"), "netchunk", None),
            bool(getattr(a_, "NeRFW", False)), bool(getattr(a_, "transient_at_test", False)),
            bool(getattr(a_, "nerfh_nff", False)), bool(getattr(a_, "use_fine_only", False)),
-           float(kw_.get("near", 0.)), float(kw_.get("far", 1.)))
+           float(kw_.get("near", 0.)), float(kw_.get("far", 1.)), bool(lietorch), tuple(_chain6(lietorch, world_setup_dict)))
     while len(_REFINERS) >= _MAX_REFINERS:           # bounded: a refiner pins its GPU workspaces
         _REFINERS.pop(next(iter(_REFINERS)))
     if (engine is None or engine) and dev.type == "cuda" and H * W <= chunk and \
@@ -250,7 +303,7 @@ def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=
         ref = _REFINERS.get(("engine",) + key)
         if ref is None:
             ref = _REFINERS[("engine",) + key] = EnginePoseRefiner(H, W, focal, render_kwargs_test, lr_r, lr_t, dev,
-                                                                   feat_target.shape[0])
+                                                                   feat_target.shape[0], lietorch, world_setup_dict)
         return ref.refine(init_c2w.to(dev), feat_target, n_iters, use_graph=use_graph)
     if engine:
         raise RuntimeError("nefes_b200: the engine-resident refinement iteration does not cover this configuration "
@@ -258,15 +311,18 @@ def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=
     if use_graph:
         ref = _REFINERS.get(key)
         if ref is None:
-            ref = _REFINERS[key] = PoseRefiner(H, W, focal, render_kwargs_test, lr_r, lr_t, chunk, dev, tuple(feat_target.shape))
+            ref = _REFINERS[key] = PoseRefiner(H, W, focal, render_kwargs_test, lr_r, lr_t, chunk, dev, tuple(feat_target.shape),
+                                               lietorch, world_setup_dict)
         return ref.refine(init_c2w, feat_target, n_iters, hist)
-    pose = LearnPose(1, True, True, init_c2w[None].to(dev)).to(dev)
+    pose = LearnPose(1, True, True, init_c2w[None].to(dev), lietorch=lietorch).to(dev)
     opt = torch.optim.Adam([{"params": [pose.r], "lr": lr_r}, {"params": [pose.t], "lr": lr_t}])
     hist = torch.zeros(1, 10, device=dev) if hist is None else hist
     losses = []
     for _ in range(n_iters):
-        c2w = pose(0)
-        rgb, disp, acc, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], img_idx=hist, **render_kwargs_test)
+        c2w = pose(0)[:3, :4]
+        if world_setup_dict is not None:
+            c2w = fix_coord_supp(None, c2w[None], world_setup_dict)[0]
+        rgb, disp, acc, extras = render(H, W, focal, chunk=chunk, c2w=c2w, img_idx=hist, **render_kwargs_test)
         loss = feature_loss(extras["feat_map"].t(), feat_target)
         opt.zero_grad(set_to_none=True)
         loss.backward()

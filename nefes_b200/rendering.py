@@ -97,16 +97,13 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
                 i_epoch=-1, embedding_a=None, embedding_t=None, test_time=False, args=None, volume=None,
                 t_rand=None, u=None, noise=None, return_aux=False):
-    """Drop-in for rendering.py:68-180."""
-    if lindisp:
-        raise RuntimeError("nefes_b200: lindisp sampling is not built (no reference config uses it)")
+    """Drop-in for rendering.py:68-180.  lindisp / white_bkgd (dormant in every reference config) take the staged route."""
     L.need_cuda(ray_batch)
     ray_batch = ray_batch if ray_batch.dtype == torch.float32 else ray_batch.float()
     if not ray_batch.is_contiguous():
         ray_batch = ray_batch.contiguous()
-    if white_bkgd:
-        raise RuntimeError("nefes_b200: white_bkgd=True is not supported (no reference config uses it)")
-    if _fused_applies(ray_batch, network_fn, network_query_fn, N_samples, N_importance, network_fine, args):
+    if not lindisp and not white_bkgd and \
+            _fused_applies(ray_batch, network_fn, network_query_fn, N_samples, N_importance, network_fine, args):
         return _render_rays_fused(ray_batch, network_fn, N_samples, perturb, N_importance, network_fine, raw_noise_std, pytest,
                                   test_time, args, t_rand, u, noise, return_aux)
     N_rays, width = ray_batch.shape
@@ -117,8 +114,18 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
 
     if perturb > 0. and t_rand is None:
         t_rand = torch.rand(N_rays, N_samples, device=dev)                        # rendering.py:110
-    z_vals = ops.sample_coarse(ray_batch.detach()[:, 6], ray_batch.detach()[:, 7], width, N_rays, N_samples,
-                               t_rand if perturb > 0. else None)
+    if lindisp:                                                                   # rendering.py:100, :104-112: glue, as written
+        near, far = ray_batch.detach()[:, 6:7], ray_batch.detach()[:, 7:8]
+        t_vals = ops.linspace01(N_samples, dev)
+        z_vals = (1. / (1. / near * (1. - t_vals) + 1. / far * t_vals)).expand(N_rays, N_samples)
+        if perturb > 0.:
+            mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+            upper, lower = torch.cat([mids, z_vals[..., -1:]], -1), torch.cat([z_vals[..., :1], mids], -1)
+            z_vals = lower + (upper - lower) * t_rand
+        z_vals = z_vals.contiguous()
+    else:
+        z_vals = ops.sample_coarse(ray_batch.detach()[:, 6], ray_batch.detach()[:, 7], width, N_rays, N_samples,
+                                   t_rand if perturb > 0. else None)
     pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]      # rendering.py:114
 
     store_rgb = N_importance == 0

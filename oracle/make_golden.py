@@ -276,6 +276,73 @@ def main():
                "test/z_fine": out_o["_aux"]["z_fine"][sub], "test/c2w": c2w})
     np.savez_compressed(os.path.join(OUT, "g5_render.npz"), **npy(g5))
 
+    # ---- G7: the two dormant options of render_rays, lindisp (rendering.py:97-100) and white_bkgd (nerfh_nff.py:126-127) ----
+    for p_ in list(ref_c.parameters()) + list(ref_f.parameters()):
+        p_.requires_grad_(True)
+    g7 = {}
+    rays7 = (ro.reshape(-1, 3)[pix[:32]], rd.reshape(-1, 3)[pix[:32]])
+    base7 = dict(base)
+    base7.update(near=0.5, far=4., lindisp=True, white_bkgd=True)
+    torch.manual_seed(77)
+    rgb, disp, acc, ex = R.render(H, W, focal, chunk=32768, rays=rays7, img_idx=hist, perturb=1.0, raw_noise_std=0., test_time=False,
+                                  retraw=True, **base7)
+    t_rand7, u7 = O.draw_train_randoms(32, seed=77)
+    out7 = O.render(H, W, focal, Pc, Pf, rays=rays7, near=0.5, far=4., hist=hist, test_time=False, t_rand=t_rand7, u=u7,
+                    lindisp=True, white_bkgd=True)
+    for k, v in dict(rgb_map=rgb, disp_map=disp, acc_map=acc, **ex).items():
+        eq("render[lindisp, white_bkgd]." + k, out7[k], v)
+        g7["train/" + k] = v
+    g7.update({"rays_o": rays7[0], "rays_d": rays7[1], "t_rand": t_rand7, "u": u7})
+    np.savez_compressed(os.path.join(OUT, "g7_options.npz"), **npy(g7))
+
+    # ---- G8: FusionNet (nerfh_nff.py:356-418) through run_fusion_net (:578-603), training and eval mode, forward + backward ----
+    import nefes_b200.nerfh_nff as NB
+    torch.manual_seed(5)
+    ref_fn = M.FusionNet(128)
+    torch.manual_seed(5)
+    my_fn = NB.FusionNet(128)
+    for (ka, va), (kb, vb) in zip(ref_fn.state_dict().items(), my_fn.state_dict().items()):
+        assert ka == kb, (ka, kb)
+        eq("FusionNet init " + ka, vb, va)
+    g = torch.Generator().manual_seed(8)
+    Bf, Hf, Wf = 2, 16, 16
+    rgb8, feat8 = torch.rand(Bf * Hf * Wf, 3, generator=g), torch.randn(Bf * Hf * Wf, 128, generator=g)
+    cot8 = torch.randn(Bf, 128, Hf, Wf, generator=g)
+    with torch.no_grad():                                  # non-trivial BatchNorm affine and running statistics
+        ref_fn.net[7].weight.copy_(torch.rand(128, generator=g) + 0.5)
+        ref_fn.net[7].bias.copy_(torch.randn(128, generator=g) * 0.1)
+        ref_fn.net[7].running_mean.copy_(torch.randn(128, generator=g) * 0.05)
+        ref_fn.net[7].running_var.copy_(torch.rand(128, generator=g) * 0.5 + 0.1)
+    bn_init = {k: v.clone() for k, v in ref_fn.net[7].state_dict().items()}
+    holder = types.SimpleNamespace(fusion_net=ref_fn, W_features=128)
+    g8 = {"rgb": rgb8, "feat": feat8, "cot": cot8, "B": Bf, "H": Hf, "W": Wf}
+    g8.update({"bn/" + k: v for k, v in bn_init.items()})
+    g8["w_checksum"] = torch.stack([v.double().abs().sum() for k, v in ref_fn.state_dict().items() if k.endswith("weight")])
+    for mode in ("train", "eval"):
+        ref_fn.net[7].load_state_dict(bn_init)
+        ref_fn.train(mode == "train")
+        ref_fn.zero_grad()
+        a, b = rgb8.clone().requires_grad_(True), feat8.clone().requires_grad_(True)
+        _, _, out_r = M.NeRFH_NFF.run_fusion_net(holder, a, b, Hf, Wf, Bf)
+        (out_r * cot8).sum().backward()
+        Pfn = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in ref_fn.state_dict().items()}
+        Pfn["net.7.running_mean"], Pfn["net.7.running_var"] = bn_init["running_mean"].clone(), bn_init["running_var"].clone()
+        a2, b2 = rgb8.clone().requires_grad_(True), feat8.clone().requires_grad_(True)
+        out_o = O.fusion_net(Pfn, a2, b2, Bf, Hf, Wf, training=(mode == "train"))
+        (out_o * cot8).sum().backward()
+        eq(f"fusion_net[{mode}]", out_o, out_r)
+        close(f"fusion_net[{mode}] d_rgb", a2.grad, a.grad)
+        close(f"fusion_net[{mode}] d_feat", b2.grad, b.grad)
+        g8[f"{mode}/out"], g8[f"{mode}/d_rgb"], g8[f"{mode}/d_feat"] = out_r, a.grad, b.grad
+        for k, v in ref_fn.named_parameters():
+            close(f"fusion_net[{mode}] grad {k}", Pfn[k].grad, v.grad, rtol=1e-4, atol=1e-6)
+            g8[f"{mode}/grad/{k}"] = v.grad.reshape(-1)[::37] if v.grad.numel() > 4096 else v.grad
+        if mode == "train":
+            eq("fusion_net running_mean", Pfn["net.7.running_mean"], ref_fn.net[7].running_mean)
+            eq("fusion_net running_var", Pfn["net.7.running_var"], ref_fn.net[7].running_var)
+            g8["train/running_mean"], g8["train/running_var"] = ref_fn.net[7].running_mean.clone(), ref_fn.net[7].running_var.clone()
+    np.savez_compressed(os.path.join(OUT, "g8_fusion.npz"), **npy(g8))
+
     # ---- G6: stage-2/3 loss, ColorFeatureFusionNerfWLoss (losses.py:134-173), L1 and MSE feature terms -------------
     import models.losses as RLoss
     g = torch.Generator().manual_seed(6)

@@ -114,10 +114,13 @@ def pack_rays(rays_o, rays_d, near: float, far: float, hist: torch.Tensor):
 # --------------------------------------------------------------------------------------
 # sampling
 # --------------------------------------------------------------------------------------
-def coarse_depths(near, far, n: int, t_rand: Optional[torch.Tensor], dtype=torch.float32):
-    """script/models/rendering.py:96-112 (lindisp=False).  near/far: [N,1]."""
+def coarse_depths(near, far, n: int, t_rand: Optional[torch.Tensor], dtype=torch.float32, lindisp=False):
+    """script/models/rendering.py:96-112.  near/far: [N,1].  lindisp: linear in disparity (:100)."""
     t = torch.linspace(0., 1., steps=n).to(dtype)
-    z = near * (1. - t) + far * t
+    if lindisp:
+        z = 1. / (1. / near * (1. - t) + 1. / far * t)
+    else:
+        z = near * (1. - t) + far * t
     z = z.expand(near.shape[0], n)
     if t_rand is not None:                                     # perturb > 0
         mid = .5 * (z[..., 1:] + z[..., :-1])
@@ -256,8 +259,9 @@ def _exclusive_cumprod(one_minus_alpha):
 
 
 def composite(raw, z, noise=None, output_transient=False, beta_min=0.1, test_time=False,
-              typ="coarse", store_rgb=False, transient_at_test=False) -> Composite:
-    """script/models/nerfh_nff.py:25-166.  `noise` = randn*raw_noise_std (or None = 0)."""
+              typ="coarse", store_rgb=False, transient_at_test=False, white_bkgd=False) -> Composite:
+    """script/models/nerfh_nff.py:25-166.  `noise` = randn*raw_noise_std (or None = 0).  white_bkgd acts in the one branch
+    where the reference still applies it (:126-127, transient compositing of the fine pass); elsewhere it is commented out."""
     sigma_only = typ == "coarse" and test_time and not store_rgb
     if sigma_only:
         s_sig, t_sig = raw[..., 0], None
@@ -290,7 +294,10 @@ def composite(raw, z, noise=None, output_transient=False, beta_min=0.1, test_tim
             disp = 1. / torch.max(1e-10 * torch.ones_like(depth), depth / w_s.sum(-1))
             return Composite(rgb, feat, disp, acc, w_s, depth, t_sig, torch.zeros_like(acc))
         w_s, w_t = a_s * T, a_t * T
-        rgb = (w_s[..., None] * s_rgb[..., :3]).sum(1) + (w_t[..., None] * t_rgb).sum(1)    # :119-150
+        rgb_s = (w_s[..., None] * s_rgb[..., :3]).sum(1)
+        if white_bkgd:
+            rgb_s = rgb_s + (1 - acc[..., None])                                             # :126-127
+        rgb = rgb_s + (w_t[..., None] * t_rgb).sum(1)                                        # :119-150
         feat = (w_s.detach()[..., None] * s_rgb[..., 3:]).sum(1)                            # :122-125
         beta = (w_t * t_beta).sum(-1) + beta_min                                             # :133-137
     else:
@@ -307,7 +314,7 @@ def composite(raw, z, noise=None, output_transient=False, beta_min=0.1, test_tim
 # --------------------------------------------------------------------------------------
 def march_rays(ray_batch, P_coarse, P_fine, n_coarse=64, n_fine=64, test_time=False,
                t_rand=None, noise=None, u=None, transient=True, transient_at_test=True,
-               beta_min=0.1, return_aux=False, emulate_bf16=False):
+               beta_min=0.1, return_aux=False, emulate_bf16=False, lindisp=False, white_bkgd=False):
     """script/models/rendering.py:68-180 with args.nerfh_nff=True, use_fine_only=False,
     NeRFW=`transient`.  Train mode needs t_rand [N,n_coarse] and u [N,n_fine];
     test mode (perturb=0) uses neither.
@@ -319,10 +326,10 @@ def march_rays(ray_batch, P_coarse, P_fine, n_coarse=64, n_fine=64, test_time=Fa
     o, d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     view = ray_batch[:, 8:11]
     near, far = ray_batch[:, 6:7], ray_batch[:, 7:8]
-    z_c = coarse_depths(near, far, n_coarse, None if test_time else t_rand, ray_batch.dtype)
+    z_c = coarse_depths(near, far, n_coarse, None if test_time else t_rand, ray_batch.dtype, lindisp=lindisp)
     pts = o[:, None, :] + d[:, None, :] * z_c[..., None]
     raw_c = query_field(P_coarse, pts, view, "coarse", False, test_time, q=q)
-    c0 = composite(raw_c, z_c, noise=noise, test_time=test_time, typ="coarse")
+    c0 = composite(raw_c, z_c, noise=noise, test_time=test_time, typ="coarse", white_bkgd=white_bkgd)
     mids = .5 * (z_c[..., 1:] + z_c[..., :-1])
     z_s, inds, cdf = importance_depths(mids, c0.weights[..., 1:-1], n_fine, None if test_time else u)
     z_s = z_s.detach()
@@ -330,7 +337,7 @@ def march_rays(ray_batch, P_coarse, P_fine, n_coarse=64, n_fine=64, test_time=Fa
     pts_f = o[:, None, :] + d[:, None, :] * z_f[..., None]
     raw_f = query_field(P_fine, pts_f, view, "fine", transient, test_time, q=q)
     c1 = composite(raw_f, z_f, output_transient=transient, beta_min=beta_min, test_time=test_time,
-                   typ="fine", transient_at_test=transient_at_test)
+                   typ="fine", transient_at_test=transient_at_test, white_bkgd=white_bkgd)
     ret = {"rgb_map": c1.rgb, "disp_map": c1.disp, "acc_map": c1.acc, "feat_map": c1.feat}
     if not test_time:                                                                        # rendering.py:163-176
         ret.update(rgb0=c0.rgb, disp0=c0.disp, acc0=c0.acc,
@@ -404,6 +411,48 @@ def color_feature_fusion_nerfw_loss(results, targets, switch_on=True, color_only
     if switch_on:
         return loss, loss_f, f(results["feat_fusion"], targets["feat"])
     return loss, loss_f
+
+
+IMG_MEAN, IMG_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)                # script/models/nerfh_nff.py:359-360
+
+
+def fusion_net(P, rgb, feat, B, H, W, training=True, no_bn=False, residual=False, running=None, momentum=0.1, eps=1e-5):
+    """script/models/nerfh_nff.py:578-603 (run_fusion_net) + :356-418 (FusionNet.forward): rgb [B*H*W,3], feat [B*H*W,128] ->
+    feature_output [B,128,H,W].  P: the FusionNet state_dict (net.0/2/4/6 convolutions, net.7 BatchNorm2d); `running` =
+    (running_mean, running_var) tensors, updated in place when training (torch semantics)."""
+    x = torch.cat([rgb.reshape(B, H, W, 3).permute(0, 3, 1, 2), feat.reshape(B, H, W, -1).permute(0, 3, 1, 2)], 1)
+    mean, std = x.new_tensor(IMG_MEAN), x.new_tensor(IMG_STD)
+    x = torch.cat([(x[:, :3] - mean[:, None, None]) / std[:, None, None], x[:, 3:]], 1)
+    h = F.relu(F.conv2d(x, P["net.0.weight"], P["net.0.bias"], padding=1))
+    h = F.relu(F.conv2d(h, P["net.2.weight"], P["net.2.bias"], padding=1))
+    h = F.relu(F.conv2d(h, P["net.4.weight"], P["net.4.bias"], padding=1))
+    y = F.conv2d(h, P["net.6.weight"], P["net.6.bias"], padding=2)
+    if not no_bn:
+        rm, rv = running if running is not None else (P["net.7.running_mean"], P["net.7.running_var"])
+        y = F.batch_norm(y, rm, rv, P["net.7.weight"], P["net.7.bias"], training, momentum, eps)
+    return x[:, 3:] + y if residual else y
+
+
+def exposure_mlp(params, hist):
+    """The exposure network (script/models/nerfh_nff.py:511-522): tiny-cuda-nn FullyFusedMLP 10 -> 32 -> 32 -> 32 -> 12, ReLU, no
+    biases.  tiny-cuda-nn is not vendored and not pinned by the reference: PARITY UNPINNED -- restated from its published
+    layout (flat buffer of [out, in] row-major matrices, 10 inputs padded to 16 with ONES, 12 outputs padded to 16), fp32."""
+    h = F.pad(hist.long().to(params.dtype), (0, 6), value=1.0)
+    off = 0
+    for li, (o, i) in enumerate(((32, 16), (32, 32), (32, 32), (16, 32))):
+        h = h @ params[off:off + o * i].view(o, i).t()
+        off += o * i
+        if li < 3:
+            h = torch.relu(h)
+    return h[:, :12]
+
+
+def affine_color(params, rgb, hist, B):
+    """script/models/nerfh_nff.py:605-626: rgb [B*N,3] -> sigmoid(K_b rgb + bias_b), [K_b | bias_b] = exposure_mlp(hist_b)."""
+    a = exposure_mlp(params, hist)
+    K, bias = a[:, :9].reshape(-1, 3, 3), a[:, 9:].reshape(-1, 3, 1)
+    out = torch.bmm(K, rgb.reshape(B, -1, 3).transpose(1, 2)) + bias
+    return torch.sigmoid(out.transpose(1, 2).reshape(-1, 3))
 
 
 def cosine_feature_loss(feat_render, feat_target):

@@ -226,10 +226,15 @@ def test_one_call_render_rays_matches_staged_path(precision, test_time):
         assert c.flat.grad is None or float(c.flat.grad.abs().max()) == 0.0
 
 
-def test_refinement_glue_kernels_match_torch():
+WORLD = {"pose_scale": 0.75, "move_all_cam_vec": [0.1, -0.3, 0.2], "pose_scale2": 1.6}
+
+
+@pytest.mark.parametrize("lietorch,world", [(False, None), (True, None), (True, WORLD), (False, WORLD)])
+def test_refinement_glue_kernels_match_torch(lietorch, world):
     """nefes_pose_rays_fwd/_bwd, nefes_cosine_loss_fwd/_bwd and nefes_pose_adam_step against the torch chain they
-    replace: LearnPose (so(3) exponential) -> get_rays -> render()'s packing; F.cosine_similarity loss; autograd to
-    (r, t); torch.optim.Adam with two parameter groups -- three consecutive steps from a non-zero rotation."""
+    replace: LearnPose (so(3) exponential, or SE3.exp([t, r]) with lietorch=True) -> fix_coord_supp -> get_rays ->
+    render()'s packing; F.cosine_similarity loss; autograd to (r, t); torch.optim.Adam with two parameter groups -- three
+    consecutive steps from a non-zero rotation."""
     import nefes_b200 as nb
     from nefes_b200 import _lib as L, refine
     lib, p = L.lib(), L.ptr
@@ -242,7 +247,8 @@ def test_refinement_glue_kernels_match_torch():
     init = torch.cat([init, torch.randn(3, 1, device=dev, generator=g)], 1).contiguous()
     target = torch.randn(C_, N, device=dev, generator=g)
     mix = torch.randn(21, C_, device=dev, generator=g)            # a differentiable stand-in for the render: feat = rays @ mix
-    pose_t = refine.LearnPose(1, True, True, init[None]).to(dev)
+    pose_t = refine.LearnPose(1, True, True, init[None], lietorch=lietorch).to(dev)
+    chain = refine._chain6(lietorch, world)
     with torch.no_grad():
         pose_t.r.copy_(torch.tensor([[0.03, -0.02, 0.05]]))
         pose_t.t.copy_(torch.tensor([[0.1, 0.0, -0.2]]))
@@ -254,6 +260,8 @@ def test_refinement_glue_kernels_match_torch():
     for it in range(3):
         # torch chain
         m = pose_t(0)
+        if world is not None:
+            m = refine.fix_coord_supp(None, m[None, :3, :4], world)[0]
         ro, rd = nb.get_rays(H, W, focal, m[:3, :4])
         rd_f, ro_f = rd.reshape(-1, 3), ro.reshape(-1, 3)
         vd = rd_f / torch.norm(rd_f, dim=-1, keepdim=True)
@@ -264,7 +272,7 @@ def test_refinement_glue_kernels_match_torch():
         opt.zero_grad()
         loss_t.backward()
         # engine chain
-        L.check(lib.nefes_pose_rays_fwd(p(pose6), p(init), H, W, focal, 0.5, 4.0, p(c2w), p(rays), 21, st), "fwd")
+        L.check(lib.nefes_pose_rays_fwd(p(pose6), p(init), H, W, focal, 0.5, 4.0, p(c2w), p(rays), 21, chain, st), "fwd")
         assert float((c2w - m[:3, :4]).abs().max()) < 2e-6
         assert float((rays - rb).abs().max()) < 1e-5
         feat = (rays @ mix).contiguous()
@@ -274,7 +282,7 @@ def test_refinement_glue_kernels_match_torch():
         d_rays = (d_feat @ mix.t()).contiguous()
         L.check(lib.nefes_pose_rays_bwd(p(d_rays), p(rays), 21, H, W, focal, p(d_c2w), st), "bwd")
         opt.step()
-        L.check(lib.nefes_pose_adam_step(p(pose6), p(init), p(d_c2w), p(stats), 3 * C_, p(state), 0.0087, 0.01, 0.9, 0.999, 1e-8, st), "adam")
+        L.check(lib.nefes_pose_adam_step(p(pose6), p(init), p(d_c2w), p(stats), 3 * C_, p(state), 0.0087, 0.01, 0.9, 0.999, 1e-8, chain, st), "adam")
         assert float(d_c2w.abs().max()) == 0.0 and float(stats.abs().max()) == 0.0 and float(state[12]) == it + 1
         ref6 = torch.cat([pose_t.r.detach().reshape(-1), pose_t.t.detach().reshape(-1)])
         # Adam's first steps are lr * sign(g): any error in the gradient chain shows up at full step size
