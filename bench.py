@@ -18,7 +18,8 @@ read back every step.  `--impl reference` times the UNMODIFIED reference (staged
 oracle/build_ref.py; the oracle port when that copy is absent) on the host cores, same workload.
 
 Workloads: train = C2 (the default and the headline); c3 = the stage-2 step (C2 + the 128-channel
-feature L1 term, so the feature cotangent path runs); refine = C4 (50 pose-gradient iterations per query, queries sharded
+feature L1 term, so the feature cotangent path runs); c3s3 = the stage-3 step (7 patches of 16x16 per image, affine colour
+transform, FusionNet, colour + 0.02 feature + 0.02 fusion losses; the fields AND the FusionNet / exposure network train); refine = C4 (50 pose-gradient iterations per query, queries sharded
 over ranks, final gather; metric refine iters/s); sweep = C5-shaped inference render of 2^12..2^20 rays (ray ranges sharded).
 --scaling strong keeps the GLOBAL batch at 6144 rays (6144 / N per GPU) for train / c3.
 """
@@ -118,7 +119,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-def host_batches(n_steps, seed, pinned=True, n_rand=N_RAND, feat=False):
+def host_batches(n_steps, seed, pinned=True, n_rand=N_RAND, feat=False, patches=False):
     """Per-step host inputs, as the reference's DataLoader + np.random.choice produce them
     (run_nefes.py:47-71): poses [4,3,4], pixel indices [4,n_rand], target rgb [4*n_rand,3], hist [4,10]
     (+ target features [4*n_rand,128] for the stage-2 step)."""
@@ -128,10 +129,15 @@ def host_batches(n_steps, seed, pinned=True, n_rand=N_RAND, feat=False):
     pin = (lambda t: t.pin_memory()) if (pinned and torch.cuda.is_available()) else (lambda t: t)
     out = []
     for _ in range(n_steps):
-        idx = np.stack([rng.choice(H * W, n_rand, replace=False) for _ in range(N_IMAGES)])
+        if patches:                                  # run_nefes.py:86-98: the same 7 random 16x16 crops for every image of the batch
+            h0, w0 = rng.randint(0, H - 16, 7), rng.randint(0, W - 16, 7)
+            one = np.concatenate([((h0[i] + np.arange(16))[:, None] * W + (w0[i] + np.arange(16))[None, :]).reshape(-1) for i in range(7)])
+            idx = np.stack([one] * N_IMAGES)
+        else:
+            idx = np.stack([rng.choice(H * W, n_rand, replace=False) for _ in range(N_IMAGES)])
         b = dict(pose=pin(poses.clone()), idx=pin(torch.from_numpy(idx).long()),
                  target=pin(torch.from_numpy(rng.rand(N_IMAGES * n_rand, 3).astype(np.float32))),
-                 hist=pin(torch.zeros(N_IMAGES, 10)))
+                 hist=pin(torch.zeros(N_IMAGES, 10) if not patches else torch.from_numpy(rng.randint(0, 30, (N_IMAGES, 10)).astype(np.float32))))
         if feat:
             b["target_f"] = pin(torch.from_numpy(rng.randn(N_IMAGES * n_rand, 128).astype(np.float32)))
         out.append(b)
@@ -204,11 +210,21 @@ def run_train(a, c):
     from nefes_b200 import _lib, ops, parallel
     nb, dev, world, rank, coarse, fine, kw = c["nb"], c["dev"], c["world"], c["rank"], c["coarse"], c["fine"], c["kw"]
     barrier, max_over_ranks = c["barrier"], c["max_over_ranks"]
-    stage2 = a.workload == "c3"
+    stage2 = a.workload in ("c3", "c3s3")
+    stage3 = a.workload == "c3s3"
     n_rand = N_RAND // world if a.scaling == "strong" else N_RAND
+    if stage3:
+        n_rand = 7 * 16 * 16                                                     # run_nefes.py:86-94: 7 crops of 16x16 per image
     rays = N_IMAGES * n_rand
     params = [coarse.flat, fine.flat]          # stages 1-2 train the two fields (FusionNet joins at stage 3)
     opt = nb.FlatAdam(params, lr=5e-4)
+    extra = []
+    if stage3:                                 # nerfh_nff.py:661-682: grad_vars = every parameter of both models
+        extra = list(coarse.fusion_net.parameters()) + list(coarse.exposure_embedding.parameters())
+        opt_extra = torch.optim.Adam(extra, lr=5e-4, betas=(0.9, 0.999), capturable=True)
+
+    class EncArgs:
+        encode_hist = True
     loss_fn = nb.NerfWLoss(coef=1, lambda_u=0.01)                                # losses.py:96-132 on two kernels
     loss_fn2 = nb.ColorFeatureFusionNerfWLoss(coef=1, L1_loss=True)              # run_nefes.py:360
 
@@ -220,21 +236,35 @@ def run_train(a, c):
         hist = b["hist"][:, None, :].expand(-1, n_rand, -1).reshape(-1, 10)
         rgb, disp, acc, ex = nb.render(H, W, FOCAL, chunk=32768, rays=(ro, rd), img_idx=hist, **kw)
         res = {"rgb_coarse": ex["rgb0"], "rgb_fine": rgb, "beta": ex["beta"], "transient_sigmas": ex["transient_sigmas"]}
-        if stage2:                                                               # run_nefes.py:244-248
+        if stage3:                                                               # run_nefes.py:150-161, 238-243
+            rgb_t = coarse.affine_color_transform(EncArgs(), rgb, b["hist"], N_IMAGES)
+            _, _, fus = coarse.run_fusion_net(rgb_t, ex["feat_map"], 16, 16, N_IMAGES * 7)
+            res.update(rgb_fine=rgb_t, feat_fine=ex["feat_map"], feat_fusion=fus.permute(0, 2, 3, 1).reshape(-1, 128))
+            l_rgb, l_f, l_fu = loss_fn2(res, {"rgb": b["target"], "feat": b["target_f"]}, switch_on=True, color_only_switch=False)
+            loss = l_rgb + 0.02 * l_f + 0.02 * l_fu
+        elif stage2:                                                             # run_nefes.py:244-248
             res["feat_fine"] = ex["feat_map"]
             l_rgb, l_f = loss_fn2(res, {"rgb": b["target"], "feat": b["target_f"]}, switch_on=False, color_only_switch=False)
             loss = l_rgb + 0.04 * l_f
         else:
             loss = loss_fn(res, b["target"])
         opt.zero_grad(set_to_none=True)
+        if stage3:
+            opt_extra.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:
             parallel.allreduce_grads(params)
+            for p_ in extra:                   # BatchNorm statistics stay per rank (the reference is single-GPU): stated deviation
+                dist_.all_reduce(p_.grad)
+                p_.grad.div_(world)
         opt.step(grad_scale=1.0 / world)
+        if stage3:
+            opt_extra.step()
         return loss
 
+    dist_ = c["dist"]
     n_total = a.warmup + a.steps
-    host = host_batches(n_total, seed=1000 + rank, n_rand=n_rand, feat=stage2)
+    host = host_batches(n_total, seed=1000 + rank, n_rand=n_rand, feat=stage2, patches=stage3)
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
     torch.cuda.synchronize()
 
@@ -340,7 +370,9 @@ def run_train(a, c):
                 "hbm": {"bound": "hbm", "achieved": t["GB_per_s"], "peak": hbm_peak, "unit": "GB/s", "frac": t["hbm_frac"],
                         "note": "algorithmic bytes include the bf16 activation copies saved for backward (design choice, DESIGN.md 4)"}}
     wl = ("C2 stage-1 colour-only NeRF-W training step" if not stage2 else
-          "C3 stage-2 training step (C2 + 0.04 x L1 of the rendered 128-channel feature map against target features)")
+          "C3 stage-2 training step (C2 + 0.04 x L1 of the rendered 128-channel feature map against target features)" if not stage3 else
+          "C3 stage-3 training step (7 patches of 16x16 per image; affine colour transform, FusionNet (BatchNorm batch statistics per rank), "
+          "colour + 0.02 x feature L1 + 0.02 x fusion L1; fields, FusionNet and exposure network all train)")
     out = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
@@ -519,7 +551,7 @@ def run_sweep(a, c):
 
 def run_engine(a):
     c = engine_setup(a)
-    if a.workload in ("train", "c3"):
+    if a.workload in ("train", "c3", "c3s3"):
         run_train(a, c)
     elif a.workload == "refine":
         run_refine(a, c)
@@ -604,7 +636,7 @@ def reference_arm(workload, n_rays):
     from oracle import ref_loader
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    hb = host_batches(1, seed=7, pinned=False, feat=True)[0]
+    hb = host_batches(1, seed=7, pinned=False, feat=True, patches=(workload == "c3s3"), n_rand=(1792 if workload == "c3s3" else N_RAND))[0]
     g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
     root = ref_loader.reference_root()
     if root is not None:
@@ -612,7 +644,8 @@ def reference_arm(workload, n_rays):
         import models.losses as RLoss
         coarse, fine, base = ref_loader.reference_render_kwargs(M)
         params = list(coarse.parameters()) + list(fine.parameters())           # nerfh_nff.py:661-680 grad_vars
-        if workload in ("train", "c3"):
+        if workload in ("train", "c3", "c3s3"):
+            n_img_rays = 1792 if workload == "c3s3" else N_RAND
             opt = torch.optim.Adam(params=params, lr=5e-4, betas=(0.9, 0.999))  # nerfh_nff.py:682
             import contextlib
             import io
@@ -622,14 +655,21 @@ def reference_arm(workload, n_rays):
             idx = hb["idx"][..., None].expand(-1, -1, 3)
             ro = torch.gather(ro.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n_rays]
             rd = torch.gather(rd.reshape(N_IMAGES, -1, 3), 1, idx).reshape(-1, 3)[:n_rays]
-            hist = hb["hist"][:, None, :].expand(-1, N_RAND, -1).reshape(-1, 10)[:n_rays]
+            hist = hb["hist"][:, None, :].expand(-1, n_img_rays, -1).reshape(-1, 10)[:n_rays]
 
             def step():
                 rgb, disp, acc, ex = R.render(H, W, FOCAL, chunk=32768, rays=torch.stack([ro, rd], 0), retraw=True, img_idx=hist,
                                               perturb=1., raw_noise_std=0., test_time=False, near=NEAR, far=FAR, **base)
                 res = {"rgb_fine": rgb, "rgb_coarse": ex["rgb0"], "feat_fine": ex["feat_map"], "beta": ex["beta"],
                        "transient_sigmas": ex["transient_sigmas"]}                # run_nefes.py:217-231
-                if workload == "c3":
+                if workload == "c3s3":
+                    # the exposure network is tiny-cuda-nn (absent here): the reference arm skips affine_color_transform
+                    _, _, fus = coarse.run_fusion_net(rgb, ex["feat_map"], 16, 16, N_IMAGES * 7)
+                    res["feat_fusion"] = fus.permute(0, 2, 3, 1).reshape(-1, 128)
+                    l_rgb, l_f, l_fu = loss_func(res, {"rgb": hb["target"][:n_rays], "feat": hb["target_f"][:n_rays]}, switch_on=True,
+                                                 color_only_switch=False)
+                    loss = l_rgb + 0.02 * l_f + 0.02 * l_fu
+                elif workload == "c3":
                     l_rgb, l_f = loss_func(res, {"rgb": hb["target"][:n_rays], "feat": hb["target_f"][:n_rays]}, switch_on=False,
                                            color_only_switch=False)
                     loss = l_rgb + 0.04 * l_f
@@ -676,7 +716,7 @@ def reference_arm(workload, n_rays):
     # ---- no reference tree: the oracle restatement --------------------------------------------------------------------------
     from oracle import nefes_oracle as O
     Pc, Pf = O.clone_params(O.init_field("coarse"), requires_grad=True), O.clone_params(O.init_field("fine"), requires_grad=True)
-    if workload in ("train", "c3"):
+    if workload in ("train", "c3", "c3s3"):
         opt = torch.optim.Adam(list(Pc.values()) + list(Pf.values()), lr=5e-4)
         ro, rd = O.camera_rays_batch(H, W, FOCAL, hb["pose"])
         idx = hb["idx"][..., None].expand(-1, -1, 3)
@@ -687,7 +727,7 @@ def reference_arm(workload, n_rays):
             t_rand, u = torch.rand(n_rays, 64), torch.rand(n_rays, 64)
             ret = O.render(H, W, FOCAL, Pc, Pf, rays=(ro, rd), near=NEAR, far=FAR, test_time=False, t_rand=t_rand, u=u)
             loss = nerfw_loss(ret, hb["target"][:n_rays])
-            if workload == "c3":
+            if workload in ("c3", "c3s3"):       # the port has no FusionNet: stage 3 falls back to the stage-2 loss
                 loss = loss + 0.04 * (ret["feat_map"] - hb["target_f"][:n_rays]).abs().mean()
             opt.zero_grad()
             loss.backward()
@@ -723,7 +763,7 @@ def reference_arm(workload, n_rays):
     return step, "port", "oracle port of the reference path (no reference tree on this box), torch CPU fp32, anomaly mode off"
 
 
-WORK_UNIT = {"train": ("rays/s", RAYS), "c3": ("rays/s", RAYS), "refine": ("iters/s", 1), "sweep": ("rays/s", 4096)}
+WORK_UNIT = {"train": ("rays/s", RAYS), "c3": ("rays/s", RAYS), "c3s3": ("rays/s", 7168), "refine": ("iters/s", 1), "sweep": ("rays/s", 4096)}
 
 
 def cpu_baseline(a, budget_s=25.0):
@@ -763,14 +803,15 @@ def run_reference(a):
             break
     k, tot = len(times), sum(times)
     v = units / tot
-    metric = {"train": METRIC, "c3": METRIC, "refine": "NeFeS refine iters/sec (50 pose-gradient iterations per query, 60x80 render, 64+64 samples)",
+    metric = {"train": METRIC, "c3": METRIC, "c3s3": METRIC, "refine": "NeFeS refine iters/sec (50 pose-gradient iterations per query, 60x80 render, 64+64 samples)",
               "sweep": "NeFeS rays/sec (inference render, 64+64 samples)"}[a.workload]
     wl = {"train": "C2 stage-1 colour-only NeRF-W training step (same as the engine arm), full 6144 rays per step",
           "c3": "C3 stage-2 training step (same as the engine arm), full 6144 rays per step",
+          "c3s3": "C3 stage-3 training step (patches + FusionNet; the tiny-cuda-nn exposure network is absent, so no affine colour transform), 7168 rays per step",
           "refine": "C4 refinement: one step = ONE pose-gradient iteration (full 60x80 render + cosine loss + backward to the pose + Adam)",
           "sweep": "C5-shaped inference render, one step = 4096 rays"}[a.workload]
     out = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": k,
-           "warmup": warm, "ms_per_step": 1e3 * tot / k, "higher_is_better": True, "scaling": a.scaling if a.workload in ("train", "c3") else "weak",
+           "warmup": warm, "ms_per_step": 1e3 * tot / k, "higher_is_better": True, "scaling": a.scaling if a.workload in ("train", "c3", "c3s3") else "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": wl, "units_per_step": n},
            "cpu_baseline": {"value": v, "unit": unit, "cores": os.cpu_count() or 1, "kind": kind,
@@ -789,7 +830,7 @@ def main():
     p.add_argument("--precision", default=os.environ.get("NEFES_PRECISION", "bf16"), choices=["fp32", "bf16"])
     p.add_argument("--no-extras", action="store_true", help="skip the fp32-path and refinement side measurements")
     p.add_argument("--no-graph", action="store_true", help="time eager steps instead of a captured CUDA graph of the step")
-    p.add_argument("--workload", default="train", choices=["train", "c3", "refine", "sweep"])
+    p.add_argument("--workload", default="train", choices=["train", "c3", "c3s3", "refine", "sweep"])
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     a = p.parse_args()

@@ -5,7 +5,8 @@ own lietorch=False path), dm/DFM_pose_refine.py:236-255 (cosine feature loss, pe
 
 The render + its backward to the camera pose run on the engine; the 6-parameter pose chain, the loss
 and Adam are the caller's few-element torch ops ("next" row).  FusionNet / exposure MLP /
-DFNet are outside the path and excluded, as stated in SURVEY.md 8d config C4."""
+DFNet is outside the path.  FusionNet and the affine colour transform (the stage right behind the render, 8f-2) run on the engine
+too and join the iteration with `refine_pose(..., fusion=True)`; SURVEY.md 8d config C4 (the pinned benchmark definition) excludes them."""
 from __future__ import annotations
 
 import torch
@@ -104,16 +105,34 @@ def feature_loss(feature_rgb, feature_target):
     return 1 - torch.nn.functional.cosine_similarity(feature_rgb, feature_target, dim=1, eps=1e-6).mean()
 
 
+class _EncodeHist:
+    encode_hist = True
+
+
+def _fused_features(kw, rgb, feat_map, hist, H, W, fusion, encode_hist):
+    """What the loss sees ([C, H*W]).  fusion=False: the rendered feature map (the pinned definition).
+    fusion=True: the reference's full step, DFM_pose_refine.py:324-329 -- rgb -> affine_color_transform (args.encode_hist) ->
+    FusionNet(rgb, feat_map) -- so the pose gradient also flows through the rendered colours."""
+    if not fusion:
+        return feat_map.t()
+    net = kw["network_fn"]
+    if encode_hist:
+        rgb = net.affine_color_transform(_EncodeHist(), rgb, hist, 1)
+    return net.run_fusion_net(rgb, feat_map, H, W, 1)[2][0].reshape(feat_map.shape[1], -1)
+
+
 class PoseRefiner:
     """The refinement iteration -- pose chain, render, loss, backward, Adam; ~250 launches, most of them few-element
     torch ops -- captured ONCE into a CUDA graph and replayed for every iteration of every query of the same shape.
     A query only rewrites the graph's static inputs (initial pose, target features) and zeroes the pose delta and the
     Adam state; the arithmetic is that of the eager loop (`refine_pose(..., graph=False)`)."""
 
-    def __init__(self, H, W, focal, render_kwargs_test, lr_r, lr_t, chunk, device, feat_shape, lietorch=False, world_setup_dict=None):
+    def __init__(self, H, W, focal, render_kwargs_test, lr_r, lr_t, chunk, device, feat_shape, lietorch=False, world_setup_dict=None,
+                 fusion=False, encode_hist=False):
         self.args = (H, W, focal, chunk)
         self.kw = render_kwargs_test
         self.world = world_setup_dict
+        self.fusion, self.encode_hist = bool(fusion), bool(encode_hist)
         self.pose = LearnPose(1, True, True, torch.eye(4, device=device)[:3][None], lietorch=lietorch).to(device)
         self.opt = torch.optim.Adam([{"params": [self.pose.r], "lr": lr_r}, {"params": [self.pose.t], "lr": lr_t}], capturable=True)
         self.target = torch.zeros(feat_shape, device=device)
@@ -126,7 +145,7 @@ class PoseRefiner:
         if self.world is not None:
             c2w = fix_coord_supp(None, c2w[None], self.world)[0]
         rgb, disp, acc, extras = render(H, W, focal, chunk=chunk, c2w=c2w, img_idx=self.hist, **self.kw)
-        loss = feature_loss(extras["feat_map"].t(), self.target)
+        loss = feature_loss(_fused_features(self.kw, rgb, extras["feat_map"], self.hist, H, W, self.fusion, self.encode_hist), self.target)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self.opt.step()
@@ -272,7 +291,8 @@ def clear_refiner_cache():
 
 
 def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=50, lr_r=0.0087, lr_t=0.01,
-                hist=None, chunk=32768, graph=None, engine=None, lietorch=False, world_setup_dict=None):
+                hist=None, chunk=32768, graph=None, engine=None, lietorch=False, world_setup_dict=None, fusion=False,
+                encode_hist=False):
     """One query: `n_iters` Adam steps on the se(3)-style delta (DFM_pose_refine.py:380-440).
     feat_target [C, H*W].  Returns (refined c2w [3,4], list of losses).
     graph (default: on for n_iters >= 10 on CUDA): run the iterations as replays of a captured CUDA graph (PoseRefiner),
@@ -281,7 +301,10 @@ def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=
     keeps the torch pose chain / loss / optimiser around the engine render; True raises where it does not apply.
     lietorch: the pose delta goes through SE3.exp([t, r]) (poses.py:31-32, what DFM_pose_refine.py:374 constructs) instead of
     the reference's pure-torch [Exp(r) | t].  world_setup_dict: fix_coord_supp's pose_scale / move_all_cam_vec / pose_scale2
-    (direct_pose_model.py:210-232) between the learned pose and the renderer; the returned pose is the learned one."""
+    (direct_pose_model.py:210-232) between the learned pose and the renderer; the returned pose is the learned one.
+    fusion: the loss is taken on FusionNet(affine_color_transform(rgb), feat_map) as DFM_pose_refine.py:324-337 does on nerfh_nff
+    configs (feat_target is then the DFNet feature map); the engine-only iteration does not cover it, the graph-replayed
+    torch-glue iteration (render, FusionNet and colour transform on the engine) does."""
     dev = feat_target.device
     use_graph = ((n_iters >= 10) if graph is None else bool(graph)) and dev.type == "cuda"
     kw_ = render_kwargs_test
@@ -295,10 +318,11 @@ def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=
            kw_.get("N_samples"), kw_.get("N_importance"), getattr(kw_.get("network_query_fn"), "netchunk", None),
            bool(getattr(a_, "NeRFW", False)), bool(getattr(a_, "transient_at_test", False)),
            bool(getattr(a_, "nerfh_nff", False)), bool(getattr(a_, "use_fine_only", False)),
-           float(kw_.get("near", 0.)), float(kw_.get("far", 1.)), bool(lietorch), tuple(_chain6(lietorch, world_setup_dict)))
+           float(kw_.get("near", 0.)), float(kw_.get("far", 1.)), bool(lietorch), tuple(_chain6(lietorch, world_setup_dict)),
+           bool(fusion), bool(encode_hist))
     while len(_REFINERS) >= _MAX_REFINERS:           # bounded: a refiner pins its GPU workspaces
         _REFINERS.pop(next(iter(_REFINERS)))
-    if (engine is None or engine) and dev.type == "cuda" and H * W <= chunk and \
+    if (engine is None or engine) and not fusion and dev.type == "cuda" and H * W <= chunk and \
             _engine_refiner_applies(feat_target, H, W, render_kwargs_test, hist):
         ref = _REFINERS.get(("engine",) + key)
         if ref is None:
@@ -312,7 +336,7 @@ def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=
         ref = _REFINERS.get(key)
         if ref is None:
             ref = _REFINERS[key] = PoseRefiner(H, W, focal, render_kwargs_test, lr_r, lr_t, chunk, dev, tuple(feat_target.shape),
-                                               lietorch, world_setup_dict)
+                                               lietorch, world_setup_dict, fusion, encode_hist)
         return ref.refine(init_c2w, feat_target, n_iters, hist)
     pose = LearnPose(1, True, True, init_c2w[None].to(dev), lietorch=lietorch).to(dev)
     opt = torch.optim.Adam([{"params": [pose.r], "lr": lr_r}, {"params": [pose.t], "lr": lr_t}])
@@ -323,7 +347,7 @@ def refine_pose(init_c2w, feat_target, H, W, focal, render_kwargs_test, n_iters=
         if world_setup_dict is not None:
             c2w = fix_coord_supp(None, c2w[None], world_setup_dict)[0]
         rgb, disp, acc, extras = render(H, W, focal, chunk=chunk, c2w=c2w, img_idx=hist, **render_kwargs_test)
-        loss = feature_loss(extras["feat_map"].t(), feat_target)
+        loss = feature_loss(_fused_features(render_kwargs_test, rgb, extras["feat_map"], hist, H, W, fusion, encode_hist), feat_target)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()

@@ -91,3 +91,47 @@ def test_c4_refined_pose_vs_oracle(problem, prec):
         assert np.abs(l_eng - fx["loss32"]).max() < 2e-4
         # and the refinement does its job as well as the fp32 reference does: no further from the ground truth
         assert mine_left[0] <= left[0] + 1e-3 and mine_left[1] <= left[1] + 0.01
+
+
+def test_refinement_with_fusion_stage_vs_oracle(problem):
+    """The reference's full refinement step on nerfh_nff configs (DFM_pose_refine.py:321-337): render -> FusionNet(rgb, feat_map)
+    -> cosine loss on the FUSED features, so the pose gradient also flows through the rendered colours.  Three Adam iterations
+    at 30x40 on the engine (render, FusionNet and their backwards as engine launches, iteration replayed from a CUDA graph)
+    against the same loop on the oracle (fp32, CPU): Adam's first steps are lr * sign(g), any error in the chain shows at
+    full step size."""
+    import nefes_b200 as nb
+    import nefes_b200.nerfh_nff as NB
+    from nefes_b200 import refine
+    wc, wf, fx, init, _ = problem
+    h, w_, focal = 30, 40, FOCAL / 2
+    torch.manual_seed(13)
+    fus = NB.FusionNet(128).eval()
+    Pfus = {k: v.clone() for k, v in fus.state_dict().items()}
+    gt = torch.from_numpy(fx["gt"])
+    with torch.no_grad():
+        o = O.render(h, w_, focal, wc, wf, c2w=gt, near=NEAR, far=FAR, test_time=True)
+        target = O.fusion_net(Pfus, o["rgb_map"], o["feat_map"], 1, h, w_, training=False)[0].reshape(128, -1).contiguous()
+    # oracle loop
+    r, t = torch.zeros(3, requires_grad=True), torch.zeros(3, requires_grad=True)
+    opt = torch.optim.Adam([{"params": [r], "lr": 0.0087}, {"params": [t], "lr": 0.01}])
+    ref_losses = []
+    for _ in range(3):
+        o = O.render(h, w_, focal, wc, wf, c2w=O.learn_pose_c2w(r, t, init), near=NEAR, far=FAR, test_time=True)
+        f = O.fusion_net(Pfus, o["rgb_map"], o["feat_map"], 1, h, w_, training=False)[0].reshape(128, -1)
+        loss = O.cosine_feature_loss(f, target)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref_losses.append(float(loss))
+    ref_pose = O.learn_pose_c2w(r, t, init).detach()
+    kw = engine_kwargs(nb, wc, wf, "fp32")
+    kw["network_fn"].fusion_net = fus.to(DEV)
+    for p in kw["network_fn"].parameters():
+        p.requires_grad_(False)
+    for graph in (False, True):
+        refine.clear_refiner_cache()
+        pose, losses = refine.refine_pose(init.to(DEV), target.to(DEV), h, w_, focal, kw, n_iters=3, fusion=True, graph=graph)
+        dt, dang = O.pose_error(pose.cpu().double(), ref_pose.double())
+        print(f"[fusion, graph={graph}] engine vs oracle after 3 iterations: {dt * 1e3:.4f} mm / {dang:.5f} deg; losses {[float(x) for x in losses]} vs {ref_losses}")
+        assert dt < 1e-3 and dang < 1e-2
+        assert max(abs(float(a) - b) for a, b in zip(losses, ref_losses)) < 1e-5
