@@ -316,7 +316,8 @@ int nefes_render_rays_bwd(const nefes_render_cfg_t* cfg_host, const nefes_render
  *                        (rendering.py:197-243: o, d, near, far, d/|d|, zeros) with get_rays' arithmetic (ray_utils.py:5-16)
  *   nefes_pose_rays_bwd  cotangent of ray_batch -> d_c2w [3,4], ACCUMULATED (caller zero-fills once)
  *   nefes_cosine_loss_*  loss = 1 - mean_c cosine_similarity(feat[:, c], target[c, :]) (DFM_pose_refine.py:236-255,
- *                        per_pixel=False); feat [N,C] row-major, target [C,N]; stats [3,C] ACCUMULATED by _fwd (caller
+ *                        per_pixel=False); mask [N] (may be NULL): only pixels with mask > 0 enter (masked_feature_loss,
+ *                        DFM_pose_refine.py:257-288); feat [N,C] row-major, target [C,N]; stats [3,C] ACCUMULATED by _fwd (caller
  *                        zero-fills once); _bwd writes loss (1 float, may be NULL), loss_hist[(int)*step] when both are
  *                        given, and d_feat [N,C] (may be NULL)
  *   nefes_pose_adam_step d_c2w -> (d_r, d_t) through the exponential, torch.optim.Adam on the two groups (lr_r, lr_t);
@@ -326,9 +327,14 @@ int nefes_pose_rays_fwd(const float* pose6, const float* init_c2w, int H, int W,
                         float* c2w_out, float* ray_batch, int ld, const float* chain6, void* stream);
 int nefes_pose_rays_bwd(const float* d_ray_batch, const float* ray_batch, int ld, int H, int W, float focal, float* d_c2w,
                         void* stream);
-int nefes_cosine_loss_fwd(const float* feat, const float* target, int N, int C, float* stats, void* stream);
-int nefes_cosine_loss_bwd(const float* feat, const float* target, const float* stats, int N, int C, float* loss,
+int nefes_cosine_loss_fwd(const float* feat, const float* target, const float* mask, int N, int C, float* stats, void* stream);
+int nefes_cosine_loss_bwd(const float* feat, const float* target, const float* mask, const float* stats, int N, int C, float* loss,
                           float* loss_hist, const float* step, int hist_cap, float* d_feat, void* stream);
+/* bicubic up-sampling + border crop of a pixel-major map (dm/DFM_APR_refine.py:114-124: torch.nn.Upsample(size=(H, W),
+ * mode='bicubic') followed by [:, :, crop:-crop, crop:-crop]): x [h*w, C] -> out [(H - 2 crop) * (W - 2 crop), C];
+ * _bwd: d_out -> d_x [h*w, C] (overwritten), tmp = h * (W - 2 crop) * C floats of scratch */
+int nefes_upsample_crop_fwd(const float* x, int h, int w, int C, int H, int W, int crop, float* out, void* stream);
+int nefes_upsample_crop_bwd(const float* d_out, int h, int w, int C, int H, int W, int crop, float* tmp, float* d_x, void* stream);
 int nefes_pose_adam_step(float* pose6, const float* init_c2w, float* d_c2w, float* zero, int n_zero, float* state13,
                          float lr_r, float lr_t, float beta1, float beta2, float eps, const float* chain6, void* stream);
 

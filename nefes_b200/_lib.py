@@ -110,8 +110,10 @@ _SIGS = {
     "nefes_mlp_wgrad": (i32, [vp, i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
     "nefes_pose_rays_fwd": (i32, [vp, vp, i32, i32, f32, f32, f32, vp, vp, i32, vp, vp]),
     "nefes_pose_rays_bwd": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
-    "nefes_cosine_loss_fwd": (i32, [vp, vp, i32, i32, vp, vp]),
-    "nefes_cosine_loss_bwd": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]),
+    "nefes_cosine_loss_fwd": (i32, [vp, vp, vp, i32, i32, vp, vp]),
+    "nefes_cosine_loss_bwd": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]),
+    "nefes_upsample_crop_fwd": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "nefes_upsample_crop_bwd": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "nefes_pose_adam_step": (i32, [vp, vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, vp, vp]),
     "nefes_prof_enable": (i32, [i32]),
     "nefes_prof_report": (i32, [C.c_char_p, i32]),

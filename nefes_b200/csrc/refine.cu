@@ -159,8 +159,8 @@ __global__ void pose_rays_bwd_kernel(const float* __restrict__ d_rays, const flo
 // a = feat[n][c] (row-major [N,C]) and b = target[c][n] ([C,N]).  Block = C threads (thread = channel) x 32 pixels; the
 // target tile goes through shared memory so that both tensors are read along their contiguous axis.
 constexpr int kLossPix = 32;
-__global__ void cosine_stats_kernel(const float* __restrict__ feat, const float* __restrict__ target, int N, int C,
-                                    float* __restrict__ stats) {
+__global__ void cosine_stats_kernel(const float* __restrict__ feat, const float* __restrict__ target, const float* __restrict__ mask,
+                                    int N, int C, float* __restrict__ stats) {
   extern __shared__ float tile[];                    // [C][kLossPix + 1]
   const int n0 = blockIdx.x * kLossPix, c = threadIdx.x;
   for (int e = threadIdx.x; e < C * kLossPix; e += blockDim.x) {
@@ -170,6 +170,7 @@ __global__ void cosine_stats_kernel(const float* __restrict__ feat, const float*
   __syncthreads();
   float ab = 0.f, aa = 0.f, bb = 0.f;
   for (int nn = 0; nn < kLossPix && n0 + nn < N; ++nn) {
+    if (mask != nullptr && !(mask[n0 + nn] > 0.f)) continue;        // masked_feature_loss: only the valid pixels enter the sums
     const float a = feat[(int64_t)(n0 + nn) * C + c], b = tile[c * (kLossPix + 1) + nn];
     ab += a * b; aa += a * a; bb += b * b;
   }
@@ -181,8 +182,8 @@ __global__ void cosine_stats_kernel(const float* __restrict__ feat, const float*
 // loss = 1 - mean_c cos_c, cos_c = ab / (max(|a|, eps) max(|b|, eps))  (F.cosine_similarity, eps = 1e-6);
 // d_feat[n][c] = -(1/C) (b / (|a| |b|) - cos_c a / |a|^2).  Block 0 also writes the loss, to loss[0] and, when a
 // history is kept, to loss_hist[(int)*step] (the device-side iteration counter of pose_adam_step).
-__global__ void cosine_grad_kernel(const float* __restrict__ feat, const float* __restrict__ target, const float* __restrict__ stats,
-                                   int N, int C, float* __restrict__ loss, float* __restrict__ loss_hist, const float* __restrict__ step,
+__global__ void cosine_grad_kernel(const float* __restrict__ feat, const float* __restrict__ target, const float* __restrict__ mask,
+                                   const float* __restrict__ stats, int N, int C, float* __restrict__ loss, float* __restrict__ loss_hist, const float* __restrict__ step,
                                    int hist_cap, float* __restrict__ d_feat) {
   extern __shared__ float tile[];                    // [C][kLossPix + 1] + [C] cos
   float* s_cos = tile + C * (kLossPix + 1);
@@ -210,7 +211,91 @@ __global__ void cosine_grad_kernel(const float* __restrict__ feat, const float* 
   const float k1 = -1.f / ((float)C * na * nb), k2 = cosc / ((float)C * na * na);
   for (int nn = 0; nn < kLossPix && n0 + nn < N; ++nn) {
     const int64_t o = (int64_t)(n0 + nn) * C + c;
-    d_feat[o] = k1 * tile[c * (kLossPix + 1) + nn] + k2 * feat[o];
+    const bool on = mask == nullptr || mask[n0 + nn] > 0.f;
+    d_feat[o] = on ? k1 * tile[c * (kLossPix + 1) + nn] + k2 * feat[o] : 0.f;
+  }
+}
+
+// ---- bicubic up-sampling + crop of a pixel-major feature map (dm/DFM_APR_refine.py:114-124: torch.nn.Upsample(size=(H, W),
+// mode='bicubic'), align_corners=False, then [:, :, crop:-crop, crop:-crop]).  torch's kernel: cubic convolution with
+// A = -0.75, source coordinate (X + 0.5) * w / W - 0.5, the four taps clamped to the image.  Only the pixels inside the crop
+// window are produced: out [(H - 2 crop) * (W - 2 crop), C].
+__device__ __forceinline__ void cubic_taps(int X, int in_size, int out_size, int idx[4], float wt[4]) {
+  const float A = -0.75f;
+  const float src = ((float)X + 0.5f) * ((float)in_size / (float)out_size) - 0.5f;
+  const float fl = floorf(src);
+  const float t = src - fl;
+  const int i0 = (int)fl;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  wt[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  wt[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  wt[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  wt[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) idx[k] = min(max(i0 - 1 + k, 0), in_size - 1);
+}
+__global__ void upsample_crop_fwd_kernel(const float* __restrict__ x, int h, int w, int C, int H, int W, int crop, float* __restrict__ out) {
+  const int Wc = W - 2 * crop, Hc = H - 2 * crop;
+  const int64_t n = (int64_t)Hc * Wc * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const int64_t p = e / C;
+    const int X = (int)(p % Wc) + crop, Y = (int)(p / Wc) + crop;
+    int ix[4], iy[4]; float wx[4], wy[4];
+    cubic_taps(X, w, W, ix, wx);
+    cubic_taps(Y, h, H, iy, wy);
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float r = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) r += wx[b] * x[((int64_t)iy[a] * w + ix[b]) * C + c];
+      s += wy[a] * r;
+    }
+    out[e] = s;
+  }
+}
+// transpose of the above, separable and deterministic: rows first (tmp [h, Wc, C]), then columns (d_x [h, w, C])
+__global__ void upsample_crop_bwd_rows_kernel(const float* __restrict__ g, int h, int C, int H, int W, int crop, float* __restrict__ tmp) {
+  const int Wc = W - 2 * crop;
+  const int64_t n = (int64_t)h * Wc * C;
+  const int reach = 2 * ((H + h - 1) / h) + 2;          // output rows whose taps can touch input row y
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const int64_t q = e / C;
+    const int Xc = (int)(q % Wc), y = (int)(q / Wc);
+    const int Yc = (int)(((float)y + 0.5f) * ((float)H / (float)h));
+    float s = 0.f;
+    for (int Y = max(crop, Yc - reach); Y <= min(H - crop - 1, Yc + reach); ++Y) {
+      int iy[4]; float wy[4];
+      cubic_taps(Y, h, H, iy, wy);
+      float wsum = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) wsum += iy[a] == y ? wy[a] : 0.f;
+      if (wsum != 0.f) s += wsum * g[((int64_t)(Y - crop) * Wc + Xc) * C + c];
+    }
+    tmp[e] = s;
+  }
+}
+__global__ void upsample_crop_bwd_cols_kernel(const float* __restrict__ tmp, int h, int w, int C, int W, int crop, float* __restrict__ dx) {
+  const int Wc = W - 2 * crop;
+  const int64_t n = (int64_t)h * w * C;
+  const int reach = 2 * ((W + w - 1) / w) + 2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const int64_t q = e / C;
+    const int x = (int)(q % w), y = (int)(q / w);
+    const int Xm = (int)(((float)x + 0.5f) * ((float)W / (float)w));
+    float s = 0.f;
+    for (int X = max(crop, Xm - reach); X <= min(W - crop - 1, Xm + reach); ++X) {
+      int ix[4]; float wx[4];
+      cubic_taps(X, w, W, ix, wx);
+      float wsum = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) wsum += ix[b] == x ? wx[b] : 0.f;
+      if (wsum != 0.f) s += wsum * tmp[((int64_t)y * Wc + (X - crop)) * C + c];
+    }
+    dx[e] = s;
   }
 }
 
@@ -326,23 +411,48 @@ int nefes_pose_rays_bwd(const float* d_ray_batch, const float* ray_batch, int ld
   return NEFES_OK;
 }
 
-int nefes_cosine_loss_fwd(const float* feat, const float* target, int N, int C, float* stats, void* stream) {
+int nefes_cosine_loss_fwd(const float* feat, const float* target, const float* mask, int N, int C, float* stats, void* stream) {
   NEFES_REQUIRE(feat && target && stats, NEFES_EINVAL, "nefes_cosine_loss_fwd: null pointer");
   NEFES_REQUIRE(N > 0 && C > 0 && C <= 1024 && C % 32 == 0, NEFES_EINVAL, "nefes_cosine_loss_fwd: bad shape N=%d C=%d", N, C);
   const size_t smem = sizeof(float) * C * (nefes::kLossPix + 1);
-  nefes::cosine_stats_kernel<<<(unsigned)nefes::ceil_div(N, nefes::kLossPix), C, smem, (cudaStream_t)stream>>>(feat, target, N, C, stats);
+  nefes::cosine_stats_kernel<<<(unsigned)nefes::ceil_div(N, nefes::kLossPix), C, smem, (cudaStream_t)stream>>>(feat, target, mask, N, C, stats);
   NEFES_CHECK_LAUNCH("cosine_stats");
   return NEFES_OK;
 }
 
-int nefes_cosine_loss_bwd(const float* feat, const float* target, const float* stats, int N, int C, float* loss,
+int nefes_cosine_loss_bwd(const float* feat, const float* target, const float* mask, const float* stats, int N, int C, float* loss,
                           float* loss_hist, const float* step, int hist_cap, float* d_feat, void* stream) {
   NEFES_REQUIRE(feat && target && stats, NEFES_EINVAL, "nefes_cosine_loss_bwd: null pointer");
   NEFES_REQUIRE(N > 0 && C > 0 && C <= 1024 && C % 32 == 0, NEFES_EINVAL, "nefes_cosine_loss_bwd: bad shape N=%d C=%d", N, C);
   const size_t smem = sizeof(float) * (C * (nefes::kLossPix + 1) + C);
   nefes::cosine_grad_kernel<<<(unsigned)nefes::ceil_div(N, nefes::kLossPix), C, smem, (cudaStream_t)stream>>>(
-      feat, target, stats, N, C, loss, loss_hist, step, hist_cap, d_feat);
+      feat, target, mask, stats, N, C, loss, loss_hist, step, hist_cap, d_feat);
   NEFES_CHECK_LAUNCH("cosine_grad");
+  return NEFES_OK;
+}
+
+int nefes_upsample_crop_fwd(const float* x, int h, int w, int C, int H, int W, int crop, float* out, void* stream) {
+  NEFES_REQUIRE(x && out, NEFES_EINVAL, "nefes_upsample_crop_fwd: null pointer");
+  NEFES_REQUIRE(h > 0 && w > 0 && C > 0 && H >= h && W >= w && crop >= 0 && H > 2 * crop && W > 2 * crop, NEFES_EINVAL,
+                "nefes_upsample_crop_fwd: bad shape %dx%d -> %dx%d crop %d", h, w, H, W, crop);
+  const int64_t n = (int64_t)(H - 2 * crop) * (W - 2 * crop) * C;
+  const int64_t b = nefes::ceil_div(n, 256);
+  nefes::upsample_crop_fwd_kernel<<<(unsigned)(b < 148 * 16 ? b : 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, h, w, C, H, W, crop, out);
+  NEFES_CHECK_LAUNCH("upsample_crop_fwd");
+  return NEFES_OK;
+}
+
+int nefes_upsample_crop_bwd(const float* d_out, int h, int w, int C, int H, int W, int crop, float* tmp, float* d_x, void* stream) {
+  NEFES_REQUIRE(d_out && tmp && d_x, NEFES_EINVAL, "nefes_upsample_crop_bwd: null pointer");
+  NEFES_REQUIRE(h > 0 && w > 0 && C > 0 && H >= h && W >= w && crop >= 0 && H > 2 * crop && W > 2 * crop, NEFES_EINVAL,
+                "nefes_upsample_crop_bwd: bad shape %dx%d -> %dx%d crop %d", h, w, H, W, crop);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t b = nefes::ceil_div((int64_t)h * (W - 2 * crop) * C, 256);
+  nefes::upsample_crop_bwd_rows_kernel<<<(unsigned)(b < 148 * 16 ? b : 148 * 16), 256, 0, st>>>(d_out, h, C, H, W, crop, tmp);
+  NEFES_CHECK_LAUNCH("upsample_crop_bwd_rows");
+  b = nefes::ceil_div((int64_t)h * w * C, 256);
+  nefes::upsample_crop_bwd_cols_kernel<<<(unsigned)(b < 148 * 16 ? b : 148 * 16), 256, 0, st>>>(tmp, h, w, C, W, crop, d_x);
+  NEFES_CHECK_LAUNCH("upsample_crop_bwd_cols");
   return NEFES_OK;
 }
 

@@ -105,6 +105,94 @@ def feature_loss(feature_rgb, feature_target):
     return 1 - torch.nn.functional.cosine_similarity(feature_rgb, feature_target, dim=1, eps=1e-6).mean()
 
 
+class _CosineLossPM(torch.autograd.Function):
+    """1 - mean_c cos(feat[:, c], target[c, :]) on the engine (nefes_cosine_loss_{fwd,bwd}): feat [N,C] PIXEL-major (what the
+    render / FusionNet / upsample kernels produce), target [C,N], optional pixel mask [N]."""
+
+    @staticmethod
+    def forward(ctx, feat, target, mask):
+        L.need_cuda(feat, target, mask)
+        f, t = L.f32c(feat), L.f32c(target)
+        m = None if mask is None else L.f32c(mask.reshape(-1).float())
+        N, C = f.shape
+        if t.shape != (C, N) or C % 32 or C > 1024 or (m is not None and m.numel() != N):
+            raise RuntimeError(f"nefes_b200: cosine loss expects feat [N,C], target [C,N] (C a multiple of 32, <= 1024), got {tuple(feat.shape)} / {tuple(target.shape)}")
+        dev = f.device
+        stats, loss, d_feat = torch.zeros(3, C, device=dev), torch.empty(1, device=dev), torch.empty_like(f)
+        with torch.cuda.device(dev):
+            st = L.stream_of(f)
+            L.check(L.lib().nefes_cosine_loss_fwd(L.ptr(f), L.ptr(t), L.ptr(m), N, C, L.ptr(stats), st), "nefes_cosine_loss_fwd")
+            L.check(L.lib().nefes_cosine_loss_bwd(L.ptr(f), L.ptr(t), L.ptr(m), L.ptr(stats), N, C, L.ptr(loss), None, None, 0, L.ptr(d_feat), st),
+                    "nefes_cosine_loss_bwd")
+        ctx.save_for_backward(d_feat)
+        ctx.shape = tuple(feat.shape)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_feat,) = ctx.saved_tensors
+        return (d_feat * g).reshape(ctx.shape), None, None
+
+
+def cosine_loss_pm(feat_pm, target, mask=None):
+    """feature_loss / masked_feature_loss (DFM_pose_refine.py:211-288, per_pixel=False) for a PIXEL-major rendered map:
+    feat_pm [N,C], target [C,N] (or [C,H,W]), mask [N] / [1,H,W] or None.  Engine kernels; differentiable in feat_pm."""
+    return _CosineLossPM.apply(feat_pm, target.reshape(target.shape[0], -1), mask)
+
+
+def masked_feature_loss(feature_rgb, feature_target, mask, img_in=True, per_pixel=False):
+    """Drop-in for DFM_pose_refine.py:257-288 (channel-major inputs [C,H,W] or [C,N], as the reference passes them)."""
+    if per_pixel:
+        raise RuntimeError("nefes_b200: per_pixel=True is not built (the reference calls per_pixel=False)")
+    C = feature_rgb.shape[0]
+    fr = feature_rgb.reshape(C, -1)
+    if fr.is_cuda:
+        return cosine_loss_pm(fr.t().contiguous(), feature_target.reshape(C, -1), mask)
+    valid = torch.nonzero(mask.reshape(-1) > 0, as_tuple=True)[0]
+    return 1 - torch.nn.functional.cosine_similarity(fr[:, valid], feature_target.reshape(C, -1)[:, valid], dim=1, eps=1e-6).mean()
+
+
+class _UpsampleCrop(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, h, w, H, W, crop):
+        L.need_cuda(x)
+        xc = L.f32c(x)
+        C = xc.shape[1]
+        if xc.shape[0] != h * w:
+            raise RuntimeError(f"nefes_b200: upsample_crop expects [h*w, C] = [{h * w}, C], got {tuple(x.shape)}")
+        out = torch.empty((H - 2 * crop) * (W - 2 * crop), C, device=xc.device)
+        with torch.cuda.device(xc.device):
+            L.check(L.lib().nefes_upsample_crop_fwd(L.ptr(xc), h, w, C, H, W, crop, L.ptr(out), L.stream_of(xc)), "nefes_upsample_crop_fwd")
+        ctx.meta = (h, w, C, H, W, crop, tuple(x.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w, C, H, W, crop, shape = ctx.meta
+        g = L.f32c(g)
+        tmp, dx = torch.empty(h * (W - 2 * crop) * C, device=g.device), torch.empty(h * w, C, device=g.device)
+        with torch.cuda.device(g.device):
+            L.check(L.lib().nefes_upsample_crop_bwd(L.ptr(g), h, w, C, H, W, crop, L.ptr(tmp), L.ptr(dx), L.stream_of(g)), "nefes_upsample_crop_bwd")
+        return dx.reshape(shape), None, None, None, None, None
+
+
+def upsample_crop(x_pm, h, w, H, W, crop=10):
+    """torch.nn.Upsample(size=(H, W), mode='bicubic') + [:, :, crop:-crop, crop:-crop] (DFM_APR_refine.py:114-124) of a
+    pixel-major map x_pm [h*w, C] -> [(H - 2 crop) * (W - 2 crop), C]; engine kernels, differentiable."""
+    return _UpsampleCrop.apply(x_pm, int(h), int(w), int(H), int(W), int(crop))
+
+
+def apr_feature_loss(feature_pm, feature_target, h, w, crop=10, mask=None):
+    """The loss of the APR-refinement step (DFM_APR_refine.py:114-129): the fused feature map rendered at h x w is up-sampled
+    bicubically to the target's H x W, both are cropped by `crop` pixels, cosine feature loss (optionally masked).
+    feature_pm [h*w, C] pixel-major (FusionNet output), feature_target [C,H,W]."""
+    C, H, W = feature_target.shape
+    up = upsample_crop(feature_pm, h, w, H, W, crop)
+    tgt = feature_target[:, crop:H - crop, crop:W - crop].reshape(C, -1)
+    m = None if mask is None else mask.reshape(H, W)[crop:H - crop, crop:W - crop].reshape(-1)
+    return cosine_loss_pm(up, tgt, m)
+
+
 class _EncodeHist:
     encode_hist = True
 
@@ -227,9 +315,9 @@ class EnginePoseRefiner:
             L.check(lib.nefes_pose_rays_fwd(p(self.pose6), p(self.init), self.H, self.W, self.focal, self.near, self.far,
                                             p(self.c2w), p(self.call.rays), 21, self.chain, st), "nefes_pose_rays_fwd")
             self.call.forward()
-            L.check(lib.nefes_cosine_loss_fwd(p(self.call.feat), p(self.target), self.N, self.C, p(self.stats), st),
+            L.check(lib.nefes_cosine_loss_fwd(p(self.call.feat), p(self.target), None, self.N, self.C, p(self.stats), st),
                     "nefes_cosine_loss_fwd")
-            L.check(lib.nefes_cosine_loss_bwd(p(self.call.feat), p(self.target), p(self.stats), self.N, self.C, p(self.loss),
+            L.check(lib.nefes_cosine_loss_bwd(p(self.call.feat), p(self.target), None, p(self.stats), self.N, self.C, p(self.loss),
                                               p(self.loss_hist), p(self.state[12:]), self.HIST, p(self.g_feat), st),
                     "nefes_cosine_loss_bwd")
             d_rays = self.call.backward(g_feat=self.g_feat)

@@ -166,3 +166,37 @@ def test_affine_color_transform_vs_oracle(nb):
     assert rel(out, want) < 1e-5
     assert rel(r1.grad, r2.grad) < 1e-4 and rel(params.grad, p2.grad) < 1e-4
     assert rel(coarse.a_embedded, O.exposure_mlp(p2.detach(), hist)) < 1e-5
+
+
+def test_upsample_crop_and_masked_loss_vs_torch(nb):
+    """torch.nn.Upsample(bicubic) 60x80 -> 240x320 + 10-pixel crop + (masked) cosine feature loss of the APR
+    refinement step (dm/DFM_APR_refine.py:114-129, dm/DFM_pose_refine.py:257-288) -- the reference's arithmetic IS torch's,
+    evaluated here on the CPU in fp32 -- against nefes_upsample_crop_* + nefes_cosine_loss_*: values 2e-5, gradient 1e-4."""
+    from nefes_b200 import refine
+    g = torch.Generator().manual_seed(9)
+    h, w, H, W, C, crop = 60, 80, 240, 320, 128, 10
+    x = torch.randn(h * w, C, generator=g)
+    target = torch.randn(C, H, W, generator=g)
+    mask = (torch.rand(1, H, W, generator=g) > 0.3).float()
+    for m in (None, mask):
+        xr = x.clone().requires_grad_(True)
+        up = torch.nn.Upsample(size=(H, W), mode='bicubic')(xr.t().reshape(1, C, h, w))[:, :, crop:-crop, crop:-crop]
+        tg = target[None][:, :, crop:-crop, crop:-crop]
+        if m is None:
+            want = 1 - torch.nn.functional.cosine_similarity(up[0].reshape(C, -1), tg[0].reshape(C, -1), dim=1, eps=1e-6).mean()
+        else:
+            valid = torch.nonzero(m[:, crop:-crop, crop:-crop].reshape(-1) > 0, as_tuple=True)[0]
+            want = 1 - torch.nn.functional.cosine_similarity(up[0].reshape(C, -1)[:, valid], tg[0].reshape(C, -1)[:, valid], dim=1, eps=1e-6).mean()
+        want.backward()
+        xe = x.to(DEV).requires_grad_(True)
+        got_up = refine.upsample_crop(xe, h, w, H, W, crop)
+        assert rel(got_up, up[0].reshape(C, -1).t()) < 2e-5
+        loss = refine.apr_feature_loss(xe, target.to(DEV), h, w, crop, None if m is None else m.to(DEV))
+        loss.backward()
+        assert abs(float(loss) - float(want)) < 2e-5, (float(loss), float(want))
+        assert rel(xe.grad, xr.grad) < 1e-4, rel(xe.grad, xr.grad)
+    # the drop-in with the reference's channel-major signature
+    a, b = torch.randn(C, 30, 40, generator=g), torch.randn(C, 30, 40, generator=g)
+    mk = (torch.rand(1, 30, 40, generator=g) > 0.5).float()
+    got = refine.masked_feature_loss(a.to(DEV), b.to(DEV), mk.to(DEV))
+    assert abs(float(got) - float(refine.masked_feature_loss(a, b, mk))) < 2e-6

@@ -276,8 +276,8 @@ def test_refinement_glue_kernels_match_torch(lietorch, world):
         assert float((c2w - m[:3, :4]).abs().max()) < 2e-6
         assert float((rays - rb).abs().max()) < 1e-5
         feat = (rays @ mix).contiguous()
-        L.check(lib.nefes_cosine_loss_fwd(p(feat), p(target), N, C_, p(stats), st), "loss fwd")
-        L.check(lib.nefes_cosine_loss_bwd(p(feat), p(target), p(stats), N, C_, p(loss), p(hist), p(state[12:]), 8, p(d_feat), st), "loss bwd")
+        L.check(lib.nefes_cosine_loss_fwd(p(feat), p(target), None, N, C_, p(stats), st), "loss fwd")
+        L.check(lib.nefes_cosine_loss_bwd(p(feat), p(target), None, p(stats), N, C_, p(loss), p(hist), p(state[12:]), 8, p(d_feat), st), "loss bwd")
         assert abs(float(loss) - float(loss_t)) < 1e-6 and abs(float(hist[it]) - float(loss_t)) < 1e-6
         d_rays = (d_feat @ mix.t()).contiguous()
         L.check(lib.nefes_pose_rays_bwd(p(d_rays), p(rays), 21, H, W, focal, p(d_c2w), st), "bwd")
