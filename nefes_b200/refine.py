@@ -365,6 +365,9 @@ def _engine_refiner_applies(feat_target, H, W, kw, hist):
         return False
     if c is None or f is None or c.flat.requires_grad or f.flat.requires_grad:
         return False
+    q = kw.get("network_query_fn")
+    if H * W * (int(kw.get("N_samples") or 0) + int(kw.get("N_importance") or 0)) > getattr(q, "netchunk", 0):
+        return False                                   # the iteration's RenderCall is ONE engine call
     probe = torch.empty(H * W, 21, device="meta")
     return _fused_applies(probe, c, kw.get("network_query_fn"), kw.get("N_samples"), kw.get("N_importance", 0), f, args)
 

@@ -433,3 +433,34 @@ def test_mlp_dgrad_and_wgrad_halves_match_the_combined_backward(precision):
         assert float((a - b).abs().max()) <= tol * float(a.abs().max()) + 1e-8
     assert lib.nefes_mlp_dgrad(p(flat), net, mode, prec, p(pts), p(dirs), N, S, p(raw), p(d_raw), p(saved), p(scr_b), None, None, st) == 1
     assert lib.nefes_mlp_wgrad(p(flat), net, mode, prec, p(pts), p(dirs), N, S, p(raw), p(d_raw), p(saved), p(scr_b), None, st) == 1
+
+
+def test_render_beyond_one_netchunk_takes_the_one_call_route_in_groups():
+    """The reference's defaults (chunk 32768 rays, netchunk 2^21 points) put two netchunks of fine points into one render_rays
+    call: the one-call route runs per netchunk-sized group of rays and must give the numbers (and gradients) of smaller calls."""
+    import nefes_b200 as nb
+    dev = torch.device("cuda")
+
+    class Args:
+        nerfh_nff, use_fine_only, NeRFW, transient_at_test, netchunk = True, False, True, True, 1 << 14
+    c = nb.NeRFH_NFF("coarse", W=128, precision="bf16").to(dev)
+    f = nb.NeRFH_NFF("fine", W=128, encode_appearance=True, encode_transient=True, precision="bf16").to(dev)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n = 300                                             # 300 rays x 128 fine points = 2.3 netchunks of 2^14 points
+    ro = torch.randn(n, 3, device=dev, generator=g) * 0.2
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, device=dev, generator=g), dim=-1)
+    t_rand, u = torch.rand(n, 64, device=dev, generator=g), torch.rand(n, 64, device=dev, generator=g)
+
+    def run(netchunk, chunk):
+        kw = dict(network_query_fn=nb.StandardQuery(netchunk), N_importance=64, N_samples=64, network_fn=c, network_fine=f, use_viewdirs=True,
+                  white_bkgd=False, args=Args(), ndc=False, lindisp=False, near=0., far=4., perturb=1., raw_noise_std=0., test_time=False,
+                  t_rand=t_rand, u=u)
+        c.zero_grad(), f.zero_grad()
+        rgb, disp, acc, ex = nb.render(60, 80, 65.7, chunk=chunk, rays=(ro, rd), img_idx=torch.zeros(1, 10), **kw)
+        (rgb.sum() + ex["feat_map"].mean() + ex["rgb0"].sum() + ex["beta"].sum()).backward()
+        return dict(rgb=rgb, disp=disp, acc=acc, **ex), c.flat.grad.clone(), f.flat.grad.clone()
+    a, gca, gfa = run(1 << 14, 32768)                   # one render_rays call, three engine calls
+    b, gcb, gfb = run(1 << 21, 100)                     # three render_rays calls of 100 rays, one engine call each
+    for k in a:
+        assert torch.equal(a[k], b[k]) or float((a[k] - b[k]).abs().max()) < 1e-6 * float(b[k].abs().max()), k
+    assert float((gca - gcb).abs().max()) < 2e-3 * float(gcb.abs().max()) and float((gfa - gfb).abs().max()) < 2e-3 * float(gfb.abs().max())
