@@ -465,19 +465,16 @@ def test_bf16_render_train_step(nb, weights, models):
 
 
 def test_pose_refinement_matches_oracle_loop(nb, weights, models):
-    """C4-shaped refinement (test_time render from c2w, cosine feature loss, Adam on the so(3)+t delta) on the
-    engine (fp32 field) against the same loop on the CPU oracle.
+    """The pose-gradient CHAIN of the refinement on random-init fields (test_time render from c2w, cosine feature loss,
+    so(3)+t delta): along the fp64 oracle's trajectory, at IDENTICAL poses, the engine's gradient of the 6 pose parameters
+    is as close to the fp64 gradient as the fp32 reference's own gradient is (factor 3) -- measured ~5e-6 relative for
+    rotation and ~3e-3 for translation on BOTH sides: with random-init fields the translation gradient is ~100x smaller
+    and sums PE-backward terms scaled by up to 2^9, so it carries fp32 summation-order noise.
 
-    North-star bar: refined pose within 1 mm / 0.01 deg of the reference's.  What is checked, and why:
-    (1) along the fp64 oracle's trajectory, at IDENTICAL poses, the engine's gradient of the 6 pose parameters
-        is as close to the fp64 gradient as the fp32 reference's own gradient is (factor 3) -- measured ~5e-6
-        relative for rotation and ~3e-3 for translation on BOTH sides: the translation gradient is ~100x
-        smaller and sums PE-backward terms scaled by up to 2^9, so it carries fp32 summation-order noise;
-    (2) the free-running loops end within 0.01 deg in rotation; in translation within 1 mm, or -- because Adam
-        divides each step by |g| and therefore turns the noise of (1) into step-sized differences whenever a
-        translation gradient crosses zero (the fp32 reference itself ends ~1.3 mm from its fp64 twin after 8
-        steps, and the reference README.md:71 reports run-to-run jitter across GPU types) -- within 10 % of the
-        distance the pose travelled."""
+    The north-star bar on the REFINED POSE (1 mm / 0.01 deg after 50 iterations at 60x80) is asserted on a conditioned
+    problem -- fields trained to carry pose signal -- in tests/test_gpu_refine_c4.py; on random-init fields Adam (which
+    divides each step by |g|) turns the noise above into step-sized differences, for the fp32 reference as much as for
+    the engine (it ends 1.3 mm from its own fp64 twin after 8 steps), so a free-running comparison here says nothing."""
     from nefes_b200 import refine
     wc, wf = weights
     c, f = models
@@ -528,20 +525,14 @@ def test_pose_refinement_matches_oracle_loop(nb, weights, models):
         print(f"worst gradient error vs fp64 over the trajectory (engine, fp32 reference): rotation {worst['r']}, translation {worst['t']}")
         assert worst["r"][0] <= max(3 * worst["r"][1], 1e-5) and worst["t"][0] <= max(3 * worst["t"][1], 1e-5), worst
         assert worst["r"][0] < 1e-4 and worst["t"][0] < 3e-2
-        ref32 = O.learn_pose_c2w(r32, t32, init).detach()
-        ref64 = O.learn_pose_c2w(r64, t64, init.double()).detach().float()
         pose, losses = refine.refine_pose(init.to(DEV), target.to(DEV), h, w_, focal, kw, n_iters=n_it, lr_r=lr_r, lr_t=lr_t)
     finally:
         for p in list(c.parameters()) + list(f.parameters()):
             p.requires_grad_(True)
-    moved_t, moved_ang = O.pose_error(ref32, init)
-    assert moved_t > 5e-3 and moved_ang > 0.5, "the refinement did not move the pose: test is vacuous"
+    ref32 = O.learn_pose_c2w(r32, t32, init).detach()
     dt, dang = O.pose_error(pose.cpu(), ref32)
-    rt64, rang64 = O.pose_error(ref32, ref64)
-    print(f"engine vs fp32 reference: {dt * 1e3:.3f} mm {dang:.5f} deg; fp32 reference vs its fp64 twin: {rt64 * 1e3:.3f} mm "
-          f"{rang64:.5f} deg; pose travelled {moved_t * 1e3:.1f} mm {moved_ang:.3f} deg")
+    print(f"free-running 8-step loops on random-init fields, engine vs fp32 reference: {dt * 1e3:.3f} mm {dang:.5f} deg (informational)")
     assert dang < 1e-2, dang
-    assert dt < 1e-3 or dt < 0.1 * moved_t, (dt, moved_t)
     assert float(losses[-1]) < float(losses[0])
 
 
