@@ -221,6 +221,7 @@ def run_train(a, c):
     extra = []
     if stage3:                                 # nerfh_nff.py:661-682: grad_vars = every parameter of both models
         extra = list(coarse.fusion_net.parameters()) + list(coarse.exposure_embedding.parameters())
+        coarse.fusion_net.gemm_tf32 = a.precision != "fp32"          # the convolutions' GEMMs on tcgen05 kind::tf32
         opt_extra = torch.optim.Adam(extra, lr=5e-4, betas=(0.9, 0.999), capturable=True)
 
     class EncArgs:
@@ -376,7 +377,7 @@ def run_train(a, c):
     out = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
-        "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+        "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[a.precision], "data": "synthetic",
         "config": {"workload": f"{wl}, 7-Scenes-stairs camera 640x480 -> 60x80, 4 images x {n_rand} rays = {rays} rays/GPU/step, "
                                "64 coarse + 64 fine samples, Adam",
                    "rays_per_gpu_per_step": rays, "global_rays_per_step": rays * world, "parallelism": f"dp{world} (rays sharded, 1 gradient all-reduce)",
@@ -461,7 +462,7 @@ def run_refine(a, c):
     out = {"metric": "NeFeS refine iters/sec (50 pose-gradient iterations per query, 60x80 render, 64+64 samples)",
            "value": r["iters_per_s"], "unit": "iters/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": r["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+           "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[a.precision], "data": "synthetic",
            "config": {"workload": "C4 DFNet+NeFeS50 test-time refinement: per query 50 Adam iterations on the 6 pose parameters, each a full "
                                   "60x80 test_time render (4800 rays, 64+64 samples) + cosine feature loss + backward to the pose; "
                                   "initial poses = DFNet_stairs_results rows, random-normal target features, frozen random-init fields; "
@@ -534,7 +535,7 @@ def run_sweep(a, c):
     ach = 63.88e6 * n / (top["ms"] / 1e3) / 1e12      # refine/inference forward 63.88 MFLOP per ray
     out = {"metric": "NeFeS rays/sec (inference render, 64+64 samples)", "value": top["rays_per_s"], "unit": "rays/s", "n_gpus": world,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": top["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+           "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[a.precision], "data": "synthetic",
            "config": {"workload": "C5-shaped ray sweep, front-end A: Cambridge camera 60x106 f=93, near 0 far 10, test_time render without "
                                   "gradients, 2^12..2^20 rays in chunks of 32768; value at 2^20 rays", "global_rays": n,
                       "parallelism": f"dp{world} (contiguous ray ranges, no collective)", "mlp_precision": a.precision, "cuda_graph": False,
@@ -566,8 +567,10 @@ def side_measurements(a, nb, step, coarse, fine, resident, kw, dev):
     from nefes_b200 import refine
     ex = {}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if a.precision != "fp32":
-        coarse.precision = fine.precision = "fp32"
+    for other in ("fp32", "tf32"):
+        if a.precision == other:
+            continue
+        coarse.precision = fine.precision = other
         for b in resident[:2]:
             step(b)
         torch.cuda.synchronize()
@@ -576,7 +579,7 @@ def side_measurements(a, nb, step, coarse, fine, resident, kw, dev):
             step(b)
         ev1.record()
         torch.cuda.synchronize()
-        ex["train_step_fp32_field"] = {"rays_per_s": RAYS * 5 / (ev0.elapsed_time(ev1) / 1e3), "ms_per_step": ev0.elapsed_time(ev1) / 5}
+        ex[f"train_step_{other}_field"] = {"rays_per_s": RAYS * 5 / (ev0.elapsed_time(ev1) / 1e3), "ms_per_step": ev0.elapsed_time(ev1) / 5}
         coarse.precision = fine.precision = a.precision
     # encoder front-end B (K4b): HashGrid gather, forward and backward, at the bench step's point count
     from nefes_b200.hashgrid import HashGridEncoding
@@ -827,7 +830,7 @@ def main():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    p.add_argument("--precision", default=os.environ.get("NEFES_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    p.add_argument("--precision", default=os.environ.get("NEFES_PRECISION", "bf16"), choices=["fp32", "tf32", "bf16"])
     p.add_argument("--no-extras", action="store_true", help="skip the fp32-path and refinement side measurements")
     p.add_argument("--no-graph", action="store_true", help="time eager steps instead of a captured CUDA graph of the step")
     p.add_argument("--workload", default="train", choices=["train", "c3", "c3s3", "refine", "sweep"])

@@ -58,8 +58,10 @@ enum {
 };
 /* arithmetic of the MLP */
 enum {
-  NEFES_PREC_FP32 = 0,             /* SIMT fp32 FMA -- the 1e-3 parity path                 */
-  NEFES_PREC_BF16 = 1              /* tcgen05 bf16 operands, fp32 TMEM accumulators         */
+  NEFES_PREC_FP32 = 0,             /* SIMT fp32 FMA -- the exact parity path                 */
+  NEFES_PREC_BF16 = 1,             /* tcgen05 bf16 operands, fp32 TMEM accumulators, fused layer chains */
+  NEFES_PREC_TF32 = 2              /* the fp32 path's layer-at-a-time structure (fp32 activations in HBM) with every GEMM on
+                                      tcgen05 kind::tf32 (operands rounded to tf32, fp32 accumulate): the <= 1e-3 tensor path */
 };
 /* memory layout of the per-point network output `raw` (M points x C channels, fp32) */
 enum {
@@ -152,6 +154,9 @@ int nefes_encode_sh_bwd(const float* d, const float* d_out, int64_t M, float* d_
  *   fwd:   C[M,N] = act(A[M,K] W^T + bias)      act: 0 none, 1 relu, 3 sigmoid; bias may be NULL
  *   dgrad: dA[M,K] = dC[M,N] W, multiplied by (mask[M,K] > 0) when mask != NULL (ReLU backward)
  *   wgrad: dW[N,K] += dC^T A                     (accumulated, fp32 atomics)                          */
+/* Which GEMM nefes_linear_* (and the FusionNet convolutions of nefes_fusion_*) run on: 0 = SIMT fp32 (default), 1 = tcgen05
+ * tf32.  Process-wide; returns the previous mode.  The NEFES_PREC_TF32 entry points switch it around their own calls. */
+int nefes_gemm_mode(int tf32);
 int nefes_linear_fwd(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc,
                      int64_t M, int N, int K, int act, void* stream);
 int nefes_linear_dgrad(const float* dC, int64_t ldc, const float* W, float* dA, int64_t lda, int64_t M, int N, int K,

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnefes_b200.so")
 MAX_LAYERS = 18
 NET_COARSE, NET_FINE = 0, 1
 MODE_SIGMA, MODE_STATIC, MODE_FULL = 0, 1, 2
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
 COMP_SIGMA, COMP_STATIC, COMP_TRANSIENT, COMP_TRANSIENT_STATIC_ONLY = 0, 1, 2, 3
 RAW_CH = {MODE_SIGMA: 1, MODE_STATIC: 132, MODE_FULL: 137}
 
@@ -95,6 +95,7 @@ _SIGS = {
     "nefes_adam_step_dev": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, vp]),
     "nefes_nerfw_loss_fwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp]),
     "nefes_nerfw_loss_bwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp, vp, vp]),
+    "nefes_gemm_mode": (i32, [i32]),
     "nefes_feat_loss_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp, vp]),
     "nefes_feat_loss_bwd": (i32, [vp, vp, vp, vp, i64, i32, vp, vp, vp]),
     "nefes_fusion_workspace": (i64, [i64]),

@@ -13,7 +13,7 @@
 // the render's work and launch-bound in the reference (cuDNN, ~20 launches + NCHW shuffles).
 // The backward recomputes the im2col matrices (they are 12x the activations) and keeps only X0, A1..A3 and the pre-BN output.
 #include "common.cuh"
-#include "sgemm.cuh"
+#include "tf32_gemm.cuh"
 #include <algorithm>
 
 namespace nefes {

@@ -6,6 +6,12 @@ int mlp_fwd_fp32(const float*, int, int, const float*, const float*, int64_t, in
 int mlp_bwd_fp32(const float*, int, int, const float*, const float*, int64_t, int, const float*, const float*,
                  const void*, void*, float*, float*, float*, cudaStream_t);
 int mlp_workspace_fp32(int, int64_t, int64_t, int64_t*, int64_t*, int64_t*);
+int gemm_mode_set(int tf32);          // mlp_fp32.cu: which GEMM the fp32-structured path runs on; returns the previous mode
+struct GemmModeScope {                // NEFES_PREC_TF32 = the fp32 path with its GEMMs on tcgen05 kind::tf32
+  int prev; bool on;
+  explicit GemmModeScope(int prec) : prev(0), on(prec == NEFES_PREC_TF32) { if (on) prev = gemm_mode_set(1); }
+  ~GemmModeScope() { if (on) gemm_mode_set(prev); }
+};
 int mlp_fwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, float*, void*, void*, int, cudaStream_t);
 int mlp_bwd_bf16(const float*, int, int, const float*, const float*, int64_t, int, const float*, const float*,
                  const void*, void*, float*, float*, float*, int, cudaStream_t, const float*, const float*, const float*);
@@ -51,7 +57,7 @@ static int check_mlp(const char* who, int net, int mode, int prec, int64_t N, in
   NEFES_REQUIRE(mode >= NEFES_MODE_SIGMA && mode <= NEFES_MODE_FULL, NEFES_EINVAL, "%s: bad mode %d", who, mode);
   NEFES_REQUIRE(mode != NEFES_MODE_FULL || net == NEFES_NET_FINE, NEFES_EINVAL,
                 "%s: MODE_FULL needs the fine net (the coarse net has no transient heads)", who);
-  NEFES_REQUIRE(prec == NEFES_PREC_FP32 || prec == NEFES_PREC_BF16, NEFES_EINVAL, "%s: bad precision %d", who, prec);
+  NEFES_REQUIRE(prec == NEFES_PREC_FP32 || prec == NEFES_PREC_BF16 || prec == NEFES_PREC_TF32, NEFES_EINVAL, "%s: bad precision %d", who, prec);
   NEFES_REQUIRE(N >= 0 && S >= 1 && N * (int64_t)S < (int64_t)1 << 31, NEFES_EINVAL,
                 "%s: bad shape N=%lld S=%d", who, (long long)N, S);
   return NEFES_OK;
@@ -82,6 +88,7 @@ static int mlp_fwd_any(const char* who, int layout, const float* params, int net
   if (N == 0) return NEFES_OK;
   if (prec == NEFES_PREC_BF16)
     return nefes::mlp_fwd_bf16(params, net, mode, pts, dirs, N, S, raw, saved, scratch, layout, (cudaStream_t)stream);
+  nefes::GemmModeScope gemm(prec);
   return nefes::mlp_fwd_fp32(params, net, mode, pts, dirs, N, S, raw, saved, scratch, (cudaStream_t)stream);
 }
 
@@ -100,6 +107,7 @@ static int mlp_bwd_any(const char* who, int layout, const float* params, int net
   if (prec == NEFES_PREC_BF16)
     return nefes::mlp_bwd_bf16(params, net, mode, pts, dirs, N, S, raw, d_raw, saved, scratch, d_params, d_pts,
                                d_dirs, layout, (cudaStream_t)stream, compact, g_rgb, g_feat);
+  nefes::GemmModeScope gemm(prec);
   return nefes::mlp_bwd_fp32(params, net, mode, pts, dirs, N, S, raw, d_raw, saved, scratch, d_params, d_pts,
                              d_dirs, (cudaStream_t)stream);
 }

@@ -16,7 +16,8 @@
 //
 //   warp 0       producer: weight ring (bulk copies), the encodings of the next tile pair
 //   warp 1 / 18  MMA issuer of tile 0 / 1: CONVERGED warp, uniform operands, one elected lane issues (tc05.cuh uni())
-//   warps 2-9 / 10-17  epilogue of tile 0 / 1: warp = TMEM lane quarter x 32-column half of a 64-column block
+//   warps 2-9 / 10-17  epilogue of tile 0 / 1: warp = TMEM lane quarter x block parity (warps 0-3 of a tile serve block 0 and
+//                      a third block, warps 4-7 block 1), all columns of the block in 32-column passes
 //
 // Synchronisation is by "latest completion" of per-tile mbarriers: acc_ready[g][b] (issuer -> epilogue, block b of the
 // current step retired) and k_ready[g][b] (epilogue -> issuer: block b's operand columns written AND its accumulator
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTs2MaxSlots; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 2); }
     for (int g = 0; g < 2; ++g) {
-      for (int b = 0; b < 3; ++b) { mbar_init(&bar_acc[g][b], 1); mbar_init(&bar_k[g][b], kChainEpiWarps); }
+      for (int b = 0; b < 3; ++b) { mbar_init(&bar_acc[g][b], 1); mbar_init(&bar_k[g][b], kChainEpiWarps / 2); }
       mbar_init(&bar_x[g], 1); mbar_init(&bar_d[g], 1);
     }
     fence_mbar_init();
@@ -331,19 +332,25 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
     }
   } else {
     // ------------------------------- epilogue warps -------------------------------------------------------------------------
+    // Block-parallel: of a tile's 8 warps, warps 0-3 (one per TMEM lane quarter) serve the EVEN blocks of a step (block 0,
+    // and a third block such as the sigma column), warps 4-7 the ODD block (block 1), each warp all columns of its block in
+    // 32-column passes.  Block 1's epilogue -- which the next layer's MMAs wait for -- therefore never queues behind block
+    // 0's epilogue and saved-copy work on the same warps (measured before: block 1 picked up ~1000 cycles after block 0's
+    // hand-over with saves on).  Each block stores its own 16 KB half of the saved image (staging + bulk store behind a
+    // 4-warp barrier).
     const int ew = warp - 2;
     const int g = ew >> 3;
-    const int jj = (ew >> 2) & 1;                     // which 32 columns of a 64-column block
+    const int hgrp = (ew >> 2) & 1;                   // serves blocks b with (b & 1) == hgrp
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int gt = (ew & 7) * 32 + lane;              // 0..255 inside the tile's group
+    const int gt4 = (ew & 3) * 32 + lane;             // 0..127 inside the 4-warp group
     const uint32_t tbase = tmem + g * 256 + ((uint32_t)(q * 32) << 16);
     uint8_t* stage = smem + kTs2OffStage + g * kTs2Stage;
     uint32_t na[3] = {0u, 0u, 0u}, ecnt = 0;
-    // ONE arrival per warp: 256 per-thread arrivals on one barrier word serialise in the SM's barrier unit (32 cycles per
-    // warp instruction) and the issuer's own waits queue behind them.  Every lane has fenced its tensor-memory accesses
-    // (tcgen05.fence::before_thread_sync) before the warp meets.
+    // ONE arrival per warp: per-thread arrivals on one barrier word serialise in the SM's barrier unit (32 cycles per warp
+    // instruction).  Every lane has fenced its tensor-memory accesses (tcgen05.fence::before_thread_sync) before the warp meets.
     auto warp_arrive = [&](uint64_t* bar) { __syncwarp(); if (lane == 0) mbar_arrive(bar); };
+    auto half_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g * 2 + hgrp) : "memory"); };
     bool store_pending = false;
     const bool dbg = A.dbg != nullptr && blockIdx.x == 0 && lane == 0;
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -355,8 +362,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
         const int n_blk = A.step[s].n_blk;
         const float* bias = sBias + A.step[s].bias_off;
         uint8_t* gdst = (A.xflags & 1) ? nullptr : A.step[s].gdst;
-        const uint32_t g_stride = A.step[s].g_tile_stride, save_bytes = A.step[s].save_bytes;
-        for (int b = 0; b < n_blk; ++b) {
+        const uint32_t g_stride = A.step[s].g_tile_stride;
+        for (int b = hgrp; b < n_blk; b += 2) {
           // the block's fields as locals: later asm statements clobber "memory" and would force re-loads
           const int kind = A.step[s].blk[b].kind, n0 = A.step[s].blk[b].n0, nw = A.step[s].blk[b].nw;
           const uint32_t acc = tbase + A.step[s].blk[b].acc_col, out_col = A.step[s].blk[b].out_col;
@@ -365,93 +372,97 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
           mbar_wait(&bar_acc[g][b], (na[b] - 1) & 1);
           tc_fence_after();
           if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 8 + ew] = clock64();
-          if (dbg && ecnt < 32 && b == 1 && (ew & 7) == 0) A.dbg[ecnt * 48 + 42 + g] = clock64();
+          if (dbg && ecnt < 32 && b == 1 && (ew & 3) == 0) A.dbg[ecnt * 48 + 42 + g] = clock64();
           if (kind == BK_HID_RELU || kind == BK_HID) {
-            // 64-column block (or a 32-column one: nw == 32 is not used; nw == 64 always here): this warp's 32 columns
-            const int c = jj * 32;
-            float4 bv[8];
-            uint32_t v[32], w[16];
-            lds_bias32(bias + n0 + c, bv);
-            tmem_ld32(acc + c, v);
-            tmem_ld_wait();
-            if (kind == BK_HID_RELU) pack32<true>(v, bv, w); else pack32<false>(v, bv, w);
-            tmem_st16(tbase + out_col + (c >> 1), w);
+            const bool saving = gdst != nullptr && save != 0;
+            uint8_t* srow = stage + (n0 >> 3) * kChunkBytes + row * 16;
+            uint8_t* grow = saving ? gdst + (int64_t)tile * g_stride + (n0 >> 3) * kChunkBytes + row * 16 : nullptr;
+            if (saving && A.save_mode == 0 && store_pending) {      // the block's previous bulk store must have read its staging half
+              if (gt4 == 0) bulk_wait_read<0>();
+              half_barrier();
+              store_pending = false;
+            }
+#pragma unroll 1
+            for (int c = 0; c < nw; c += 32) {                       // 32-column passes over the block's columns
+              float4 bv[8];
+              uint32_t v[32], w[16];
+              lds_bias32(bias + n0 + c, bv);
+              tmem_ld32(acc + c, v);
+              tmem_ld_wait();
+              if (kind == BK_HID_RELU) pack32<true>(v, bv, w); else pack32<false>(v, bv, w);
+              tmem_st16(tbase + out_col + (c >> 1), w);
+              if (saving) {
+                if (A.save_mode == 1) {
+                  // straight from the registers: a warp writes 512 contiguous bytes per 8-channel chunk (rows 32 q .. 32 q + 31)
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) stg128(grow + ((c >> 3) + j) * kChunkBytes, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(srow + ((c >> 3) + j) * kChunkBytes) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                }
+              }
+            }
             tmem_st_wait();
             tc_fence_before();
             warp_arrive(&bar_k[g][b]);
             if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
-            if (dbg && ecnt < 32 && b == 1 && (ew & 7) == 0) A.dbg[ecnt * 48 + 44 + g] = clock64();
-            if (gdst != nullptr && save) {
-              // Three mechanisms measured within 4 % of each other (round 2: one 32 KB bulk store per step 0.599 ms, st.global.v4
-              // from the registers 0.607, four 512-byte bulk stores per warp and block 0.624; without saved copies 0.476): the
-              // launch then writes 4.7 TB/s and it is the memory system, not the mechanism, that holds it.
-              if (A.save_mode == 1) {
-                // straight from the registers: a warp writes 512 contiguous bytes per 8-channel chunk (rows 32 q .. 32 q + 31)
-                uint8_t* grow = gdst + (int64_t)tile * g_stride + ((n0 + c) >> 3) * kChunkBytes + row * 16;
+            if (dbg && ecnt < 32 && b == 1 && (ew & 3) == 0) A.dbg[ecnt * 48 + 44 + g] = clock64();
+            if (saving && A.save_mode == 0) {
+              // Saved copy: this block's nw channels are nw * 256 contiguous bytes of the image.  (Measured within 4 % of each
+              // other in round 2: one 32 KB bulk store per step, st.global.v4 from the registers, 512-byte bulk stores per warp.)
+              fence_async_smem();
+              half_barrier();
+              if (gt4 == 0) {
+                bulk_s2g(gdst + (int64_t)tile * g_stride + (n0 >> 3) * kChunkBytes, stage + (n0 >> 3) * kChunkBytes, (uint32_t)nw * 256u);
+                bulk_commit();
+              }
+              store_pending = true;
+            }
+          } else if (kind == BK_RAW) {
+            // raw channels [raw_c0, raw_c0 + raw_n) from accumulator columns [0, raw_n) of the block: 32-column passes, then the
+            // tail beyond 64 (the three channels 128..130 of the colour head)
+            uint32_t t4[4] = {0u, 0u, 0u, 0u};
+            if (raw_n > 64)
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(t4[0]), "=r"(t4[1]), "=r"(t4[2]), "=r"(t4[3]) : "r"(acc + 64) : "memory");
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 32) {
+              uint32_t v[32];
+              tmem_ld32(acc + c, v);
+              tmem_ld_wait();
+              if (c == 32) {                                          // every column of the block is in registers: hand over
+                tc_fence_before();
+                warp_arrive(&bar_k[g][b]);
+                if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
+              }
+              if (ok && !(A.xflags & 4)) {
+                const float* bp = bias + n0 + c;
+                float* rp = rawt + (raw_c0 + c) * kTile;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) stg128(grow + j * kChunkBytes, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-              } else {
-                if (store_pending) {                     // the previous bulk store must have read the staging image
-                  if (gt == 0) bulk_wait_read<0>();
-                  group_barrier(g);
-                  store_pending = false;
-                }
-                uint8_t* srow = stage + ((n0 + c) >> 3) * kChunkBytes + row * 16;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  *reinterpret_cast<uint4*>(srow + j * kChunkBytes) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-                if (save == 2) {
-                  fence_async_smem();
-                  group_barrier(g);
-                  if (gt == 0) {
-                    bulk_s2g(gdst + (int64_t)tile * g_stride, stage, save_bytes);
-                    bulk_commit();
-                  }
-                  store_pending = true;
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(bp + 4 * j);
+                  stg32f(rp + (4 * j + 0) * kTile, __uint_as_float(v[4 * j + 0]) + b4.x);
+                  stg32f(rp + (4 * j + 1) * kTile, __uint_as_float(v[4 * j + 1]) + b4.y);
+                  stg32f(rp + (4 * j + 2) * kTile, __uint_as_float(v[4 * j + 2]) + b4.z);
+                  stg32f(rp + (4 * j + 3) * kTile, __uint_as_float(v[4 * j + 3]) + b4.w);
                 }
               }
             }
-          } else if (kind == BK_RAW) {
-            // raw channels [raw_c0, raw_c0 + raw_n) from accumulator columns [0, raw_n): warp jj takes columns [32 jj, 32 jj + 32),
-            // the jj == 0 warps also the tail beyond 64 (the three channels 128..130 of the colour head)
-            const int c = jj * 32;
-            uint32_t v[32], t4[4] = {0u, 0u, 0u, 0u};
-            tmem_ld32(acc + c, v);
-            if (jj == 0 && raw_n > 64)
-              asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(t4[0]), "=r"(t4[1]), "=r"(t4[2]), "=r"(t4[3]) : "r"(acc + 64) : "memory");
+            if (ok && !(A.xflags & 4) && raw_n > 64) {
+              for (int e = 0; e < raw_n - 64 && e < 4; ++e)
+                stg32f(rawt + (raw_c0 + 64 + e) * kTile, __uint_as_float(t4[e]) + bias[n0 + 64 + e]);
+            }
+          } else {                                     // BK_SIGMA / BK_HEADS: a few activated columns
+            uint32_t v[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                         : "r"(acc) : "memory");
             tmem_ld_wait();
             tc_fence_before();
             warp_arrive(&bar_k[g][b]);
             if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
-            if (ok && !(A.xflags & 4)) {
-              const float* bp = bias + n0 + c;
-              float* rp = rawt + (raw_c0 + c) * kTile;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bp + 4 * j);
-                stg32f(rp + (4 * j + 0) * kTile, __uint_as_float(v[4 * j + 0]) + b4.x);
-                stg32f(rp + (4 * j + 1) * kTile, __uint_as_float(v[4 * j + 1]) + b4.y);
-                stg32f(rp + (4 * j + 2) * kTile, __uint_as_float(v[4 * j + 2]) + b4.z);
-                stg32f(rp + (4 * j + 3) * kTile, __uint_as_float(v[4 * j + 3]) + b4.w);
-              }
-              if (jj == 0 && raw_n > 64) {
-                for (int e = 0; e < raw_n - 64 && e < 4; ++e)
-                  stg32f(rawt + (raw_c0 + 64 + e) * kTile, __uint_as_float(t4[e]) + bias[n0 + 64 + e]);
-              }
-            }
-          } else {                                     // BK_SIGMA / BK_HEADS: a few activated columns
-            uint32_t v[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            if (jj == 0) {
-              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                           : "r"(acc) : "memory");
-              tmem_ld_wait();
-            }
-            tc_fence_before();
-            warp_arrive(&bar_k[g][b]);
-            if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
-            if (jj == 0 && ok) {
+            if (ok) {
               if (kind == BK_SIGMA) {
                 stg32f(rawt + raw_c0 * kTile, softplus_f(__uint_as_float(v[0]) + bias[n0]));
               } else {
@@ -466,7 +477,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
         }
       }
     }
-    if (gt == 0) bulk_wait_all();
+    if (gt4 == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();

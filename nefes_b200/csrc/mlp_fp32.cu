@@ -2,7 +2,7 @@
 // This is the parity anchor (<= 1e-3 rel of the reference, in practice ~1e-5) and the numerical
 // reference the tcgen05 bf16 path is debugged against.  script/models/nerfh_nff.py:168-231,
 // :525-576.  Forward keeps every post-activation tensor backward needs in `saved`.
-#include "sgemm.cuh"
+#include "tf32_gemm.cuh"
 
 extern "C" int nefes_encode_pe_fwd(const float*, int64_t, int, float*, int, void*);
 extern "C" int nefes_encode_pe_bwd(const float*, const float*, int, int64_t, int, float*, void*);
@@ -275,9 +275,16 @@ int mlp_workspace_fp32(int mode, int64_t M, int64_t N, int64_t* saved, int64_t* 
   return NEFES_OK;
 }
 
+int gemm_mode_set(int tf32) {
+  const int prev = gemm_tf32();
+  gemm_tf32() = tf32 ? 1 : 0;
+  return prev;
+}
+
 }  // namespace nefes
 
 extern "C" {
+int nefes_gemm_mode(int tf32) { return nefes::gemm_mode_set(tf32); }
 int nefes_linear_fwd(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc, int64_t M,
                      int N, int K, int act, void* stream) {
   if (M == 0) return NEFES_OK;

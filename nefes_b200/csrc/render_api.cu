@@ -99,7 +99,7 @@ static int make_plan(const char* who, const nefes_render_cfg_t* cfg, int64_t N, 
   NEFES_REQUIRE(cfg->n_samples >= 2 && cfg->n_samples <= 256 && cfg->n_importance >= 0 && cfg->n_importance <= 256 &&
                 cfg->n_samples + cfg->n_importance <= 256, NEFES_EINVAL, "%s: bad sample counts %d + %d", who,
                 cfg->n_samples, cfg->n_importance);
-  NEFES_REQUIRE(cfg->prec == NEFES_PREC_FP32 || cfg->prec == NEFES_PREC_BF16, NEFES_EINVAL, "%s: bad precision", who);
+  NEFES_REQUIRE(cfg->prec == NEFES_PREC_FP32 || cfg->prec == NEFES_PREC_BF16 || cfg->prec == NEFES_PREC_TF32, NEFES_EINVAL, "%s: bad precision", who);
   RenderPlan& p = *P;
   p.fine = cfg->n_importance > 0;
   p.Sc = cfg->n_samples;

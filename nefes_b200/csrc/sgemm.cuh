@@ -136,27 +136,4 @@ inline int launch_sgemm(const GemmArgs& g, cudaStream_t st, const char* what) {
   return NEFES_OK;
 }
 
-// C[M,N] = act( (accumulate ? C : 0) + A[M,K] W[N,K]^T + bias )
-inline int linear_fwd(cudaStream_t st, const float* A, int64_t lda, const float* W, int64_t ldw,
-                      const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int act,
-                      int accumulate) {
-  GemmArgs g = {A, lda, W, ldw, C, ldc, bias, nullptr, 0, M, N, K, act, accumulate, 0, 0};
-  return launch_sgemm<true, true>(g, st, "linear_fwd");
-}
-// dA[M,K] = relu_mask( (accumulate ? dA : 0) + dD[M,N] W[N,K] )
-inline int linear_dgrad(cudaStream_t st, const float* dD, int64_t ldd, const float* W, int64_t ldw,
-                        float* dA, int64_t lda, int64_t M, int N, int K, const float* mask,
-                        int64_t ldm, int accumulate) {
-  GemmArgs g = {dD, ldd, W, ldw, dA, lda, nullptr, mask, ldm, M, K, N, ACT_NONE, accumulate, 0, 0};
-  return launch_sgemm<true, false>(g, st, "linear_dgrad");
-}
-// dW[N,K] += dD[M,N]^T A[M,K]      (split over M, fp32 atomics)
-inline int linear_wgrad(cudaStream_t st, const float* dD, int64_t ldd, const float* A, int64_t lda,
-                        float* dW, int64_t ldw, int64_t M, int N, int K) {
-  int64_t chunk = round_up(ceil_div(M, 592), 16);      // ~4 CTAs per SM worth of splits
-  if (chunk < 512) chunk = 512;
-  GemmArgs g = {dD, ldd, A, lda, dW, ldw, nullptr, nullptr, 0, N, K, M, ACT_NONE, 0, 1, chunk};
-  return launch_sgemm<false, false>(g, st, "linear_wgrad");
-}
-
 }  // namespace nefes

@@ -31,7 +31,7 @@ class _FusionNetFn(Function):
     """out [P,128] = FusionNet(rgb [P,3], feat [P,128]); parameters: 4 conv weights, 4 biases, (BN weight, bias)."""
 
     @staticmethod
-    def forward(ctx, rgb, feat, B, H, W, training, residual, momentum, eps, run_mean, run_var, *params):
+    def forward(ctx, rgb, feat, B, H, W, training, residual, momentum, eps, run_mean, run_var, tf32, *params):
         L.need_cuda(rgb, feat, *params)
         no_bn = len(params) == 8
         rgb_c, feat_c = L.f32c(rgb), L.f32c(feat)
@@ -44,24 +44,24 @@ class _FusionNetFn(Function):
         out = torch.empty(P, 128, device=dev)
         bn = None if no_bn else (ps[8], ps[9], run_mean, run_var)
         st = _params_struct(ps[0:4], ps[4:8], bn)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _GemmMode(tf32):
             L.check(L.lib().nefes_fusion_fwd(ctypes.byref(st), L.ptr(rgb_c), L.ptr(feat_c), B, H, W, int(training), int(no_bn), int(residual),
                                              float(momentum), float(eps), L.ptr(ws), L.ptr(out), L.stream_of(rgb_c)), "nefes_fusion_fwd")
         ctx.save_for_backward(ws, *ps)
-        ctx.meta = (B, H, W, int(training), int(no_bn), int(residual), run_mean, run_var, tuple(rgb.shape), tuple(feat.shape))
+        ctx.meta = (B, H, W, int(training), int(no_bn), int(residual), run_mean, run_var, tuple(rgb.shape), tuple(feat.shape), tf32)
         return out
 
     @staticmethod
     def backward(ctx, g):
         ws, *ps = ctx.saved_tensors
-        B, H, W, training, no_bn, residual, run_mean, run_var, s_rgb, s_feat = ctx.meta
+        B, H, W, training, no_bn, residual, run_mean, run_var, s_rgb, s_feat, tf32 = ctx.meta
         P = B * H * W
         dev = ws.device
         g = L.f32c(g)
         need = ctx.needs_input_grad
         d_rgb = torch.empty(P, 3, device=dev) if need[0] else None
         d_feat = torch.empty(P, 128, device=dev) if need[1] else None
-        grads = [torch.zeros_like(p) if need[11 + i] else None for i, p in enumerate(ps)]
+        grads = [torch.zeros_like(p) if need[12 + i] else None for i, p in enumerate(ps)]
         gs = _FusionGrads()
         for i in range(4):
             gs.weight[i] = grads[i].data_ptr() if grads[i] is not None else None
@@ -71,11 +71,27 @@ class _FusionNetFn(Function):
             gs.bn_bias = grads[9].data_ptr() if grads[9] is not None else None
         bn = None if no_bn else (ps[8], ps[9], run_mean, run_var)
         st = _params_struct(ps[0:4], ps[4:8], bn)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _GemmMode(tf32):
             L.check(L.lib().nefes_fusion_bwd(ctypes.byref(st), ctypes.byref(gs), L.ptr(g), B, H, W, training, no_bn, residual, L.ptr(ws),
                                              L.ptr(d_rgb), L.ptr(d_feat), L.stream_of(g)), "nefes_fusion_bwd")
         return (None if d_rgb is None else d_rgb.reshape(s_rgb), None if d_feat is None else d_feat.reshape(s_feat),
-                None, None, None, None, None, None, None, None, None, *grads)
+                None, None, None, None, None, None, None, None, None, None, *grads)
+
+
+class _GemmMode:
+    """The convolutions' GEMMs run on the SIMT fp32 GEMM (default: fp32 parity) or, with `module.gemm_tf32 = True`, on the tcgen05
+    tf32 GEMM (operands rounded to tf32: ~3e-4 of scale)."""
+
+    def __init__(self, tf32):
+        self.tf32, self.prev = bool(tf32), 0
+
+    def __enter__(self):
+        if self.tf32:
+            self.prev = L.lib().nefes_gemm_mode(1)
+
+    def __exit__(self, *a):
+        if self.tf32:
+            L.lib().nefes_gemm_mode(self.prev)
 
 
 def fusion_net(module, rgb, feat, B, H, W):
@@ -92,7 +108,8 @@ def fusion_net(module, rgb, feat, B, H, W):
         run_mean, run_var, momentum, eps = bn.running_mean, bn.running_var, bn.momentum, bn.eps
         if training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
-    return _FusionNetFn.apply(rgb, feat, int(B), int(H), int(W), training, bool(module.fusion_residule), momentum, eps, run_mean, run_var, *params)
+    return _FusionNetFn.apply(rgb, feat, int(B), int(H), int(W), training, bool(module.fusion_residule), momentum, eps, run_mean, run_var,
+                              bool(getattr(module, "gemm_tf32", False)), *params)
 
 
 class _AffineColorFn(Function):

@@ -24,9 +24,10 @@ img2mse = lambda x, y: torch.mean((x - y) ** 2)
 mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
-# default arithmetic of the MLP: "fp32" (parity path) or "bf16" (tcgen05); see NeRFH_NFF.precision
+# default arithmetic of the MLP: "fp32" (exact SIMT path), "tf32" (tcgen05 kind::tf32 GEMMs under the fp32 path's structure:
+# the <= 1e-3 tensor-core path) or "bf16" (fused tcgen05 layer chains, what bench.py times); see NeRFH_NFF.precision
 DEFAULT_PRECISION = os.environ.get("NEFES_PRECISION", "fp32")
-_PREC = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}
+_PREC = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16, "tf32": L.PREC_TF32}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -397,16 +398,20 @@ def create_nerf(args, device=None):
         embeddirs_fn, input_ch_views, _ = get_embedder(args.multires_views, args.i_embed,
                                                        getattr(args, "reduce_embedding", -1))
     skips = [4]
+    # The factory the reference's scripts enter through builds the FAST path: bf16 tcgen05 layer chains (1.9 M rays/s; stated
+    # tolerances in DESIGN.md section 3, refined poses within 1 mm / 0.01 deg of the fp32 reference).  args.nefes_precision or
+    # NEFES_PRECISION select "tf32" (tensor cores at <= 1e-3 of the reference, 0.2 M rays/s) or "fp32" (exact SIMT path).
+    precision = getattr(args, "nefes_precision", None) or os.environ.get("NEFES_PRECISION", "bf16")
     model = NeRFH_NFF("coarse", D=args.netdepth, W=args.netwidth, skips=skips, in_channels_xyz=input_ch,
                       in_channels_dir=input_ch_views, fusion_residule=getattr(args, "use_fusion_res", False),
-                      no_BN=getattr(args, "no_fusion_BN", False)).to(device)
+                      no_BN=getattr(args, "no_fusion_BN", False), precision=precision).to(device)
     grad_vars = list(model.parameters())
     model_fine = None
     if args.N_importance > 0:
         model_fine = NeRFH_NFF("fine", D=args.netdepth, W=args.netwidth, skips=skips, in_channels_xyz=input_ch,
                                in_channels_dir=input_ch_views, encode_appearance=True, encode_transient=True,
                                in_channels_a=getattr(args, "in_channels_a", 48),
-                               in_channels_t=getattr(args, "in_channels_t", 16)).to(device)
+                               in_channels_t=getattr(args, "in_channels_t", 16), precision=precision).to(device)
         grad_vars += list(model_fine.parameters())
 
     network_query_fn = StandardQuery(args.netchunk, embed_fn, embeddirs_fn)

@@ -127,6 +127,9 @@ def test_create_nerf_and_tar_roundtrip(nb, tmp_path):
     assert kw_test["raw_noise_std"] == 0. and kw_train["ndc"] is False
     assert isinstance(opt, nb.FlatAdam) and len(grad_vars) > 0
     c, f = kw_train["network_fn"], kw_train["network_fine"]
+    assert c.precision == "bf16" and f.precision == "bf16"          # the factory builds the fast tensor-core path ...
+    args_tf = types.SimpleNamespace(**dict(vars(args), nefes_precision="tf32", no_reload=True))
+    assert nb.create_nerf(args_tf, device=DEV)[0]["network_fine"].precision == "tf32"     # ... unless told otherwise
     # one optimiser step changes the weights; save the reference's checkpoint layout; a fresh create_nerf reloads it
     o, d = O.camera_rays(H, W, FOCAL, torch.eye(4)[:3])
     rays = (o.reshape(-1, 3)[:256].to(DEV).contiguous(), d.reshape(-1, 3)[:256].to(DEV).contiguous())

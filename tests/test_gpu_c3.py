@@ -141,7 +141,10 @@ def test_fusion_net_full_image_and_options(nb):
         coarse.fusion_net = m.to(DEV)
         with torch.no_grad():
             out = coarse.run_fusion_net(rgb.to(DEV), feat.to(DEV), H, W, B)[2]
+            coarse.fusion_net.gemm_tf32 = True              # the same convolutions on the tcgen05 tf32 GEMM
+            out_tf = coarse.run_fusion_net(rgb.to(DEV), feat.to(DEV), H, W, B)[2]
         assert rel(out, want) < 1e-4, (no_bn, res, rel(out, want))
+        assert rel(out_tf, want) < 1e-3, (no_bn, res, rel(out_tf, want))
 
 
 def test_affine_color_transform_vs_oracle(nb):

@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick A/B of the TS2 forward chain: env assignments in $1 (e.g. "NEFES_TS2_TURNS=0"), timing + stamps + parity subset
 mkdir -p gpurun_out
-export NEFES_FWD_TS2=1
+export NEFES_X=1
 for v in "$@"; do
   echo "== $v" | tee -a gpurun_out/ts2_quick.log
   env $v timeout 300 python tools/prof_fwd.py 2>&1 | grep "saves=on.*chain_fwd" | tee -a gpurun_out/ts2_quick.log
