@@ -144,30 +144,42 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
       bulk_wait_all();
     }
   } else if (warp == 1 || warp == 10) {
-    if (lane == 0 && n_my > 0) {
+    if (n_my > 0) {
       // ------------------------------- MMA issuers: warp 1 data gradients, warp 10 weight gradients ----------------------
-      const FMmaOp* prog = s_mma[warp == 1 ? 0 : 1];
+      // CONVERGED warp: all lanes walk the program and wait, one elected lane issues with uniform operands (tc05.cuh uni()).
+      // From a lane-0 branch every tcgen05.mma / commit is wrapped in a waterfall loop (50-100 cycles each), and warp
+      // sampling had these two threads 65 % busy in their own code with one tile in flight (round 2).
+      const bool leader = elect_one();
+      const int which = uni(warp == 1 ? 0 : 1);
+      const FMmaOp* prog = s_mma[which];
+      const uint32_t sb = uni(sbase), tm = uni(tmem);
       for (int it = 0; it < n_my; ++it) {
         for (int i = 0; prog[i].kind != FO_END; ++i) {
           const FMmaOp& o = prog[i];
-          if (o.kind == FO_WAIT) {
-            if (o.flags & FW_PREV) { if (it > 0) mbar_wait(&bars[o.bar], (it - 1) & 1); }
-            else if (o.flags & FW_ONCE) { if (it == 0) mbar_wait(&bars[o.bar], 0); }
-            else mbar_wait(&bars[o.bar], it & 1);
-          } else if (o.kind == FO_MMA) {
+          const int kind = uni((int)o.kind), bar = uni((int)o.bar), flags = uni((int)o.flags);
+          if (kind == FO_WAIT) {
+            if (flags & FW_PREV) { if (it > 0) mbar_wait(&bars[bar], (it - 1) & 1); }
+            else if (flags & FW_ONCE) { if (it == 0) mbar_wait(&bars[bar], 0); }
+            else mbar_wait(&bars[bar], it & 1);
+          } else if (kind == FO_MMA) {
             tc_fence_after();
-            uint64_t da = smem_desc(sbase + o.a_off, (uint32_t)o.a_lbo << 4, (uint32_t)o.a_sbo << 4);
-            uint64_t db = smem_desc(sbase + o.b_off, (uint32_t)o.b_lbo << 4, (uint32_t)o.b_sbo << 4);
-            const uint32_t d = tmem + o.tmem_col;
-            const uint32_t acc0 = (o.accmode == FA_LAUNCH && it > 0) ? 1u : 0u;
-            for (int k = 0; k < o.ksteps; ++k, da += o.a_adv, db += o.b_adv) mma_ss(d, da, db, o.idesc, (k > 0) ? 1u : acc0);
-          } else if (o.kind == FO_COMMIT) {
-            mma_commit(&bars[o.bar]);
+            const uint64_t da0 = uni(smem_desc(sb + o.a_off, (uint32_t)o.a_lbo << 4, (uint32_t)o.a_sbo << 4));
+            const uint64_t db0 = uni(smem_desc(sb + o.b_off, (uint32_t)o.b_lbo << 4, (uint32_t)o.b_sbo << 4));
+            const uint32_t d = tm + uni((uint32_t)o.tmem_col), idesc = uni(o.idesc);
+            const uint32_t acc0 = (uni((int)o.accmode) == FA_LAUNCH && it > 0) ? 1u : 0u;
+            const int ks = uni((int)o.ksteps);
+            const uint64_t a_adv = uni((uint32_t)o.a_adv), b_adv = uni((uint32_t)o.b_adv);
+            if (leader)
+              for (int k = 0; k < ks; ++k) mma_ss(d, da0 + (uint64_t)k * a_adv, db0 + (uint64_t)k * b_adv, idesc, (k > 0) ? 1u : acc0);
+          } else if (kind == FO_COMMIT) {
+            if (leader) mma_commit(&bars[bar]);
           }
-          if (kFusedDbg && F.dbg != nullptr && blockIdx.x == 0 && warp == 1 && it < 4 && i < 48) F.dbg[(1 * 4 + it) * 48 + i] = clock64();
+          if (kFusedDbg && F.dbg != nullptr && blockIdx.x == 0 && warp == 1 && lane == 0 && it < 4 && i < 48) F.dbg[(1 * 4 + it) * 48 + i] = clock64();
+          __syncwarp();
         }
       }
-      mma_commit(&bar_done);
+      if (leader) mma_commit(&bar_done);
+      __syncwarp();
     }
   } else {
     // --------------------------------- epilogue warps ----------------------------------------------------------------

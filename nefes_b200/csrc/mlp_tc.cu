@@ -690,7 +690,7 @@ int num_sms() {
 }
 
 // image bookkeeping: all images of a workspace are carved from one allocation
-struct Img { uint8_t* p; int ch; int64_t tile_stride() const { return (int64_t)ch * 256; } };
+struct Img { uint8_t* p; int ch; int64_t stride = 0; int64_t tile_stride() const { return stride ? stride : (int64_t)ch * 256; } };
 
 struct Ws {             // saved-for-backward (forward writes, backward reads)
   uint8_t* arena;
@@ -712,12 +712,31 @@ Ws carve_ws(void* base, int64_t T, int mode) {
   auto img = [&](int ch) { Img i; i.ch = ch; i.p = take(T * ch * 256); return i; };
   w.arena = take(packed_arena().bytes);
   w.X = img(64);
-  for (int l = 0; l < 8; ++l) w.H[l] = img(128);
+  if (mode != NEFES_MODE_SIGMA) w.DIRPE = img(32);
+  // NEFES_WS_INTERLEAVE=1 (experiment): the saved activation images of a TILE are contiguous ([tile][image][ch * 256 B])
+  // instead of one array per image -- same bytes, same total size; every consumer addresses (base, tile stride)
+  static const bool interleave = getenv("NEFES_WS_INTERLEAVE") != nullptr;
+  int chs[12], n = 0;
+  for (int l = 0; l < 8; ++l) chs[n++] = 128;
   if (mode != NEFES_MODE_SIGMA) {
-    w.DIRPE = img(32);
-    w.FIN = img(128);
-    w.DT = img(mode == NEFES_MODE_FULL ? 128 : 64);
-    if (mode == NEFES_MODE_FULL) { w.T2 = img(64); w.T3 = img(64); }
+    chs[n++] = 128;                                           // FIN
+    chs[n++] = mode == NEFES_MODE_FULL ? 128 : 64;            // DT
+    if (mode == NEFES_MODE_FULL) { chs[n++] = 64; chs[n++] = 64; }
+  }
+  Img im[12];
+  if (interleave) {
+    int64_t per_tile = 0;
+    for (int i = 0; i < n; ++i) per_tile += (int64_t)chs[i] * 256;
+    uint8_t* blk = take(T * per_tile);
+    int64_t off = 0;
+    for (int i = 0; i < n; ++i) { im[i].ch = chs[i]; im[i].p = blk + off; im[i].stride = per_tile; off += (int64_t)chs[i] * 256; }
+  } else {
+    for (int i = 0; i < n; ++i) im[i] = img(chs[i]);
+  }
+  for (int l = 0; l < 8; ++l) w.H[l] = im[l];
+  if (mode != NEFES_MODE_SIGMA) {
+    w.FIN = im[8]; w.DT = im[9];
+    if (mode == NEFES_MODE_FULL) { w.T2 = im[10]; w.T3 = im[11]; }
   }
   w.bytes = (int64_t)(p - (uint8_t*)base);
   return w;
