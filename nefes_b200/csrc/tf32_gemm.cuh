@@ -26,8 +26,8 @@ constexpr uint32_t kTfLboA = 128 * 16 + 16;             // chunk-column stride o
 constexpr uint32_t kTfStageA = (kTfRK / 4) * kTfLboA;   // 16 512 B
 __host__ __device__ constexpr uint32_t tf_lbo_b(int jt) { return (uint32_t)jt * 16u + 16u; }
 __host__ __device__ constexpr uint32_t tf_stage_b(int jt) { return (kTfRK / 4) * tf_lbo_b(jt); }
-__host__ __device__ constexpr uint32_t tf_smem(int jt) {       // two operand stages, re-used by the epilogue as a [128][jt + 1] fp32 tile
-  return (2u * (kTfStageA + tf_stage_b(jt)) > 128u * (uint32_t)(jt + 1) * 4u ? 2u * (kTfStageA + tf_stage_b(jt)) : 128u * (uint32_t)(jt + 1) * 4u) + 128u;
+__host__ __device__ constexpr uint32_t tf_smem(int jt) {       // two operand stages, re-used by the epilogue as a [128][jt + 4] fp32 tile
+  return (2u * (kTfStageA + tf_stage_b(jt)) > 128u * (uint32_t)(jt + 4) * 4u ? 2u * (kTfStageA + tf_stage_b(jt)) : 128u * (uint32_t)(jt + 4) * 4u) + 128u;
 }
 
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {      // tf32 x tf32 -> fp32, both operands K-major
@@ -94,7 +94,55 @@ __device__ __forceinline__ void tf_put(const float4 (&v)[NS], int rows, uint32_t
   }
 }
 
-template <bool A_RC, bool B_RC>
+// Per-slot state computed ONCE per CTA (warp sampling: the generic fetch / put above re-derived row, chunk column, 64-bit
+// address, bounds and alignment for every slot of every chunk -- the kernel was 61 % issue-bound): the global pointer of the
+// slot in chunk 0 (null: row out of range -> zeros), whether it can be read as one 16-byte load, its byte offset in a stage.
+template <int NS>
+struct TfSlots { const float* p[NS]; uint32_t soff[NS]; bool vec[NS], live[NS]; };
+template <bool RC, int NS>
+__device__ __forceinline__ void tf_slots(const float* __restrict__ P, int64_t ld, int64_t x0, int64_t x_end, int64_t r_begin, int rows,
+                                         uint32_t lbo, TfSlots<NS>& S) {
+  const int slots = rows * (kTfRK / 4);
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    const int idx = threadIdx.x + n * 256;
+    int x = 0, c = 0;
+    S.live[n] = idx < slots;
+    if (S.live[n]) {
+      if (RC) { c = idx & 7; x = idx >> 3; }
+      else { x = idx % rows; c = idx / rows; }
+    }
+    S.soff[n] = (uint32_t)c * lbo + (uint32_t)x * 16u;
+    const bool in = S.live[n] && x0 + x < x_end;
+    S.p[n] = in ? (RC ? P + (x0 + x) * ld + r_begin + c * 4 : P + (r_begin + c * 4) * ld + (x0 + x)) : nullptr;
+    S.vec[n] = RC && in && ((reinterpret_cast<uintptr_t>(S.p[n]) & 15) == 0) && ((ld & 3) == 0);
+  }
+}
+// a FULL chunk (all 32 reduction elements inside the range): chunk kc of the slots
+template <bool RC, int NS>
+__device__ __forceinline__ void tf_fetch_fast(const TfSlots<NS>& S, int64_t adv, int64_t ld, float4 (&v)[NS]) {
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    v[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (S.p[n] == nullptr) continue;
+    const float* p = S.p[n] + adv;
+    if (RC) {
+      if (S.vec[n]) v[n] = __ldg(reinterpret_cast<const float4*>(p));
+      else v[n] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    } else {
+      v[n] = make_float4(__ldg(p), __ldg(p + ld), __ldg(p + 2 * ld), __ldg(p + 3 * ld));
+    }
+  }
+}
+template <int NS>
+__device__ __forceinline__ void tf_put_fast(const TfSlots<NS>& S, const float4 (&v)[NS], uint8_t* dst) {
+#pragma unroll
+  for (int n = 0; n < NS; ++n)
+    if (S.live[n])
+      *reinterpret_cast<float4*>(dst + S.soff[n]) = make_float4(to_tf32(v[n].x), to_tf32(v[n].y), to_tf32(v[n].z), to_tf32(v[n].w));
+}
+
+template <bool A_RC, bool B_RC, int NSB>              // NSB = B slots per thread: 4 (Jt <= 128) or 8 (Jt <= 256)
 __global__ void __launch_bounds__(256) tf32_gemm_kernel(const GemmArgs g, int jt_max) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_mma[2];
@@ -125,21 +173,29 @@ __global__ void __launch_bounds__(256) tf32_gemm_kernel(const GemmArgs g, int jt
   const int n_chunks = (int)((r_end - r_begin + kTfRK - 1) / kTfRK);
   const bool leader = warp == 0 ? elect_one() : false;
 
-  float4 va[4], vb[8];                                  // the next chunk, in flight: 128 x 8 / 256 and up to 256 x 8 / 256 slots per thread
-  if (n_chunks > 0) {
-    tf_fetch<A_RC, 4>(g.A, g.lda, i0, g.I, r_begin, r_end, 128, va);
-    tf_fetch<B_RC, 8>(g.B, g.ldb, j0, g.J, r_begin, r_end, jt, vb);
-  }
+  float4 va[4], vb[NSB];                                // the next chunk, in flight (registers)
+  TfSlots<4> SA;
+  TfSlots<NSB> SB;
+  tf_slots<A_RC, 4>(g.A, g.lda, i0, g.I, r_begin, 128, kTfLboA, SA);
+  tf_slots<B_RC, NSB>(g.B, g.ldb, j0, g.J, r_begin, jt, lbo_b, SB);
+  const int64_t adv_a = A_RC ? kTfRK : kTfRK * g.lda, adv_b = B_RC ? kTfRK : kTfRK * g.ldb;
+  auto fetch = [&](int kc) {
+    const int64_t r0 = r_begin + (int64_t)kc * kTfRK;
+    if (r0 + kTfRK <= r_end) {
+      tf_fetch_fast<A_RC, 4>(SA, kc * adv_a, g.lda, va);
+      tf_fetch_fast<B_RC, NSB>(SB, kc * adv_b, g.ldb, vb);
+    } else {                                                             // the ragged last chunk: bounds-checked path
+      tf_fetch<A_RC, 4>(g.A, g.lda, i0, g.I, r0, r_end, 128, va);
+      tf_fetch<B_RC, NSB>(g.B, g.ldb, j0, g.J, r0, r_end, jt, vb);
+    }
+  };
+  if (n_chunks > 0) fetch(0);
   for (int kc = 0; kc < n_chunks; ++kc) {
     const int s = kc & 1;
     if (kc >= 2) mbar_wait(&bar_mma[s], ((kc >> 1) - 1) & 1);           // the MMAs that read this stage two chunks ago retired
-    tf_put<A_RC, 4>(va, 128, kTfLboA, sA[s]);
-    tf_put<B_RC, 8>(vb, jt, lbo_b, sB[s]);
-    if (kc + 1 < n_chunks) {                                             // loads of the next chunk fly during the MMAs of this one
-      const int64_t r1 = r_begin + (int64_t)(kc + 1) * kTfRK;
-      tf_fetch<A_RC, 4>(g.A, g.lda, i0, g.I, r1, r_end, 128, va);
-      tf_fetch<B_RC, 8>(g.B, g.ldb, j0, g.J, r1, r_end, jt, vb);
-    }
+    tf_put_fast<4>(SA, va, sA[s]);
+    tf_put_fast<NSB>(SB, vb, sB[s]);
+    if (kc + 1 < n_chunks) fetch(kc + 1);                                // loads of the next chunk fly during the MMAs of this one
     fence_async_smem();
     __syncthreads();
     if (warp == 0) {
@@ -164,7 +220,7 @@ __global__ void __launch_bounds__(256) tf32_gemm_kernel(const GemmArgs g, int jt
   // epilogue: tensor memory -> shared memory (the stages are dead; row-major [128][jt + 1]) -> coalesced global access:
   // a warp handles one output row at a time, 32 consecutive columns per instruction
   float* sC = reinterpret_cast<float*>(smem);
-  const int ldsc = jt + 1;
+  const int ldsc = jt + 4;                               // rows 16-byte aligned; 128-bit accesses spread over all banks
   if (warp < 4 && n_chunks > 0) {
     const int row = warp * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
@@ -173,7 +229,8 @@ __global__ void __launch_bounds__(256) tf32_gemm_kernel(const GemmArgs g, int jt
       tmem_ld16(taddr + c0, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) sC[row * ldsc + c0 + e] = __uint_as_float(v[e]);
+      for (int e = 0; e < 16; e += 4)
+        *reinterpret_cast<uint4*>(sC + row * ldsc + c0 + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
     }
     tc_fence_before();
   }
@@ -187,14 +244,30 @@ __global__ void __launch_bounds__(256) tf32_gemm_kernel(const GemmArgs g, int jt
         for (int c = lane; c < n_cols; c += 32) atomicAdd(g.C + (i0 + row) * g.ldc + j0 + c, sC[row * ldsc + c]);
     } else if (!g.accumulate && (g.act == ACT_NONE || g.act == ACT_RELU)) {
       const bool relu = g.act == ACT_RELU;
+      const bool vec = (n_cols & 3) == 0 && (g.ldc & 3) == 0 && (j0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                       (g.mask == nullptr || ((g.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)) &&
+                       (g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
       for (int row = warp; row < 128 && i0 + row < g.I; row += 8) {
         const int64_t i = i0 + row;
-        for (int c = lane; c < n_cols; c += 32) {
-          float x = sC[row * ldsc + c];
-          if (g.bias) x += __ldg(g.bias + j0 + c);
-          if (relu) x = fmaxf(x, 0.f);
-          if (g.mask) x = (__ldg(g.mask + i * g.ldm + j0 + c) > 0.f) ? x : 0.f;
-          g.C[i * g.ldc + j0 + c] = x;
+        if (vec) {
+          for (int c = lane * 4; c < n_cols; c += 128) {
+            float4 x = *reinterpret_cast<const float4*>(sC + row * ldsc + c);
+            if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + j0 + c)); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if (g.mask) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(g.mask + i * g.ldm + j0 + c));
+              x.x = m.x > 0.f ? x.x : 0.f; x.y = m.y > 0.f ? x.y : 0.f; x.z = m.z > 0.f ? x.z : 0.f; x.w = m.w > 0.f ? x.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(g.C + i * g.ldc + j0 + c) = x;
+          }
+        } else {
+          for (int c = lane; c < n_cols; c += 32) {
+            float x = sC[row * ldsc + c];
+            if (g.bias) x += __ldg(g.bias + j0 + c);
+            if (relu) x = fmaxf(x, 0.f);
+            if (g.mask) x = (__ldg(g.mask + i * g.ldm + j0 + c) > 0.f) ? x : 0.f;
+            g.C[i * g.ldc + j0 + c] = x;
+          }
         }
       }
     } else {
@@ -237,13 +310,12 @@ inline int launch_tf32_gemm(const GemmArgs& g, cudaStream_t st, const char* what
   dim3 grid((unsigned)ceil_div(g.I, 128), (unsigned)ceil_div(g.J, jt), gz);
   static bool attr_done = false;
   if (!attr_done) {
-    NEFES_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem(256)));
-    NEFES_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem(256)));
-    NEFES_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem(256)));
-    NEFES_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem(256)));
+    NEFES_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel<A_RC, B_RC, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem(128)));
+    NEFES_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel<A_RC, B_RC, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem(256)));
     attr_done = true;
   }
-  tf32_gemm_kernel<A_RC, B_RC><<<grid, 256, tf_smem(jt), st>>>(g, jt);
+  if (jt <= 128) tf32_gemm_kernel<A_RC, B_RC, 4><<<grid, 256, tf_smem(jt), st>>>(g, jt);
+  else tf32_gemm_kernel<A_RC, B_RC, 8><<<grid, 256, tf_smem(jt), st>>>(g, jt);
   NEFES_CHECK_LAUNCH(what);
   return NEFES_OK;
 }
