@@ -489,6 +489,20 @@ def run_sweep(a, c):
     kwt = dict(c["kw"])
     kwt.update(perturb=0., test_time=True, near=0., far=10.)
     kwt.pop("retraw", None)
+    hash_fe = a.frontend == "hash"
+    if hash_fe:
+        # front-end B: NeRFH_TCNN fields (HashGrid 16 levels x 2 features, T = 2^log2T, bound 25; SH degree 4;
+        # heads 64 wide), the tcnn query function, heads on the tf32 tensor-core GEMM
+        from nefes_b200.hashgrid import NeRFH_TCNN, TcnnQuery
+        hc = NeRFH_TCNN("coarse", bound=25, log2_hashmap_size=a.log2T).to(dev)
+        hf = NeRFH_TCNN("fine", encode_appearance=True, encode_transient=True, in_channels_a=50, in_channels_t=20, bound=25,
+                        log2_hashmap_size=a.log2T).to(dev)
+
+        class HArgs:
+            nerfh_nff, use_fine_only, NeRFW, transient_at_test = False, False, True, True
+        kwt.update(network_fn=hc, network_fine=hf, network_query_fn=TcnnQuery(1 << 21), args=HArgs())
+        if a.precision != "fp32":
+            _lib.lib().nefes_gemm_mode(1)
     Hc, Wc, fc = 60, 106, 93.0                        # Cambridge-shaped camera (cambridge_scenes.py:149)
     g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
     pose = torch.tensor(g["test_gt"][0].reshape(3, 4), dtype=torch.float32, device=dev)
@@ -498,7 +512,7 @@ def run_sweep(a, c):
     hist = torch.zeros(1, 10, device=dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     table, launches = {}, 0
-    sizes = [1 << k for k in range(12, 21)]
+    sizes = [1 << k for k in range(12, 19 if hash_fe else 21)]
     with torch.no_grad(), ClockSampler(c["local"]) as clk:
         for n in sizes:
             lo, hi = parallel.shard_range(n, rank, world)
@@ -526,12 +540,36 @@ def run_sweep(a, c):
         for _ in range(a.steps):
             r_ = (h_o.to(dev, non_blocking=True), h_d.to(dev, non_blocking=True))
             rgb, _, _, ex = nb.render(Hc, Wc, fc, chunk=32768, rays=r_, img_idx=hist, **kwt)
-            out_h = (rgb.cpu(), ex["feat_map"].cpu())
+            out_h = (rgb.cpu(), ex["feat_map"].cpu()) if "feat_map" in ex else (rgb.cpu(),)
         ev1.record()
         c["barrier"]()
         ms_e2e = c["max_over_ranks"](ev0.elapsed_time(ev1)) / a.steps
     tf_peak, hbm_peak, which = measured_peaks()
     top = table[str(n)]
+    if hash_fe:
+        _lib.lib().nefes_gemm_mode(0)
+        table_mb = float(hc.encoder.params.numel() * 4 / 1e6)
+        gather = 192 * 16 * 8 * 2 * 4                    # bytes gathered per ray (fp32 table): 192 points x 1024 B
+        out = {"metric": "NeFeS rays/sec (inference render, 64+64 samples)", "value": top["rays_per_s"], "unit": "rays/s", "n_gpus": world,
+               "steps": a.steps, "warmup": a.warmup, "ms_per_step": top["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32 tables, tf32 heads" if a.precision != "fp32" else "f32", "data": "synthetic",
+               "config": {"workload": f"C5-shaped ray sweep, front-end B (HashGrid L=16 F=2 T=2^{a.log2T}, bound 25, SH degree 4, heads 64 wide; "
+                                      "PARITY UNPINNED: tiny-cuda-nn is not vendored), Cambridge camera, test_time render without gradients, "
+                                      f"2^12..2^{len(sizes) + 11} rays in chunks of 32768; value at the largest size",
+                          "global_rays": n, "parallelism": f"dp{world}", "table_MB_per_field": table_mb, "cuda_graph": False,
+                          "l2": f"hash tables {table_mb:.0f} MB per field x 2 fields against 126 MB of L2"},
+               "sweep": table,
+               "e2e": {"value": n / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": (hi - lo) * 24, "d2h_bytes_per_step": (hi - lo) * 12,
+                       "ms_per_step": ms_e2e},
+               "gpu_launches": launches * a.steps,
+               "roofline": {"bound": "hbm", "kernel": "hash gather (all levels, both fields)", "achieved": gather * n / (top["ms"] / 1e3) / 1e9,
+                            "peak": hbm_peak, "unit": "GB/s", "frac": gather * n / (top["ms"] / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                            "peak_source": which,
+                            "note": "algorithmic gather bytes of the WHOLE render over its duration (the staged route also spends time in the "
+                                    "heads and torch glue); a table of 2^19 entries per level is L2-resident, 2^21 / 2^22 spill to HBM"},
+               "clocks": clk.summary()}
+        finish(c, out)
+        return
     ach = 63.88e6 * n / (top["ms"] / 1e3) / 1e12      # refine/inference forward 63.88 MFLOP per ray
     out = {"metric": "NeFeS rays/sec (inference render, 64+64 samples)", "value": top["rays_per_s"], "unit": "rays/s", "n_gpus": world,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": top["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -835,6 +873,8 @@ def main():
     p.add_argument("--no-graph", action="store_true", help="time eager steps instead of a captured CUDA graph of the step")
     p.add_argument("--workload", default="train", choices=["train", "c3", "c3s3", "refine", "sweep"])
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    p.add_argument("--frontend", default="pe", choices=["pe", "hash"], help="sweep only: front-end A (PE + NeFeS MLP) or B (HashGrid + SH, nerfh_tcnn)")
+    p.add_argument("--log2T", type=int, default=19, help="sweep --frontend hash: log2 of the hash-table size per level (reference: 19)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     a = p.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "engine" else a.warmup

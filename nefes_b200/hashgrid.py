@@ -78,6 +78,9 @@ class _Linear(Function):
         xc, Wc = L.f32c(x), W.detach()
         M, K = xc.shape
         N = Wc.shape[0]
+        if Wc.shape[1] != K:
+            raise RuntimeError(f"nefes_b200: linear layer expects {Wc.shape[1]} input channels, got {K} (front-end B: in_channels_a / "
+                               "in_channels_t must equal 10 histogram bins x the embedding width: 50 / 20)")
         y = torch.empty(M, N, device=xc.device)
         with torch.cuda.device(xc.device):
             L.check(L.lib().nefes_linear_fwd(L.ptr(xc), K, L.ptr(Wc), None, L.ptr(y), N, M, N, K, act, L.stream_of(xc)),
@@ -198,3 +201,40 @@ class NeRFH_TCNN(nn.Module):
         if not output_transient:
             return torch.cat([rgbs, sigma[..., None]], 1)
         return torch.cat([rgbs[..., :3], sigma[..., None], rgbs[..., 3:]], 1)
+
+
+def run_NeRFH_TCNN(inputs, viewdirs, ts, fn, typ, output_transient, netchunk=1024 * 64, test_time=False, store_rgb=False):
+    """Drop-in for nerfh_tcnn.py:368-440, the `network_query_fn` of front-end B (coarse = NeRF, fine = NeRF-W): inputs
+    [N_rays, N_samples, 3], viewdirs [N_rays, 3], ts [N_rays, 10] (the image's histogram, indexes the appearance / transient
+    embeddings) -> raw [N_rays, N_samples, 1] (coarse at test time), [.., 4] (rgb, sigma) or [.., 9] (+ transient rgb, sigma,
+    beta), in netchunk-sized pieces like the reference."""
+    n_rays, n_samples = inputs.shape[0], inputs.shape[1]
+    flat = inputs.reshape(-1, 3)
+    if typ == 'coarse' and test_time and not store_rgb:
+        out = torch.cat([fn(flat[i:i + netchunk], None, sigma_only=True) for i in range(0, flat.shape[0], netchunk)], 0)
+        return out.reshape(n_rays, n_samples, -1)
+    dirs = viewdirs[:, None].expand(inputs.shape).reshape(-1, 3)
+    if typ == 'coarse':
+        out = torch.cat([fn(flat[i:i + netchunk], dirs[i:i + netchunk], output_transient=output_transient)
+                         for i in range(0, flat.shape[0], netchunk)], 0)
+        return out.reshape(n_rays, n_samples, -1)
+    if n_samples == 1 and test_time:
+        ts_pt = ts[0:1].expand(n_rays, -1)
+    else:
+        ts_pt = ts[:, None, :].expand(-1, n_samples, -1).reshape(-1, ts.shape[-1])     # repeat 'n1 c -> (n1 n2) c'
+    out = torch.cat([fn(flat[i:i + netchunk], dirs[i:i + netchunk], ts=ts_pt[i:i + netchunk], output_transient=output_transient)
+                     for i in range(0, flat.shape[0], netchunk)], 0)
+    return out.reshape(n_rays, n_samples, -1)
+
+
+class TcnnQuery:
+    """The `network_query_fn` closure the tcnn create_nerf builds (nerfh_tcnn.py:330-340) as an object.  render_rays takes
+    the staged route with it (sampling, compositing and sample_pdf on the engine; the hash / SH gathers and the small heads
+    are nefes_encode_hash_*, nefes_encode_sh_* and the engine GEMM)."""
+
+    def __init__(self, netchunk=1024 * 64):
+        self.netchunk = int(netchunk)
+
+    def __call__(self, inputs, viewdirs, ts, network_fn, typ, output_transient, test_time, store_rgb):
+        return run_NeRFH_TCNN(inputs, viewdirs, ts, network_fn, typ, output_transient, netchunk=self.netchunk,
+                              test_time=test_time, store_rgb=store_rgb)

@@ -41,6 +41,17 @@ def raw2outputs_NeRFH_NFF(raw, z_vals, raw_noise_std=0, output_transient=False, 
     if typ == "coarse" and test_time and not store_rgb:                      # :33-35, :83-89
         acc, weights = ops.composite(raw[..., :1], z_vals, None, L.COMP_SIGMA, beta_min)
         return None, None, None, acc, weights, None, None, None
+    if not isinstance(raw, ops.TiledRaw) and raw.shape[-1] in (4, 9) and raw.shape[-1] == (9 if output_transient else 4):
+        # front-end B (nerfh_tcnn.py): rgb + sigma [+ transient rgb, sigma, beta] and NO feature channels (ch_rgbs = 3, :38-44).
+        # The compositing kernels are built for the 3 + 128-channel head: the raw goes through them with the 128 feature
+        # channels zero-filled, and the (empty) feature map comes back with zero channels, as the reference's slicing gives.
+        pad = raw.new_zeros(raw.shape[:2] + (137 if output_transient else 132,))
+        pad[..., :3] = raw[..., :3]
+        pad[..., 131:131 + raw.shape[-1] - 3] = raw[..., 3:]
+        out = list(raw2outputs_NeRFH_NFF(pad, z_vals, raw_noise_std, output_transient, beta_min, white_bkgd, test_time, typ,
+                                         store_rgb, transient_at_test, noise))
+        out[1] = out[1][..., :0]
+        return tuple(out)
     if output_transient:
         if raw.shape[-1] != 137:
             raise RuntimeError(f"nefes_b200: transient compositing expects 137 channels, got {raw.shape[-1]}")

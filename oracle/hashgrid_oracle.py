@@ -104,3 +104,26 @@ def tcnn_field_forward(P, x, d, bound=25.0, levels=None, sigma_only=False):
     c = torch.relu(c @ P["color.1"].t())
     rgb = torch.sigmoid(c @ P["color.2"].t())                      # :220
     return torch.cat([rgb, sigma[:, None]], 1)
+
+
+def tcnn_field_forward_fine(P, x, d, ts, bound=25.0, levels=None):
+    """script/models/nerfh_tcnn.py:151-284, fine form with the NeRF-W heads (`output_transient=True`): appearance embedding
+    nn.Embedding(1000, 5) and transient embedding nn.Embedding(1000, 2) indexed by the 10-bin histogram `ts` [M,10] (:107, :125,
+    :213, :229) -> 50 / 20 extra inputs; colour net (16 + 64 + 50) -> 64 -> 64 -> 3 sigmoid; transient net (16 + 64 + 20) -> 64 x 3
+    -> 5: relu sigma_t (column 0), sigmoid rgb_t (1:4), relu beta (4) (:229-241).  Returns [M,9] = rgb, sigma, rgb_t, sigma_t, beta."""
+    xn = (x + bound) / (2 * bound)
+    h = hash_encode(xn, P["table"], levels)
+    h = torch.relu(h @ P["sigma.0"].t()) @ P["sigma.1"].t()
+    sigma = torch.relu(h[:, 0])
+    geo = h[:, 1:]
+    e = sh_encode((d + 1) / 2)
+    a = P["emb_a"][ts.long()].reshape(ts.shape[0], -1)
+    c = torch.cat([e, geo, a], -1)
+    c = torch.relu(c @ P["color.0"].t())
+    c = torch.relu(c @ P["color.1"].t())
+    rgb = torch.sigmoid(c @ P["color.2"].t())
+    t = torch.cat([e, geo, P["emb_t"][ts.long()].reshape(ts.shape[0], -1)], -1)
+    for k in ("trans.0", "trans.1", "trans.2"):
+        t = torch.relu(t @ P[k].t())
+    t = t @ P["trans.3"].t()
+    return torch.cat([rgb, sigma[:, None], torch.sigmoid(t[:, 1:4]), torch.relu(t[:, 0:1]), torch.relu(t[:, 4:5])], 1)
