@@ -148,6 +148,18 @@ class Args:
     nerfh_nff, use_fine_only, NeRFW, transient_at_test, netchunk = True, False, True, True, 1 << 21
 
 
+def train_workload(workload, n_rand, world=1):
+    """The part of `config` both arms share for the training workloads: same string, same numbers."""
+    wl = {"train": "C2 stage-1 colour-only NeRF-W training step",
+          "c3": "C3 stage-2 training step (C2 + 0.04 x L1 of the rendered 128-channel feature map against target features)",
+          "c3s3": "C3 stage-3 training step (7 patches of 16x16 per image; affine colour transform, FusionNet (BatchNorm batch statistics per "
+                  "rank), colour + 0.02 x feature L1 + 0.02 x fusion L1; fields, FusionNet and exposure network all train)"}[workload]
+    rays = N_IMAGES * n_rand
+    return {"workload": f"{wl}, 7-Scenes-stairs camera 640x480 -> 60x80, 4 images x {n_rand} rays = {rays} rays/GPU/step, "
+                        "64 coarse + 64 fine samples, Adam",
+            "rays_per_gpu_per_step": rays, "global_rays_per_step": rays * world}
+
+
 def engine_setup(a):
     """Process group, device, the two fields and the render kwargs create_nerf builds."""
     import torch.distributed as dist
@@ -370,17 +382,11 @@ def run_train(a, c):
                 "share_of_step": t["ms_per_step"] / (ms / a.steps),
                 "hbm": {"bound": "hbm", "achieved": t["GB_per_s"], "peak": hbm_peak, "unit": "GB/s", "frac": t["hbm_frac"],
                         "note": "algorithmic bytes include the bf16 activation copies saved for backward (design choice, DESIGN.md 4)"}}
-    wl = ("C2 stage-1 colour-only NeRF-W training step" if not stage2 else
-          "C3 stage-2 training step (C2 + 0.04 x L1 of the rendered 128-channel feature map against target features)" if not stage3 else
-          "C3 stage-3 training step (7 patches of 16x16 per image; affine colour transform, FusionNet (BatchNorm batch statistics per rank), "
-          "colour + 0.02 x feature L1 + 0.02 x fusion L1; fields, FusionNet and exposure network all train)")
     out = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[a.precision], "data": "synthetic",
-        "config": {"workload": f"{wl}, 7-Scenes-stairs camera 640x480 -> 60x80, 4 images x {n_rand} rays = {rays} rays/GPU/step, "
-                               "64 coarse + 64 fine samples, Adam",
-                   "rays_per_gpu_per_step": rays, "global_rays_per_step": rays * world, "parallelism": f"dp{world} (rays sharded, 1 gradient all-reduce)",
+        "config": {**train_workload(a.workload, n_rand, world), "parallelism": f"dp{world} (rays sharded, 1 gradient all-reduce)",
                    "mlp_precision": a.precision, "cuda_graph": graph is not None,
                    "l2": "no explicit flush: each step streams >20 GB of activation / gradient tiles through HBM (>> 126 MB L2); "
                          "only the 1.4 MB of weights is legitimately L2-resident"},
@@ -639,7 +645,9 @@ def side_measurements(a, nb, step, coarse, fine, resident, kw, dev):
         # in backward) + 128 B of output row (+ 128 B of cotangent)
         bytes_pt = 16 * 8 * 8 + 128 if not need_grad else 2 * (16 * 8 * 8 + 128) + 16 * 8 * 8
         ex[f"hashgrid_{tag}"] = {"points": npts, "ms": ms, "gather_GB_per_s": npts * bytes_pt / ms / 1e6,
-                                 "table_MB": float(enc.params.numel() * 4 / 1e6), "note": "fp32 table, T=2^19, L2-resident"}
+                                 "table_MB": float(enc.params.numel() * 4 / 1e6),
+                                 "note": "fp32 table, T=2^19: 49 MB, resident in the 126 MB L2 -- the gather rate is an L2 / L1 figure and has no "
+                                         "HBM roofline; at T=2^21 / 2^22 (169 / 316 MB) it spills (bench.py --workload sweep --frontend hash)"}
     del enc, xs
     g = np.load(os.path.join(ROOT, "tests", "golden", "poses_stairs.npz"))
     init = torch.tensor(g["dfnet_init"][0].reshape(3, 4), dtype=torch.float32, device=dev)
@@ -854,7 +862,8 @@ def run_reference(a):
     out = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": k,
            "warmup": warm, "ms_per_step": 1e3 * tot / k, "higher_is_better": True, "scaling": a.scaling if a.workload in ("train", "c3", "c3s3") else "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": wl, "units_per_step": n},
+           "config": ({**train_workload(a.workload, 1792 if a.workload == "c3s3" else N_RAND), "parallelism": "host cores (no GPU)",
+                       "note": wl} if a.workload in ("train", "c3", "c3s3") else {"workload": wl, "units_per_step": n}),
            "cpu_baseline": {"value": v, "unit": unit, "cores": os.cpu_count() or 1, "kind": kind,
                             "sample": f"{k} steps x {n} {'rays' if unit == 'rays/s' else 'iteration'}; {what}; all host threads"},
            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
