@@ -225,6 +225,8 @@ def run_train(a, c):
     stage2 = a.workload in ("c3", "c3s3")
     stage3 = a.workload == "c3s3"
     n_rand = N_RAND // world if a.scaling == "strong" else N_RAND
+    if a.as_world > 1:                         # tuning aid: one GPU doing the per-GPU share of a strong-scaling job of that size
+        n_rand = N_RAND // a.as_world
     if stage3:
         n_rand = 7 * 16 * 16                                                     # run_nefes.py:86-94: 7 crops of 16x16 per image
     rays = N_IMAGES * n_rand
@@ -885,6 +887,8 @@ def main():
     p.add_argument("--frontend", default="pe", choices=["pe", "hash"], help="sweep only: front-end A (PE + NeFeS MLP) or B (HashGrid + SH, nerfh_tcnn)")
     p.add_argument("--log2T", type=int, default=19, help="sweep --frontend hash: log2 of the hash-table size per level (reference: 19)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--as-world", type=int, default=1, help="train workloads, tuning aid: run the per-GPU share (N_RAND / k rays per image) "
+                   "of a k-GPU strong-scaling job on the GPUs present; the line's config states the ray count")
     a = p.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "engine" else a.warmup
     if a.impl == "reference":

@@ -32,6 +32,28 @@
 
 namespace nefes {
 
+// ---- epilogue helpers -------------------------------------------------------------------------------------------------
+// st.global spelled out: a generic store through a pointer the compiler cannot place makes it assume the store may alias
+// shared memory and re-load every shared value (step table fields, biases) after each one -- measured in round 1's
+// variant as four dependent LDS + branch chains per 32-column block.
+__device__ __forceinline__ void stg128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ void stg32f(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v)); }
+__device__ __forceinline__ void lds_bias32(const float* bp, float4 (&b)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = *reinterpret_cast<const float4*>(bp + 4 * j);
+}
+template <bool RELU>
+__device__ __forceinline__ void pack32(const uint32_t (&v)[32], const float4 (&b)[8], uint32_t (&w)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    w[4 * j + 0] = bias_pack<RELU>(v[8 * j + 0], v[8 * j + 1], b[2 * j].x, b[2 * j].y);
+    w[4 * j + 1] = bias_pack<RELU>(v[8 * j + 2], v[8 * j + 3], b[2 * j].z, b[2 * j].w);
+    w[4 * j + 2] = bias_pack<RELU>(v[8 * j + 4], v[8 * j + 5], b[2 * j + 1].x, b[2 * j + 1].y);
+    w[4 * j + 3] = bias_pack<RELU>(v[8 * j + 6], v[8 * j + 7], b[2 * j + 1].z, b[2 * j + 1].w);
+  }
+}
 enum { BK_HID_RELU = 0,   // bias + ReLU -> bf16 pairs -> out_col (+ staging image)
        BK_HID = 1,        // bias        -> bf16 pairs -> out_col (+ staging image)       (xyz_encoding_final)
        BK_RAW = 2,        // bias -> fp32 raw channels [raw_c0, raw_c0 + raw_n)            (rgb + feature head)
@@ -97,7 +119,7 @@ struct Ts2Args {
   int n_slots; uint32_t off_ring;   // depth and position of the weight ring (see ts2_off_ring)
   long long* dbg;
   int xflags;                 // timing experiments (NEFES_CHAIN_X): 1 no saves, 4 no raw stores
-  int save_mode;              // 0: staging image + one bulk store per step; 1: st.global.v4 from the epilogue registers
+  int save_mode;              // 0: staging image + one bulk store per block; 1: st.global.v4 from the epilogue registers; 2 (default): as 0 with an L2 evict_first policy
 };
 
 // Shared memory: [ bias table | xyz encodings x2 | direction encodings x2 | staging images x2 (only when the launch saves) |
@@ -352,6 +374,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
     auto warp_arrive = [&](uint64_t* bar) { __syncwarp(); if (lane == 0) mbar_arrive(bar); };
     auto half_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g * 2 + hgrp) : "memory"); };
     bool store_pending = false;
+    const uint64_t evict_first = l2_evict_first_policy();
     const bool dbg = A.dbg != nullptr && blockIdx.x == 0 && lane == 0;
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int tile = pair * 2 + g;
@@ -377,7 +400,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
             const bool saving = gdst != nullptr && save != 0;
             uint8_t* srow = stage + (n0 >> 3) * kChunkBytes + row * 16;
             uint8_t* grow = saving ? gdst + (int64_t)tile * g_stride + (n0 >> 3) * kChunkBytes + row * 16 : nullptr;
-            if (saving && A.save_mode == 0 && store_pending) {      // the block's previous bulk store must have read its staging half
+            if (saving && A.save_mode != 1 && store_pending) {      // the block's previous bulk store must have read its staging half
               if (gt4 == 0) bulk_wait_read<0>();
               half_barrier();
               store_pending = false;
@@ -408,13 +431,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_fwd_ts2_kernel(const _
             warp_arrive(&bar_k[g][b]);
             if (dbg && ecnt < 32 && b == 0) A.dbg[ecnt * 48 + 24 + ew] = clock64();
             if (dbg && ecnt < 32 && b == 1 && (ew & 3) == 0) A.dbg[ecnt * 48 + 44 + g] = clock64();
-            if (saving && A.save_mode == 0) {
+            if (saving && A.save_mode != 1) {
               // Saved copy: this block's nw channels are nw * 256 contiguous bytes of the image.  (Measured within 4 % of each
-              // other in round 2: one 32 KB bulk store per step, st.global.v4 from the registers, 512-byte bulk stores per warp.)
+              // other in round 2: one 32 KB bulk store per step, st.global.v4 from the registers, 512-byte bulk stores per warp.
+              // The L2 evict_first policy on the store is worth 5-6 % of the launch: 0.600 against 0.635 ms, fine query, same box.)
               fence_async_smem();
               half_barrier();
               if (gt4 == 0) {
-                bulk_s2g(gdst + (int64_t)tile * g_stride + (n0 >> 3) * kChunkBytes, stage + (n0 >> 3) * kChunkBytes, (uint32_t)nw * 256u);
+                if (A.save_mode == 2) bulk_s2g_hint(gdst + (int64_t)tile * g_stride + (n0 >> 3) * kChunkBytes, stage + (n0 >> 3) * kChunkBytes, (uint32_t)nw * 256u, evict_first);
+                else bulk_s2g(gdst + (int64_t)tile * g_stride + (n0 >> 3) * kChunkBytes, stage + (n0 >> 3) * kChunkBytes, (uint32_t)nw * 256u);
                 bulk_commit();
               }
               store_pending = true;

@@ -30,6 +30,11 @@ constexpr int kThreads = 192;
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
+// the same with an L2 evict_first policy: data nobody re-reads before it leaves L2 (saved activation images, 2.65 GB per launch)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() { return l2_policy_evict_first(); }
+__device__ __forceinline__ void bulk_s2g_hint(void* gdst, const void* ssrc, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -660,7 +665,6 @@ __global__ void ray_reduce_kernel(const float* __restrict__ src, int ld, int nco
 
 }  // namespace nefes
 #include "mlp_chain.cuh"
-#include "mlp_chain_ts.cuh"
 #include "mlp_chain_ts2.cuh"
 #include "mlp_trunk_bwd.cuh"
 #include "mlp_fused_bwd.cuh"
@@ -1050,67 +1054,6 @@ void chain_ts_dbg_dump(long long* dbg, int n_steps, cudaStream_t st) {
   }
 }
 
-// The same forward chain with the activations in tensor memory (mlp_chain_ts.cuh): step operands are TMEM columns.
-int launch_chain_fwd_ts(const Ws& w, const Arena& A, int mode, int64_t M, float* raw_t, cudaStream_t st) {
-  const int T = (int)ceil_div(M, kTile);
-  TsArgs c = {};
-  int n = 0, bias_floats = 0;
-  auto add = [&](int pl, uint32_t a_col, int kind, uint32_t out_col, int out_ch, const Img* save) {
-    ChainStep& s = c.step[n++];
-    const PackedDims pd = packed_dims(pl);
-    s.a_off = a_col; s.out_off = out_col; s.K = (uint16_t)pd.K; s.N = (uint16_t)pd.N; s.out_ch = (uint16_t)out_ch;
-    s.kind = (uint8_t)kind; s.wait_load = -1; s.wait_load2 = -1; s.acc0 = 0;
-    s.bias = A.bias(pl); s.bias_off = (uint16_t)bias_floats;
-    bias_floats += (pd.N + 3) & ~3;
-    set_weights(s, A.W(pl), pd.K / 8, pd.N, 0, pd.N);
-    const bool keep = save && !forward_only();       // no saved copies when nobody will run the backward
-    s.gdst = keep ? save->p : nullptr; s.g_tile_stride = keep ? (uint32_t)save->tile_stride() : 0u;
-  };
-  add(PL_T0, kTsX, CK_HIDDEN, kTsH, 128, &w.H[0]);
-  for (int l = 1; l < 8; ++l) add(PL_T0 + l, l == 4 ? kTsX : kTsH, CK_HIDDEN, kTsH, 128, &w.H[l]);
-  if (mode == NEFES_MODE_SIGMA) {
-    add(PL_SIG, kTsH, CK_SIGMA, 0, 0, nullptr);
-  } else {
-    add(PL_FS, kTsH, CK_FS, kTsH, 128, &w.FIN);
-    if (mode == NEFES_MODE_FULL) {
-      add(PL_DT, kTsH, CK_HIDDEN, kTsH, 128, &w.DT);                 // [final | dirPE] = columns 176..255
-      add(PL_TE1, kTsH + 32, CK_HIDDEN, kTsX, 64, &w.T2);            // t1 (channels 64..127) -> t2, parked in the xyzPE columns
-      add(PL_TE2, kTsX, CK_HIDDEN, kTsH + 32, 64, &w.T3);            // t2 -> t3 (over t1)
-      add(PL_TH, kTsH + 32, CK_HEADS, 0, 0, nullptr);
-    } else {
-      add(PL_DIR, kTsH, CK_HIDDEN, kTsH, 64, &w.DT);
-    }
-    add(PL_RGB, kTsH, CK_RGB, 0, 0, nullptr);
-  }
-  NEFES_REQUIRE(n <= kChainMaxSteps && bias_floats * 4 <= (int)kChainBiasBytes, NEFES_EINVAL, "chain_fwd_ts: step table overflow");
-  for (int i = 0; i < n; ++i)
-    NEFES_REQUIRE(c.step[i].w_bytes <= kTsWSlot, NEFES_EINVAL, "chain_fwd_ts: weight image of step %d exceeds the ring slot", i);
-  c.n_steps = n; c.M = M; c.n_tiles = T;
-  c.raw = raw_t; c.C = (mode == NEFES_MODE_SIGMA) ? 1 : (mode == NEFES_MODE_STATIC ? 132 : 137);
-  c.x_img = w.X.p; c.d_img = (mode == NEFES_MODE_SIGMA) ? nullptr : w.DIRPE.p;
-  static bool attr_done = false;
-  if (!attr_done) {
-    NEFES_CUDA(cudaFuncSetAttribute(chain_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmem));
-    attr_done = true;
-  }
-  const int n_pairs = (T + 1) / 2;
-  const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
-  {
-    const double save_ch = forward_only() ? 0 : ((mode == NEFES_MODE_SIGMA) ? 8 * 128 : (mode == NEFES_MODE_STATIC ? 8 * 128 + 128 + 64 : 8 * 128 + 128 + 128 + 64 + 64));
-    const double in_ch = (mode == NEFES_MODE_SIGMA) ? 64 : 96;
-    const double macs = (mode == NEFES_MODE_SIGMA) ? 130944 : (mode == NEFES_MODE_STATIC ? 165632 : 184064);
-    prof_begin(mode == NEFES_MODE_FULL ? "chain_fwd_fine" : (mode == NEFES_MODE_STATIC ? "chain_fwd_coarse" : "chain_fwd_sigma"), st,
-               (double)M * (2.0 * (save_ch + in_ch) + 4.0 * c.C), (double)M * 2.0 * macs);
-  }
-  c.dbg = chain_dbg_buf();
-  c.xflags = chain_xflags();
-  chain_fwd_ts_kernel<<<grid, kChainThreads, kTsSmem, st>>>(c);
-  prof_end(st);
-  NEFES_CHECK_LAUNCH("chain_fwd_ts");
-  chain_ts_dbg_dump(c.dbg, c.n_steps, st);
-  return NEFES_OK;
-}
-
 // Round-2 forward chain (mlp_chain_ts2.cuh): N-split layers, double-buffered activations in tensor memory.
 int launch_chain_fwd_ts2(const Ws& w, const Arena& A, int mode, int64_t M, float* raw_t, cudaStream_t st) {
   const int T = (int)ceil_div(M, kTile);
@@ -1316,7 +1259,7 @@ int launch_chain_fwd_ts2(const Ws& w, const Arena& A, int mode, int64_t M, float
   }
   c.dbg = chain_dbg_buf();
   c.xflags = chain_xflags();
-  static const int save_mode = [] { const char* e = getenv("NEFES_TS2_STG"); return e ? atoi(e) : 0; }();
+  static const int save_mode = [] { const char* e = getenv("NEFES_TS2_STG"); return e ? atoi(e) : 2; }();
   c.save_mode = save_mode;
   chain_fwd_ts2_kernel<<<grid, kChainThreads, ts2_smem(saves), st>>>(c);
   prof_end(st);
@@ -1752,13 +1695,12 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   NEFES_CHECK_LAUNCH("encode_images");
   const bool direct = (layout == NEFES_RAW_TILES) || C == 1;      // C == 1: the two layouts coincide
   float* raw_t = direct ? raw : reinterpret_cast<float*>(scratch);
-  // Three forward chains.  Default since round 2: mlp_chain_ts2.cuh (activations in tensor memory, N-split layers, straight-
-  // line issuer) -- fine query at 6144 rays 0.599 ms with saved copies / 0.476 without, against 0.65 / 0.55 for the shared-
-  // memory-operand chain (mlp_chain.cuh, NEFES_FWD_SS=1) and 0.79 / 0.52 for the first tensor-memory chain (mlp_chain_ts.cuh,
-  // NEFES_FWD_TS=1).  All three are parity-tested against the same oracle.
-  static const bool force_ts = getenv("NEFES_FWD_TS") != nullptr, force_ss = getenv("NEFES_FWD_SS") != nullptr;
+  // Two forward chains.  Default since round 2: mlp_chain_ts2.cuh (activations in tensor memory, N-split layers, straight-
+  // line issuer) -- fine query at 6144 rays 0.60 ms with saved copies / 0.476 without, against 0.65 / 0.55 for the shared-
+  // memory-operand chain (mlp_chain.cuh, NEFES_FWD_SS=1; its template also serves the data-gradient chains).  Round 1's
+  // first tensor-memory chain (0.79 / 0.52 ms) was removed once TS2 superseded it.  Both are parity-tested against the oracle.
+  static const bool force_ss = getenv("NEFES_FWD_SS") != nullptr;
   if (force_ss) TRY(launch_chain_fwd(w, A, mode, M, raw_t, st));
-  else if (force_ts) TRY(launch_chain_fwd_ts(w, A, mode, M, raw_t, st));
   else TRY(launch_chain_fwd_ts2(w, A, mode, M, raw_t, st));
   if (!direct) {
     static bool t2r_attr = false;
