@@ -593,6 +593,8 @@ def run_sweep(a, c):
            "roofline": {"bound": "tensor", "kernel": "inference render (all launches)", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
                         "frac": ach / tf_peak, "traffic": None, "peak_source": which},
            "clocks": clk.summary()}
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(a)          # the reference's render() on the host cores, 4096-ray inference renders
     finish(c, out)
 
 
