@@ -35,6 +35,11 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() { return l2_policy_e
 __device__ __forceinline__ void bulk_s2g_hint(void* gdst, const void* ssrc, uint32_t bytes, uint64_t pol) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol) : "memory");
 }
+// bulk reduction shared -> global: the TMA engine adds a contiguous fp32 block into global memory (split accumulators of the
+// persistent CTAs into the flat gradient buffer); part of the same bulk groups as the stores
+__device__ __forceinline__ void bulk_red_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -1347,6 +1352,10 @@ int launch_chain_bwd(const Ws& w, const WsB& b, const Arena& A, int mode, int64_
 }  // namespace
 
 namespace {
+bool bulk_flush() {
+  static const bool on = [] { const char* e = getenv("NEFES_BULK_FLUSH"); return e == nullptr || atoi(e) != 0; }();
+  return on;
+}
 // Fused data + weight gradients of the eight trunk layers: four launches of two layers each (mlp_trunk_bwd.cuh).
 int launch_trunk_bwd(const Ws& w, const WsB& b, const Arena& A, int net, int64_t M, float* dP, cudaStream_t st) {
   const int T = (int)ceil_div(M, kTile);
@@ -1372,7 +1381,7 @@ int launch_trunk_bwd(const Ws& w, const WsB& b, const Arena& A, int net, int64_t
       if (l == 5) { s.g_save = b.G[4].p; s.g_save_tile_stride = (uint32_t)b.G[4].tile_stride(); }   // operand of the T4 xyz-part job
     }
     if (l1 > 0) { t.g_out = b.G[l1 - 1].p; t.g_out_tile_stride = (uint32_t)b.G[l1 - 1].tile_stride(); }
-    t.n_tiles = T; t.ps = pack_src(net); t.d_flat = dP;
+    t.n_tiles = T; t.ps = pack_src(net); t.d_flat = dP; t.bulk_flush = bulk_flush() ? 1 : 0;
     {
       double ch = 128 + t.step[0].act_ch + t.step[1].act_ch + (t.g_out ? 128 : 0) + (t.step[0].g_save ? 128 : 0);
       double macs = 0;

@@ -34,6 +34,7 @@ struct TrunkArgs {
   const uint8_t* g_in; uint32_t g_in_tile_stride;   // gradient image entering the pair of layers
   uint8_t* g_out; uint32_t g_out_tile_stride;       // gradient image leaving it (null: none)
   int n_tiles;
+  int bulk_flush;                                   // 1: contiguous weight-gradient blocks leave as bulk reductions
   PackSrc ps; float* d_flat;
 };
 
@@ -255,25 +256,45 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const Trunk
       mbar_wait(&bar_done, 0);
       tc_fence_after();
       const int n = row;                              // output channel of this thread
+      bool any_bulk = false;
       for (int j = 0; j < (two ? 2 : 1); ++j) {
         const TrunkStep& s = T.step[j];
         const uint32_t dw = taddr + (j == 0 ? kTrDW0 : kTrDW1);
         const int c_lo = half * (s.act_ch >> 1), c_hi = c_lo + (s.act_ch >> 1);
-        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(dw + c0, v);
-          tmem_ld_wait();
-          const int64_t i0 = packed_weight_index(T.ps, s.pl, n, s.k_off + c0);
-          const int64_t i15 = packed_weight_index(T.ps, s.pl, n, s.k_off + c0 + 15);
-          if (i0 >= 0 && i15 == i0 + 15 && (i0 & 3) == 0) {
+        // A weight block that is one contiguous, 16-byte aligned range of the flat buffer (every 128 x 128 trunk layer) leaves
+        // as ONE bulk reduction: the accumulator is transposed through shared memory (operand regions are dead by now; the
+        // G region is not -- the last G_out store may still be reading it) and the TMA engine adds the 64 KB block.  The
+        // per-thread vector reductions it replaces (148 CTAs x 128 x 128 x 2 layers) cost ~25 us per launch whatever the batch.
+        const int64_t i00 = packed_weight_index(T.ps, s.pl, 0, s.k_off);
+        const int64_t i11 = packed_weight_index(T.ps, s.pl, 127, s.k_off + s.act_ch - 1);
+        const bool bulk = T.bulk_flush && i00 >= 0 && (i00 & 3) == 0 && i11 == i00 + (int64_t)128 * s.act_ch - 1;
+        if (bulk) {
+          float* stage = reinterpret_cast<float*>(smem + (j == 0 ? kTrOffWT : kTrOffA)) + (size_t)n * s.act_ch;   // 64 KB each, both dead
+          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(dw + c0, v);
+            tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 16; e += 4)
-              red_add_v4(T.d_flat + i0 + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-          } else {
+            for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(stage + c0 + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          }
+          any_bulk = true;
+        } else {
+          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(dw + c0, v);
+            tmem_ld_wait();
+            const int64_t i0 = packed_weight_index(T.ps, s.pl, n, s.k_off + c0);
+            const int64_t i15 = packed_weight_index(T.ps, s.pl, n, s.k_off + c0 + 15);
+            if (i0 >= 0 && i15 == i0 + 15 && (i0 & 3) == 0) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int64_t idx = packed_weight_index(T.ps, s.pl, n, s.k_off + c0 + e);
-              if (idx >= 0) atomicAdd(T.d_flat + idx, __uint_as_float(v[e]));
+              for (int e = 0; e < 16; e += 4)
+                red_add_v4(T.d_flat + i0 + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int64_t idx = packed_weight_index(T.ps, s.pl, n, s.k_off + c0 + e);
+                if (idx >= 0) atomicAdd(T.d_flat + idx, __uint_as_float(v[e]));
+              }
             }
           }
         }
@@ -283,6 +304,23 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const Trunk
           tmem_ld_wait();
           const int64_t idx = packed_bias_index(T.ps, s.pl, n);
           if (idx >= 0) atomicAdd(T.d_flat + idx, __uint_as_float(v[0]));
+        }
+      }
+      if (any_bulk) {                                  // uniform over the 256 epilogue threads
+        fence_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ew == 0 && lane == 0) {
+          for (int j = 0; j < (two ? 2 : 1); ++j) {
+            const TrunkStep& s = T.step[j];
+            const int64_t i00 = packed_weight_index(T.ps, s.pl, 0, s.k_off);
+            const int64_t i11 = packed_weight_index(T.ps, s.pl, 127, s.k_off + s.act_ch - 1);
+            if (!(i00 >= 0 && (i00 & 3) == 0 && i11 == i00 + (int64_t)128 * s.act_ch - 1)) continue;
+            const uint32_t bytes = 128u * (uint32_t)s.act_ch * 4u;
+            for (uint32_t off = 0; off < bytes; off += 16384u)
+              bulk_red_add_f32(T.d_flat + i00 + off / 4, smem + (j == 0 ? kTrOffWT : kTrOffA) + off, min(16384u, bytes - off));
+          }
+          bulk_commit();
+          bulk_wait_all();
         }
       }
       tc_fence_before();
