@@ -1365,9 +1365,14 @@ int launch_trunk_bwd(const Ws& w, const WsB& b, const Arena& A, int net, int64_t
     attr_done = true;
   }
   const int grid = T < num_sms() ? T : num_sms();
+  // one launch walking the four layer pairs (TrunkMulti), or -- NEFES_TRUNK_PASSES=1 -- four launches of one pair each
+  static const int per_launch = [] { const char* e = getenv("NEFES_TRUNK_PASSES"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+  TrunkMulti mp = {};
+  double bytes = 0, flops = 0;
   for (int grp = 0; grp < 4; ++grp) {
-    const int l0 = 7 - 2 * grp, l1 = l0 - 1;        // layers of this launch: T_l0 then T_l1
-    TrunkArgs t = {};
+    const int l0 = 7 - 2 * grp, l1 = l0 - 1;        // layers of this pass: T_l0 then T_l1
+    TrunkArgs& t = mp.pass[mp.n_pass++];
+    t = TrunkArgs{};
     t.g_in = b.G[l0].p; t.g_in_tile_stride = (uint32_t)b.G[l0].tile_stride();
     for (int j = 0; j < 2; ++j) {
       const int l = j == 0 ? l0 : l1;
@@ -1382,15 +1387,15 @@ int launch_trunk_bwd(const Ws& w, const WsB& b, const Arena& A, int net, int64_t
     }
     if (l1 > 0) { t.g_out = b.G[l1 - 1].p; t.g_out_tile_stride = (uint32_t)b.G[l1 - 1].tile_stride(); }
     t.n_tiles = T; t.ps = pack_src(net); t.d_flat = dP; t.bulk_flush = bulk_flush() ? 1 : 0;
-    {
-      double ch = 128 + t.step[0].act_ch + t.step[1].act_ch + (t.g_out ? 128 : 0) + (t.step[0].g_save ? 128 : 0);
-      double macs = 0;
-      for (int j = 0; j < 2; ++j) macs += (t.step[j].has_dgrad ? 128.0 * 128 : 0) + 128.0 * t.step[j].act_ch;
-      prof_begin("trunk_bwd", st, (double)M * 2.0 * ch, (double)M * 2.0 * macs);
+    bytes += (double)M * 2.0 * (128 + t.step[0].act_ch + t.step[1].act_ch + (t.g_out ? 128 : 0) + (t.step[0].g_save ? 128 : 0));
+    for (int j = 0; j < 2; ++j) flops += (double)M * 2.0 * ((t.step[j].has_dgrad ? 128.0 * 128 : 0) + 128.0 * t.step[j].act_ch);
+    if (mp.n_pass == per_launch || grp == 3) {
+      prof_begin("trunk_bwd", st, bytes, flops);
+      trunk_bwd_kernel<<<grid, kTrunkThreads, kTrunkSmem, st>>>(mp);
+      prof_end(st);
+      NEFES_CHECK_LAUNCH("trunk_bwd");
+      mp.n_pass = 0; bytes = flops = 0;
     }
-    trunk_bwd_kernel<<<grid, kTrunkThreads, kTrunkSmem, st>>>(t);
-    prof_end(st);
-    NEFES_CHECK_LAUNCH("trunk_bwd");
   }
   return NEFES_OK;
 }

@@ -50,20 +50,29 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const TrunkArgs T) {
+// One launch walks up to four pairs of layers ("passes"): the gradient image a pass writes for a tile is read back by the
+// SAME CTA in the next pass (tile -> CTA assignment is fixed), so no grid-wide barrier separates the passes -- only a CTA-local
+// one at which the weight-gradient accumulators are flushed, the mbarriers re-initialised and the next pair of weight
+// matrices loaded.  Against four launches this saves three launch gaps, TMEM allocations and pipeline drains that wait for
+// the slowest CTA of the grid.
+struct TrunkMulti { TrunkArgs pass[4]; int n_pass; };
+
+__global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const __grid_constant__ TrunkMulti P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_w, bar_gin[2], bar_afull[2], bar_afree[2], bar_acc, bar_gmid, bar_gout, bar_done;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool has_out = T.g_out != nullptr;          // step 1 has a data gradient (and an epilogue)
-  const bool two = T.step[1].act != nullptr;        // the launch covers two layers
-
-  if (threadIdx.x == 0) {
+  auto init_bars = [&](bool again) {
+    if (again) {
+      mbar_inval(&bar_w); mbar_inval(&bar_acc); mbar_inval(&bar_gmid); mbar_inval(&bar_gout); mbar_inval(&bar_done);
+      for (int i = 0; i < 2; ++i) { mbar_inval(&bar_gin[i]); mbar_inval(&bar_afull[i]); mbar_inval(&bar_afree[i]); }
+    }
     mbar_init(&bar_w, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_gin[i], 1); mbar_init(&bar_afull[i], 1); mbar_init(&bar_afree[i], 257); }
     mbar_init(&bar_acc, 1); mbar_init(&bar_gmid, 256); mbar_init(&bar_gout, 256); mbar_init(&bar_done, 2);
     fence_mbar_init();
-  }
+  };
+  if (threadIdx.x == 0) init_bars(false);
   if (warp == 1) tmem_alloc<512>(&tmem_slot);
   {  // sixteen "ones" channels read MN-major: 8 channels x 128 points, both 8-channel groups alias the same 2 KB (SBO = 0)
     uint4 ones;
@@ -76,8 +85,19 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const Trunk
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   int n_my = 0;
-  for (int t = blockIdx.x; t < T.n_tiles; t += gridDim.x) ++n_my;
+  for (int t = blockIdx.x; t < P.pass[0].n_tiles; t += gridDim.x) ++n_my;
 
+  for (int pass = 0; pass < P.n_pass; ++pass) {
+  const TrunkArgs& T = P.pass[pass];
+  const bool has_out = T.g_out != nullptr;          // step 1 has a data gradient (and an epilogue)
+  const bool two = T.step[1].act != nullptr;        // the pass covers two layers
+  if (pass > 0) {                                   // every role finished the previous pass: accumulators flushed, stores complete
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) init_bars(true);
+    __syncthreads();
+    tc_fence_after();
+  }
   if (warp == 0) {
     if (lane == 0 && n_my > 0) {
       // ------------------------------- producer ---------------------------------------------------------------------
@@ -326,6 +346,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const Trunk
       tc_fence_before();
     }
   }
+  }  // passes
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
