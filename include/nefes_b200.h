@@ -273,6 +273,9 @@ typedef struct {
   int net_coarse, net_fine;        /* NEFES_NET_* of network_fn / network_fine                            */
   float beta_min;                  /* network_fine.beta_min                                               */
   int forward_only;                /* 1: no backward call will follow (inference): activations are not saved */
+  int weights_packed;              /* 1: frozen parameters (pose refinement): the bf16 operand images in `keep` were written by
+                                      nefes_render_rays_prepack (or an earlier forward call) with this cfg, N and keep, and the
+                                      parameters have not changed since -- the forward skips its re-pack.  0: re-pack (default) */
 } nefes_render_cfg_t;
 typedef struct {
   const float* rays;               /* ray_batch [N, ld_rays]: o 0:3, d 3:6, near 6, far 7, viewdirs 8:11  */
@@ -297,6 +300,12 @@ typedef struct {
 } nefes_render_out_t;
 int nefes_render_rays_workspace(const nefes_render_cfg_t* cfg_host, int64_t N, int64_t* keep_bytes_host,
                                 int64_t* scratch_fwd_bytes_host, int64_t* scratch_bwd_bytes_host);
+/* Packs the parameters of both fields into the bf16 operand images inside `keep` (what every forward call does first unless
+ * cfg.weights_packed is set).  A caller whose parameters are frozen -- the refinement loop, dm/DFM_pose_refine.py:290-348, renders
+ * the same two fields 50 times per query -- calls this once per query and runs its iterations with weights_packed = 1.
+ * No-op for the fp32 / tf32 precisions. */
+int nefes_render_rays_prepack(const nefes_render_cfg_t* cfg_host, const nefes_render_in_t* in_host, int64_t N, void* keep,
+                              void* stream);
 int nefes_render_rays_fwd(const nefes_render_cfg_t* cfg_host, const nefes_render_in_t* in_host, int64_t N,
                           const nefes_render_out_t* out_host, void* keep, void* scratch, void* stream);
 /* g_coarse / g_fine: cotangents of the two composited output sets (NULL or all-NULL = none).  d_params_* are

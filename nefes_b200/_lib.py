@@ -39,7 +39,7 @@ class CompGrad(C.Structure):
 
 class RenderCfg(C.Structure):
     _fields_ = [(n, i32) for n in ("n_samples", "n_importance", "prec", "test_time", "output_transient",
-                                   "transient_at_test", "net_coarse", "net_fine")] + [("beta_min", f32), ("forward_only", i32)]
+                                   "transient_at_test", "net_coarse", "net_fine")] + [("beta_min", f32), ("forward_only", i32), ("weights_packed", i32)]
 
 
 class RenderIn(C.Structure):
@@ -104,6 +104,7 @@ _SIGS = {
     "nefes_affine_color_fwd": (i32, [vp, vp, vp, i32, i64, vp, vp, vp, vp]),
     "nefes_affine_color_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp]),
     "nefes_render_rays_workspace": (i32, [C.POINTER(RenderCfg), i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+    "nefes_render_rays_prepack": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, vp, vp]),
     "nefes_render_rays_fwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), vp, vp, vp]),
     "nefes_render_rays_bwd": (i32, [C.POINTER(RenderCfg), C.POINTER(RenderIn), i64, C.POINTER(RenderOut), C.POINTER(CompGrad),
                                     C.POINTER(CompGrad), vp, vp, vp, vp, vp, vp]),

@@ -23,6 +23,9 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static thread_local bool t_forward_only = false;
 void set_forward_only(bool on) { t_forward_only = on; }
 bool forward_only() { return t_forward_only; }
+static thread_local bool t_weights_packed = false;
+void set_weights_packed(bool on) { t_weights_packed = on; }
+bool weights_packed() { return t_weights_packed; }
 
 namespace {
 struct ProfRec { const char* tag; cudaEvent_t e0, e1; double bytes, flops; };

@@ -19,6 +19,15 @@ void prof_end(cudaStream_t st);
 // calling thread, the bf16 forward chain does not write the saved activation copies (nobody will run the backward).
 void set_forward_only(bool on);
 bool forward_only();
+// While set, the bf16 forward does not re-pack the weights: the operand images in the caller's `saved` workspace are the
+// ones an earlier call wrote from the same (unchanged) parameters (nefes_render_cfg_t.weights_packed).
+void set_weights_packed(bool on);
+bool weights_packed();
+struct WeightsPackedScope {
+  bool prev;
+  explicit WeightsPackedScope(bool on) : prev(weights_packed()) { set_weights_packed(on); }
+  ~WeightsPackedScope() { set_weights_packed(prev); }
+};
 struct ForwardOnlyScope {
   bool prev;
   explicit ForwardOnlyScope(bool on) : prev(forward_only()) { set_forward_only(on); }

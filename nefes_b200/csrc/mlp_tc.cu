@@ -1692,6 +1692,16 @@ int mlp_workspace_bf16(int net, int mode, int64_t M, int64_t N, int64_t* saved, 
   return NEFES_OK;
 }
 
+// the weight re-pack of mlp_fwd_bf16 on its own: fp32 parameters -> bf16 operand images in the `saved` workspace of an (N, S, mode) query
+int mlp_prepack_bf16(const float* P, int net, int mode, int64_t N, int S, void* saved, cudaStream_t st) {
+  const int T = (int)ceil_div(N * S, kTile);
+  Ws w = carve_ws(saved, T, mode);
+  Arena A = {w.arena, packed_arena()};
+  prepack_kernel<<<256, 256, 0, st>>>(P, pack_src(net), A.ar, w.arena, net == NEFES_NET_FINE ? 1 : 0);
+  NEFES_CHECK_LAUNCH("prepack");
+  return NEFES_OK;
+}
+
 int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const float* dirs, int64_t N, int S, float* raw,
                  void* saved, void* scratch, int layout, cudaStream_t st) {
   const int64_t M = N * S;
@@ -1702,8 +1712,10 @@ int mlp_fwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   const bool fine = net == NEFES_NET_FINE;
   Arena A = {w.arena, packed_arena()};
 
-  prepack_kernel<<<256, 256, 0, st>>>(P, pack_src(net), A.ar, w.arena, fine ? 1 : 0);
-  NEFES_CHECK_LAUNCH("prepack");
+  if (!weights_packed()) {                           // frozen-weight callers (refinement) pack once per query: mlp_prepack_bf16
+    prepack_kernel<<<256, 256, 0, st>>>(P, pack_src(net), A.ar, w.arena, fine ? 1 : 0);
+    NEFES_CHECK_LAUNCH("prepack");
+  }
   encode_images_kernel<<<(unsigned)ceil_div(Mp, 128), 128, 0, st>>>(pts, dirs, S, M, Mp, w.X.p,
                                                                     mode == NEFES_MODE_SIGMA ? nullptr : w.DIRPE.p);
   NEFES_CHECK_LAUNCH("encode_images");

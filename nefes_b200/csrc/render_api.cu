@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 namespace nefes {
+int mlp_prepack_bf16(const float* P, int net, int mode, int64_t N, int S, void* saved, cudaStream_t st);   // mlp_tc.cu
 
 // pts[i,s,:] = o_i + d_i * z[i,s] (rendering.py:114/:143: a multiply then an add, no FMA, so the points are the
 // reference's bit for bit); optionally the contiguous copy of the view directions and, for the fine pass,
@@ -169,6 +170,21 @@ int nefes_render_rays_workspace(const nefes_render_cfg_t* cfg, int64_t N, int64_
   return NEFES_OK;
 }
 
+int nefes_render_rays_prepack(const nefes_render_cfg_t* cfg, const nefes_render_in_t* in, int64_t N, void* keep, void* stream) {
+  using namespace nefes;
+  const char* who = "nefes_render_rays_prepack";
+  RenderPlan P;
+  if (int e = make_plan(who, cfg, N, &P)) return e;
+  if (N == 0 || cfg->prec != NEFES_PREC_BF16) return NEFES_OK;     // the fp32 / tf32 paths read the parameters directly
+  NEFES_REQUIRE(in && keep && in->params_coarse && (!P.fine || in->params_fine), NEFES_EINVAL, "%s: null pointer", who);
+  NEFES_REQUIRE(((uintptr_t)keep & 255) == 0, NEFES_EALIGN, "%s: workspaces must be 256-byte aligned", who);
+  char* K = (char*)keep;
+  if (int e = mlp_prepack_bf16(in->params_coarse, cfg->net_coarse, P.mode_c, N, P.Sc, K + P.saved_c, (cudaStream_t)stream)) return e;
+  if (P.fine)
+    if (int e = mlp_prepack_bf16(in->params_fine, cfg->net_fine, P.mode_f, N, P.Sf, K + P.saved_f, (cudaStream_t)stream)) return e;
+  return NEFES_OK;
+}
+
 int nefes_render_rays_fwd(const nefes_render_cfg_t* cfg, const nefes_render_in_t* in, int64_t N,
                           const nefes_render_out_t* out, void* keep, void* scratch, void* stream) {
   using namespace nefes;
@@ -199,6 +215,7 @@ int nefes_render_rays_fwd(const nefes_render_cfg_t* cfg, const nefes_render_in_t
   {
     // nothing flows back into the sigma-only coarse pass of a test-time render (the importance samples are detached)
     ForwardOnlyScope fo(cfg->forward_only != 0 || P.mode_c == NEFES_MODE_SIGMA);
+    WeightsPackedScope wp(cfg->weights_packed != 0);
     if (int e = (P.tiled_c ? nefes_mlp_fwd_tiles : nefes_mlp_fwd)(in->params_coarse, cfg->net_coarse, P.mode_c, cfg->prec, pts_c,
                                                                   dirs, N, P.Sc, raw_c, K + P.saved_c, scratch, stream)) return e;
   }
@@ -218,6 +235,7 @@ int nefes_render_rays_fwd(const nefes_render_cfg_t* cfg, const nefes_render_in_t
   const int net_f = cfg->net_fine;
   {
     ForwardOnlyScope fo(cfg->forward_only != 0);
+    WeightsPackedScope wp(cfg->weights_packed != 0);
     if (int e = (P.tiled_f ? nefes_mlp_fwd_tiles : nefes_mlp_fwd)(in->params_fine, net_f, P.mode_f, cfg->prec, pts_f, dirs, N, P.Sf,
                                                                   raw_f, K + P.saved_f, scratch, stream)) return e;
   }

@@ -474,15 +474,18 @@ def render_rays_fused(rays, flat_c, flat_f, cfg, t_rand=None, u=None, noise_c=No
 class RenderCall:
     """nefes_render_rays_fwd / _bwd on buffers allocated ONCE (no autograd): the form a captured refinement iteration
     replays.  `forward()` renders the rays in `self.rays`; `backward(g_feat=..., g_rgb=...)` turns cotangents of the fine
-    composited outputs into `self.d_rays` (frozen fields: no parameter gradients)."""
+    composited outputs into `self.d_rays` (frozen fields: no parameter gradients).  With `frozen_weights=True` the forward
+    does not re-pack the parameters into the tensor path's operand images: the caller runs `prepack()` whenever they may
+    have changed (the refiner: once per query)."""
 
-    def __init__(self, n_rays, ld, cfg, flat_c, flat_f, device):
+    def __init__(self, n_rays, ld, cfg, flat_c, flat_f, device, frozen_weights=False):
         dev = torch.device(device)
         S, ni = cfg["n_samples"], cfg["n_importance"]
         Sf = S + ni
         self.N, self.ld, self.dev = n_rays, ld, dev
         self.cfg = L.RenderCfg(S, ni, cfg["prec"], int(cfg["test_time"]), int(cfg["output_transient"]),
-                               int(cfg["transient_at_test"]), cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]), 0)
+                               int(cfg["transient_at_test"]), cfg["net_coarse"], cfg["net_fine"], float(cfg["beta_min"]), 0,
+                               1 if frozen_weights else 0)
         kb, sfb, sbb = C.c_int64(), C.c_int64(), C.c_int64()
         L.check(L.lib().nefes_render_rays_workspace(C.byref(self.cfg), n_rays, C.byref(kb), C.byref(sfb), C.byref(sbb)),
                 "nefes_render_rays_workspace")
@@ -507,6 +510,11 @@ class RenderCall:
                                L.CompOut(p(self.rgb), p(self.feat), p(self.disp), p(self.acc), p(self.w), p(self.depth),
                                          p(self.beta), p(self.tsig)),
                                p(self.z_c), p(self.z_f), None, None, None)
+
+    def prepack(self):
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().nefes_render_rays_prepack(C.byref(self.cfg), C.byref(self.inp), self.N, L.ptr(self.keep),
+                                                      L.stream_of(self.rays)), "nefes_render_rays_prepack")
 
     def forward(self):
         with torch.cuda.device(self.dev):

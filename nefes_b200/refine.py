@@ -301,7 +301,7 @@ class EnginePoseRefiner:
         cfg = dict(n_samples=int(kw["N_samples"]), n_importance=int(kw["N_importance"]), prec=_PREC[c.precision], test_time=True,
                    output_transient=bool(args.NeRFW), transient_at_test=bool(args.transient_at_test), net_coarse=c.net_id,
                    net_fine=f.net_id, beta_min=f.beta_min)
-        self.call = ops.RenderCall(self.N, 21, cfg, c.flat, f.flat, dev)
+        self.call = ops.RenderCall(self.N, 21, cfg, c.flat, f.flat, dev, frozen_weights=True)   # packed once per query (refine())
         z = lambda *shape: torch.zeros(*shape, device=dev)
         self.pose6, self.init, self.c2w, self.d_c2w = z(6), z(3, 4), z(3, 4), z(12)
         self.state, self.stats = z(13), z(3, self.C)
@@ -334,6 +334,7 @@ class EnginePoseRefiner:
         self.target.copy_(feat_target)
         for t in (self.pose6, self.state, self.d_c2w, self.stats):
             t.zero_()
+        self.call.prepack()                           # the fields are frozen for the query: their operand images are built here, once
         done = 0
         if use_graph and self.graph is None:
             for _ in range(min(2, n_iters)):         # warm every kernel with real steps, then capture one iteration

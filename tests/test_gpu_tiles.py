@@ -464,3 +464,42 @@ def test_render_beyond_one_netchunk_takes_the_one_call_route_in_groups():
     for k in a:
         assert torch.equal(a[k], b[k]) or float((a[k] - b[k]).abs().max()) < 1e-6 * float(b[k].abs().max()), k
     assert float((gca - gcb).abs().max()) < 2e-3 * float(gcb.abs().max()) and float((gfa - gfb).abs().max()) < 2e-3 * float(gfb.abs().max())
+
+
+def test_render_call_with_frozen_weights_packs_once():
+    """nefes_render_rays_prepack + cfg.weights_packed (the refiner packs the frozen fields once per query): the forward that
+    skips its re-pack is bit-equal to the one that re-packs; it keeps rendering the packed weights after the parameters
+    change (the documented contract) until prepack() runs again."""
+    from nefes_b200 import ops, _lib as L
+    from nefes_b200.nerfh_nff import _PREC
+    c, f = _nets()
+    c.precision = f.precision = "bf16"
+    n = 333
+    cfg = dict(n_samples=64, n_importance=64, prec=_PREC["bf16"], test_time=True, output_transient=True, transient_at_test=True,
+               net_coarse=c.net_id, net_fine=f.net_id, beta_min=f.beta_min)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    rays = torch.zeros(n, 21, device="cuda")
+    rays[:, 0:3] = torch.randn(n, 3, device="cuda", generator=gen) * 0.1
+    d = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda", generator=gen), dim=-1)
+    rays[:, 3:6], rays[:, 8:11], rays[:, 7] = d, d, 4.0
+    plain = ops.RenderCall(n, 21, cfg, c.flat, f.flat, "cuda")
+    frozen = ops.RenderCall(n, 21, cfg, c.flat, f.flat, "cuda", frozen_weights=True)
+    for rc in (plain, frozen):
+        rc.rays.copy_(rays)
+    plain.forward()
+    frozen.prepack()
+    frozen.forward()
+    torch.cuda.synchronize()
+    assert torch.equal(plain.feat, frozen.feat) and torch.equal(plain.rgb, frozen.rgb) and torch.equal(plain.w, frozen.w)
+    feat0 = frozen.feat.clone()
+    with torch.no_grad():
+        f.flat.mul_(1.05)
+    frozen.forward()                                     # still the packed images
+    assert torch.equal(frozen.feat, feat0)
+    frozen.prepack()
+    frozen.forward()
+    plain.forward()
+    torch.cuda.synchronize()
+    assert not torch.equal(frozen.feat, feat0) and torch.equal(plain.feat, frozen.feat)
+    with torch.no_grad():
+        f.flat.div_(1.05)
