@@ -72,14 +72,37 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region: NVML in-process every 5 ms (what nvidia-smi reads; a
+    timed region of 20 steps is ~60 ms, shorter than one nvidia-smi start-up on an 8-GPU box), plus the recipe's
+    `nvidia-smi -lms` line as a second source when it manages to print inside the region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nv, self.nv_max, self.nv_reasons, self.stop, self.nth = [], None, set(), False, None
+
+    def _nvml(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = (("hw_slowdown", N.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", N.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksThrottleReasonSwPowerCap))
+            while not self.stop:
+                self.nv.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits:
+                    if r & bit:
+                        self.nv_reasons.add(name)
+                time.sleep(0.005)
+        except Exception:
+            pass
 
     def __enter__(self):
+        self.nth = threading.Thread(target=self._nvml, daemon=True)
+        self.nth.start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -95,8 +118,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop = True
+        if self.nth is not None:
+            self.nth.join(timeout=1)
         if self.proc is not None:
-            time.sleep(0.15)
+            if not self.nv:
+                time.sleep(0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -113,9 +140,13 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        if self.nv:
+            out = {"sm_mhz": float(np.median(self.nv)), "sm_max_mhz": max([self.nv_max or 0.0] + mx), "reasons": sorted(reasons | self.nv_reasons),
+                   "samples": len(self.nv), "source": "nvml (in-process, 5 ms)" + (f" + nvidia-smi ({len(sm)} lines)" if sm else "")}
+            return out
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # --------------------------------------------------------------------------------------------------
