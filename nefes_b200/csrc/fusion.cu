@@ -32,18 +32,29 @@ __global__ void fusion_pack_kernel(const float* __restrict__ rgb, const float* _
   }
 }
 
-// col[p][c*k*k + kh*k + kw] = x[image(p)][y + kh - pad][x + kw - pad][c], zero outside the image
+// col[p][c*k*k + kh*k + kw] = x[image(p)][y + kh - pad][x + kw - pad][c], zero outside the image.
+// One block per pixel: its k x k x C neighbourhood is read tap by tap (C contiguous floats each) into shared memory and leaves
+// as the pixel's K contiguous columns -- both sides coalesced.  (One thread per element gathered 4-byte words at 0.56 TB/s of
+// writes: 60 us per call, eight calls per stage-3 step.)
 __global__ void im2col_kernel(const float* __restrict__ x, int B, int H, int W, int C, int k, float* __restrict__ col) {
+  extern __shared__ float patch[];                            // [k*k][C]
   const int kk = k * k, pad = k / 2, K = C * kk;
-  const int64_t n = (int64_t)B * H * W * K;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = e / K;
-    const int j = (int)(e % K);
-    const int c = j / kk, kh = (j % kk) / k, kw = j % k;
+  const int64_t P = (int64_t)B * H * W;
+  for (int64_t p = blockIdx.x; p < P; p += gridDim.x) {
     const int px = (int)(p % W), py = (int)((p / W) % H);
     const int64_t img = p / ((int64_t)H * W);
-    const int yy = py + kh - pad, xx = px + kw - pad;
-    col[e] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((img * H + yy) * W + xx) * C + c] : 0.f;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const int tap = i / C, c = i - tap * C;
+      const int yy = py + tap / k - pad, xx = px + tap % k - pad;
+      patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((img * H + yy) * W + xx) * C + c] : 0.f;
+    }
+    __syncthreads();
+    float* row = col + p * K;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+      const int c = j / kk, tap = j - c * kk;
+      row[j] = patch[tap * C + c];
+    }
+    __syncthreads();
   }
 }
 
@@ -185,7 +196,7 @@ inline int conv_fwd(cudaStream_t st, const float* x, int B, int H, int W, int Ci
                     int act, float* col, float* y) {
   const int64_t P = (int64_t)B * H * W;
   const int K = Cin * k * k;
-  im2col_kernel<<<grid_for(P * K), 256, 0, st>>>(x, B, H, W, Cin, k, col);
+  im2col_kernel<<<(unsigned)(P < 148 * 64 ? P : 148 * 64), 256, (size_t)K * 4, st>>>(x, B, H, W, Cin, k, col);
   NEFES_CHECK_LAUNCH("im2col");
   return linear_fwd(st, col, K, wgt, K, bias, y, Cout, P, Cout, K, act, 0);
 }
@@ -195,7 +206,7 @@ inline int conv_bwd(cudaStream_t st, const float* x, const float* dy, int B, int
   const int64_t P = (int64_t)B * H * W;
   const int K = Cin * k * k;
   if (dW != nullptr) {
-    im2col_kernel<<<grid_for(P * K), 256, 0, st>>>(x, B, H, W, Cin, k, col);
+    im2col_kernel<<<(unsigned)(P < 148 * 64 ? P : 148 * 64), 256, (size_t)K * 4, st>>>(x, B, H, W, Cin, k, col);
     NEFES_CHECK_LAUNCH("im2col");
     if (int e = linear_wgrad(st, dy, Cout, col, K, dW, K, P, Cout, K)) return e;
   }
