@@ -1665,6 +1665,8 @@ int launch_heads2(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
   B.a.bar_count[bW] = (uint16_t)n_w;
   const int L_GDT = B.bar(1), L_GSIG = B.bar(1), L_A0 = B.bar(2), L_H7 = B.bar(1);
   const int ACC0 = B.bar(1), ACC1 = B.bar(1), E0 = B.bar(256), E1 = B.bar(256), D0 = B.bar(1), D1 = B.bar(1);
+  static const bool g7_over_gfin = [] { const char* e = getenv("NEFES_HEADS2_OUT"); return e == nullptr || atoi(e) != 0; }();
+  const int OUTFREE = g7_over_gfin ? B.bar(1) : -1;
   const uint32_t gdt_bytes = (uint32_t)dt_ch * 256u;
   // ---- producer: first-tile loads, then per tile
   B.p_load(L_GDT, b.GDT.p, (uint32_t)b.GDT.tile_stride(), gdt_bytes, G0, 1);
@@ -1679,13 +1681,25 @@ int launch_heads2(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
     int li = 0;
     for (; B.a.prod[li].kind == FO_LOAD && B.a.prod[li].next == 2; ++li) reload(li);
     const int iGDT = li, iGSIG = li + 1, iFIN = li + 2, iDIRPE = li + 3, iH7 = li + 4;
-    // G7 (output) is written over the [final | dirPE] slot A0, which only the weight-gradient GEMM of the first layer
-    // reads: the gradient input slot G0 is then free early in the tile and the NEXT tile's GDT -- the head of the
-    // serial data-gradient chain -- is prefetched; what waits for the store is A0, needed only by the weight-gradient stream
-    P.p_wait(D0); P.p_wait(E0); reload(iGDT);
-    P.p_wait(D1); P.p_wait(E1); reload(iH7); reload(iGSIG);
-    P.p_store(b.G[7].p, (uint32_t)b.G[7].tile_stride(), 32768, A0);
-    reload(iFIN); reload(iDIRPE);
+    if (g7_over_gfin) {
+      // G7 (output) is written over the gFIN image in G1 once BOTH streams are done with it (ACC1, D1 -- they finish about
+      // together): the [final | dirPE] slot A0 is then free as soon as the first weight-gradient GEMM retired, and the next
+      // tile's FIN / DIRPE -- which gate that GEMM, and through D0 nothing else any more -- are fetched early in the tile
+      // instead of behind the store at its very end.
+      P.p_wait(D0); reload(iFIN); reload(iDIRPE);
+      P.p_wait(E0); reload(iGDT);
+      P.p_wait(D1); P.p_wait(E1); reload(iH7); reload(iGSIG);
+      P.p_store(b.G[7].p, (uint32_t)b.G[7].tile_stride(), 32768, G1);
+      P.p_arrive(OUTFREE);
+    } else {
+      // G7 (output) is written over the [final | dirPE] slot A0, which only the weight-gradient GEMM of the first layer
+      // reads: the gradient input slot G0 is then free early in the tile and the NEXT tile's GDT -- the head of the
+      // serial data-gradient chain -- is prefetched; what waits for the store is A0, needed only by the weight-gradient stream
+      P.p_wait(D0); P.p_wait(E0); reload(iGDT);
+      P.p_wait(D1); P.p_wait(E1); reload(iH7); reload(iGSIG);
+      P.p_store(b.G[7].p, (uint32_t)b.G[7].tile_stride(), 32768, A0);
+      reload(iFIN); reload(iDIRPE);
+    }
     B = P;
   }
   // ---- data-gradient issuer
@@ -1704,8 +1718,13 @@ int launch_heads2(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
   B.m_wgrad(A1, G1 + 32768, 16, 432);                 // sigma row, transposed: D[h8 channel, 0] = sum_p h8[p, ch] * gsig[p]
   B.m_commit(D1);
   // ---- epilogue
-  B.e_wait(ACC0); B.e_wait(D1, FW_PREV); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);        // gFIN over the previous gFS
-  B.e_wait(ACC1); B.e_wait(L_H7); B.e_wait(D0); B.e_epi(0, 128, true, A1, A0); B.e_arrive(E1); // G7 over [final|dirPE] (read by D0)
+  if (g7_over_gfin) {
+    B.e_wait(ACC0); B.e_wait(D1, FW_PREV); B.e_wait(OUTFREE, FW_PREV); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);   // gFIN over the previous G7 (stored)
+    B.e_wait(ACC1); B.e_wait(L_H7); B.e_wait(D1); B.e_epi(0, 128, true, A1, G1); B.e_arrive(E1);                        // G7 over gFIN (read by ACC1, D1)
+  } else {
+    B.e_wait(ACC0); B.e_wait(D1, FW_PREV); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);        // gFIN over the previous gFS
+    B.e_wait(ACC1); B.e_wait(L_H7); B.e_wait(D0); B.e_epi(0, 128, true, A1, A0); B.e_arrive(E1); // G7 over [final|dirPE] (read by D0)
+  }
   // ---- flush: the dirPE image carries a constant 1 in its last padding channel (column 128 + 31): bias of [dir | tenc0]
   B.flush(128, 160, pl_dt, 0, 0, FF_W); B.flush(128 + 144, 16, pl_dt, 0, 15, FF_BIAS);
   B.flush(288, 128, PL_FS, 0, 0, FF_W); B.flush(288 + 128, 16, PL_FS, 0, 0, FF_BIAS);
