@@ -1389,7 +1389,7 @@ bool bulk_flush() {
   static const bool on = [] { const char* e = getenv("NEFES_BULK_FLUSH"); return e == nullptr || atoi(e) != 0; }();
   return on;
 }
-// Fused data + weight gradients of the eight trunk layers: four launches of two layers each (mlp_trunk_bwd.cuh).
+// Fused data + weight gradients of the eight trunk layers: one launch walking four passes of two layers each (mlp_trunk_bwd.cuh).
 int launch_trunk_bwd(const Ws& w, const WsB& b, const Arena& A, int net, int64_t M, float* dP, cudaStream_t st) {
   const int T = (int)ceil_div(M, kTile);
   static bool attr_done = false;
@@ -1807,7 +1807,7 @@ int mlp_bwd_bf16(const float* P, int net, int mode, const float* pts, const floa
   const Img& gsig_img = (mode == NEFES_MODE_SIGMA) ? b.GSIG : b.GFS;
   const bool tiles = layout == NEFES_RAW_TILES;
   // training (weight gradients, no gradient to the sample positions): fused data+weight-gradient launches -- two for
-  // the heads, four for the trunk; otherwise (pose refinement) the data-gradient chain runs all layers and keeps every
+  // the heads, one (four passes) for the trunk; otherwise (pose refinement) the data-gradient chain runs all layers and keeps every
   // gradient image for the input-gradient GEMMs
   const bool fused_trunk = dP != nullptr && d_pts == nullptr && getenv("NEFES_NO_FUSED_TRUNK") == nullptr;
   // (measured: a gain for the fine net's six head layers, none for the coarse net's three)
