@@ -171,9 +171,11 @@ __global__ void colsum_acc_kernel(const float* __restrict__ G, int64_t P, int C,
   atomicAdd(db + c, s);
 }
 
-struct FusionWs { float *X0, *A1, *A2, *A3, *Y, *stat, *sums, *col, *G, *G2; };
+struct FusionWs { float *X0, *A1, *A2, *A3, *Y, *stat, *sums, *col, *G, *G2, *colL[4]; };
+constexpr int kFusColK[4] = {kFusIn * 9, kFusHid * 9, kFusHid * 9, kFusHid * 25};   // im2col widths of the four convolutions
 inline int64_t fusion_ws_floats(int64_t P) {
-  return P * (kFusIn + 3 * kFusHid + kFeat) + 1024 + P * (int64_t)(kFusHid * 25) + 2 * P * (int64_t)kFusIn;
+  return P * (kFusIn + 3 * kFusHid + kFeat) + 1024 + P * (int64_t)(kFusHid * 25) + 2 * P * (int64_t)kFusIn +
+         P * (int64_t)(kFusColK[0] + kFusColK[1] + kFusColK[2] + kFusColK[3]);
 }
 inline FusionWs fusion_carve(void* ws, int64_t P) {
   FusionWs w;
@@ -187,7 +189,9 @@ inline FusionWs fusion_carve(void* ws, int64_t P) {
   w.sums = f; f += 512;
   w.col = f; f += P * (int64_t)(kFusHid * 25);       // the largest im2col matrix (conv4: 64 * 25; conv1: 131 * 9 = 1179 < 1600)
   w.G = f; f += P * (int64_t)kFusIn;                  // gradient of a layer input (<= 131 channels)
-  w.G2 = f;
+  w.G2 = f; f += P * (int64_t)kFusIn;
+  // the im2col matrix of every layer is kept from the forward: the weight gradient reads it again (113 MB at 7168 pixels)
+  for (int l = 0; l < 4; ++l) { w.colL[l] = f; f += P * (int64_t)kFusColK[l]; }
   return w;
 }
 inline unsigned grid_for(int64_t n) { const int64_t b = ceil_div(n, 256); return (unsigned)(b < 148 * 16 ? b : 148 * 16); }
@@ -201,14 +205,12 @@ inline int conv_fwd(cudaStream_t st, const float* x, int B, int H, int W, int Ci
   return linear_fwd(st, col, K, wgt, K, bias, y, Cout, P, Cout, K, act, 0);
 }
 // dy [P,Cout] (already gated by this layer's ReLU) -> dW, db accumulated; dx [P,Cin] gated by relu_src (the input's ReLU) or null
-inline int conv_bwd(cudaStream_t st, const float* x, const float* dy, int B, int H, int W, int Cin, int k, const float* wgt, int Cout,
+inline int conv_bwd(cudaStream_t st, const float* col_x, const float* dy, int B, int H, int W, int Cin, int k, const float* wgt, int Cout,
                     float* col, float* dW, float* db, const float* relu_src, float* dx) {
   const int64_t P = (int64_t)B * H * W;
   const int K = Cin * k * k;
-  if (dW != nullptr) {
-    im2col_kernel<<<(unsigned)(P < 148 * 64 ? P : 148 * 64), 256, (size_t)K * 4, st>>>(x, B, H, W, Cin, k, col);
-    NEFES_CHECK_LAUNCH("im2col");
-    if (int e = linear_wgrad(st, dy, Cout, col, K, dW, K, P, Cout, K)) return e;
+  if (dW != nullptr) {                                  // col_x: im2col of the layer's input, kept by the forward
+    if (int e = linear_wgrad(st, dy, Cout, col_x, K, dW, K, P, Cout, K)) return e;
   }
   if (db != nullptr) {
     const int64_t rpb = 64;
@@ -345,10 +347,10 @@ int nefes_fusion_fwd(const nefes_fusion_params_t* p, const float* rgb, const flo
   FusionWs w = fusion_carve(workspace, P);
   fusion_pack_kernel<<<grid_for(P * kFusIn), 256, 0, st>>>(rgb, feat, P, w.X0);
   NEFES_CHECK_LAUNCH("fusion_pack");
-  if (int e = conv_fwd(st, w.X0, B, H, W, kFusIn, 3, p->weight[0], p->bias[0], kFusHid, ACT_RELU, w.col, w.A1)) return e;
-  if (int e = conv_fwd(st, w.A1, B, H, W, kFusHid, 3, p->weight[1], p->bias[1], kFusHid, ACT_RELU, w.col, w.A2)) return e;
-  if (int e = conv_fwd(st, w.A2, B, H, W, kFusHid, 3, p->weight[2], p->bias[2], kFusHid, ACT_RELU, w.col, w.A3)) return e;
-  if (int e = conv_fwd(st, w.A3, B, H, W, kFusHid, 5, p->weight[3], p->bias[3], kFeat, ACT_NONE, w.col, w.Y)) return e;
+  if (int e = conv_fwd(st, w.X0, B, H, W, kFusIn, 3, p->weight[0], p->bias[0], kFusHid, ACT_RELU, w.colL[0], w.A1)) return e;
+  if (int e = conv_fwd(st, w.A1, B, H, W, kFusHid, 3, p->weight[1], p->bias[1], kFusHid, ACT_RELU, w.colL[1], w.A2)) return e;
+  if (int e = conv_fwd(st, w.A2, B, H, W, kFusHid, 3, p->weight[2], p->bias[2], kFusHid, ACT_RELU, w.colL[2], w.A3)) return e;
+  if (int e = conv_fwd(st, w.A3, B, H, W, kFusHid, 5, p->weight[3], p->bias[3], kFeat, ACT_NONE, w.colL[3], w.Y)) return e;
   if (!no_bn) {
     if (training) {
       NEFES_CUDA(cudaMemsetAsync(w.sums, 0, 2 * kFeat * sizeof(float), st));
@@ -386,11 +388,11 @@ int nefes_fusion_bwd(const nefes_fusion_params_t* p, const nefes_fusion_grads_t*
   }
   // conv4 <- A3, conv3 <- A2, conv2 <- A1, conv1 <- X0; G holds the gradient of the layer being processed's INPUT
   const bool need_in = d_rgb != nullptr || d_feat != nullptr;
-  if (int e = conv_bwd(st, w.A3, dY, B, H, W, kFusHid, 5, p->weight[3], kFeat, w.col, g->weight[3], g->bias[3], w.A3, w.G)) return e;
+  if (int e = conv_bwd(st, w.colL[3], dY, B, H, W, kFusHid, 5, p->weight[3], kFeat, w.col, g->weight[3], g->bias[3], w.A3, w.G)) return e;
   // the three 64-channel gradients alternate between G and G2 (G2 is free once conv4 has consumed dY)
-  if (int e = conv_bwd(st, w.A2, w.G, B, H, W, kFusHid, 3, p->weight[2], kFusHid, w.col, g->weight[2], g->bias[2], w.A2, w.G2)) return e;
-  if (int e = conv_bwd(st, w.A1, w.G2, B, H, W, kFusHid, 3, p->weight[1], kFusHid, w.col, g->weight[1], g->bias[1], w.A1, w.G)) return e;
-  if (int e = conv_bwd(st, w.X0, w.G, B, H, W, kFusIn, 3, p->weight[0], kFusHid, w.col, g->weight[0], g->bias[0], nullptr, need_in ? w.G2 : nullptr)) return e;
+  if (int e = conv_bwd(st, w.colL[2], w.G, B, H, W, kFusHid, 3, p->weight[2], kFusHid, w.col, g->weight[2], g->bias[2], w.A2, w.G2)) return e;
+  if (int e = conv_bwd(st, w.colL[1], w.G2, B, H, W, kFusHid, 3, p->weight[1], kFusHid, w.col, g->weight[1], g->bias[1], w.A1, w.G)) return e;
+  if (int e = conv_bwd(st, w.colL[0], w.G, B, H, W, kFusIn, 3, p->weight[0], kFusHid, w.col, g->weight[0], g->bias[0], nullptr, need_in ? w.G2 : nullptr)) return e;
   if (need_in) {
     fusion_unpack_grad_kernel<<<grid_for(P * kFusIn), 256, 0, st>>>(w.G2, P, d_rgb, d_feat, residual ? d_out : nullptr);
     NEFES_CHECK_LAUNCH("fusion_unpack_grad");
