@@ -119,3 +119,40 @@ def test_stage23_loss_golden(golden):
             out = out if isinstance(out, tuple) else (out,)
             for i, v in enumerate(out):
                 assert torch.equal(v, g[f"{'l1' if l1 else 'mse'}/{tag}/{i}"]), (l1, tag, i)
+
+
+def test_lindisp_and_white_bkgd_golden(golden, weights):
+    """The oracle's two dormant render options (rendering.py:97-100 lindisp, nerfh_nff.py:126-127 white_bkgd) against the
+    fixture rendered by the unmodified reference (G7)."""
+    g = golden("g7_options.npz")
+    wc, wf = weights
+    out = O.render(60, 80, 525.505 / 2 / 4, wc, wf, rays=(g["rays_o"], g["rays_d"]), near=0.5, far=4., test_time=False,
+                   t_rand=g["t_rand"], u=g["u"], lindisp=True, white_bkgd=True)
+    for k in ("rgb_map", "disp_map", "acc_map", "feat_map", "rgb0", "disp0", "acc0", "z_std", "transient_sigmas", "beta", "feat0"):
+        assert torch.equal(out[k], g["train/" + k]), k
+
+
+def test_fusion_net_golden(golden):
+    """The oracle's FusionNet restatement (nerfh_nff.py:356-418, :578-603) against the reference module's outputs and input
+    gradients (G8), training and eval mode.  The weights are the seeded default init of the constructor (checksum in the
+    fixture); BatchNorm state from the fixture."""
+    import nefes_b200.nerfh_nff as NB
+    g = golden("g8_fusion.npz")
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    torch.manual_seed(5)
+    m = NB.FusionNet(128)
+    m.net[7].load_state_dict({k[3:]: v for k, v in g.items() if k.startswith("bn/")})
+    chk = torch.stack([v.double().abs().sum() for k, v in m.state_dict().items() if k.endswith("weight")])
+    assert float((chk - g["w_checksum"]).abs().max()) < 1e-9
+    for mode in ("train", "eval"):
+        P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        rgb, feat = g["rgb"].clone().requires_grad_(True), g["feat"].clone().requires_grad_(True)
+        out = O.fusion_net(P, rgb, feat, B, H, W, training=(mode == "train"))
+        scale = float(g[f"{mode}/out"].abs().max())
+        assert float((out.detach() - g[f"{mode}/out"]).abs().max()) < 1e-5 * scale, mode
+        (out * g["cot"]).sum().backward()
+        for got, want in ((rgb.grad, g[f"{mode}/d_rgb"]), (feat.grad, g[f"{mode}/d_feat"])):
+            assert float((got - want).abs().max()) < 1e-4 * float(want.abs().max()), mode
+        if mode == "train":
+            assert torch.allclose(P["net.7.running_mean"], g["train/running_mean"], rtol=1e-5, atol=1e-7)
+            assert torch.allclose(P["net.7.running_var"], g["train/running_var"], rtol=1e-5, atol=1e-7)
