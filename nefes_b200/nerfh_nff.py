@@ -1,5 +1,6 @@
-"""Host-side mirror of the reference's script/models/nerfh_nff.py for the render hot path:
-same names, argument meaning and return conventions, arithmetic on the B200 kernels.
+"""The reference's script/models/nerfh_nff.py interface for the render hot path on the B200 kernels: same names,
+argument meaning and return conventions (the drop-in boundary -- `create_nerf`'s dict keys and the module's attribute /
+state_dict names ARE the interface and are restated as such); the arithmetic behind them is the engine's.
 
     raw2outputs_NeRFH_NFF   nerfh_nff.py:25-166
     run_network_NeRFH_NFF   nerfh_nff.py:168-231

@@ -1,5 +1,7 @@
-"""Mirror of script/models/rendering.py:23-243 -- sample_pdf, render_rays, batchify_rays, render --
-same signatures and return conventions, arithmetic on the B200 kernels.
+"""The reference's render interface (script/models/rendering.py:23-243: sample_pdf, render_rays, batchify_rays, render)
+on the B200 kernels.  This file is the DROP-IN BOUNDARY: callers use these names, keyword arguments, packing order of the
+ray batch and result-dict keys, so `render()`'s argument handling and `render_rays()`'s output assembly necessarily restate
+the reference's control flow (same conditions, same key names); the arithmetic behind them is the engine's.
 
 Extra keyword arguments (all optional, default = reference behaviour):
     t_rand, u, noise : explicit random draws ([N,N_samples], [N,N_importance], [N,N_samples]) so a
