@@ -1622,17 +1622,19 @@ int launch_heads1(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
   if (fine) {
     B.m_wait(L_GTH); B.m_wait(L_T3);
     B.m_wgrad(G1, At3, 80, 224); B.m_commit(D1);
-    B.m_wait(E1); B.m_wait(L_T2);                              // GT3 written by epilogue 1
+    B.m_wait(L_T2); B.m_wait(E1);                              // GT3 written by epilogue 1
     B.m_wgrad(G2, At2, 80, 304); B.m_commit(D2);
-    B.m_wait(E2); B.m_wait(L_TENC);                            // GT2 written by epilogue 2
+    B.m_wait(L_TENC); B.m_wait(E2);                            // GT2 written by epilogue 2
     B.m_wgrad(G3, Atenc, 80, 384); B.m_commit(D3);
   }
   // ---- epilogue (a gradient image may be overwritten only when BOTH streams finished reading its previous content)
-  B.e_wait(ACC0); B.e_wait(L_DIR); B.e_wait(OUTFREE, FW_PREV); B.e_epi(0, 64, true, Adir, G4); B.e_arrive(E0);
+  // (every wait costs the interpreter ~300 cycles even when its barrier completed long ago -- stamps, profiles/ -- so the
+  //  barrier that completes LAST, the round's accumulator, is waited for last: the others are checked while its MMAs run)
+  B.e_wait(L_DIR); B.e_wait(OUTFREE, FW_PREV); B.e_wait(ACC0); B.e_epi(0, 64, true, Adir, G4); B.e_arrive(E0);
   if (fine) {
-    B.e_wait(ACC1); B.e_wait(L_T3); B.e_wait(D2, FW_PREV); B.e_epi(0, 64, true, At3, G2); B.e_arrive(E1);
-    B.e_wait(ACC2); B.e_wait(L_T2); B.e_wait(D3, FW_PREV); B.e_epi(0, 64, true, At2, G3); B.e_arrive(E2);
-    B.e_wait(ACC3); B.e_wait(L_TENC); B.e_epi(0, 64, true, Atenc, G4 + 16384); B.e_arrive(E3);
+    B.e_wait(L_T3); B.e_wait(D2, FW_PREV); B.e_wait(ACC1); B.e_epi(0, 64, true, At3, G2); B.e_arrive(E1);
+    B.e_wait(L_T2); B.e_wait(D3, FW_PREV); B.e_wait(ACC2); B.e_epi(0, 64, true, At2, G3); B.e_arrive(E2);
+    B.e_wait(L_TENC); B.e_wait(ACC3); B.e_epi(0, 64, true, Atenc, G4 + 16384); B.e_arrive(E3);
   }
   // ---- flush
   B.flush(64, 64, PL_RGB, 0, 0, FF_W); B.flush(128, 16, PL_RGB, 0, 0, FF_BIAS);
@@ -1707,20 +1709,20 @@ int launch_heads2(const Ws& w, const WsB& b, const Arena& A, int net, int mode, 
   B.m_wait(bW, FW_ONCE);
   B.m_wait(L_GDT); B.m_wait(E1, FW_PREV);
   B.m_dgrad(G0, dt_ch, W0, 128, 128, 0); B.m_commit(ACC0);
-  B.m_wait(E0); B.m_wait(L_GSIG);
+  B.m_wait(L_GSIG); B.m_wait(E0);
   B.m_dgrad(G1, 144, W1, 128, 128, 0); B.m_commit(ACC1);
   // ---- weight-gradient issuer
   B.mp = 1;
   B.m_wait(L_GDT); B.m_wait(L_A0);
   B.m_wgrad(G0, A0, 160, 128); B.m_commit(D0);
-  B.m_wait(E0); B.m_wait(L_GSIG); B.m_wait(L_H7);
+  B.m_wait(L_GSIG); B.m_wait(L_H7); B.m_wait(E0);
   B.m_wgrad(G1, A1, 144, 288);
   B.m_wgrad(A1, G1 + 32768, 16, 432);                 // sigma row, transposed: D[h8 channel, 0] = sum_p h8[p, ch] * gsig[p]
   B.m_commit(D1);
   // ---- epilogue
   if (g7_over_gfin) {
-    B.e_wait(ACC0); B.e_wait(D1, FW_PREV); B.e_wait(OUTFREE, FW_PREV); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);   // gFIN over the previous G7 (stored)
-    B.e_wait(ACC1); B.e_wait(L_H7); B.e_wait(D1); B.e_epi(0, 128, true, A1, G1); B.e_arrive(E1);                        // G7 over gFIN (read by ACC1, D1)
+    B.e_wait(D1, FW_PREV); B.e_wait(OUTFREE, FW_PREV); B.e_wait(ACC0); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);   // gFIN over the previous G7 (stored)
+    B.e_wait(L_H7); B.e_wait(ACC1); B.e_wait(D1); B.e_epi(0, 128, true, A1, G1); B.e_arrive(E1);                        // G7 over gFIN (read by ACC1, D1)
   } else {
     B.e_wait(ACC0); B.e_wait(D1, FW_PREV); B.e_epi(0, 128, false, 0, G1); B.e_arrive(E0);        // gFIN over the previous gFS
     B.e_wait(ACC1); B.e_wait(L_H7); B.e_wait(D0); B.e_epi(0, 128, true, A1, A0); B.e_arrive(E1); // G7 over [final|dirPE] (read by D0)

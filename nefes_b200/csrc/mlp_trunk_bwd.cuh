@@ -236,12 +236,12 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_bwd_kernel(const __gri
         const TrunkStep& s = T.step[j];
         if (s.has_dgrad) {
           mbar_wait(&bar_afull[j], it & 1);           // the mask comes from the activation image
-          mbar_wait(&bar_acc, acc_ph);
-          acc_ph ^= 1u;
           // the destination image must be dead in BOTH MMA streams: G_mid was read by the weight-gradient GEMMs of step 1
           // of the previous tile, G_out lands on G_in, read by those of step 0 of this tile
           if (j == 0) { if (it > 0 && two) mbar_wait(&bar_afree[1], (it - 1) & 1); }
           else mbar_wait(&bar_afree[0], it & 1);
+          mbar_wait(&bar_acc, acc_ph);                // the accumulator completes last: waited for last
+          acc_ph ^= 1u;
           tc_fence_after();
           // input activation of layer j: channels [act_ch - 128, act_ch) of the slot gate the 128 gradient columns
           const uint8_t* a_row = smem + kTrOffA + j * 32768 + (uint32_t)(s.act_ch - 128) * 256u + (half * 8) * kChunkBytes + row * 16;
