@@ -26,6 +26,7 @@
 namespace nefes {
 
 enum { FO_END = 0, FO_WAIT, FO_LOAD, FO_STORE, FO_ARRIVE, FO_MMA, FO_COMMIT, FO_EPI };
+enum { FX_THEN = 8 };                       // MMA op: then COMMIT to `bar`; EPI op: then ARRIVE on `bar` (one interpreter step less on the critical path)
 enum { FW_PREV = 1, FW_ONCE = 2 };          // wait flags: the barrier phase of the previous tile / first tile only (weights)
 enum { FA_FRESH = 0, FA_LAUNCH = 1 };       // MMA accumulate mode: zero-init per group / accumulate over the launch
 enum { FF_W = 0, FF_BIAS = 1, FF_WT = 2 };  // flush kinds
@@ -169,8 +170,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
             const uint32_t acc0 = (uni((int)o.accmode) == FA_LAUNCH && it > 0) ? 1u : 0u;
             const int ks = uni((int)o.ksteps);
             const uint64_t a_adv = uni((uint32_t)o.a_adv), b_adv = uni((uint32_t)o.b_adv);
-            if (leader)
+            if (leader) {
               for (int k = 0; k < ks; ++k) mma_ss(d, da0 + (uint64_t)k * a_adv, db0 + (uint64_t)k * b_adv, idesc, (k > 0) ? 1u : acc0);
+              if (flags & FX_THEN) mma_commit(&bars[bar]);
+            }
           } else if (kind == FO_COMMIT) {
             if (leader) mma_commit(&bars[bar]);
           }
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
           }
           tc_fence_before();
           fence_async_smem();
+          if (o.flags & FX_THEN) mbar_arrive(&bars[o.bar]);
         }
         if (kFusedDbg && F.dbg != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 4 && i < 48) F.dbg[(2 * 4 + it) * 48 + i] = clock64();
       }

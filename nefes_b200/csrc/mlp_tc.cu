@@ -1454,7 +1454,12 @@ struct FusedBuilder {
   void p_arrive(int b) { FProdOp& o = a.prod[np++]; o.kind = FO_ARRIVE; o.bar = (uint8_t)b; }
   // MMA issuer
   void m_wait(int b, int flags = 0) { FMmaOp& o = a.mma[mp][nm[mp]++]; o.kind = FO_WAIT; o.bar = (uint8_t)b; o.flags = (uint8_t)flags; }
-  void m_commit(int b) { FMmaOp& o = a.mma[mp][nm[mp]++]; o.kind = FO_COMMIT; o.bar = (uint8_t)b; }
+  void m_commit(int b) {                                       // folded into the MMA op it follows
+    if (nm[mp] > 0 && a.mma[mp][nm[mp] - 1].kind == FO_MMA && !(a.mma[mp][nm[mp] - 1].flags & FX_THEN)) {
+      FMmaOp& m = a.mma[mp][nm[mp] - 1]; m.flags |= FX_THEN; m.bar = (uint8_t)b; return;
+    }
+    FMmaOp& o = a.mma[mp][nm[mp]++]; o.kind = FO_COMMIT; o.bar = (uint8_t)b;
+  }
   // data gradient: acc[128 pts, n] = G[pts, k_ch] (K-major image at g_off) * WT (image [k_ch/8][wt_rows][8] at w_off)
   void m_dgrad(uint32_t g_off, int k_ch, uint32_t w_off, int wt_rows, int n, int col) {
     FMmaOp& o = a.mma[mp][nm[mp]++]; o.kind = FO_MMA; o.accmode = FA_FRESH; o.ksteps = (uint8_t)(k_ch / 16);
@@ -1471,7 +1476,10 @@ struct FusedBuilder {
   }
   // epilogue
   void e_wait(int b, int flags = 0) { FEpiOp& o = a.epi[ne++]; o.kind = FO_WAIT; o.bar = (uint8_t)b; o.flags = (uint8_t)flags; }
-  void e_arrive(int b) { FEpiOp& o = a.epi[ne++]; o.kind = FO_ARRIVE; o.bar = (uint8_t)b; }
+  void e_arrive(int b) {                                       // folded into the EPI op it follows
+    if (ne > 0 && a.epi[ne - 1].kind == FO_EPI && !(a.epi[ne - 1].flags & FX_THEN)) { a.epi[ne - 1].flags |= FX_THEN; a.epi[ne - 1].bar = (uint8_t)b; return; }
+    FEpiOp& o = a.epi[ne++]; o.kind = FO_ARRIVE; o.bar = (uint8_t)b;
+  }
   void e_epi(int col, int n, bool mask, uint32_t mask_off, uint32_t out_off) {
     FEpiOp& o = a.epi[ne++]; o.kind = FO_EPI; o.acc_col = (uint16_t)col; o.n = (uint16_t)n; o.has_mask = mask ? 1 : 0;
     o.mask_off = mask_off; o.out_off = out_off;
