@@ -44,6 +44,12 @@ struct FMmaOp {
   uint16_t a_adv, b_adv;                    // descriptor advance per k-step in 16-byte units
   uint16_t tmem_col, pad2;
   uint32_t idesc;
+  // host-built at finish(): the two shared-memory descriptors relative to the smem base (the kernel adds base >> 4 to the
+  // address field -- 14 bits, no carry below 256 KB) and the small fields packed into one word: the issuer is a single warp
+  // at ~4 cycles per instruction, and building these from the fields above was ~60 of the ~100 instructions of an MMA step
+  uint64_t da_rel, db_rel;
+  uint32_t misc;                            // tmem_col | ksteps << 16 | accmode << 24
+  uint32_t adv;                             // a_adv | b_adv << 16
 };
 struct FEpiOp {
   uint8_t kind, bar, flags, has_mask;
@@ -153,7 +159,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
       const bool leader = elect_one();
       const int which = uni(warp == 1 ? 0 : 1);
       const FMmaOp* prog = s_mma[which];
-      const uint32_t sb = uni(sbase), tm = uni(tmem);
+      const uint32_t tm = uni(tmem);
+      const uint64_t sb16 = uni((uint64_t)(sbase >> 4));
       for (int it = 0; it < n_my; ++it) {
         for (int i = 0; prog[i].kind != FO_END; ++i) {
           const FMmaOp& o = prog[i];
@@ -164,12 +171,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_bwd_kernel(const __gri
             else mbar_wait(&bars[bar], it & 1);
           } else if (kind == FO_MMA) {
             tc_fence_after();
-            const uint64_t da0 = uni(smem_desc(sb + o.a_off, (uint32_t)o.a_lbo << 4, (uint32_t)o.a_sbo << 4));
-            const uint64_t db0 = uni(smem_desc(sb + o.b_off, (uint32_t)o.b_lbo << 4, (uint32_t)o.b_sbo << 4));
-            const uint32_t d = tm + uni((uint32_t)o.tmem_col), idesc = uni(o.idesc);
-            const uint32_t acc0 = (uni((int)o.accmode) == FA_LAUNCH && it > 0) ? 1u : 0u;
-            const int ks = uni((int)o.ksteps);
-            const uint64_t a_adv = uni((uint32_t)o.a_adv), b_adv = uni((uint32_t)o.b_adv);
+            const uint64_t da0 = uni(o.da_rel) + sb16, db0 = uni(o.db_rel) + sb16;
+            const uint32_t misc = uni(o.misc), adv = uni(o.adv), idesc = uni(o.idesc);
+            const uint32_t d = tm + (misc & 0xFFFFu);
+            const uint32_t acc0 = ((misc >> 24) == FA_LAUNCH && it > 0) ? 1u : 0u;
+            const int ks = (int)((misc >> 16) & 0xFFu);
+            const uint64_t a_adv = adv & 0xFFFFu, b_adv = adv >> 16;
             if (leader) {
               for (int k = 0; k < ks; ++k) mma_ss(d, da0 + (uint64_t)k * a_adv, db0 + (uint64_t)k * b_adv, idesc, (k > 0) ? 1u : acc0);
               if (flags & FX_THEN) mma_commit(&bars[bar]);

@@ -1503,6 +1503,18 @@ struct FusedBuilder {
                   nbar <= kFMaxBars && a.n_ones <= 4,
                   NEFES_EINVAL, "%s: program table overflow (%d %d %d %d %d %d)", what, np, nm[0], nm[1], ne, a.n_flush, nbar);
     a.prod[np].kind = FO_END; a.mma[0][nm[0]].kind = FO_END; a.mma[1][nm[1]].kind = FO_END; a.epi[ne].kind = FO_END;
+    for (int t = 0; t < 2; ++t)
+      for (int i = 0; i < nm[t]; ++i) {
+        FMmaOp& o = a.mma[t][i];
+        if (o.kind != FO_MMA) continue;
+        auto rel = [](uint32_t off, uint32_t lbo16, uint32_t sbo16) {      // tc05.cuh smem_desc with the address relative to the base
+          return (uint64_t)((off >> 4) & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+        };
+        o.da_rel = rel(o.a_off, o.a_lbo, o.a_sbo);
+        o.db_rel = rel(o.b_off, o.b_lbo, o.b_sbo);
+        o.misc = (uint32_t)o.tmem_col | ((uint32_t)o.ksteps << 16) | ((uint32_t)o.accmode << 24);
+        o.adv = (uint32_t)o.a_adv | ((uint32_t)o.b_adv << 16);
+      }
     a.n_tiles = n_tiles; a.ps = pack_src(net); a.d_flat = dP;
     return NEFES_OK;
   }
